@@ -1,0 +1,292 @@
+/*
+ * ref_shim.cpp — C entry points onto the UNMODIFIED reference (primihub/hehub).
+ *
+ * TEST INFRASTRUCTURE ONLY.  oracle/Makefile compiles this file together with the
+ * reference's own sources where they lie under $(REF) (default /root/reference)
+ * into oracle/_ref/libhehub_ref.so.  No reference source is copied into this
+ * repository.  The entry points mirror oracle/hehub_oracle.h one-for-one
+ * (prefix ref_ instead of orc_) so the same harness can drive either; they
+ * call the reference's public functions on its own containers.
+ */
+#include "fhe/bgv/bgv.h"
+#include "fhe/ckks/ckks.h"
+#include "fhe/common/mod_arith.h"
+#include "fhe/common/ntt.h"
+#include "fhe/common/permutation.h"
+#include "fhe/common/primelists.h"
+#include "fhe/primitives/keys.h"
+#include "fhe/primitives/rgsw.h"
+
+#include <cstring>
+#include <vector>
+
+using namespace hehub;
+
+namespace {
+
+RnsPolynomial load_poly(size_t n, size_t L, const u64 *moduli, const u64 *src, bool value_form) {
+    RnsPolynomial p(n, L, std::vector<u64>(moduli, moduli + L));
+    for (size_t k = 0; k < L; k++) std::memcpy(p[k].data(), src + k * n, n * sizeof(u64));
+    p.rep_form = value_form ? PolyRepForm::value : PolyRepForm::coeff;
+    return p;
+}
+
+void store_poly(const RnsPolynomial &p, u64 *dst) {
+    const size_t n = p.dimension();
+    for (size_t k = 0; k < p.component_count(); k++)
+        std::memcpy(dst + k * n, p[k].data(), n * sizeof(u64));
+}
+
+RlweKsk load_key(size_t n, size_t L, const u64 *ext_moduli, const u64 *key) {
+    RlweKsk ksk;
+    for (size_t p = 0; p < L; p++) {
+        RlweCt row{load_poly(n, L + 1, ext_moduli, key + (p * 2 + 0) * (L + 1) * n, true),
+                   load_poly(n, L + 1, ext_moduli, key + (p * 2 + 1) * (L + 1) * n, true)};
+        ksk.push_back(std::move(row));
+    }
+    return ksk;
+}
+
+template <class F> int guarded(F &&f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::invalid_argument &) {
+        return 1;
+    } catch (const std::logic_error &) {
+        return 3;
+    } catch (const char *) {
+        return 4;
+    } catch (...) {
+        return 5;
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+u64 ref_harvey_lazy(u64 q, u64 x, u64 w, u64 wh) { return mul_mod_harvey_lazy(q, x, w, wh); }
+u64 ref_inverse_mod_prime(u64 elem, u64 prime) { return inverse_mod_prime(elem, prime); }
+void ref_barrett_lazy(u64 q, size_t n, u64 *x) { batched_barrett_lazy(q, n, x); }
+void ref_barrett(u64 q, size_t n, u64 *x) { batched_barrett(q, n, x); }
+void ref_reduce_strict(u64 q, size_t n, u64 *x) { batched_reduce_strict(q, n, x); }
+void ref_mul_hybrid_lazy(u64 q, size_t n, const u64 *a, const u64 *b, u64 *c) {
+    batched_mul_mod_hybrid_lazy(q, n, a, b, c);
+}
+void ref_mul_barrett_lazy(u64 q, size_t n, const u64 *a, const u64 *b, u64 *c) {
+    batched_mul_mod_barrett_lazy(q, n, a, b, c);
+}
+void ref_montgomery128_lazy(u64 q, size_t n, const u64 *in_lohi, u64 *out) {
+    std::vector<u128> in(n);
+    for (size_t i = 0; i < n; i++) in[i] = ((u128)in_lohi[2 * i + 1] << 64) | in_lohi[2 * i];
+    batched_montgomery_128_lazy(q, n, in.data(), out);
+}
+
+int ref_ntt_fwd_lazy(unsigned logn, u64 q, u64 *x) {
+    return guarded([&] { ntt_negacyclic_inplace_lazy(logn, q, x); });
+}
+int ref_intt_lazy(unsigned logn, u64 q, u64 *x) {
+    return guarded([&] { intt_negacyclic_inplace_lazy(logn, q, x); });
+}
+
+/* RnsPolynomial-level elementwise ops: rns.cpp:58-171 */
+int ref_poly_add(unsigned logn, size_t L, const u64 *moduli, u64 *x, const u64 *y) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        auto a = load_poly(n, L, moduli, x, true), b = load_poly(n, L, moduli, y, true);
+        a += b;
+        store_poly(a, x);
+    });
+}
+int ref_poly_sub(unsigned logn, size_t L, const u64 *moduli, u64 *x, const u64 *y) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        auto a = load_poly(n, L, moduli, x, true), b = load_poly(n, L, moduli, y, true);
+        a -= b;
+        store_poly(a, x);
+    });
+}
+int ref_poly_mul_scalar(unsigned logn, size_t L, const u64 *moduli, u64 *x, u64 scalar) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        auto a = load_poly(n, L, moduli, x, true);
+        a *= scalar;
+        store_poly(a, x);
+    });
+}
+int ref_poly_ntt_fwd(unsigned logn, size_t L, const u64 *moduli, u64 *x) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        auto a = load_poly(n, L, moduli, x, false);
+        ntt_negacyclic_inplace_lazy(a);
+        store_poly(a, x);
+    });
+}
+int ref_poly_intt(unsigned logn, size_t L, const u64 *moduli, u64 *x, int strict) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        auto a = load_poly(n, L, moduli, x, true);
+        if (strict)
+            intt_negacyclic_inplace(a);
+        else
+            intt_negacyclic_inplace_lazy(a);
+        store_poly(a, x);
+    });
+}
+
+int ref_ckks_tensor(unsigned logn, size_t L, const u64 *moduli, const u64 *ct1, const u64 *ct2,
+                    u64 *quad) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        CkksCt a, b;
+        for (int h = 0; h < 2; h++) {
+            a[h] = load_poly(n, L, moduli, ct1 + h * L * n, true);
+            b[h] = load_poly(n, L, moduli, ct2 + h * L * n, true);
+        }
+        auto prod = ckks::mult_low_level(a, b);
+        for (int j = 0; j < 3; j++) store_poly(prod[j], quad + j * L * n);
+    });
+}
+
+int ref_ext_prod(unsigned logn, size_t L, const u64 *ext_moduli, const u64 *in, const u64 *key,
+                 u64 *out) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        auto pt = load_poly(n, L, ext_moduli, in, true);
+        auto ksk = load_key(n, L, ext_moduli, key);
+        auto ct = ext_prod_montgomery(pt, ksk);
+        for (int h = 0; h < 2; h++) store_poly(ct[h], out + h * (L + 1) * n);
+    });
+}
+
+int ref_ckks_rescale(unsigned logn, size_t L, const u64 *moduli, const u64 *ct, u64 *out) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        CkksCt c;
+        for (int h = 0; h < 2; h++) c[h] = load_poly(n, L, moduli, ct + h * L * n, true);
+        ckks::rescale_inplace(c);
+        for (int h = 0; h < 2; h++) store_poly(c[h], out + h * (L - 1) * n);
+    });
+}
+
+int ref_bgv_mod_switch(unsigned logn, size_t L, const u64 *moduli, u64 t, const u64 *ct,
+                       u64 *out) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        BgvCt c;
+        for (int h = 0; h < 2; h++) c[h] = load_poly(n, L, moduli, ct + h * L * n, true);
+        c.plain_modulus = t;
+        bgv::mod_switch_inplace(c);
+        for (int h = 0; h < 2; h++) store_poly(c[h], out + h * (L - 1) * n);
+    });
+}
+
+int ref_ckks_relinearize(unsigned logn, size_t L, const u64 *ext_moduli, const u64 *quad,
+                         const u64 *key, u64 *out) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        ckks::CkksQuadraticCt q3;
+        for (int j = 0; j < 3; j++) q3[j] = load_poly(n, L, ext_moduli, quad + j * L * n, true);
+        auto ksk = load_key(n, L, ext_moduli, key);
+        auto ct = ckks::relinearize(q3, ksk);
+        for (int h = 0; h < 2; h++) store_poly(ct[h], out + h * L * n);
+    });
+}
+
+/* bgv::relinearize always mod-switches with the default plain_modulus 1
+ * (bgv/arith.cpp:72-73), so `t` is accepted only for signature symmetry. */
+int ref_bgv_relinearize(unsigned logn, size_t L, const u64 *ext_moduli, u64 t, const u64 *quad,
+                        const u64 *key, u64 *out) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        bgv::BgvQuadraticCt q3;
+        for (int j = 0; j < 3; j++) q3[j] = load_poly(n, L, ext_moduli, quad + j * L * n, true);
+        q3.plain_modulus = t;
+        auto ksk = load_key(n, L, ext_moduli, key);
+        auto ct = bgv::relinearize(q3, ksk);
+        for (int h = 0; h < 2; h++) store_poly(ct[h], out + h * L * n);
+    });
+}
+
+int ref_ckks_mult_relin(unsigned logn, size_t L, const u64 *ext_moduli, const u64 *ct1,
+                        const u64 *ct2, const u64 *key, u64 *out) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        CkksCt a, b;
+        for (int h = 0; h < 2; h++) {
+            a[h] = load_poly(n, L, ext_moduli, ct1 + h * L * n, true);
+            b[h] = load_poly(n, L, ext_moduli, ct2 + h * L * n, true);
+        }
+        auto ksk = load_key(n, L, ext_moduli, key);
+        auto ct = ckks::mult(a, b, ksk);
+        for (int h = 0; h < 2; h++) store_poly(ct[h], out + h * L * n);
+    });
+}
+
+int ref_galois_cycle(unsigned logn, size_t L, const u64 *in, u64 *out, size_t step) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        std::vector<u64> moduli(L, 65537);
+        auto p = load_poly(n, L, moduli.data(), in, true);
+        store_poly(cycle(p, step), out);
+    });
+}
+
+int ref_galois_involution(unsigned logn, size_t L, const u64 *in, u64 *out) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        std::vector<u64> moduli(L, 65537);
+        auto p = load_poly(n, L, moduli.data(), in, true);
+        store_poly(involution(p), out);
+    });
+}
+
+int ref_ckks_rotate(unsigned logn, size_t L, const u64 *ext_moduli, const u64 *ct, const u64 *key,
+                    size_t step, u64 *out) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        CkksCt c;
+        for (int h = 0; h < 2; h++) c[h] = load_poly(n, L, ext_moduli, ct + h * L * n, true);
+        auto ksk = load_key(n, L, ext_moduli, key);
+        auto r = ckks::rotate(c, ksk, step);
+        for (int h = 0; h < 2; h++) store_poly(r[h], out + h * L * n);
+    });
+}
+
+int ref_ckks_conjugate(unsigned logn, size_t L, const u64 *ext_moduli, const u64 *ct,
+                       const u64 *key, u64 *out) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        CkksCt c;
+        for (int h = 0; h < 2; h++) c[h] = load_poly(n, L, ext_moduli, ct + h * L * n, true);
+        auto ksk = load_key(n, L, ext_moduli, key);
+        auto r = ckks::conjugate(c, ksk);
+        for (int h = 0; h < 2; h++) store_poly(r[h], out + h * L * n);
+    });
+}
+
+/* the raw prime table, for checking the restated selection rule */
+int ref_prime_row(unsigned bits, size_t count, u64 *out) {
+    if (bits >= prime_lists.size()) return 0;
+    const auto &row = prime_lists[bits];
+    size_t m = row.size() < count ? row.size() : count;
+    for (size_t i = 0; i < m; i++) out[i] = row[i];
+    return (int)m;
+}
+
+int ref_ckks_pick_moduli(const unsigned *moduli_bits, size_t L, unsigned additional_bits,
+                         u64 *moduli_out, u64 *additional_out) {
+    return guarded([&] {
+        std::vector<size_t> bits(moduli_bits, moduli_bits + L);
+        auto params = ckks::create_params(8, bits, additional_bits, 1.0);
+        for (size_t k = 0; k < L; k++) moduli_out[k] = params.moduli[k];
+        *additional_out = params.additional_mod;
+    });
+}
+
+void ref_cache_ntt_factors(unsigned logn, const u64 *moduli, size_t count) {
+    cache_ntt_factors_strict(logn, std::vector<u64>(moduli, moduli + count));
+}
+
+} // extern "C"
