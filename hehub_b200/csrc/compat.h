@@ -1,0 +1,58 @@
+// compat.h — the few macros that let the kernel sources be compiled twice:
+//
+//   * by nvcc for sm_100a — the product (libhehub_b200.so);
+//   * by g++ against tests/kernel_sim/cuda_sim.h — a CTA emulator used ONLY by the CPU test
+//     suite to check the kernels' index arithmetic, table layouts and host logic without a
+//     GPU (tests/kernel_sim/README.md).  The emulator is never built into, linked with or
+//     loaded by the product library; the product has no CPU path.
+#pragma once
+
+#if defined(HB_KERNEL_SIM)
+#include "cuda_sim.h" // tests/kernel_sim
+#define HB_D inline
+#define HB_CX constexpr
+#define HB_GLOBAL(threads, minblocks) static void
+#define HB_SHARED_U64(name) u64 *name = ::hbsim::shared_u64()
+// sync != 0: the kernel calls __syncthreads() (the emulator then runs real threads)
+#define HB_LAUNCH(kern, grid, block, smem, stream, sync, ...) \
+    ::hbsim::launch((grid), (block), (smem), (sync), [&]() { kern(__VA_ARGS__); })
+// thread-block cluster of `cluster` consecutive CTAs (the emulator runs them concurrently)
+#define HB_LAUNCH_CLUSTER(kern, grid, block, smem, stream, cluster, ...) \
+    (::hbsim::launch((grid), (block), (smem), 1, [&]() { kern(__VA_ARGS__); }, (cluster)), cudaSuccess)
+inline void hb_cluster_sync() { ::hbsim::cluster_sync(); }
+template <class T>
+inline T hb_ldcg(const T *p) { return *p; }
+#else
+#include <cuda_runtime.h>
+#define HB_D __device__ __forceinline__
+#define HB_CX __host__ __device__ constexpr
+#define HB_GLOBAL(threads, minblocks) __global__ void __launch_bounds__(threads, minblocks)
+#define HB_SHARED_U64(name) extern __shared__ __align__(16) unsigned long long name[]
+#define HB_LAUNCH(kern, grid, block, smem, stream, sync, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define HB_LAUNCH_CLUSTER(kern, grid, block, smem, stream, cluster, ...) \
+    ::hb_launch_cluster(kern, (grid), (block), (smem), (stream), (cluster), __VA_ARGS__)
+#include <utility>
+template <class... KArgs, class... Args>
+inline cudaError_t hb_launch_cluster(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                                     unsigned cluster, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+// barrier over the thread-block cluster with release/acquire ordering of global and shared writes
+__device__ __forceinline__ void hb_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <class T>
+__device__ __forceinline__ T hb_ldcg(const T *p) { return __ldcg(p); }
+#endif

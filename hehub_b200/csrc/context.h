@@ -1,0 +1,78 @@
+// context.h — host-side state behind the opaque hehub_b200_ctx handle.
+//
+// Holds the CUDA stream, the per-(modulus, ring size) twiddle tables (the device analogue of
+// the reference's global NTTFactors caches, src/fhe/common/ntt.cpp:107-143), per-chain
+// LimbConst arrays, a pooled slab allocator (device analogue of FixedBlockAllocator,
+// src/fhe/common/allocator.h:12-103) and grow-only scratch workspaces.
+#pragma once
+#include "compat.h"
+
+#include <cstdint>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "modarith.cuh"
+#include "ntt_engine.cuh"
+
+namespace hb {
+
+struct ModTables {
+    LimbConst lc;     // host copy; pointer members are device addresses
+    void *dev_block;  // one allocation holding every table of this (q, logn)
+};
+
+// extra per-limb constants of rescale / mod-switch (rescaling.cpp:36-44, mod_switch.cpp:36-44)
+struct DropConst {
+    u64 qlast_mod_q;        // q_last mod q_i
+    u64 inv_qlast, inv_qlast_h; // q_last^{-1} mod q_i and Harvey companion
+    u64 t_mod_q, t_mod_q_h;     // BGV: t mod q_i
+    u64 qlt_mod_q, qlt_mod_q_h; // BGV: (q_last mod t) mod q_i
+};
+
+struct DropSet {
+    DropConst *dev;   // [L-1]
+    u64 half_qlast;   // q_last / 2
+    u64 inv_t, inv_t_h; // BGV: t^{-1} mod q_last
+};
+
+struct Context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    bool force_generic = false;
+    size_t scratch_cap_bytes = (size_t)2 << 30; // bound on the per-call workspace; batches run in waves
+    std::string last_error;
+    LaunchStats stats;
+
+    std::map<std::pair<u64, unsigned>, ModTables> tables;
+    std::map<std::vector<u64>, LimbConst *> chains;      // key: {logn, q0, q1, ...}
+    std::map<std::vector<u64>, DropSet> drops;           // key: {logn, t, q0, ..., q_last}
+    std::map<std::vector<u64>, u64 *> scalar_sets;       // uploaded (s, s') pairs for mul_scalar
+    std::map<size_t, std::vector<u64 *>> slab_free;      // pooled slabs by size
+    std::map<u64 *, size_t> slab_live;
+    std::vector<std::pair<u64 *, size_t>> scratch;       // grow-only workspaces, by slot
+
+    ~Context();
+    int fail(int code, const std::string &msg) {
+        last_error = msg;
+        return code;
+    }
+    int cuda_fail(cudaError_t e, const char *where);
+
+    // returns nullptr and sets last_error on invalid modulus
+    const ModTables *get_tables(u64 q, unsigned logn, int *err);
+    // device array of LimbConst for the chain (tables built on demand)
+    const LimbConst *get_chain(unsigned logn, const u64 *moduli, size_t L, int *err);
+    const DropSet *get_drop(unsigned logn, const u64 *moduli, size_t L, u64 t, int *err);
+    u64 *get_scratch(size_t slot, size_t words, int *err);
+};
+
+// host helpers (exact restatements of the reference's parameter arithmetic)
+u64 host_pow_mod(u64 q, u64 base, u64 e);
+u64 host_root_2n(u64 q, u64 n);
+u64 host_inverse_mod_prime(u64 elem, u64 prime);
+inline u64 host_harvey_quotient(u64 w, u64 q) { return (u64)(((unsigned __int128)w << 64) / q); }
+
+} // namespace hb

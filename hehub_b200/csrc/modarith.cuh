@@ -1,0 +1,120 @@
+// modarith.cuh — word-level modular arithmetic on the device (sm_100a).
+//
+// Every function reproduces the *raw lazy representative* the reference computes
+// (primihub/hehub, src/fhe/common/mod_arith.{h,cpp}); file:line cited per function.
+// All products are exact 64x64->128 pieces built from 32-bit IMADs: this is 64-bit
+// integer modular arithmetic, tensor cores are not applicable.
+#pragma once
+#include <cstdint>
+
+#include "compat.h"
+
+namespace hb {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// Per-modulus constants and table pointers, resident in device memory.
+struct LimbConst {
+    u64 q;          // modulus
+    u64 q2;         // 2q
+    u64 nq;         // -q mod 2^64
+    u64 minus_qinv; // -q^{-1} mod 2^64          (mod_arith.cpp:49-52)
+    u64 r;          // 2^64 mod q                 (mod_arith.cpp:54-57)
+    u64 r_h;        // floor(r * 2^64 / q)        (mod_arith.cpp:59-62)
+    u64 barrett_c;  // floor((2^64-1)/q)          (mod_arith.cpp:10)
+    u32 logq;       // (u64)(log2(q)+0.5)         (ntt.cpp:171)
+    u32 fix;        // q >= 2^logq                (ntt.cpp:172)
+    const ulonglong2 *fwd;       // forward twiddles (w, w'), pass/slot-major layout (tables.cu)
+    const ulonglong2 *inv;       // inverse twiddles, pass/slot-major layout
+    const ulonglong2 *inv_scale; // psi^{-i}/N (strict) and its Harvey companion, natural order
+    const ulonglong2 *fwd_nat;   // reference order T[i] = psi^{bitrev(i)}      (ntt.cpp:54-58)
+    const ulonglong2 *inv_nat;   // reference order, per-level inverse twiddles (ntt.cpp:64-74)
+};
+
+// lo64(x*w + h*n): one accumulation chain of 2 wide + 4 narrow IMADs, no carries needed.
+HB_D u64 mul2_lo64(u64 x, u64 w, u64 h, u64 n) {
+#if defined(HB_KERNEL_SIM)
+    return x * w + h * n;
+#else
+    u64 t;
+    asm("{\n\t"
+        ".reg .u64 acc;\n\t"
+        ".reg .u32 x0, x1, w0, w1, h0, h1, n0, n1, lo, hi;\n\t"
+        "mov.b64 {x0, x1}, %1;\n\t"
+        "mov.b64 {w0, w1}, %2;\n\t"
+        "mov.b64 {h0, h1}, %3;\n\t"
+        "mov.b64 {n0, n1}, %4;\n\t"
+        "mul.wide.u32 acc, x0, w0;\n\t"
+        "mad.wide.u32 acc, h0, n0, acc;\n\t"
+        "mov.b64 {lo, hi}, acc;\n\t"
+        "mad.lo.u32 hi, x0, w1, hi;\n\t"
+        "mad.lo.u32 hi, x1, w0, hi;\n\t"
+        "mad.lo.u32 hi, h0, n1, hi;\n\t"
+        "mad.lo.u32 hi, h1, n0, hi;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t"
+        "}"
+        : "=l"(t)
+        : "l"(x), "l"(w), "l"(h), "l"(n));
+    return t;
+#endif
+}
+
+// mul_mod_harvey_lazy — mod_arith.h:74-78.  r = lo64(x*w) - lo64(hi64(x*w')*q), any x < 2^64,
+// w < q  ->  r in [0, 2q).  `nq` is -q mod 2^64 so the subtraction folds into the IMAD chain.
+HB_D u64 harvey_lazy(u64 x, u64 w, u64 wh, u64 nq) {
+    u64 qhat = __umul64hi(x, wh); // exact: the low partial product's carry is kept
+    return mul2_lo64(x, w, qhat, nq);
+}
+
+// the sweep at ntt.cpp:171-175: x -= ((x >> logq) - fix) * q
+HB_D u64 approx_reduce(u64 x, const LimbConst &c) {
+    return x - ((x >> c.logq) - (u64)c.fix) * c.q;
+}
+
+// batched_reduce_strict — mod_arith.h:58-63
+HB_D u64 reduce_strict(u64 x, u64 q) { return x - ((x >= q) ? q : 0ull); }
+
+// batched_barrett_lazy — mod_arith.cpp:9-17
+HB_D u64 barrett_lazy(u64 x, const LimbConst &c) {
+    return x - c.q * __umul64hi(x, c.barrett_c);
+}
+
+// lazy add / sub — rns.cpp:78-84, 109-115
+HB_D u64 add_lazy(u64 x, u64 y, u64 q2) {
+    x += y;
+    return x - ((x >= q2) ? q2 : 0ull);
+}
+HB_D u64 sub_lazy(u64 x, u64 y, u64 q2) {
+    x += q2 - y;
+    return x - ((x >= q2) ? q2 : 0ull);
+}
+
+// 128-bit a = (hi, lo);  Montgomery reduce: (a + (lo*minus_qinv mod 2^64)*q) >> 64
+// — mod_arith.cpp:126-133 (also the first half of the hybrid mulmod, :80-87).
+HB_D u64 montgomery128(u64 lo, u64 hi, const LimbConst &c) {
+    u64 u = lo * c.minus_qinv;
+    u64 plo = u * c.q;
+    u64 phi = __umul64hi(u, c.q);
+    // lo + plo == 0 mod 2^64 by construction; the carry is (lo != 0)
+    u64 carry = (lo + plo < lo) ? 1ull : 0ull;
+    return hi + phi + carry;
+}
+
+// batched_mul_mod_hybrid_lazy — mod_arith.cpp:64-92
+HB_D u64 mul_hybrid_lazy(u64 a, u64 b, const LimbConst &c) {
+    u64 lo = a * b;
+    u64 hi = __umul64hi(a, b);
+    u64 t = montgomery128(lo, hi, c);
+    return harvey_lazy(t, c.r, c.r_h, c.nq);
+}
+
+// 128-bit accumulate acc += a*b (exact; rgsw.cpp:131-134)
+HB_D void mac128(u64 &lo, u64 &hi, u64 a, u64 b) {
+    u64 plo = a * b;
+    u64 phi = __umul64hi(a, b);
+    lo += plo;
+    hi += phi + ((lo < plo) ? 1ull : 0ull);
+}
+
+} // namespace hb

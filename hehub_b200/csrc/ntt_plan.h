@@ -1,0 +1,77 @@
+// ntt_plan.h — compile-time decomposition of an N-point negacyclic NTT into register-resident
+// passes, shared by the device kernels (ntt_engine.cuh) and the host table builder (tables.cu).
+//
+// A row of N = 2^logn coefficients is processed by 2^lpre CTAs, each owning NC = N >> lpre
+// coefficients in shared memory.  The logn - lpre CTA-local butterfly levels are split into
+// `npass` passes; in pass p every thread keeps 2^k[p] coefficients in registers and runs k[p]
+// levels on them before the CTA exchanges through shared memory.  The forward transform runs
+// the passes in the listed order (gaps shrink N/2 -> 1, last pass touches contiguous
+// coefficients); the inverse transform runs the mirrored list (gaps grow 1 -> N/2).
+//
+// The twiddle tables are laid out per pass as [slot][block] so that the lanes of a warp read
+// consecutive 16-byte (w, w') pairs in every pass (see tables.cu).
+#pragma once
+#include "compat.h"
+
+namespace hb {
+
+constexpr int kMaxPasses = 5;
+
+struct NttPlan {
+    int logn;
+    int lpre;    // levels handled outside the CTA-local network (0, or 1 for N = 32768)
+    int npass;   // CTA-local passes
+    int k[kMaxPasses];
+    int threads; // CTA size
+    int min_blocks;
+};
+
+constexpr int kFastLogMin = 10;
+constexpr int kFastLogMax = 15;
+constexpr int kGenericLogMax = 14; // one row must fit one CTA's shared memory
+
+HB_CX NttPlan plan_for(int logn) {
+    switch (logn) {
+    case 10: return NttPlan{10, 0, 3, {3, 3, 4, 0, 0}, 64, 8};
+    case 11: return NttPlan{11, 0, 3, {4, 3, 4, 0, 0}, 128, 6};
+    case 12: return NttPlan{12, 0, 3, {4, 4, 4, 0, 0}, 256, 3};
+    case 13: return NttPlan{13, 0, 4, {3, 3, 3, 4, 0}, 256, 2};
+    case 14: return NttPlan{14, 0, 4, {4, 3, 3, 4, 0}, 512, 1};
+    default: return NttPlan{15, 1, 4, {4, 3, 3, 4, 0}, 512, 1};
+    }
+}
+
+// ---- forward layout --------------------------------------------------------------------
+// local levels completed before CTA pass p
+HB_CX int fwd_lambda0(const NttPlan &pl, int p) {
+    int s = 0;
+    for (int i = 0; i < p; i++) s += pl.k[i];
+    return s;
+}
+// entry offset of CTA pass p in the forward table: the lpre pre-level (one entry, T[1]) first
+HB_CX int fwd_pass_offset(const NttPlan &pl, int p) {
+    int off = pl.lpre ? 1 : 0;
+    for (int i = 0; i < p; i++) off += ((1 << pl.k[i]) - 1) << (pl.lpre + fwd_lambda0(pl, i));
+    return off;
+}
+
+// ---- inverse layout (mirrored pass list) -------------------------------------------------
+HB_CX int inv_k(const NttPlan &pl, int p) { return pl.k[pl.npass - 1 - p]; }
+HB_CX int inv_s0(const NttPlan &pl, int p) {
+    int s = 0;
+    for (int i = 0; i < p; i++) s += inv_k(pl, i);
+    return s;
+}
+// entry offset of inverse pass p; p == npass addresses the lpre post-stage (gap N/2)
+HB_CX int inv_pass_offset(const NttPlan &pl, int p) {
+    int off = 0;
+    for (int i = 0; i < p; i++) off += ((1 << inv_k(pl, i)) - 1) << inv_s0(pl, i);
+    return off;
+}
+
+// shared-memory padding: 2 words after every 16 keeps 128-bit accesses of 16-word-strided
+// owners and 64-bit accesses of consecutive lanes conflict-free
+HB_CX int smem_phys(int i) { return i + ((i >> 4) << 1); }
+HB_CX int smem_words(int nc) { return nc + (nc >> 3); }
+
+} // namespace hb

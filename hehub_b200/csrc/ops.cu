@@ -1,0 +1,374 @@
+// ops.cu — scheme-level operations composed from the transform engine and fused
+// coefficient-wise kernels.  Reference call stacks: SURVEY.md §3.1.
+//
+//   tensor       ckks::mult_low_level            src/fhe/ckks/arith.cpp:55-62
+//   ext_prod     ext_prod_montgomery             src/fhe/primitives/rgsw.cpp:57-156
+//   drop_last    rescale_by_one_prime_inplace    src/fhe/ckks/rescaling.cpp:14-78
+//                mod_drop_one_prime_inplace      src/fhe/bgv/mod_switch.cpp:13-78
+//   relinearize  ckks::relinearize               src/fhe/ckks/arith.cpp:64-73 (bgv/arith.cpp:71-79)
+//   galois       cycle / involution              src/fhe/common/permutation.cpp:28-75
+//
+// Prologue / epilogue arithmetic (Barrett + centring before the forward transforms of a
+// rescale, lazy subtract + q_last^{-1} multiply + addend after them, strict reduction after
+// the inverse transforms) lives in the IO policies of the transform kernels, so those values
+// never make a separate trip through HBM.
+#include "internal.h"
+
+namespace hb {
+
+// ------------------------------------------------------------------------------------------
+// tensor product: one pass, 4 loads + 3 stores per coefficient
+// ------------------------------------------------------------------------------------------
+HB_GLOBAL(256, 1)
+tensor_kernel(const u64 *__restrict__ ct1, const u64 *__restrict__ ct2, u64 *__restrict__ quad,
+              const LimbConst *__restrict__ limbs, int L, int logn, size_t pairs_total) {
+    // one thread per pair of adjacent coefficients of one (ct, limb)
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= pairs_total) return;
+    const size_t row = gid >> (logn - 1);              // b * L + l
+    const size_t i = (gid & (((size_t)1 << (logn - 1)) - 1)) * 2;
+    const size_t b = row / L, l = row % L;
+    const LimbConst lc = limbs[l];
+    const size_t n = (size_t)1 << logn, poly = (size_t)L << logn;
+    const size_t in0 = b * 2 * poly + l * n + i, in1 = in0 + poly;
+    const size_t o0 = b * 3 * poly + l * n + i;
+    const ulonglong2 a0 = *reinterpret_cast<const ulonglong2 *>(ct1 + in0), a1 = *reinterpret_cast<const ulonglong2 *>(ct1 + in1);
+    const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(ct2 + in0), b1 = *reinterpret_cast<const ulonglong2 *>(ct2 + in1);
+    ulonglong2 d0, d1, d2;
+    d0.x = mul_hybrid_lazy(a0.x, b0.x, lc);
+    d0.y = mul_hybrid_lazy(a0.y, b0.y, lc);
+    d1.x = add_lazy(mul_hybrid_lazy(a0.x, b1.x, lc), mul_hybrid_lazy(a1.x, b0.x, lc), lc.q2);
+    d1.y = add_lazy(mul_hybrid_lazy(a0.y, b1.y, lc), mul_hybrid_lazy(a1.y, b0.y, lc), lc.q2);
+    d2.x = mul_hybrid_lazy(a1.x, b1.x, lc);
+    d2.y = mul_hybrid_lazy(a1.y, b1.y, lc);
+    *reinterpret_cast<ulonglong2 *>(quad + o0) = d0;
+    *reinterpret_cast<ulonglong2 *>(quad + o0 + poly) = d1;
+    *reinterpret_cast<ulonglong2 *>(quad + o0 + 2 * poly) = d2;
+}
+
+int op_ckks_tensor(Context &c, unsigned logn, const u64 *moduli, size_t L, const u64 *ct1, const u64 *ct2, u64 *quad,
+                   size_t batch) {
+    if (!moduli || !ct1 || !ct2 || !quad) return c.fail(1, "null operand");
+    if (batch == 0) return 0;
+    for (size_t k = 0; k < L; k++)
+        if (!(moduli[k] & 1)) return c.fail(1, "Montgomery multiplication needs odd moduli");
+    int err = 0;
+    const LimbConst *limbs = c.get_chain(0, moduli, L, &err);
+    if (!limbs) return err;
+    const size_t pairs = (batch * L) << (logn - 1);
+    const size_t blocks = (pairs + 255) / 256;
+    if (blocks > 0x7fffffffull) return c.fail(1, "operand too large for one launch");
+    HB_LAUNCH(tensor_kernel, (unsigned)blocks, 256, 0, c.stream, 0, ct1, ct2, quad, limbs, (int)L, (int)logn, pairs);
+    c.stats.launches++;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : c.cuda_fail(e, "tensor launch");
+}
+
+// ------------------------------------------------------------------------------------------
+// key switch (ext_prod_montgomery)
+// ------------------------------------------------------------------------------------------
+// step 1: c[b][p] = strict(INTT_{q_p}(in[b][p]))                     rgsw.cpp:103-105
+struct ExtInttIO {
+    const u64 *in;
+    size_t in_batch_stride;
+    u64 *c; // [batch][L][N]
+    int L, logn;
+    HB_D int limb(int row) const { return row % L; }
+    HB_D u64 load(int row, int i, const LimbConst &) const {
+        return in[(size_t)(row / L) * in_batch_stride + ((size_t)(row % L) << logn) + i];
+    }
+    HB_D void store(int row, int i, u64 v, const LimbConst &lc) const { c[((size_t)row << logn) + i] = reduce_strict(v, lc.q); }
+    HB_D u64 *raw(int row) const { return c + ((size_t)row << logn); }
+};
+
+// step 2: dec[b][p][k] = NTT_{q_k}(c[b][p]) for k != p, k in [0, L]   rgsw.cpp:108-119
+struct ExtFanoutIO {
+    const u64 *c; // [batch][L][N]
+    u64 *dec;     // [batch][L][L+1][N]; slot k == p is not written (the diagonal keeps in[p])
+    int L, logn;
+    HB_D void split(int row, int &b, int &p, int &k) const {
+        b = row / (L * L);
+        const int rem = row - b * L * L;
+        p = rem / L;
+        const int kk = rem - p * L;
+        k = kk < p ? kk : kk + 1;
+    }
+    HB_D int limb(int row) const {
+        int b, p, k;
+        split(row, b, p, k);
+        return k;
+    }
+    HB_D u64 load(int row, int i, const LimbConst &) const {
+        int b, p, k;
+        split(row, b, p, k);
+        return c[((size_t)(b * L + p) << logn) + i];
+    }
+    HB_D void store(int row, int i, u64 v, const LimbConst &) const {
+        int b, p, k;
+        split(row, b, p, k);
+        dec[((size_t)((b * L + p) * (L + 1) + k) << logn) + i] = v;
+    }
+    HB_D u64 *raw(int) const { return nullptr; }
+};
+
+// step 3: out[b][h][k][i] = Mont128_{q_k}( sum_p dec[p][k][i] * key[p][h][k][i] )   rgsw.cpp:126-153
+HB_GLOBAL(256, 1)
+ext_mac_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
+               u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, int logn, size_t total) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // (b, k, i)
+    if (gid >= total) return;
+    const int L1 = L + 1;
+    const size_t i = gid & (((size_t)1 << logn) - 1);
+    const size_t bk = gid >> logn;
+    const int k = (int)(bk % L1);
+    const size_t b = bk / L1;
+    const LimbConst lc = limbs[k];
+    u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+    for (int p = 0; p < L; p++) {
+        const u64 d = (p == k) ? in[b * in_batch_stride + ((size_t)p << logn) + i]
+                               : dec[((size_t)((b * L + p) * L1 + k) << logn) + i];
+        const size_t kb = ((size_t)(p * 2) * L1 + k) << logn; // key[p][0][k]
+        mac128(lo0, hi0, d, __ldg(key + kb + i));
+        mac128(lo1, hi1, d, __ldg(key + kb + ((size_t)L1 << logn) + i));
+    }
+    const size_t ob = ((b * 2) * L1 + k) << logn;
+    out[ob + i] = montgomery128(lo0, hi0, lc);
+    out[ob + ((size_t)L1 << logn) + i] = montgomery128(lo1, hi1, lc);
+}
+
+// one wave of at most `wave` ciphertexts; scratch slots 0 (c) and 1 (dec)
+static int ext_prod_wave(Context &c, unsigned logn, const LimbConst *limbs, size_t L, const u64 *in, size_t in_batch_stride,
+                         const u64 *key, u64 *out, size_t batch, u64 *cbuf, u64 *dec) {
+    const size_t n = (size_t)1 << logn;
+    ExtInttIO io1{in, in_batch_stride, cbuf, (int)L, (int)logn};
+    cudaError_t e = launch_ntt(false, c.stream, logn, io1, limbs, (int)(batch * L), c.force_generic, c.stats);
+    if (e != cudaSuccess) return c.cuda_fail(e, "ext_prod: intt launch");
+    ExtFanoutIO io2{cbuf, dec, (int)L, (int)logn};
+    e = launch_ntt(true, c.stream, logn, io2, limbs, (int)(batch * L * L), c.force_generic, c.stats);
+    if (e != cudaSuccess) return c.cuda_fail(e, "ext_prod: ntt launch");
+    const size_t total = batch * (L + 1) * n;
+    HB_LAUNCH(ext_mac_kernel, (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, in_batch_stride, dec, key, out, limbs,
+              (int)L, (int)logn, total);
+    c.stats.launches++;
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : c.cuda_fail(e, "ext_prod: mac launch");
+}
+
+static size_t wave_size(const Context &c, size_t words_per_ct, size_t batch) {
+    size_t w = c.scratch_cap_bytes / (words_per_ct * 8);
+    if (w < 1) w = 1;
+    return w < batch ? w : batch;
+}
+
+int op_ext_prod(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *in, size_t in_batch_stride,
+                const u64 *key, u64 *out, size_t batch) {
+    if (!ext_moduli || !in || !key || !out) return c.fail(1, "null operand");
+    if (L == 0) return c.fail(1, "Empty RGSW ciphertext."); // rgsw.cpp:59-61
+    if (batch == 0) return 0;
+    for (size_t k = 0; k <= L; k++)
+        if (!(ext_moduli[k] & 1)) return c.fail(1, "Montgomery reduction needs odd moduli");
+    int err = 0;
+    const LimbConst *limbs = c.get_chain(logn, ext_moduli, L + 1, &err);
+    if (!limbs) return err;
+    const size_t n = (size_t)1 << logn;
+    const size_t per_ct = L * n + L * (L + 1) * n;
+    const size_t wave = wave_size(c, per_ct, batch);
+    u64 *cbuf = c.get_scratch(0, wave * L * n, &err);
+    if (!cbuf) return err;
+    u64 *dec = c.get_scratch(1, wave * L * (L + 1) * n, &err);
+    if (!dec) return err;
+    for (size_t b0 = 0; b0 < batch; b0 += wave) {
+        const size_t nb = (batch - b0 < wave) ? batch - b0 : wave;
+        if (int rc = ext_prod_wave(c, logn, limbs, L, in + b0 * in_batch_stride, in_batch_stride, key, out + b0 * 2 * (L + 1) * n,
+                                   nb, cbuf, dec))
+            return rc;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// drop the last prime (CKKS rescale / BGV mod-switch)
+// ------------------------------------------------------------------------------------------
+// step 1: z[b][h] = strict( [H(., t^{-1})] INTT_{q_last}(ct[b][h][L-1]) )   rescaling.cpp:47-50, mod_switch.cpp:48-51
+struct DropInttIO {
+    const u64 *ct;
+    u64 *z; // [batch][2][N]
+    int L, logn;
+    u64 inv_t, inv_t_h; // 0 for CKKS
+    int bgv;
+    HB_D int limb(int) const { return L - 1; }
+    HB_D u64 load(int row, int i, const LimbConst &) const { return ct[((size_t)(row * L + L - 1) << logn) + i]; }
+    HB_D void store(int row, int i, u64 v, const LimbConst &lc) const {
+        if (bgv) v = harvey_lazy(v, inv_t, inv_t_h, lc.nq);
+        z[((size_t)row << logn) + i] = reduce_strict(v, lc.q);
+    }
+    HB_D u64 *raw(int row) const { return z + ((size_t)row << logn); }
+};
+
+// step 2: per remaining limb k: r = centre(barrett(z)); NTT; out = H(lazy_sub(ct, r), q_last^{-1}) [...]
+struct DropFwdIO {
+    const u64 *ct;
+    const u64 *z;
+    u64 *out; // [batch][2][L-1][N]
+    const DropConst *dc;
+    const u64 *addend; // optional, lazy-added to the first add_halves polynomials
+    size_t add_batch_stride, add_poly_stride;
+    u64 half_qlast;
+    int L, logn, bgv, add_halves;
+    HB_D int limb(int row) const { return row % (L - 1); }
+    HB_D u64 load(int row, int i, const LimbConst &lc) const {
+        const int poly = row / (L - 1), k = row - poly * (L - 1);
+        const u64 zz = z[((size_t)poly << logn) + i];
+        u64 r = reduce_strict(barrett_lazy(zz, lc), lc.q);          // rescaling.cpp:58-59
+        if (zz >= half_qlast) r += lc.q - dc[k].qlast_mod_q;        // rescaling.cpp:63-68
+        if (bgv) r = harvey_lazy(r, dc[k].t_mod_q, dc[k].t_mod_q_h, lc.nq); // mod_switch.cpp:70
+        return r;
+    }
+    HB_D void store(int row, int i, u64 v, const LimbConst &lc) const {
+        const int poly = row / (L - 1), k = row - poly * (L - 1);
+        const DropConst d = dc[k];
+        u64 x = ct[((size_t)(poly * L + k) << logn) + i];
+        x = sub_lazy(x, v, lc.q2);                                   // rescaling.cpp:73
+        x = harvey_lazy(x, d.inv_qlast, d.inv_qlast_h, lc.nq);       // rescaling.cpp:74
+        if (bgv) x = harvey_lazy(x, d.qlt_mod_q, d.qlt_mod_q_h, lc.nq); // mod_switch.cpp:76
+        const int h = poly & 1, b = poly >> 1;
+        if (h < add_halves) // ckks/arith.cpp:70-71, 84, 91
+            x = add_lazy(x, addend[(size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn) + i], lc.q2);
+        out[((size_t)row << logn) + i] = x;
+    }
+    HB_D u64 *raw(int) const { return nullptr; }
+};
+
+int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, const u64 *ct, u64 *out, size_t batch,
+                 const u64 *addend, size_t add_batch_stride, size_t add_poly_stride, int add_halves) {
+    if (!moduli || !ct || !out) return c.fail(1, "null operand");
+    if (L < 2) return c.fail(1, "Unable to drop the only one prime.");
+    if (batch == 0) return 0;
+    int err = 0;
+    const LimbConst *limbs = c.get_chain(logn, moduli, L, &err);
+    if (!limbs) return err;
+    const DropSet *ds = c.get_drop(logn, moduli, L, t, &err);
+    if (!ds) return err;
+    const size_t n = (size_t)1 << logn;
+    u64 *z = c.get_scratch(2, batch * 2 * n, &err);
+    if (!z) return err;
+    DropInttIO io1{ct, z, (int)L, (int)logn, ds->inv_t, ds->inv_t_h, t ? 1 : 0};
+    cudaError_t e = launch_ntt(false, c.stream, logn, io1, limbs, (int)(batch * 2), c.force_generic, c.stats);
+    if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: intt launch");
+    DropFwdIO io2{ct, z, out, ds->dev, addend, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, t ? 1 : 0,
+                  addend ? add_halves : 0};
+    e = launch_ntt(true, c.stream, logn, io2, limbs, (int)(batch * 2 * (L - 1)), c.force_generic, c.stats);
+    if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: ntt launch");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// relinearize / mult
+// ------------------------------------------------------------------------------------------
+int op_relinearize(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u64 t, const u64 *quad, const u64 *key,
+                   u64 *out, size_t batch) {
+    if (!ext_moduli || !quad || !key || !out) return c.fail(1, "null operand");
+    if (L == 0) return c.fail(1, "Empty RGSW ciphertext.");
+    if (batch == 0) return 0;
+    const size_t n = (size_t)1 << logn;
+    // waves bound the scratch: per ct  c: L, dec: L(L+1), e: 2(L+1), z: 2  rows of N words
+    const size_t per_ct = (L + L * (L + 1) + 2 * (L + 1) + 2) * n;
+    const size_t wave = wave_size(c, per_ct, batch);
+    int err = 0;
+    u64 *ebuf = c.get_scratch(3, wave * 2 * (L + 1) * n, &err);
+    if (!ebuf) return err;
+    for (size_t b0 = 0; b0 < batch; b0 += wave) {
+        const size_t nb = (batch - b0 < wave) ? batch - b0 : wave;
+        const u64 *q = quad + b0 * 3 * L * n;
+        if (int rc = op_ext_prod(c, logn, ext_moduli, L, q + 2 * L * n, 3 * L * n, key, ebuf, nb)) return rc;
+        if (int rc = op_drop_last(c, logn, ext_moduli, L + 1, t, ebuf, out + b0 * 2 * L * n, nb, q, 3 * L * n, L * n, 2)) return rc;
+    }
+    return 0;
+}
+
+int op_mult_relin(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *ct1, const u64 *ct2, const u64 *key,
+                  u64 *out, size_t batch) {
+    if (!ext_moduli || !ct1 || !ct2 || !key || !out) return c.fail(1, "null operand");
+    if (L == 0) return c.fail(1, "Empty RGSW ciphertext.");
+    if (batch == 0) return 0;
+    const size_t n = (size_t)1 << logn;
+    const size_t per_ct = (3 * L + L + L * (L + 1) + 2 * (L + 1) + 2) * n;
+    const size_t wave = wave_size(c, per_ct, batch);
+    int err = 0;
+    u64 *quad = c.get_scratch(4, wave * 3 * L * n, &err);
+    if (!quad) return err;
+    for (size_t b0 = 0; b0 < batch; b0 += wave) {
+        const size_t nb = (batch - b0 < wave) ? batch - b0 : wave;
+        if (int rc = op_ckks_tensor(c, logn, ext_moduli, L, ct1 + b0 * 2 * L * n, ct2 + b0 * 2 * L * n, quad, nb)) return rc;
+        if (int rc = op_relinearize(c, logn, ext_moduli, L, 0, quad, key, out + b0 * 2 * L * n, nb)) return rc;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Galois permutations on NTT-form polynomials.  Slot j holds the evaluation at psi^(2*brev(j)+1);
+// the automorphism X -> X^g moves root index e to e*g, so output slot j gathers from the slot whose
+// root index is e_j * g^{-1} (mod 2N).  cycle: g = 3^step (permutation.cpp:42-58); involution:
+// g = -1, i.e. slot j <- slot N-1-j (permutation.cpp:70-73).
+// ------------------------------------------------------------------------------------------
+HB_GLOBAL(256, 1)
+galois_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, int logn, unsigned ginv, size_t total) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const unsigned n = 1u << logn, j = (unsigned)(gid & (n - 1));
+    const size_t row = gid >> logn;
+    const unsigned mask = 2 * n - 1;
+    const unsigned e = 2 * (__brev(j) >> (32 - logn)) + 1;
+    const unsigned src_e = (e * ginv) & mask;
+    const unsigned from = __brev((src_e - 1) >> 1) >> (32 - logn);
+    out[(row << logn) + j] = in[(row << logn) + from];
+}
+
+static unsigned galois_inverse_factor(unsigned logn, bool conj, size_t step) {
+    const unsigned mask = (2u << logn) - 1;
+    if (conj) return mask; // -1 is its own inverse
+    unsigned f = 1;
+    for (size_t i = 0; i < step; i++) f *= 3u; // modulo 2^32, consistent with any smaller 2-power
+    f &= mask;
+    unsigned inv = f; // Newton: inverse of an odd number modulo 2^32
+    for (int i = 0; i < 5; i++) inv *= 2u - f * inv;
+    return inv & mask;
+}
+
+int op_galois(Context &c, unsigned logn, size_t L, const u64 *in, u64 *out, bool conj, size_t step, size_t batch) {
+    if (!in || !out) return c.fail(1, "null operand");
+    if (in == out) return c.fail(1, "Galois permutation cannot run in place");
+    const size_t total = (batch * L) << logn;
+    if (total == 0) return 0;
+    HB_LAUNCH(galois_kernel, (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, out, (int)logn,
+              galois_inverse_factor(logn, conj, step), total);
+    c.stats.launches++;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : c.cuda_fail(e, "galois launch");
+}
+
+// ckks::rotate / ckks::conjugate — ckks/arith.cpp:75-93: permute both polynomials, key-switch the
+// permuted c1, drop P, add the permuted c0 to the first half only.
+int op_galois_keyswitch(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *ct, const u64 *key, bool conj,
+                        size_t step, u64 *out, size_t batch) {
+    if (!ext_moduli || !ct || !key || !out) return c.fail(1, "null operand");
+    if (L == 0) return c.fail(1, "Empty RGSW ciphertext.");
+    if (batch == 0) return 0;
+    const size_t n = (size_t)1 << logn;
+    const size_t per_ct = (2 * L + L + L * (L + 1) + 2 * (L + 1) + 2) * n;
+    const size_t wave = wave_size(c, per_ct, batch);
+    int err = 0;
+    u64 *rot = c.get_scratch(5, wave * 2 * L * n, &err);
+    if (!rot) return err;
+    u64 *ebuf = c.get_scratch(3, wave * 2 * (L + 1) * n, &err);
+    if (!ebuf) return err;
+    for (size_t b0 = 0; b0 < batch; b0 += wave) {
+        const size_t nb = (batch - b0 < wave) ? batch - b0 : wave;
+        if (int rc = op_galois(c, logn, 2 * L, ct + b0 * 2 * L * n, rot, conj, step, nb)) return rc;
+        if (int rc = op_ext_prod(c, logn, ext_moduli, L, rot + L * n, 2 * L * n, key, ebuf, nb)) return rc;
+        if (int rc = op_drop_last(c, logn, ext_moduli, L + 1, 0, ebuf, out + b0 * 2 * L * n, nb, rot, 2 * L * n, L * n, 1)) return rc;
+    }
+    return 0;
+}
+
+} // namespace hb

@@ -1,0 +1,166 @@
+/*
+ * hehub_b200.h — C ABI of the B200-native RNS polynomial-arithmetic backend for HEhub.
+ *
+ * This is the drop-in boundary for the ciphertext-op hot path of primihub/hehub
+ * (negacyclic NTT/INTT, lazy coefficient-wise modular arithmetic, RNS rescale /
+ * mod-switch, key-switch inner product).  The reference has no FFI layer: its seam
+ * is the set of hehub:: free functions cited per entry point below (paths relative
+ * to the reference root).  A maintainer binds these symbols from the reference's
+ * C++; hehub_b200/cpp/hehub/ holds that host-side mirror.
+ *
+ * Conventions
+ *   - Every polynomial operand is a DEVICE pointer to a contiguous little-endian
+ *     u64 slab indexed [batch][poly][limb][N]; `moduli` are HOST arrays.  A
+ *     key-switch key is [row p < L][half < 2][limb k <= L][N], limb L being the
+ *     special modulus P (reference: RlweKsk = vector<RlweCt>, keys.h:19-32).
+ *   - All arithmetic is integer mod q_i and lazy exactly like the reference:
+ *     results are the same raw u64 representatives the reference CPU path
+ *     produces on the same inputs (bit-exact), not merely congruent values.
+ *   - Calls are asynchronous on the context's CUDA stream and return a status
+ *     code; no exception crosses the ABI.  A context is thread-compatible (one
+ *     thread at a time), like the reference (which is single-threaded).
+ *   - There is no CPU fallback: without a CUDA device every compute entry point
+ *     fails with HEHUB_B200_ERR_CUDA.
+ */
+#ifndef HEHUB_B200_H
+#define HEHUB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HEHUB_B200_OK 0
+#define HEHUB_B200_ERR_INVALID 1     /* std::invalid_argument in the reference      */
+#define HEHUB_B200_ERR_CUDA 2        /* CUDA runtime failure / no device            */
+#define HEHUB_B200_ERR_UNSUPPORTED 3 /* the reference throws const char* here       */
+#define HEHUB_B200_ERR_NOMEM 4
+
+typedef struct hehub_b200_ctx hehub_b200_ctx;
+
+/* ---- context ------------------------------------------------------------- */
+const char *hehub_b200_version(void);
+/* stream: a cudaStream_t (as void*) to run on, or NULL for a context-owned stream. */
+int hehub_b200_ctx_create(hehub_b200_ctx **out, int device, void *stream);
+int hehub_b200_ctx_destroy(hehub_b200_ctx *ctx);
+int hehub_b200_ctx_set_stream(hehub_b200_ctx *ctx, void *stream);
+int hehub_b200_ctx_synchronize(hehub_b200_ctx *ctx);
+const char *hehub_b200_last_error(const hehub_b200_ctx *ctx);
+/* options: "force_generic" (0/1) routes transforms through the one-level-per-sweep kernels
+ * (an on-device cross-check of the fast path); "scratch_cap_mib" bounds the workspace a
+ * batched call may use (large batches are processed in waves). */
+int hehub_b200_ctx_set_option(hehub_b200_ctx *ctx, const char *name, int64_t value);
+/* number of kernels this context has launched since creation (bench bookkeeping) */
+uint64_t hehub_b200_launch_count(const hehub_b200_ctx *ctx);
+
+/* Build and upload the twiddle tables and per-modulus constants for (logN, q) for
+ * every q in moduli[].  Optional (tables are built on first use), like
+ * cache_ntt_factors_strict — src/fhe/common/ntt.cpp:225-231.  Fails with
+ * ERR_INVALID when round(log2 q) > 59 or 2N does not divide q-1 (ntt.cpp:26-47). */
+int hehub_b200_tables_prepare(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *moduli, size_t nmod);
+
+/* ---- device slabs (the device analogue of SmartArray / FixedBlockAllocator,
+ *      src/fhe/common/allocator.h:12-223: pooled per block size, reused on free) -- */
+int hehub_b200_slab_alloc(hehub_b200_ctx *ctx, size_t n_words, uint64_t **out_dev);
+int hehub_b200_slab_free(hehub_b200_ctx *ctx, uint64_t *dev);
+int hehub_b200_slab_h2d(hehub_b200_ctx *ctx, uint64_t *dev, const uint64_t *host, size_t n_words);
+int hehub_b200_slab_d2h(hehub_b200_ctx *ctx, uint64_t *host, const uint64_t *dev, size_t n_words);
+int hehub_b200_slab_d2d(hehub_b200_ctx *ctx, uint64_t *dst, const uint64_t *src, size_t n_words);
+/* pinned host staging buffers for the host-buffer entry points */
+int hehub_b200_host_alloc(hehub_b200_ctx *ctx, size_t n_words, uint64_t **out_host);
+int hehub_b200_host_free(hehub_b200_ctx *ctx, uint64_t *host);
+
+/* ---- transforms ------------------------------------------------------------
+ * x: [batch][L][N] in place.  Forward: natural-order coefficients in, bit-reversed
+ * evaluation order out, values < 2q under the reference's approximate reduction.
+ *   ntt_negacyclic_inplace_lazy  — src/fhe/common/ntt.cpp:145-176, ntt.h:41-51
+ *   intt_negacyclic_inplace_lazy — src/fhe/common/ntt.cpp:178-223, ntt.h:72-82
+ *   strict != 0 adds reduce_strict (intt_negacyclic_inplace, ntt.h:89-92). */
+int hehub_b200_ntt_fwd_lazy(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *moduli, size_t L,
+                            uint64_t *x, size_t batch);
+int hehub_b200_intt_lazy(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *moduli, size_t L,
+                         uint64_t *x, size_t batch, int strict);
+
+/* ---- coefficient-wise kernels (n = words per limb; slabs are [batch][L][n]) --
+ *   mulmod_hybrid_lazy : batched_mul_mod_hybrid_lazy, mod_arith.cpp:64-92 via
+ *                        RnsIntVec operator*, rns.cpp:120-140  (c may alias a or b)
+ *   add_lazy / sub_lazy: operator+= / operator-=, rns.cpp:58-118   (x op= y)
+ *   mul_scalar_lazy    : operator*=(vector<u64>), rns.cpp:155-171; scalars[L] host
+ *   reduce_strict      : batched_reduce_strict, mod_arith.h:58-72
+ *   barrett_lazy/barrett: mod_arith.cpp:9-17, mod_arith.h:18-25
+ *   montgomery128_lazy : mod_arith.cpp:113-134; in = n (lo,hi) pairs, one modulus */
+int hehub_b200_mulmod_hybrid_lazy(hehub_b200_ctx *ctx, size_t n, const uint64_t *moduli, size_t L,
+                                  const uint64_t *a, const uint64_t *b, uint64_t *c, size_t batch);
+int hehub_b200_add_lazy(hehub_b200_ctx *ctx, size_t n, const uint64_t *moduli, size_t L,
+                        uint64_t *x, const uint64_t *y, size_t batch);
+int hehub_b200_sub_lazy(hehub_b200_ctx *ctx, size_t n, const uint64_t *moduli, size_t L,
+                        uint64_t *x, const uint64_t *y, size_t batch);
+int hehub_b200_mul_scalar_lazy(hehub_b200_ctx *ctx, size_t n, const uint64_t *moduli, size_t L,
+                               uint64_t *x, const uint64_t *scalars, size_t batch);
+int hehub_b200_reduce_strict(hehub_b200_ctx *ctx, size_t n, const uint64_t *moduli, size_t L,
+                             uint64_t *x, size_t batch);
+int hehub_b200_barrett_lazy(hehub_b200_ctx *ctx, size_t n, const uint64_t *moduli, size_t L,
+                            uint64_t *x, size_t batch);
+int hehub_b200_barrett(hehub_b200_ctx *ctx, size_t n, const uint64_t *moduli, size_t L,
+                       uint64_t *x, size_t batch);
+int hehub_b200_montgomery128_lazy(hehub_b200_ctx *ctx, uint64_t q, size_t n, const uint64_t *in_lohi,
+                                  uint64_t *out);
+
+/* ---- Galois permutations on NTT-form polynomials (next row §8(f).1) ----------
+ *   cycle / involution — src/fhe/common/permutation.cpp:28-75; in/out [batch][L][N] */
+int hehub_b200_galois_cycle(hehub_b200_ctx *ctx, unsigned logn, size_t L, const uint64_t *in,
+                            uint64_t *out, size_t step, size_t batch);
+int hehub_b200_galois_involution(hehub_b200_ctx *ctx, unsigned logn, size_t L, const uint64_t *in,
+                                 uint64_t *out, size_t batch);
+
+/* ---- scheme-level ops --------------------------------------------------------
+ * ckks_tensor: ckks::mult_low_level, src/fhe/ckks/arith.cpp:55-62 (== bgv::mult_low_level,
+ *   bgv/arith.cpp:59-69).  ct1, ct2: [batch][2][L][N] -> quad: [batch][3][L][N].
+ * ext_prod_montgomery: src/fhe/primitives/rgsw.cpp:57-156.  ext_moduli has L+1
+ *   entries (q_0..q_{L-1}, P); in: [batch][L][N]; key: [L][2][L+1][N] shared by
+ *   the batch; out: [batch][2][L+1][N].
+ * ckks_rescale: ckks::rescale_inplace(ct, 1), src/fhe/ckks/rescaling.cpp:14-90.
+ *   ct: [batch][2][L][N] -> out: [batch][2][L-1][N]  (L >= 2).
+ * bgv_mod_switch: bgv::mod_switch_inplace(ct, 1), src/fhe/bgv/mod_switch.cpp:13-90.
+ * ckks_relinearize: src/fhe/ckks/arith.cpp:64-73; quad [batch][3][L][N] -> out [batch][2][L][N].
+ * bgv_relinearize: src/fhe/bgv/arith.cpp:71-79 with plain modulus t for the internal
+ *   mod-switch (the reference always runs it with the default t = 1).
+ * ckks_mult_relin: ckks::mult, src/fhe/ckks/ckks.h:270-274 = tensor + relinearize,
+ *   fused so the degree-2 ciphertext never round-trips through host code.
+ * ckks_rotate / ckks_conjugate: src/fhe/ckks/arith.cpp:75-93 (next row §8(f).1). */
+int hehub_b200_ckks_tensor(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *moduli, size_t L,
+                           const uint64_t *ct1, const uint64_t *ct2, uint64_t *quad, size_t batch);
+int hehub_b200_ext_prod_montgomery(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli,
+                                   size_t L, const uint64_t *in, const uint64_t *key, uint64_t *out,
+                                   size_t batch);
+int hehub_b200_ckks_rescale(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *moduli, size_t L,
+                            const uint64_t *ct, uint64_t *out, size_t batch);
+int hehub_b200_bgv_mod_switch(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *moduli, size_t L,
+                              uint64_t plain_modulus, const uint64_t *ct, uint64_t *out, size_t batch);
+int hehub_b200_ckks_relinearize(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli, size_t L,
+                                const uint64_t *quad, const uint64_t *key, uint64_t *out, size_t batch);
+int hehub_b200_bgv_relinearize(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli, size_t L,
+                               uint64_t plain_modulus, const uint64_t *quad, const uint64_t *key,
+                               uint64_t *out, size_t batch);
+int hehub_b200_ckks_mult_relin(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli, size_t L,
+                               const uint64_t *ct1, const uint64_t *ct2, const uint64_t *key,
+                               uint64_t *out, size_t batch);
+int hehub_b200_ckks_rotate(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli, size_t L,
+                           const uint64_t *ct, const uint64_t *key, size_t step, uint64_t *out,
+                           size_t batch);
+int hehub_b200_ckks_conjugate(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli, size_t L,
+                              const uint64_t *ct, const uint64_t *key, uint64_t *out, size_t batch);
+
+/* ---- harness helpers (synthetic inputs generated on the device) --------------
+ * lcg_fill: row r of x ([rows][n]) = SURVEY Appendix B LCG with seed seed0 + r*seed_stride,
+ *   reduced mod moduli[r % L].  fnv1a: FNV-1a over the words of x (device reduction
+ *   is order-dependent, so this one runs single-threaded per row then chains on host). */
+int hehub_b200_lcg_fill(hehub_b200_ctx *ctx, size_t n, const uint64_t *moduli, size_t L, uint64_t *x,
+                        size_t rows, uint64_t seed0, uint64_t seed_stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

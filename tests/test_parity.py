@@ -1,0 +1,357 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference's golden values.
+
+Every test runs against two back ends:
+  * ``gpu``  (marked ``gpu``): hehub_b200/libhehub_b200.so on a real B200 — the parity tests proper;
+  * ``sim``  (CPU suite): the same kernel sources compiled for the CTA emulator in tests/kernel_sim —
+    checks index arithmetic, table layouts and host logic without a GPU.
+The bar is bit-exact raw u64 words (all arithmetic is integer mod q_i).
+"""
+import numpy as np
+import pytest
+
+from conftest import fill_ct, fill_key, fnv
+
+Q59 = 576460752272228353
+NTT_MODULI = [65537, 260898817, 35184358850561, 36028796997599233, Q59]
+
+
+def hx(a):
+    return f"{fnv(a):016x}"
+
+
+@pytest.fixture(scope="module", params=["sim", pytest.param("gpu", marks=pytest.mark.gpu)])
+def dev(request):
+    from hehub_b200.binding import Context
+    if request.param == "sim":
+        import __graft_entry__ as ge
+        ctx = Context(lib_path=ge.build_sim())
+    else:
+        ctx = Context(device=0)  # fails loudly without the CUDA library or a device
+    ctx.kind = request.param
+    yield ctx
+    ctx.close()
+
+
+# ------------------------------------------------------------------ transforms
+@pytest.mark.parametrize("logn", [1, 2, 4, 7, 9, 10, 11, 12, 13, 14, 15])
+def test_ntt_intt_raw_words_match_oracle(dev, oracle, logn):
+    n = 1 << logn
+    rng = np.random.default_rng(logn)
+    for q in NTT_MODULI:
+        x = np.stack([rng.integers(0, q, n, dtype=np.uint64), oracle.lcg_fill(42, q, n),
+                      np.eye(1, n, 0, dtype=np.uint64)[0], np.eye(1, n, 1 % n, dtype=np.uint64)[0]])
+        want = np.stack([oracle.ntt_fwd_lazy(logn, q, r) for r in x])
+        got = dev.poly_ntt_fwd(logn, [q], x)
+        assert np.array_equal(got, want), (logn, q)
+        assert (got < 2 * q).all()  # tests/ntt_t.cpp:114-118
+        back = dev.poly_intt(logn, [q], want)
+        want_back = np.stack([oracle.intt_lazy(logn, q, r) for r in want])
+        assert np.array_equal(back, want_back), (logn, q)
+        # tests/ntt_t.cpp:120-125: one more reduction gives the input back
+        strict = dev.poly_intt(logn, [q], want, strict=True)
+        assert np.array_equal(strict, x), (logn, q)
+        # lazy inputs anywhere in [0, 2^64) are legal for the first butterfly level
+        wild = rng.integers(0, 1 << 63, n, dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+        if (2 + 2 * logn) * q < (1 << 62):  # headroom so the reference itself does not wrap
+            wild = wild >> np.uint64(3)
+            assert np.array_equal(dev.poly_ntt_fwd(logn, [q], wild), oracle.ntt_fwd_lazy(logn, q, wild))
+
+
+def test_ntt_hashes_match_reference_golden(dev, oracle, kat):
+    """SURVEY Appendix B / tests/golden: hashes recorded from the unmodified reference."""
+    for row in kat["ntt_hashes"]:
+        q, logn = row["q"], row["logn"]
+        if logn > 15:
+            continue
+        x = oracle.lcg_fill(42, q, 1 << logn)
+        y = dev.ntt_fwd_lazy(logn, q, x)
+        assert hx(y) == row["ntt"], (q, logn)
+        assert hx(dev.intt_lazy(logn, q, y)) == row["intt_ntt"], (q, logn)
+        assert hx(dev.intt_lazy(logn, q, x)) == row["intt"], (q, logn)
+
+
+def test_ntt_small_raw_vectors(dev, kat):
+    for name, logn in (("ntt_n8", 3), ("ntt_n16", 4)):
+        v = kat[name]
+        y = dev.ntt_fwd_lazy(logn, v["q"], np.array(v["in"], dtype=np.uint64))
+        assert y.tolist() == v["ntt"]
+        assert dev.intt_lazy(logn, v["q"], y).tolist() == v["intt"]
+
+
+@pytest.mark.parametrize("logn", [5, 10, 12, 15])
+def test_multi_limb_batched_transform(dev, oracle, logn):
+    """[batch][L][N] slabs: limb = row % L, every row independent (ntt.h:41-51, 72-82)."""
+    n = 1 << logn
+    moduli = [Q59, 36028796997599233, 65537]
+    batch = 3
+    x = np.stack([np.stack([oracle.lcg_fill(7 + 10 * b + k, q, n) for k, q in enumerate(moduli)]) for b in range(batch)])
+    want = np.stack([oracle.poly_ntt_fwd(logn, moduli, x[b]) for b in range(batch)])
+    assert np.array_equal(dev.poly_ntt_fwd(logn, moduli, x), want)
+    want_i = np.stack([oracle.poly_intt(logn, moduli, want[b]) for b in range(batch)])
+    assert np.array_equal(dev.poly_intt(logn, moduli, want), want_i)
+    want_s = np.stack([oracle.poly_intt(logn, moduli, want[b], strict=True) for b in range(batch)])
+    assert np.array_equal(dev.poly_intt(logn, moduli, want, strict=True), want_s)
+
+
+@pytest.mark.parametrize("logn", [10, 13, 14])
+def test_generic_path_agrees_with_fast_path(dev, oracle, logn):
+    n = 1 << logn
+    x = oracle.lcg_fill(99, Q59, n)
+    fast = dev.ntt_fwd_lazy(logn, Q59, x)
+    dev.set_option("force_generic", 1)
+    try:
+        slow = dev.ntt_fwd_lazy(logn, Q59, x)
+        slow_i = dev.intt_lazy(logn, Q59, fast)
+    finally:
+        dev.set_option("force_generic", 0)
+    assert np.array_equal(fast, slow)
+    assert np.array_equal(slow_i, dev.intt_lazy(logn, Q59, fast))
+
+
+# ------------------------------------------------------------------ coefficient-wise kernels
+@pytest.mark.parametrize("n", [1, 2, 5, 1000, 4096, 4099])
+def test_coefficient_wise_kernels(dev, oracle, n):
+    rng = np.random.default_rng(n)
+    moduli = [65537, 33333333, 777777777777777, 1234567890111111111]  # tests/mod_arith_t.cpp:6-32
+    full = np.stack([rng.integers(0, 1 << 63, n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, n, dtype=np.uint64)
+                     for _ in moduli])
+    assert np.array_equal(dev.barrett_lazy(moduli, full), np.stack([oracle.barrett_lazy(q, full[k]) for k, q in enumerate(moduli)]))
+    assert np.array_equal(dev.barrett(moduli, full), np.stack([oracle.barrett(q, full[k]) for k, q in enumerate(moduli)]))
+    lazy = np.stack([rng.integers(0, 2 * q, n, dtype=np.uint64) for q in moduli])
+    lazy2 = np.stack([rng.integers(0, 2 * q, n, dtype=np.uint64) for q in moduli])
+    assert np.array_equal(dev.reduce_strict(moduli, lazy), np.stack([oracle.reduce_strict(q, lazy[k]) for k, q in enumerate(moduli)]))
+    assert np.array_equal(dev.add_lazy(moduli, lazy, lazy2), np.stack([oracle.add_lazy(q, lazy[k], lazy2[k]) for k, q in enumerate(moduli)]))
+    assert np.array_equal(dev.sub_lazy(moduli, lazy, lazy2), np.stack([oracle.sub_lazy(q, lazy[k], lazy2[k]) for k, q in enumerate(moduli)]))
+    scalars = [12345, 1 << 40, 777777777777776, (1 << 64) - 1]
+    assert np.array_equal(dev.mul_scalar_lazy(moduli, lazy, scalars),
+                          np.stack([oracle.mul_scalar_lazy(q, lazy[k], scalars[k]) for k, q in enumerate(moduli)]))
+    odd = [65537, 33333333, 777777777777777, 1234567890111111111]
+    assert np.array_equal(dev.mul_hybrid_lazy(odd, lazy, lazy2),
+                          np.stack([oracle.mul_hybrid_lazy(q, lazy[k], lazy2[k]) for k, q in enumerate(odd)]))
+
+
+def test_mod_arith_golden(dev, kat):
+    """tests/mod_arith_t.cpp generators, outputs recorded from the unmodified reference."""
+    g = kat["mulmod"]
+    q, n = g["q"], 1000
+    M = (1 << 64) - 1
+    seed, f, gg = 42, [], []
+    for _ in range(n):  # tests/mod_arith_t.cpp:40-45
+        seed = ((seed * 65968279837582827) & M) ^ 3948528936546489545
+        f.append(seed % q)
+        seed = ((seed * 43534547657678213) & M) ^ 7955436776934235466
+        gg.append(seed % q)
+    f, gg = np.array(f, dtype=np.uint64), np.array(gg, dtype=np.uint64)
+    assert hx(f) == g["f"] and hx(gg) == g["g"]
+    out = dev.mul_hybrid_lazy([q], f, gg)
+    assert hx(out) == g["hybrid_lazy"]
+    assert out[:4].tolist() == g["hybrid_head"]
+    m = kat["montgomery128"]
+    assert dev.montgomery128_lazy(m["q"], np.array(m["in_lohi"], dtype=np.uint64)).tolist() == m["out"]
+
+
+def test_montgomery128_matches_oracle(dev, oracle):
+    q = 38589379749438777  # tests/mod_arith_t.cpp:61-78
+    rng = np.random.default_rng(5)
+    lo = rng.integers(0, 1 << 63, 999, dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    hi = rng.integers(0, q, 999, dtype=np.uint64)
+    lohi = np.stack([lo, hi], axis=1).ravel()
+    assert np.array_equal(dev.montgomery128_lazy(q, lohi), oracle.montgomery128_lazy(q, lohi))
+
+
+# ------------------------------------------------------------------ scheme-level ops
+def _shape(oracle, logn, bits, pbits):
+    mods, p = oracle.ckks_pick_moduli(bits, pbits)
+    mods = [int(m) for m in mods]
+    return mods, mods + [int(p)]
+
+
+def test_small_golden_vectors(dev, kat):
+    """N=16, L=3 full vectors recorded from the unmodified reference (tests/golden)."""
+    s = kat["small"]
+    logn, mods = s["logn"], s["moduli"]
+    ext = mods + [s["P"]]
+    L, n = len(mods), 1 << logn
+    A = lambda name, shape: np.array(s[name], dtype=np.uint64).reshape(shape)
+    ct1, ct2, key = A("ct1", (2, L, n)), A("ct2", (2, L, n)), A("key", (L, 2, L + 1, n))
+    quad = dev.ckks_tensor(logn, mods, ct1, ct2)
+    assert quad.ravel().tolist() == s["tensor"]
+    assert dev.ext_prod(logn, ext, quad[2], key).ravel().tolist() == s["ext_prod"]
+    assert dev.ckks_relinearize(logn, ext, quad, key).ravel().tolist() == s["relinearize"]
+    assert dev.ckks_mult_relin(logn, ext, ct1, ct2, key).ravel().tolist() == s["mult"]
+    assert dev.ckks_rescale(logn, mods, ct1).ravel().tolist() == s["rescale"]
+    assert dev.bgv_mod_switch(logn, mods, 65537, ct1).ravel().tolist() == s["mod_switch_t65537"]
+    assert dev.bgv_mod_switch(logn, mods, 2, ct1).ravel().tolist() == s["mod_switch_t2"]
+    assert dev.bgv_relinearize(logn, ext, 1, quad, key).ravel().tolist() == s["bgv_relinearize_t1"]
+    for step, want in s["cycle"].items():
+        assert dev.galois_cycle(logn, ct1[0], int(step)).ravel().tolist() == want
+    assert dev.galois_involution(logn, ct1[0]).ravel().tolist() == s["involution"]
+    for step, want in s["rotate"].items():
+        assert dev.ckks_rotate(logn, ext, ct1, key, int(step)).ravel().tolist() == want
+    assert dev.ckks_conjugate(logn, ext, ct1, key).ravel().tolist() == s["conjugate"]
+    assert dev.add_lazy(mods, ct1[0], ct2[1]).ravel().tolist() == s["poly_add"]
+    assert dev.sub_lazy(mods, ct1[0], ct2[1]).ravel().tolist() == s["poly_sub"]
+    assert dev.mul_scalar_lazy(mods, ct1[0], [12345] * L).ravel().tolist() == s["poly_mul_scalar_12345"]
+    assert dev.poly_intt(logn, mods, ct1[0], strict=True).ravel().tolist() == s["poly_intt_strict"]
+    assert dev.poly_ntt_fwd(logn, mods, ct1[0]).ravel().tolist() == s["poly_ntt"]
+
+
+def test_c3_mult_relin_hashes(dev, oracle, kat):
+    """BASELINE config 3: ckks::mult + relinearize, N=8192, L=4 — hashes from the unmodified reference."""
+    c3 = kat["c3"]
+    logn, mods = c3["logn"], c3["moduli"]
+    ext, n = mods + [c3["P"]], 1 << c3["logn"]
+    ct1, ct2, key = fill_ct(oracle, 100, mods, n), fill_ct(oracle, 200, mods, n), fill_key(oracle, 1000, ext, n)
+    quad = dev.ckks_tensor(logn, mods, ct1, ct2)
+    assert [hx(quad[i]) for i in range(3)] == c3["tensor"]
+    e = dev.ext_prod(logn, ext, quad[2], key)
+    assert [hx(e[i]) for i in range(2)] == c3["ext_prod"]
+    r = dev.ckks_relinearize(logn, ext, quad, key)
+    assert [hx(r[i]) for i in range(2)] == c3["relinearize"]
+    m = dev.ckks_mult_relin(logn, ext, ct1, ct2, key)
+    assert [hx(m[i]) for i in range(2)] == c3["mult"]
+    rs = dev.ckks_rescale(logn, mods, m)
+    assert [hx(rs[i]) for i in range(2)] == c3["rescale"]
+    rot = dev.ckks_rotate(logn, ext, ct1, key, 5)
+    assert [hx(rot[i]) for i in range(2)] == c3["rotate5"]
+    cj = dev.ckks_conjugate(logn, ext, ct1, key)
+    assert [hx(cj[i]) for i in range(2)] == c3["conjugate"]
+    b = dev.bgv_relinearize(logn, ext, 1, quad, key)
+    assert [hx(b[i]) for i in range(2)] == c3["bgv_relinearize_t1"]
+
+
+def test_c4_rescale_hashes(dev, oracle, kat):
+    """BASELINE config 4: rescale / mod-switch N=16384, L=8->7 — hashes from the unmodified reference."""
+    c4 = kat["c4"]
+    logn, mods, n = c4["logn"], c4["moduli"], 1 << c4["logn"]
+    ct = fill_ct(oracle, 300, mods, n)
+    r = dev.ckks_rescale(logn, mods, ct)
+    assert [hx(r[i]) for i in range(2)] == c4["rescale"]
+    m = dev.bgv_mod_switch(logn, mods, 65537, ct)
+    assert [hx(m[i]) for i in range(2)] == c4["mod_switch_t65537"]
+
+
+def test_c5_shape_mult_hash(dev, oracle, kat):
+    """BASELINE config 5 shape (one ciphertext): N=32768, L=12."""
+    if dev.kind == "sim":
+        pytest.skip("182 transforms of 32768 points: GPU only (the sim covers N=32768 with L=2 below)")
+    c5 = kat["c5"]
+    logn, mods = c5["logn"], c5["moduli"]
+    ext, n = mods + [c5["P"]], 1 << c5["logn"]
+    ct1, ct2, key = fill_ct(oracle, 100, mods, n), fill_ct(oracle, 200, mods, n), fill_key(oracle, 1000, ext, n)
+    m = dev.ckks_mult_relin(logn, ext, ct1, ct2, key)
+    assert [hx(m[i]) for i in range(2)] == c5["mult"]
+
+
+@pytest.mark.parametrize("logn,bits,pbits", [(10, [40, 30, 30], 40), (12, [39, 30], 39), (15, [50, 50], 55), (6, [30, 30, 30, 30], 40)])
+def test_scheme_ops_match_oracle(dev, oracle, logn, bits, pbits):
+    mods, ext = _shape(oracle, logn, bits, pbits)
+    n, L = 1 << logn, len(mods)
+    ct1, ct2, key = fill_ct(oracle, 11, mods, n), fill_ct(oracle, 22, mods, n), fill_key(oracle, 3000, ext, n)
+    quad = oracle.ckks_tensor(logn, mods, ct1, ct2)
+    assert np.array_equal(dev.ckks_tensor(logn, mods, ct1, ct2), quad)
+    e = oracle.ext_prod(logn, ext, quad[2], key)
+    assert np.array_equal(dev.ext_prod(logn, ext, quad[2], key), e)
+    assert np.array_equal(dev.ckks_rescale(logn, ext, e), oracle.ckks_rescale(logn, ext, e))
+    for t in (2, 65537):
+        assert np.array_equal(dev.bgv_mod_switch(logn, ext, t, e), oracle.bgv_mod_switch(logn, ext, t, e))
+    assert np.array_equal(dev.ckks_relinearize(logn, ext, quad, key), oracle.ckks_relinearize(logn, ext, quad, key))
+    assert np.array_equal(dev.bgv_relinearize(logn, ext, 1, quad, key), oracle.bgv_relinearize(logn, ext, 1, quad, key))
+    assert np.array_equal(dev.ckks_mult_relin(logn, ext, ct1, ct2, key), oracle.ckks_mult_relin(logn, ext, ct1, ct2, key))
+    for step in (0, 1, 5, n // 2 - 1):
+        assert np.array_equal(dev.galois_cycle(logn, ct1[0], step), oracle.galois_cycle(logn, ct1[0], step))
+    assert np.array_equal(dev.galois_involution(logn, ct1[1]), oracle.galois_involution(logn, ct1[1]))
+    assert np.array_equal(dev.ckks_rotate(logn, ext, ct1, key, 3), oracle.ckks_rotate(logn, ext, ct1, key, 3))
+    assert np.array_equal(dev.ckks_conjugate(logn, ext, ct1, key), oracle.ckks_conjugate(logn, ext, ct1, key))
+
+
+def test_single_limb_key_switch(dev, oracle):
+    """L = 1: the decomposition has one row; rescale of the (q0, P) result leaves one limb."""
+    logn = 10
+    mods, ext = _shape(oracle, logn, [40], 40)
+    n = 1 << logn
+    ct1, ct2, key = fill_ct(oracle, 1, mods, n), fill_ct(oracle, 2, mods, n), fill_key(oracle, 3, ext, n)
+    assert np.array_equal(dev.ckks_mult_relin(logn, ext, ct1, ct2, key), oracle.ckks_mult_relin(logn, ext, ct1, ct2, key))
+
+
+def test_batched_ops_and_waves(dev, oracle):
+    """Independent ciphertexts in one call; a tiny scratch cap forces wave-by-wave processing."""
+    logn = 10
+    mods, ext = _shape(oracle, logn, [40, 30, 30], 40)
+    n, batch = 1 << logn, 5
+    ct1 = np.stack([fill_ct(oracle, 100 + 1000 * b, mods, n) for b in range(batch)])
+    ct2 = np.stack([fill_ct(oracle, 200 + 1000 * b, mods, n) for b in range(batch)])
+    key = fill_key(oracle, 7000, ext, n)
+    want = np.stack([oracle.ckks_mult_relin(logn, ext, ct1[b], ct2[b], key) for b in range(batch)])
+    assert np.array_equal(dev.ckks_mult_relin(logn, ext, ct1, ct2, key), want)
+    dev.set_option("scratch_cap_mib", 1)
+    try:
+        assert np.array_equal(dev.ckks_mult_relin(logn, ext, ct1, ct2, key), want)
+        want_rot = np.stack([oracle.ckks_rotate(logn, ext, ct1[b], key, 2) for b in range(batch)])
+        assert np.array_equal(dev.ckks_rotate(logn, ext, ct1, key, 2), want_rot)
+    finally:
+        dev.set_option("scratch_cap_mib", 2048)
+    want_rs = np.stack([oracle.ckks_rescale(logn, mods, ct1[b]) for b in range(batch)])
+    assert np.array_equal(dev.ckks_rescale(logn, mods, ct1), want_rs)
+    want_t = np.stack([oracle.ckks_tensor(logn, mods, ct1[b], ct2[b]) for b in range(batch)])
+    assert np.array_equal(dev.ckks_tensor(logn, mods, ct1, ct2), want_t)
+
+
+def test_rescale_is_exact_rounded_division(dev, oracle):
+    """tests/ckks_t.cpp:136-175: CRT-composed (x + q_last/2) / q_last == rescaled, per coefficient."""
+    logn, n = 3, 8
+    mods = [int(m) for m in oracle.prime_row(34, 3)]
+    big_q = mods[0] * mods[1] * mods[2]
+    rng = np.random.default_rng(3)
+    coeffs = [int(rng.integers(0, 1 << 62)) * int(rng.integers(0, 1 << 38)) % big_q for _ in range(n)]
+    poly = np.array([[c % q for c in coeffs] for q in mods], dtype=np.uint64)
+    ntt = oracle.poly_ntt_fwd(logn, mods, poly)
+    ct = np.stack([ntt, ntt])
+    out = dev.ckks_rescale(logn, mods, ct)
+    back = oracle.poly_intt(logn, mods[:2], out[0], strict=True)
+    q01 = mods[0] * mods[1]
+    for i, c in enumerate(coeffs):
+        want = ((c + mods[2] // 2) // mods[2]) % q01
+        r0, r1 = int(back[0][i]), int(back[1][i])
+        inv = pow(mods[0], -1, mods[1])
+        got = (r0 + mods[0] * (((r1 - r0) * inv) % mods[1])) % q01
+        assert got == want, i
+
+
+# ------------------------------------------------------------------ size-independent properties at full size
+@pytest.mark.parametrize("logn", [12, 15])
+def test_linearity_and_round_trip_full_batch(dev, oracle, logn):
+    """NTT(a) + NTT(b) == NTT(a + b) (mod q) and INTT(NTT(x)) == x over a batch (generated on the device)."""
+    n = 1 << logn
+    batch = 4096 if dev.kind == "gpu" else 8
+    x = dev.lcg_fill([Q59], n, batch, 42, 1)
+    if dev.kind == "sim" or logn == 12:
+        assert np.array_equal(x[0], oracle.lcg_fill(42, Q59, n)) and np.array_equal(x[-1], oracle.lcg_fill(42 + batch - 1, Q59, n))
+    y = dev.poly_ntt_fwd(logn, [Q59], x)
+    for b in (0, batch // 2, batch - 1):
+        assert np.array_equal(y[b], oracle.ntt_fwd_lazy(logn, Q59, x[b]))
+    back = dev.poly_intt(logn, [Q59], y, strict=True)
+    assert np.array_equal(back, x)
+    q = np.uint64(Q59)
+    s = (x[: batch // 2] + x[batch // 2:]) % q
+    ys = dev.poly_ntt_fwd(logn, [Q59], s)
+    assert np.array_equal(ys % q, (y[: batch // 2] % q + y[batch // 2:] % q) % q)
+
+
+# ------------------------------------------------------------------ argument errors (reference: exceptions)
+def test_argument_errors(dev):
+    from hehub_b200.binding import InvalidArgument, Unsupported
+    x = np.zeros(1 << 10, dtype=np.uint64)
+    with pytest.raises(InvalidArgument):  # ntt.cpp:43-47: primes above 59 bits
+        dev.ntt_fwd_lazy(10, (1 << 60) + 33, x)
+    with pytest.raises(InvalidArgument):  # ntt.cpp:27-29: 2N must divide q - 1
+        dev.ntt_fwd_lazy(10, 1000003, x)
+    with pytest.raises((InvalidArgument, Unsupported)):
+        dev.poly_ntt_fwd(16, [65537], np.zeros(1 << 16, dtype=np.uint64))
+    ct = np.zeros((2, 1, 1 << 10), dtype=np.uint64)
+    with pytest.raises(InvalidArgument):  # rescaling.cpp:27-29
+        dev.ckks_rescale(10, [1073479681], ct)
+    with pytest.raises(InvalidArgument):
+        dev.mul_hybrid_lazy([1 << 20], x, x)  # Montgomery needs an odd modulus
+    # an empty batch is a no-op, not an error
+    assert dev.poly_ntt_fwd(10, [1073479681], np.zeros((0, 1, 1 << 10), dtype=np.uint64)).size == 0
