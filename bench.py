@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the hehub_b200 hot path (contract: see DESIGN.md §Measurement).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path, one rank per GPU
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on the host cores
+
+Step      one forward negacyclic NTT launch over a batch of 4096 single-limb polynomials, N = 4096,
+          Q = 576460752272228353 (BASELINE.json configs[1] at the north-star size; bench/ntt_bm.cpp:9-26).
+value     NTTs per second, whole job (all ranks), inputs resident in HBM; rotating over 4 slabs of
+          128 MiB so every step streams from HBM, not from the 126 MB L2.
+e2e       the same metric through the host-buffer C-ABI call (hehub_b200_ntt_host): pinned host words in,
+          host words out, H2D + kernel + D2H inside the timed region.
+roofline  algorithmic bytes (16*N per transform) / CUDA-event launch time vs MEASURED_PEAKS.json hbm_gbs.
+extras    the other BASELINE configs (sweep over N, INTT, ckks mult+relin C3/C5, rescale C4), each timed
+          the same way; informational.
+Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+Q59 = 576460752272228353
+LOGN = 12
+POLYS = 4096
+SLABS = 4
+METRIC = "NTT/s (N=4096, one 59-bit modulus, batch 4096)"
+UNIT = "NTT/s"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation on the host cores (rank 0 only)
+# ---------------------------------------------------------------------------------------------
+def _cpu_lib():
+    from oracle.binding import Oracle, Reference, build_oracle
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libhehub_ref.so")) or os.path.isdir("/root/reference/src/fhe"):
+        try:
+            return Reference(), "reference"
+        except Exception:
+            pass
+    build_oracle()
+    return Oracle(), "port"
+
+
+def _cpu_worker(barrier, rows, steps, warmup, out_q, idx):
+    import numpy as np
+    lib, _ = _cpu_lib()
+    n = 1 << LOGN
+    rng = np.random.default_rng(idx)
+    x = rng.integers(0, Q59, (rows, n), dtype=np.uint64)
+    for _ in range(warmup):
+        lib.bench_ntt(LOGN, Q59, x, True)
+    barrier.wait()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        lib.bench_ntt(LOGN, Q59, x, True)
+    barrier.wait()
+    out_q.put(time.perf_counter() - t0)
+
+
+def cpu_throughput(workers: int, rows: int, steps: int, warmup: int):
+    """`workers` independent processes (the reference is single-threaded and not thread-safe:
+    global unsynchronised caches, ntt.cpp:107-115), each transforming `rows` polynomials per step."""
+    import multiprocessing as mp
+    ctxm = mp.get_context("fork")
+    barrier = ctxm.Barrier(workers)
+    q = ctxm.Queue()
+    procs = [ctxm.Process(target=_cpu_worker, args=(barrier, rows, steps, warmup, q, i)) for i in range(workers)]
+    for p in procs:
+        p.start()
+    times = [q.get() for _ in procs]
+    for p in procs:
+        p.join()
+    elapsed = max(times)
+    return workers * rows * steps / elapsed, elapsed
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    _, kind = _cpu_lib()
+    workers = os.cpu_count() or 1
+    rows = 256  # bounded sample per worker per step (~15 ms of CPU work each)
+    value, elapsed = cpu_throughput(workers, rows, args.steps, max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "forward negacyclic NTT, N=4096, L=1, Q=576460752272228353",
+                   "sample": f"{workers} processes x {rows} polynomials per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind,
+                         "sample": f"{workers} independent processes x {rows} transforms per step x {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks: sample NVML while the GPU is under load
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, device_index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr:
+            self._stop.set()
+            self._thr.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from hehub_b200.binding import Context, _mod
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (hehub_b200 has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    stream = torch.cuda.Stream()
+    ctx = Context(device=local, stream=stream.cuda_stream)
+    n = 1 << LOGN
+    mod1, mod1p = _mod([Q59])
+
+    def timed(fn, steps, warmup):
+        """device time of `steps` calls of fn(i) on the context's stream, max over ranks, in seconds"""
+        with torch.cuda.stream(stream):
+            for i in range(warmup):
+                fn(i)
+            torch.cuda.synchronize()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(steps):
+                fn(i)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            barrier()
+        return max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+
+    # ---- headline: forward NTT, 4096 polys x N=4096, rotating over SLABS slabs -------------------
+    slabs = [torch.empty(POLYS * n, dtype=torch.int64, device="cuda") for _ in range(SLABS)]
+    for i, s in enumerate(slabs):
+        ctx._call("lcg_fill", n, mod1p, 1, s.data_ptr(), POLYS, 42 + rank * 100003 + i * POLYS, 1)
+    ctx.tables_prepare(LOGN, [Q59])
+    ctx.synchronize()
+
+    def step(i):
+        ctx._call("ntt_fwd_lazy", LOGN, mod1p, 1, slabs[i % SLABS].data_ptr(), POLYS)
+
+    sampler = ClockSampler(local)
+    launches0 = ctx.launch_count()
+    sampler.start()
+    elapsed = timed(step, args.steps, args.warmup)
+    launches = ctx.launch_count() - launches0 - args.warmup
+    # keep the GPU under the same load a little longer so the clock sampler sees it (untimed)
+    t_end = time.perf_counter() + 0.4
+    with torch.cuda.stream(stream):
+        while time.perf_counter() < t_end:
+            for i in range(16):
+                step(i)
+            torch.cuda.synchronize()
+    sampler.stop()
+    value = world * POLYS * args.steps / elapsed
+    ms_per_step = 1e3 * elapsed / args.steps
+
+    peaks, peak_src = measured_peaks()
+    alg_bytes = 16 * n * POLYS  # read + write of every coefficient, SURVEY §8(d)
+    achieved = alg_bytes / (elapsed / args.steps) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ntt_fwd_traffic.json")) as fh:
+            traffic = json.load(fh).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                "kernel": "ntt_fwd_fast_kernel<12>", "algorithmic_bytes_per_launch": alg_bytes}
+
+    # ---- e2e: host words in, host words out through hehub_b200_ntt_host ---------------------------
+    hx = ctx.pinned((POLYS, n))
+    hy = ctx.pinned((POLYS, n))
+    rng = np.random.default_rng(rank)
+    hx[:] = rng.integers(0, Q59, (POLYS, n), dtype=np.uint64)
+    e2e_steps = max(1, min(args.steps, 10))
+    for _ in range(2):
+        ctx.ntt_host(True, LOGN, [Q59], hx, hy)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.ntt_host(True, LOGN, [Q59], hx, hy)  # returns when hy holds the result
+    torch.cuda.synchronize()
+    barrier()
+    e2e_elapsed = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": world * POLYS * e2e_steps / e2e_elapsed, "unit": UNIT, "h2d_bytes_per_step": POLYS * n * 8,
+           "d2h_bytes_per_step": POLYS * n * 8, "steps": e2e_steps,
+           "call": "hehub_b200_ntt_host (pinned host buffers, 3-stage chunked pipeline)"}
+
+    # ---- extras: the other BASELINE configs -------------------------------------------------------
+    extras = {}
+    if args.extras:
+        extras = run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist if world > 1 else None)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        lib, kind = _cpu_lib()
+        rows = 1024
+        x = np.random.default_rng(7).integers(0, Q59, (rows, n), dtype=np.uint64)
+        lib.bench_ntt(LOGN, Q59, x[:8].copy(), True)
+        reps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < 8.0:
+            lib.bench_ntt(LOGN, Q59, x, True)
+            reps += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": reps * rows / dt, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": f"{reps * rows} forward NTTs (N=4096) on one host core, {dt:.1f} s; host has {os.cpu_count()} cores"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": "forward negacyclic NTT, N=4096, L=1, Q=576460752272228353, 4096 polynomials per step per GPU",
+                       "l2_policy": f"inputs larger than L2: {SLABS} slabs of {POLYS * n * 8 >> 20} MiB visited round-robin",
+                       "sharding": "independent polynomials per rank, no data-path collective"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world,
+            "clocks": sampler.summary(), "extras": extras,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist):
+    """Other BASELINE configs, device-resident, same timing discipline; values are whole-job."""
+    import numpy as np
+    from hehub_b200.binding import _mod
+    from oracle.binding import Oracle, build_oracle
+    build_oracle()
+    orc = Oracle()  # parameter selection only (prime table rule); never timed here
+    hbm = peaks["hbm_gbs"]
+    out = {}
+    mod1, mod1p = _mod([Q59])
+
+    # sweep N = 1024 .. 32768, L = 1, 4096 polys (configs[1]); two slabs >= 256 MiB total per size
+    sweep = {}
+    for logn in (10, 11, 12, 13, 14, 15):
+        n = 1 << logn
+        nsl = max(2, (256 << 20) // (POLYS * n * 8))
+        slabs = [torch.empty(POLYS * n, dtype=torch.int64, device="cuda") for _ in range(nsl)]
+        for i, s in enumerate(slabs):
+            ctx._call("lcg_fill", n, mod1p, 1, s.data_ptr(), POLYS, 42 + i * POLYS, 1)
+        ctx.tables_prepare(logn, [Q59])
+        steps = 8 if logn >= 14 else 16
+        row = {}
+        for name, fwd in (("ntt", True), ("intt", False)):
+            if fwd:
+                fn = lambda i: ctx._call("ntt_fwd_lazy", logn, mod1p, 1, slabs[i % nsl].data_ptr(), POLYS)
+            else:
+                fn = lambda i: ctx._call("intt_lazy", logn, mod1p, 1, slabs[i % nsl].data_ptr(), POLYS, 0)
+            el = timed(fn, steps, 3)
+            per = el / steps
+            gbs = 16 * n * POLYS / per / 1e9
+            row[name] = {"per_s": world * POLYS / per, "gbs": gbs, "frac_hbm": gbs / hbm, "us_per_launch": per * 1e6}
+        sweep[str(n)] = row
+        del slabs
+    out["ntt_sweep_L1_batch4096"] = sweep
+
+    def ct_bench(tag, logn, bits, pbits, batch, steps, what):
+        mods, p = orc.ckks_pick_moduli(bits, pbits)
+        mods = [int(m) for m in mods]
+        ext = mods + [int(p)]
+        L, n = len(mods), 1 << logn
+        extm, extp = _mod(ext)
+        modm, modp = _mod(mods)
+        key = torch.empty(L * 2 * (L + 1) * n, dtype=torch.int64, device="cuda")
+        if rank == 0 or dist is None:
+            ctx._call("lcg_fill", n, extp, L + 1, key.data_ptr(), L * 2 * (L + 1), 1000, 1)
+            ctx.synchronize()
+        if dist is not None:  # key-switch key: generated once, broadcast over NCCL / NVLink
+            torch.cuda.synchronize()
+            dist.broadcast(key, src=0)
+            torch.cuda.synchronize()
+        ct1 = torch.empty(batch * 2 * L * n, dtype=torch.int64, device="cuda")
+        ct2 = torch.empty_like(ct1)
+        res = torch.empty_like(ct1)
+        ctx._call("lcg_fill", n, modp, L, ct1.data_ptr(), batch * 2 * L, 100 + rank * 7919, 1)
+        ctx._call("lcg_fill", n, modp, L, ct2.data_ptr(), batch * 2 * L, 200 + rank * 7919, 1)
+        ctx.synchronize()
+        r = {}
+        if "mult" in what:
+            fn = lambda i: ctx._call("ckks_mult_relin", logn, extp, L, ct1.data_ptr(), ct2.data_ptr(), key.data_ptr(), res.data_ptr(), batch)
+            el = timed(fn, steps, 2)
+            per = el / steps / batch
+            gbs = 48 * L * n / per / 1e9
+            r["mult_relin"] = {"per_s": world / per, "us_per_ct": per * 1e6, "gbs_algorithmic": gbs, "frac_hbm": gbs / hbm,
+                               "transforms_per_ct": L * L + 3 * L + 2}
+        if "rescale" in what:
+            fn = lambda i: ctx._call("ckks_rescale", logn, modp, L, ct1.data_ptr(), res.data_ptr(), batch)
+            el = timed(fn, steps, 2)
+            per = el / steps / batch
+            gbs = 16 * n * (2 * L - 1) / per / 1e9
+            r["rescale"] = {"per_s": world / per, "us_per_ct": per * 1e6, "gbs_algorithmic": gbs, "frac_hbm": gbs / hbm}
+        if "tensor" in what:
+            quad = torch.empty(batch * 3 * L * n, dtype=torch.int64, device="cuda")
+            fn = lambda i: ctx._call("ckks_tensor", logn, modp, L, ct1.data_ptr(), ct2.data_ptr(), quad.data_ptr(), batch)
+            el = timed(fn, steps, 2)
+            per = el / steps / batch
+            gbs = 56 * L * n / per / 1e9
+            r["tensor"] = {"per_s": world / per, "us_per_ct": per * 1e6, "gbs_algorithmic": gbs, "frac_hbm": gbs / hbm}
+        if dist is not None and "mult" in what:  # result checksums gathered over NCCL
+            chk = res.view(torch.int64)[:: max(1, res.numel() // 4096)].sum().reshape(1)
+            allc = [torch.empty_like(chk) for _ in range(world)]
+            dist.all_gather(allc, chk)
+            r["rank_checksums"] = [int(c.item()) & ((1 << 64) - 1) for c in allc]
+        r["shape"] = {"N": n, "L": L, "batch_per_gpu": batch}
+        out[tag] = r
+
+    ct_bench("c3_ckks_mult_relin_N8192_L4", 13, [40, 30, 30, 30], 40, 256, 4, ("mult", "tensor"))
+    ct_bench("c4_rescale_N16384_L8", 14, [50] + [40] * 7, 50, 128, 4, ("rescale",))
+    ct_bench("c5_ckks_mult_relin_N32768_L12", 15, [50] * 12, 55, 16, 2, ("mult", "tensor"))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--extras", type=int, default=1)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

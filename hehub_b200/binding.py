@@ -70,6 +70,8 @@ _SIGS = {
     "ckks_rotate": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, sz, C.c_void_p, sz],
     "ckks_conjugate": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, C.c_void_p, sz],
     "lcg_fill": [sz, p64, sz, C.c_void_p, sz, u64, u64],
+    "ntt_host": [C.c_int, C.c_uint, p64, sz, C.c_void_p, C.c_void_p, sz, C.c_int],
+    "ckks_mult_relin_host": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, sz],
     "ctx_set_option": [C.c_char_p, C.c_int64],
     "ctx_set_stream": [C.c_void_p],
     "ctx_synchronize": [],
@@ -153,6 +155,9 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for p in getattr(self, "_pinned", []):
+                self.lib.hehub_b200_host_free(self.h, p)
+            self._pinned = []
             self.lib.hehub_b200_ctx_destroy(self.h)
             self.h = None
 
@@ -191,6 +196,28 @@ class Context:
     def to_device(self, host) -> Slab:
         host = _arr(host)
         return Slab(self, host.size).upload(host)
+
+    # ---- host-buffer entry points (pinned numpy views over hehub_b200_host_alloc memory) ----
+    def pinned(self, shape) -> np.ndarray:
+        n = int(np.prod(shape))
+        out = C.c_void_p()
+        self._call("host_alloc", max(n, 1), C.byref(out))
+        buf = (C.c_uint64 * max(n, 1)).from_address(out.value)
+        a = np.frombuffer(buf, dtype=np.uint64, count=n).reshape(shape)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(out.value)
+        return a
+
+    def ntt_host(self, forward, logn, moduli, x_in: np.ndarray, x_out: np.ndarray, strict=False):
+        m, mp = _mod(moduli)
+        batch = x_in.size // (m.size << logn)
+        self._call("ntt_host", int(forward), logn, mp, m.size, x_in.ctypes.data, x_out.ctypes.data, batch, int(strict))
+
+    def ckks_mult_relin_host(self, logn, ext_moduli, ct1: np.ndarray, ct2: np.ndarray, key: "Slab", out: np.ndarray):
+        m, mp = _mod(ext_moduli)
+        L = m.size - 1
+        batch = ct1.size // ((2 * L) << logn)
+        self._call("ckks_mult_relin_host", logn, mp, L, ct1.ctypes.data, ct2.ctypes.data, key.ptr, out.ctypes.data, batch)
 
     # ---- raw (device-pointer) entry points used by the bench -----------------------------
     def ntt_fwd_dev(self, logn, moduli, x: Slab, batch):

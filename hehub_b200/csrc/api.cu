@@ -185,13 +185,19 @@ int check_ring(Context &c, unsigned logn, size_t L, size_t batch) {
 
 } // namespace hb
 
-#define CTX_GUARD(ctx)                                        \
-    if (!(ctx)) return HEHUB_B200_ERR_INVALID;                \
-    Context &c = (ctx)->c;                                    \
-    {                                                         \
-        cudaError_t e__ = cudaSetDevice(c.device);            \
-        if (e__ != cudaSuccess) return c.cuda_fail(e__, "cudaSetDevice"); \
-    }
+namespace hb {
+int run_transform(Context &c, bool forward, unsigned logn, const u64 *moduli, size_t L, u64 *x, size_t batch, int strict) {
+    if (int rc = check_ring(c, logn, L, batch)) return rc;
+    if (batch == 0) return HEHUB_B200_OK;
+    if (!moduli || !x) return c.fail(HEHUB_B200_ERR_INVALID, "null operand");
+    int err = 0;
+    const LimbConst *limbs = c.get_chain(logn, moduli, L, &err);
+    if (!limbs) return err;
+    RowsIO io{x, (int)L, (int)logn, strict};
+    cudaError_t e = launch_ntt(forward, c.stream, logn, io, limbs, (int)(batch * L), c.force_generic, c.stats);
+    return e == cudaSuccess ? 0 : c.cuda_fail(e, forward ? "ntt launch" : "intt launch");
+}
+} // namespace hb
 
 extern "C" {
 
@@ -345,15 +351,7 @@ int hehub_b200_host_free(hehub_b200_ctx *ctx, uint64_t *host) {
 static int run_plain_ntt(hehub_b200_ctx *ctx, bool forward, unsigned logn, const uint64_t *moduli, size_t L, uint64_t *x,
                          size_t batch, int strict) {
     CTX_GUARD(ctx);
-    if (int rc = check_ring(c, logn, L, batch)) return rc;
-    if (batch == 0) return HEHUB_B200_OK;
-    if (!moduli || !x) return c.fail(HEHUB_B200_ERR_INVALID, "null operand");
-    int err = 0;
-    const LimbConst *limbs = c.get_chain(logn, reinterpret_cast<const u64 *>(moduli), L, &err);
-    if (!limbs) return err;
-    RowsIO io{reinterpret_cast<u64 *>(x), (int)L, (int)logn, strict};
-    cudaError_t e = launch_ntt(forward, c.stream, logn, io, limbs, (int)(batch * L), c.force_generic, c.stats);
-    return e == cudaSuccess ? 0 : c.cuda_fail(e, forward ? "ntt launch" : "intt launch");
+    return run_transform(c, forward, logn, reinterpret_cast<const u64 *>(moduli), L, reinterpret_cast<u64 *>(x), batch, strict);
 }
 
 int hehub_b200_ntt_fwd_lazy(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *moduli, size_t L, uint64_t *x, size_t batch) {

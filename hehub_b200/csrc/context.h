@@ -54,6 +54,13 @@ struct Context {
     std::map<u64 *, size_t> slab_live;
     std::vector<std::pair<u64 *, size_t>> scratch;       // grow-only workspaces, by slot
 
+    // host-buffer entry points (host_pipe.cu): copy-in / copy-out streams and per-slot events
+    static constexpr int kPipeSlots = 3;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[kPipeSlots] = {}, ev_k[kPipeSlots] = {}, ev_out[kPipeSlots] = {};
+    bool pipe_ready = false;
+    int ensure_pipe();
+
     ~Context();
     int fail(int code, const std::string &msg) {
         last_error = msg;

@@ -6,6 +6,14 @@ struct hehub_b200_ctx {
     hb::Context c;
 };
 
+#define CTX_GUARD(ctx)                                        \
+    if (!(ctx)) return 1;                \
+    Context &c = (ctx)->c;                                    \
+    {                                                         \
+        cudaError_t e__ = cudaSetDevice(c.device);            \
+        if (e__ != cudaSuccess) return c.cuda_fail(e__, "cudaSetDevice"); \
+    }
+
 namespace hb {
 
 // Common argument checks; returns 0 or an error code with ctx.last_error set.
@@ -28,5 +36,9 @@ int op_mult_relin(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, co
 int op_galois(Context &c, unsigned logn, size_t L, const u64 *in, u64 *out, bool conj, size_t step, size_t batch);
 int op_galois_keyswitch(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *ct, const u64 *key,
                         bool conj, size_t step, u64 *out, size_t batch);
+
+
+// api.cu — plain in-place transform on device rows [batch][L][N]
+int run_transform(Context &c, bool forward, unsigned logn, const u64 *moduli, size_t L, u64 *x, size_t batch, int strict);
 
 } // namespace hb

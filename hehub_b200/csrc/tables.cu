@@ -79,6 +79,15 @@ Context::~Context() {
     for (auto &kv : slab_live) cudaFree(kv.first);
     for (auto &s : scratch)
         if (s.first) cudaFree(s.first);
+    if (pipe_ready) {
+        for (int i = 0; i < kPipeSlots; i++) {
+            cudaEventDestroy(ev_in[i]);
+            cudaEventDestroy(ev_k[i]);
+            cudaEventDestroy(ev_out[i]);
+        }
+        cudaStreamDestroy(s_in);
+        cudaStreamDestroy(s_out);
+    }
     if (owns_stream && stream) cudaStreamDestroy(stream);
 }
 

@@ -153,6 +153,20 @@ int hehub_b200_ckks_rotate(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *e
 int hehub_b200_ckks_conjugate(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli, size_t L,
                               const uint64_t *ct, const uint64_t *key, uint64_t *out, size_t batch);
 
+/* ---- host-buffer variants --------------------------------------------------------
+ * The reference keeps every RnsPolynomial in host memory (rns.cpp:25-27), so a caller that has
+ * not moved its data to device slabs calls these: operands are HOST pointers (pinned memory from
+ * hehub_b200_host_alloc gives full PCIe speed), the batch is streamed through device staging
+ * slabs in chunks with copy-in, kernels and copy-out overlapped on three streams, and the call
+ * returns when host_out holds the result.  ntt_host: forward != 0 -> ntt_fwd_lazy, else intt_lazy
+ * (+strict); host_in may equal host_out.  ckks_mult_relin_host: ciphertexts on the host, the
+ * key-switch key resident on the device (it is reused by every call). */
+int hehub_b200_ntt_host(hehub_b200_ctx *ctx, int forward, unsigned logn, const uint64_t *moduli, size_t L,
+                        const uint64_t *host_in, uint64_t *host_out, size_t batch, int strict);
+int hehub_b200_ckks_mult_relin_host(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli, size_t L,
+                                    const uint64_t *host_ct1, const uint64_t *host_ct2, const uint64_t *dev_key,
+                                    uint64_t *host_out, size_t batch);
+
 /* ---- harness helpers (synthetic inputs generated on the device) --------------
  * lcg_fill: row r of x ([rows][n]) = SURVEY Appendix B LCG with seed seed0 + r*seed_stride,
  *   reduced mod moduli[r % L].  fnv1a: FNV-1a over the words of x (device reduction

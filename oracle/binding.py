@@ -114,6 +114,14 @@ class _CpuLib:
             raise ValueError(f"intt_lazy rc={rc}")
         return x
 
+    def bench_ntt(self, logn, q, x, forward=True):
+        """In place on the caller's [rows][N] array (timing helper; no copy)."""
+        assert x.dtype == np.uint64 and x.flags.c_contiguous
+        rows = x.size >> logn
+        rc = self._fn("bench_ntt", C.c_int, C.c_uint, u64, p64, C.c_size_t, C.c_int)(logn, q, _ptr(x), rows, int(forward))
+        if rc:
+            raise ValueError(f"bench_ntt rc={rc}")
+
     def poly_ntt_fwd(self, logn, moduli, x):
         m, x = _arr(moduli), _arr(x).copy()
         rc = self._fn("poly_ntt_fwd", C.c_int, C.c_uint, C.c_size_t, p64, p64)(logn, m.size, _ptr(m), _ptr(x))

@@ -338,6 +338,16 @@ int orc_intt_lazy_folded(unsigned logn, u64 q, u64 *x) {
 /* ------------------------------------------------------------------ */
 
 /* src/fhe/common/ntt.h:41-51 */
+/* timing helper for bench.py's cpu_baseline leg: `rows` single-limb transforms back to back */
+int orc_bench_ntt(unsigned logn, u64 q, u64 *x, size_t rows, int forward) {
+    const size_t n = (size_t)1 << logn;
+    for (size_t r = 0; r < rows; r++) {
+        int rc = forward ? orc_ntt_fwd_lazy(logn, q, x + r * n) : orc_intt_lazy(logn, q, x + r * n);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 int orc_poly_ntt_fwd(unsigned logn, size_t L, const u64 *moduli, u64 *x) {
     const size_t n = (size_t)1 << logn;
     for (size_t k = 0; k < L; k++)

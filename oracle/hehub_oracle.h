@@ -61,6 +61,8 @@ int orc_ntt_tables(unsigned logn, orc_u64 q, orc_u64 *fwd, orc_u64 *fwd_h,
                    orc_u64 *inv, orc_u64 *inv_h);
 void orc_clear_caches(void);
 
+int orc_bench_ntt(unsigned logn, orc_u64 q, orc_u64 *x, size_t rows, int forward);
+
 /* ---- composite ops on [poly][limb][N] slabs ---- */
 int orc_poly_ntt_fwd(unsigned logn, size_t L, const orc_u64 *moduli, orc_u64 *x);
 int orc_poly_intt(unsigned logn, size_t L, const orc_u64 *moduli, orc_u64 *x, int strict);

@@ -285,6 +285,20 @@ int ref_ckks_pick_moduli(const unsigned *moduli_bits, size_t L, unsigned additio
     });
 }
 
+/* timing helper: `rows` independent single-limb transforms back to back, exactly the calls
+ * bench/ntt_bm.cpp:17-25 times (twiddle cache already warm after the first row) */
+int ref_bench_ntt(unsigned logn, u64 q, u64 *x, size_t rows, int forward) {
+    return guarded([&] {
+        const size_t n = (size_t)1 << logn;
+        for (size_t r = 0; r < rows; r++) {
+            if (forward)
+                ntt_negacyclic_inplace_lazy(logn, q, x + r * n);
+            else
+                intt_negacyclic_inplace_lazy(logn, q, x + r * n);
+        }
+    });
+}
+
 void ref_cache_ntt_factors(unsigned logn, const u64 *moduli, size_t count) {
     cache_ntt_factors_strict(logn, std::vector<u64>(moduli, moduli + count));
 }

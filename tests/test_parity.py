@@ -355,3 +355,33 @@ def test_argument_errors(dev):
         dev.mul_hybrid_lazy([1 << 20], x, x)  # Montgomery needs an odd modulus
     # an empty batch is a no-op, not an error
     assert dev.poly_ntt_fwd(10, [1073479681], np.zeros((0, 1, 1 << 10), dtype=np.uint64)).size == 0
+
+
+# ------------------------------------------------------------------ host-buffer entry points
+def test_host_buffer_pipeline(dev, oracle):
+    """ntt_host / ckks_mult_relin_host stream a host batch through device staging slabs in chunks."""
+    logn, n = 10, 1 << 10
+    batch = 7  # not a multiple of the chunk count
+    moduli = [Q59, 65537]
+    x = dev.pinned((batch, 2, n))
+    for b in range(batch):
+        for k, q in enumerate(moduli):
+            x[b, k] = oracle.lcg_fill(5 + 10 * b + k, q, n)
+    want = np.stack([oracle.poly_ntt_fwd(logn, moduli, x[b]) for b in range(batch)])
+    y = dev.pinned((batch, 2, n))
+    dev.ntt_host(True, logn, moduli, x, y)
+    assert np.array_equal(y, want)
+    dev.ntt_host(False, logn, moduli, y, y, strict=True)  # in place on the host buffer
+    assert np.array_equal(y, x)
+    mods, ext = _shape(oracle, logn, [40, 30], 40)
+    ct1, ct2 = dev.pinned((batch, 2, 2, n)), dev.pinned((batch, 2, 2, n))
+    for b in range(batch):
+        ct1[b] = fill_ct(oracle, 100 + 1000 * b, mods, n)
+        ct2[b] = fill_ct(oracle, 200 + 1000 * b, mods, n)
+    key = fill_key(oracle, 9000, ext, n)
+    dkey = dev.to_device(key)
+    out = dev.pinned((batch, 2, 2, n))
+    dev.ckks_mult_relin_host(logn, ext, ct1, ct2, dkey, out)
+    dkey.free()
+    want = np.stack([oracle.ckks_mult_relin(logn, ext, ct1[b], ct2[b], key) for b in range(batch)])
+    assert np.array_equal(out, want)
