@@ -195,6 +195,7 @@ def run_cuda(args):
 
     stream = torch.cuda.Stream()
     ctx = Context(device=local, stream=stream.cuda_stream)
+    ctx.set_option("pipeline", args.pipeline)
     n = 1 << LOGN
     mod1, mod1p = _mod([Q59])
 
@@ -409,6 +410,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--extras", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=1, help="0: one-CTA-per-row kernels (A/B of the persistent pipeline)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "reference":

@@ -20,7 +20,8 @@ struct RowsIO {
     int logn;
     int strict;
     HB_D int limb(int row) const { return row % L; }
-    HB_D u64 load(int row, int i, const LimbConst &) const { return x[((size_t)row << logn) + i]; }
+    HB_D const u64 *src(int row) const { return x + ((size_t)row << logn); }
+    HB_D u64 pre(int, int, u64 raw, const LimbConst &) const { return raw; }
     HB_D void store(int row, int i, u64 v, const LimbConst &lc) const {
         x[((size_t)row << logn) + i] = strict ? reduce_strict(v, lc.q) : v;
     }
@@ -194,7 +195,7 @@ int run_transform(Context &c, bool forward, unsigned logn, const u64 *moduli, si
     const LimbConst *limbs = c.get_chain(logn, moduli, L, &err);
     if (!limbs) return err;
     RowsIO io{x, (int)L, (int)logn, strict};
-    cudaError_t e = launch_ntt(forward, c.stream, logn, io, limbs, (int)(batch * L), c.force_generic, c.stats);
+    cudaError_t e = launch_ntt(forward, c.env(), logn, io, limbs, (int)(batch * L), aligned16(x));
     return e == cudaSuccess ? 0 : c.cuda_fail(e, forward ? "ntt launch" : "intt launch");
 }
 } // namespace hb
@@ -226,6 +227,14 @@ int hehub_b200_ctx_create(hehub_b200_ctx **out, int device, void *stream) {
     }
     const char *fg = std::getenv("HEHUB_B200_FORCE_GENERIC");
     ctx->c.force_generic = fg && fg[0] == '1';
+#if defined(HB_KERNEL_SIM)
+    ctx->c.sm_count = 2; // small persistent grids so the emulator exercises the row loop
+#else
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->c.sm_count = sms;
+    }
+#endif
     *out = ctx;
     return HEHUB_B200_OK;
 }
@@ -260,6 +269,8 @@ int hehub_b200_ctx_set_option(hehub_b200_ctx *ctx, const char *name, int64_t val
     if (!name) return c.fail(HEHUB_B200_ERR_INVALID, "null option name");
     if (!std::strcmp(name, "force_generic")) {
         c.force_generic = value != 0;
+    } else if (!std::strcmp(name, "pipeline")) {
+        c.pipeline = value != 0;
     } else if (!std::strcmp(name, "scratch_cap_mib")) {
         if (value < 1) return c.fail(HEHUB_B200_ERR_INVALID, "scratch_cap_mib must be positive");
         c.scratch_cap_bytes = (size_t)value << 20;

@@ -42,6 +42,9 @@ struct Context {
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
     bool force_generic = false;
+    bool pipeline = true; // persistent double-buffered transforms where available
+    int sm_count = 148;
+    LaunchEnv env() { return LaunchEnv{stream, sm_count, force_generic, pipeline, &stats}; }
     size_t scratch_cap_bytes = (size_t)2 << 30; // bound on the per-call workspace; batches run in waves
     std::string last_error;
     LaunchStats stats;

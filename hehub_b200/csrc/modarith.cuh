@@ -60,12 +60,48 @@ HB_D u64 mul2_lo64(u64 x, u64 w, u64 h, u64 n) {
 #endif
 }
 
+// hi64(x * w), exact.  Same value as __umul64hi; the x0*w0 partial product only contributes its
+// high word, so it is asked for as a 32-bit high multiply (IMAD.HI) instead of a full IMAD.WIDE,
+// which occupies the multiplier pipe for twice as long on sm_100 (profiles/r1*_int_peak.json).
+HB_D u64 umul64hi_split(u64 x, u64 w) {
+#if defined(HB_KERNEL_SIM)
+    return __umul64hi(x, w);
+#else
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 x0, x1, w0, w1, p00h, ml, mh, m2h, unused;\n\t"
+        ".reg .u64 mid, mid2, acc;\n\t"
+        "mov.b64 {x0, x1}, %1;\n\t"
+        "mov.b64 {w0, w1}, %2;\n\t"
+        "mul.hi.u32 p00h, x0, w0;\n\t"
+        "cvt.u64.u32 mid, p00h;\n\t"
+        "mad.wide.u32 mid, x0, w1, mid;\n\t"   // x0*w1 + hi32(x0*w0)            < 2^64
+        "mov.b64 {ml, mh}, mid;\n\t"
+        "cvt.u64.u32 mid2, ml;\n\t"
+        "mad.wide.u32 mid2, x1, w0, mid2;\n\t" // x1*w0 + lo32(mid)              < 2^64
+        "mov.b64 {unused, m2h}, mid2;\n\t"
+        "cvt.u64.u32 acc, mh;\n\t"
+        "mad.wide.u32 acc, x1, w1, acc;\n\t"   // x1*w1 + hi32(mid)
+        "cvt.u64.u32 mid, m2h;\n\t"
+        "add.u64 %0, acc, mid;\n\t"            // + hi32(mid2): the true high word, no wrap
+        "}"
+        : "=l"(r)
+        : "l"(x), "l"(w));
+    return r;
+#endif
+}
+
 // mul_mod_harvey_lazy — mod_arith.h:74-78.  r = lo64(x*w) - lo64(hi64(x*w')*q), any x < 2^64,
 // w < q  ->  r in [0, 2q).  `nq` is -q mod 2^64 so the subtraction folds into the IMAD chain.
 HB_D u64 harvey_lazy(u64 x, u64 w, u64 wh, u64 nq) {
+#if defined(HB_HI64_SPLIT)
+    u64 qhat = umul64hi_split(x, wh);
+#else
     u64 qhat = __umul64hi(x, wh); // exact: the low partial product's carry is kept
+#endif
     return mul2_lo64(x, w, qhat, nq);
 }
+HB_D u64 harvey_lazy_split(u64 x, u64 w, u64 wh, u64 nq) { return mul2_lo64(x, w, umul64hi_split(x, wh), nq); }
 
 // the sweep at ntt.cpp:171-175: x -= ((x >> logq) - fix) * q
 HB_D u64 approx_reduce(u64 x, const LimbConst &c) {

@@ -6,30 +6,39 @@
 // operation for operation, so outputs are the same raw u64 words as the CPU path.  Only the
 // *order* in which independent butterflies run is changed:
 //
-//   * one CTA owns a whole row (N <= 16384) in shared memory; a row of N = 32768 (256 KiB, more
-//     than one SM holds) is owned by a 2-CTA thread-block cluster, half a row each: the single
-//     cross-CTA level (gap N/2) is computed from global/L2 reads on the way in (forward) or
-//     exchanged through the row's own global words between two cluster barriers (inverse);
-//   * each thread keeps 8 or 16 coefficients in registers and runs 3-4 levels on them
-//     ("pass"), so the row crosses shared memory 2-3 times instead of log2(N) times;
-//   * the inverse uses the folded form (no bit-reversal permutations).
+//   * a row (one limb of one polynomial, N words) lives in shared memory; each thread keeps 8 or
+//     16 coefficients in registers and runs 3-4 levels on them ("pass"), so the row crosses
+//     shared memory 2-3 times instead of log2(N) times;
+//   * the inverse uses the folded form (no bit-reversal permutations);
+//   * N <= 8192: PERSISTENT kernel, one CTA per resident slot looping over rows; the next row's
+//     words are streamed into a second shared-memory buffer with cp.async while the current row
+//     is being transformed, so HBM latency and the copy-in never stall the integer pipes;
+//   * N = 16384: one CTA per row; N = 32768 (256 KiB, more than one SM holds): a 2-CTA
+//     thread-block cluster per row, half a row each; the single cross-CTA level (gap N/2) is
+//     computed from global/L2 reads on the way in (forward) or exchanged through the row's own
+//     global words between two cluster barriers (inverse).
 //
-// Kernels are parameterised by an IO policy that supplies the row's input words and consumes
-// its output words; the fused rescale / key-switch kernels (ops.cu) are instantiations with
-// prologue/epilogue arithmetic inside the policy, so the coefficient slab is read from and
-// written to HBM exactly once per transform.
+// Kernels are parameterised by an IO policy; the fused rescale / key-switch kernels (ops.cu)
+// are instantiations with prologue/epilogue arithmetic inside the policy, so those values are
+// read from and written to HBM exactly once per transform.
 //
 // IO policy interface (all __device__):
-//   int  limb(int row)                                   -> index into the LimbConst array
-//   u64  load(int row, int i, const LimbConst&)          -> input word i of the row
-//   void store(int row, int i, u64 v, const LimbConst&)  -> output word i of the row
-//   u64 *raw(int row)                                    -> row-sized exchange area in global memory
-//                                                           (N = 32768 inverse only; may be the output row)
+//   int        limb(int row)                              -> index into the LimbConst array
+//   const u64 *src(int row)                               -> the row's N contiguous input words
+//   u64        pre(int row, int i, u64 raw, LimbConst&)   -> input word i from the raw word read at src(row)[i]
+//   void       store(int row, int i, u64 v, LimbConst&)   -> consumes output word i
+//   u64       *raw(int row)                               -> row-sized exchange area in global memory
+//                                                            (N = 32768 inverse only; may be the output row)
 #pragma once
 #include "modarith.cuh"
 #include "ntt_plan.h"
 
 namespace hb {
+
+template <class IO>
+HB_D u64 io_load(const IO &io, int row, int i, const LimbConst &lc) {
+    return io.pre(row, i, io.src(row)[i], lc);
+}
 
 // ------------------------------------------------------------------------------------------
 // butterfly — ntt.cpp:161-167 (identical for both directions)
@@ -43,8 +52,7 @@ HB_D void bfly(u64 &lo, u64 &hi, const ulonglong2 tw, u64 nq, u64 q2) {
 // K forward levels on 2^K registers.  Level m pairs registers 2^(K-m) apart; twiddle slot
 // (2^(m-1) - 1 + blk) is read at tw[slot * stride].
 template <int K, int M = 1>
-HB_D void fwd_levels(u64 (&v)[1 << K], const ulonglong2 *__restrict__ tw,
-                                           int stride, u64 nq, u64 q2) {
+HB_D void fwd_levels(u64 (&v)[1 << K], const ulonglong2 *__restrict__ tw, int stride, u64 nq, u64 q2) {
     constexpr int half = 1 << (K - M);
 #pragma unroll
     for (int blk = 0; blk < (1 << (M - 1)); blk++) {
@@ -58,8 +66,7 @@ HB_D void fwd_levels(u64 (&v)[1 << K], const ulonglong2 *__restrict__ tw,
 // K inverse (folded) stages on 2^K registers.  Stage m pairs registers 2^(m-1) apart; twiddle
 // slot (2^(m-1) - 1 + jj) depends on the register's index modulo 2^(m-1).
 template <int K, int M = 1>
-HB_D void inv_levels(u64 (&v)[1 << K], const ulonglong2 *__restrict__ tw,
-                                           int stride, u64 nq, u64 q2) {
+HB_D void inv_levels(u64 (&v)[1 << K], const ulonglong2 *__restrict__ tw, int stride, u64 nq, u64 q2) {
     constexpr int d = 1 << (M - 1);
 #pragma unroll
     for (int jj = 0; jj < d; jj++) {
@@ -90,13 +97,21 @@ HB_D void sts_contig(u64 *sm, int base, const u64 (&v)[1 << K]) {
     for (int c = 0; c < (1 << K) / 2; c++) p[c] = make_ulonglong2(v[2 * c], v[2 * c + 1]);
 }
 
+// stream a row of NC raw words into the padded shared-memory layout, 16 bytes per cp.async
+template <int NC, int T>
+HB_D void prefetch_row(u64 *sm, const u64 *__restrict__ src) {
+    for (int c = threadIdx.x; c < NC / 2; c += T) hb_cp_async16(sm + sphys(2 * c), src + 2 * c);
+    hb_cp_async_commit();
+}
+
 // ------------------------------------------------------------------------------------------
-// forward, fast path
+// forward passes.  SRC: 0 = first pass reads global memory, 1 = first pass reads the raw words
+// a prefetch left in shared memory.
 // ------------------------------------------------------------------------------------------
-template <int LOGN, int P, class IO>
+template <int LOGN, int T, int P, int SRC, class IO>
 HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     constexpr NttPlan pl = plan_for(LOGN);
-    constexpr int LOGNC = LOGN - pl.lpre, NC = 1 << LOGNC, T = pl.threads;
+    constexpr int LOGNC = LOGN - pl.lpre, NC = 1 << LOGNC;
     constexpr int K = pl.k[P], L0 = fwd_lambda0(pl, P), GSL = LOGNC - L0 - K; // log2(smallest gap)
     constexpr int NG = NC >> K;
     constexpr bool first = (P == 0), last = (P == pl.npass - 1);
@@ -109,10 +124,17 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
         const int lo = g & ((1 << GSL) - 1), hb = g >> GSL;
         const int base = (hb << (LOGNC - L0)) + lo;
         u64 v[1 << K];
-        if constexpr (first) {
+        if constexpr (first && SRC == 1) {
+            static_assert(pl.lpre == 0, "prefetched rows are whole rows");
+#pragma unroll
+            for (int j = 0; j < (1 << K); j++) {
+                const int i = base + (j << GSL);
+                v[j] = io.pre(row, i, sm[sphys(i)], lc);
+            }
+        } else if constexpr (first) {
             if constexpr (pl.lpre == 0) {
 #pragma unroll
-                for (int j = 0; j < (1 << K); j++) v[j] = io.load(row, base + (j << GSL), lc);
+                for (int j = 0; j < (1 << K); j++) v[j] = io_load(io, row, base + (j << GSL), lc);
             } else {
                 // level 1 of the full row (gap N/2) is computed here by both CTAs of the row;
                 // CTA B keeps the low (B = 0) or high (B = 1) output — ntt.cpp:161-167
@@ -120,7 +142,7 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
 #pragma unroll
                 for (int j = 0; j < (1 << K); j++) {
                     const int i = base + (j << GSL);
-                    u64 a = io.load(row, i, lc), b = io.load(row, i + NC, lc);
+                    u64 a = io_load(io, row, i, lc), b = io_load(io, row, i + NC, lc);
                     u64 t = harvey_lazy(b, z.x, z.y, lc.nq);
                     v[j] = B ? (a + lc.q2 - t) : (a + t);
                 }
@@ -145,10 +167,10 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     }
 }
 
-template <int LOGN, int P, class IO>
+template <int LOGN, int T, int P, int SRC, class IO>
 HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     constexpr NttPlan pl = plan_for(LOGN);
-    fwd_pass<LOGN, P>(sm, io, lc, row, B);
+    fwd_pass<LOGN, T, P, SRC>(sm, io, lc, row, B);
     if constexpr (P == 0 && pl.lpre == 1) {
         // both CTAs of the row have read all of it: from here on either may overwrite it
         // (in-place transforms store into the words the sibling CTA has just read)
@@ -156,9 +178,10 @@ HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B)
     } else {
         __syncthreads();
     }
-    if constexpr (P + 1 < pl.npass) fwd_passes<LOGN, P + 1>(sm, io, lc, row, B);
+    if constexpr (P + 1 < pl.npass) fwd_passes<LOGN, T, P + 1, SRC>(sm, io, lc, row, B);
 }
 
+// one CTA (or one CTA of a 2-CTA cluster) per row
 template <int LOGN, class IO>
 HB_GLOBAL(plan_for(LOGN).threads, plan_for(LOGN).min_blocks)
 ntt_fwd_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
@@ -167,17 +190,41 @@ ntt_fwd_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     HB_SHARED_U64(sm);
     const int row = blockIdx.x >> pl.lpre, B = blockIdx.x & ((1 << pl.lpre) - 1);
     const LimbConst lc = limbs[io.limb(row)];
-    fwd_passes<LOGN, 0>(sm, io, lc, row, B);
+    fwd_passes<LOGN, T, 0, 0>(sm, io, lc, row, B);
     for (int i = threadIdx.x; i < NC; i += T) io.store(row, B * NC + i, sm[sphys(i)], lc);
 }
 
+// persistent, double-buffered: grid = resident CTA slots, rows visited with stride gridDim.x
+template <int LOGN, class IO>
+HB_GLOBAL(pipe_plan_for(LOGN).threads, pipe_plan_for(LOGN).min_blocks)
+ntt_fwd_pipe_kernel(const IO io, const LimbConst *__restrict__ limbs, int rows) {
+    constexpr PipePlan pp = pipe_plan_for(LOGN);
+    constexpr int NC = 1 << LOGN, T = pp.threads, BUF = smem_words(NC);
+    HB_SHARED_U64(smem);
+    int row = blockIdx.x;
+    if (row >= rows) return;
+    prefetch_row<NC, T>(smem, io.src(row));
+    int cur = 0;
+    for (; row < rows; row += gridDim.x) {
+        u64 *sm = smem + cur * BUF;
+        hb_cp_async_wait_all();
+        __syncthreads(); // this row has landed; every thread is done with the other buffer
+        const int next = row + gridDim.x;
+        if (next < rows) prefetch_row<NC, T>(smem + (cur ^ 1) * BUF, io.src(next));
+        const LimbConst lc = limbs[io.limb(row)];
+        fwd_passes<LOGN, T, 0, 1>(sm, io, lc, row, 0);
+        for (int i = threadIdx.x; i < NC; i += T) io.store(row, i, sm[sphys(i)], lc);
+        cur ^= 1;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
-// inverse, fast path
+// inverse passes
 // ------------------------------------------------------------------------------------------
-template <int LOGN, int P, class IO>
+template <int LOGN, int T, int P, int SRC, class IO>
 HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     constexpr NttPlan pl = plan_for(LOGN);
-    constexpr int LOGNC = LOGN - pl.lpre, NC = 1 << LOGNC, T = pl.threads;
+    constexpr int LOGNC = LOGN - pl.lpre, NC = 1 << LOGNC;
     constexpr int K = inv_k(pl, P), S0 = inv_s0(pl, P);
     constexpr int NG = NC >> K;
     constexpr bool first = (P == 0), last = (P == pl.npass - 1);
@@ -192,6 +239,10 @@ HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
         u64 v[1 << K];
         if constexpr (first) {
             lds_contig<K>(sm, base, v);
+            if constexpr (SRC == 1) { // raw prefetched words: apply the policy's input map
+#pragma unroll
+                for (int j = 0; j < (1 << K); j++) v[j] = io.pre(row, base + j, v[j], lc);
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < (1 << K); j++) v[j] = sm[sphys(base + (j << S0))];
@@ -221,13 +272,13 @@ HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     }
 }
 
-template <int LOGN, int P, class IO>
+template <int LOGN, int T, int P, int SRC, class IO>
 HB_D void inv_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     constexpr NttPlan pl = plan_for(LOGN);
-    inv_pass<LOGN, P>(sm, io, lc, row, B);
+    inv_pass<LOGN, T, P, SRC>(sm, io, lc, row, B);
     if constexpr (P + 1 < pl.npass) {
         __syncthreads();
-        inv_passes<LOGN, P + 1>(sm, io, lc, row, B);
+        inv_passes<LOGN, T, P + 1, SRC>(sm, io, lc, row, B);
     }
 }
 
@@ -239,9 +290,9 @@ intt_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     HB_SHARED_U64(sm);
     const int row = blockIdx.x >> pl.lpre, B = blockIdx.x & ((1 << pl.lpre) - 1);
     const LimbConst lc = limbs[io.limb(row)];
-    for (int i = threadIdx.x; i < NC; i += T) sm[sphys(i)] = io.load(row, B * NC + i, lc);
+    for (int i = threadIdx.x; i < NC; i += T) sm[sphys(i)] = io_load(io, row, B * NC + i, lc);
     __syncthreads();
-    inv_passes<LOGN, 0>(sm, io, lc, row, B);
+    inv_passes<LOGN, T, 0, 0>(sm, io, lc, row, B);
     if constexpr (pl.lpre == 1) {
         // last stage (gap N/2) pairs word i of CTA 0 with word i of CTA 1.  Exchange the halves
         // through the row's exchange area (L2), combine into shared memory, and only after the
@@ -267,16 +318,38 @@ intt_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     }
 }
 
+template <int LOGN, class IO>
+HB_GLOBAL(pipe_plan_for(LOGN).threads, pipe_plan_for(LOGN).min_blocks)
+intt_pipe_kernel(const IO io, const LimbConst *__restrict__ limbs, int rows) {
+    constexpr PipePlan pp = pipe_plan_for(LOGN);
+    constexpr int NC = 1 << LOGN, T = pp.threads, BUF = smem_words(NC);
+    HB_SHARED_U64(smem);
+    int row = blockIdx.x;
+    if (row >= rows) return;
+    prefetch_row<NC, T>(smem, io.src(row));
+    int cur = 0;
+    for (; row < rows; row += gridDim.x) {
+        u64 *sm = smem + cur * BUF;
+        hb_cp_async_wait_all();
+        __syncthreads();
+        const int next = row + gridDim.x;
+        if (next < rows) prefetch_row<NC, T>(smem + (cur ^ 1) * BUF, io.src(next));
+        const LimbConst lc = limbs[io.limb(row)];
+        inv_passes<LOGN, T, 0, 1>(sm, io, lc, row, 0); // the last pass stores straight from registers
+        cur ^= 1;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // generic path: any logn <= 14, one level per shared-memory sweep, reference table order.
-// Used for small rings (N < 1024) and as an on-device cross-check of the fast path.
+// Used for small rings (N < 1024) and as an on-device cross-check of the fast paths.
 // ------------------------------------------------------------------------------------------
 template <class IO>
 HB_GLOBAL(256, 1) ntt_fwd_generic_kernel(const IO io, const LimbConst *__restrict__ limbs, int logn) {
     HB_SHARED_U64(sm);
     const int n = 1 << logn, row = blockIdx.x;
     const LimbConst lc = limbs[io.limb(row)];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = io.load(row, i, lc);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = io_load(io, row, i, lc);
     __syncthreads();
     for (int level = 1; level <= logn; level++) { // ntt.cpp:155-169
         const int gl = logn - level;              // log2(gap)
@@ -294,7 +367,7 @@ HB_GLOBAL(256, 1) intt_generic_kernel(const IO io, const LimbConst *__restrict__
     HB_SHARED_U64(sm);
     const int n = 1 << logn, row = blockIdx.x;
     const LimbConst lc = limbs[io.limb(row)];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = io.load(row, i, lc);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = io_load(io, row, i, lc);
     __syncthreads();
     for (int s = 1; s <= logn; s++) { // folded form of ntt.cpp:185-212
         const int gl = s - 1;
@@ -318,49 +391,75 @@ struct LaunchStats {
     unsigned long long launches = 0;
 };
 
-template <int LOGN, class IO>
-inline cudaError_t launch_fwd_fast(cudaStream_t st, const IO &io, const LimbConst *limbs, int rows, LaunchStats &ls) {
+struct LaunchEnv {
+    cudaStream_t stream;
+    int sm_count;       // persistent grids are sized from it
+    bool force_generic; // parity cross-check path
+    bool pipeline;      // use the persistent double-buffered kernels where they exist
+    LaunchStats *stats;
+};
+
+template <int LOGN, bool FWD, class IO>
+constexpr auto fast_kernel() {
+    if constexpr (FWD) return &ntt_fwd_fast_kernel<LOGN, IO>;
+    else return &intt_fast_kernel<LOGN, IO>;
+}
+template <int LOGN, bool FWD, class IO>
+constexpr auto pipe_kernel() {
+    if constexpr (FWD) return &ntt_fwd_pipe_kernel<LOGN, IO>;
+    else return &intt_pipe_kernel<LOGN, IO>;
+}
+
+template <class K>
+inline cudaError_t configure_smem(K kern, int smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    return e;
+}
+
+template <int LOGN, bool FWD, class IO>
+inline cudaError_t launch_fast(const LaunchEnv &env, const IO &io, const LimbConst *limbs, int rows) {
     constexpr NttPlan pl = plan_for(LOGN);
     constexpr int smem = smem_words(1 << (LOGN - pl.lpre)) * 8;
-    auto kern = ntt_fwd_fast_kernel<LOGN, IO>;
+    auto kern = fast_kernel<LOGN, FWD, IO>();
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = configure_smem(kern, smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    ls.launches++;
+    env.stats->launches++;
     if constexpr (pl.lpre == 1) {
-        return HB_LAUNCH_CLUSTER(kern, (unsigned)(rows << 1), pl.threads, smem, st, 2, io, limbs);
+        return HB_LAUNCH_CLUSTER(kern, (unsigned)(rows << 1), pl.threads, smem, env.stream, 2, io, limbs);
     } else {
-        HB_LAUNCH(kern, rows, pl.threads, smem, st, 1, io, limbs);
+        HB_LAUNCH(kern, rows, pl.threads, smem, env.stream, 1, io, limbs);
         return cudaGetLastError();
     }
 }
 
-template <int LOGN, class IO>
-inline cudaError_t launch_inv_fast(cudaStream_t st, const IO &io, const LimbConst *limbs, int rows, LaunchStats &ls) {
-    constexpr NttPlan pl = plan_for(LOGN);
-    constexpr int smem = smem_words(1 << (LOGN - pl.lpre)) * 8;
-    auto kern = intt_fast_kernel<LOGN, IO>;
+template <int LOGN, bool FWD, class IO>
+inline cudaError_t launch_pipe(const LaunchEnv &env, const IO &io, const LimbConst *limbs, int rows) {
+    constexpr PipePlan pp = pipe_plan_for(LOGN);
+    constexpr int smem = 2 * smem_words(1 << LOGN) * 8;
+    auto kern = pipe_kernel<LOGN, FWD, IO>();
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = configure_smem(kern, smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    ls.launches++;
-    if constexpr (pl.lpre == 1) {
-        return HB_LAUNCH_CLUSTER(kern, (unsigned)(rows << 1), pl.threads, smem, st, 2, io, limbs);
-    } else {
-        HB_LAUNCH(kern, rows, pl.threads, smem, st, 1, io, limbs);
-        return cudaGetLastError();
-    }
+    // balanced persistent grid: every CTA visits ceil(rows / slots) rows or one fewer
+    const int slots = env.sm_count * pp.min_blocks;
+    const int per = (rows + slots - 1) / slots;
+    const int grid = (rows + per - 1) / per;
+    env.stats->launches++;
+    HB_LAUNCH(kern, grid, pp.threads, smem, env.stream, 1, io, limbs, rows);
+    return cudaGetLastError();
 }
 
 template <class IO>
-inline cudaError_t launch_generic(bool forward, cudaStream_t st, unsigned logn, const IO &io,
-                                  const LimbConst *limbs, int rows, LaunchStats &ls) {
+inline cudaError_t launch_generic(bool forward, const LaunchEnv &env, unsigned logn, const IO &io, const LimbConst *limbs,
+                                  int rows) {
     const int smem = (1 << logn) * 8;
     int threads = (1 << logn) / 2;
     threads = threads < 32 ? 32 : (threads > 256 ? 256 : threads);
@@ -372,7 +471,7 @@ inline cudaError_t launch_generic(bool forward, cudaStream_t st, unsigned logn, 
             if (e != cudaSuccess) return e;
             configured = smem;
         }
-        HB_LAUNCH(kern, rows, threads, smem, st, 1, io, limbs, (int)logn);
+        HB_LAUNCH(kern, rows, threads, smem, env.stream, 1, io, limbs, (int)logn);
     } else {
         auto kern = intt_generic_kernel<IO>;
         static int configured = 0;
@@ -381,27 +480,32 @@ inline cudaError_t launch_generic(bool forward, cudaStream_t st, unsigned logn, 
             if (e != cudaSuccess) return e;
             configured = smem;
         }
-        HB_LAUNCH(kern, rows, threads, smem, st, 1, io, limbs, (int)logn);
+        HB_LAUNCH(kern, rows, threads, smem, env.stream, 1, io, limbs, (int)logn);
     }
-    ls.launches++;
+    env.stats->launches++;
     return cudaGetLastError();
 }
 
-// Dispatch on ring size.  `force_generic` routes sizes the generic kernel supports through it
-// (parity cross-check).  Returns cudaErrorInvalidValue for unsupported sizes.
+// Dispatch on ring size.  `aligned16`: every src(row) is 16-byte aligned (cp.async granularity).
 template <class IO>
-inline cudaError_t launch_ntt(bool forward, cudaStream_t st, unsigned logn, const IO &io, const LimbConst *limbs,
-                              int rows, bool force_generic, LaunchStats &ls) {
+inline cudaError_t launch_ntt(bool forward, const LaunchEnv &env, unsigned logn, const IO &io, const LimbConst *limbs, int rows,
+                              bool aligned16) {
     if (rows <= 0) return cudaSuccess;
     if (logn < 1 || logn > kFastLogMax) return cudaErrorInvalidValue;
-    if (logn < kFastLogMin || (force_generic && logn <= kGenericLogMax)) return launch_generic(forward, st, logn, io, limbs, rows, ls);
-#define HB_CASE(LN)                                                                       \
-    case LN:                                                                              \
-        return forward ? launch_fwd_fast<LN>(st, io, limbs, rows, ls) : launch_inv_fast<LN>(st, io, limbs, rows, ls);
+    if (logn < kFastLogMin || (env.force_generic && logn <= kGenericLogMax)) return launch_generic(forward, env, logn, io, limbs, rows);
+    const bool pipe = env.pipeline && aligned16 && logn <= (unsigned)kPipeLogMax;
+#define HB_CASE_PIPE(LN)                                                                                     \
+    case LN:                                                                                                 \
+        if (pipe) return forward ? launch_pipe<LN, true>(env, io, limbs, rows) : launch_pipe<LN, false>(env, io, limbs, rows); \
+        return forward ? launch_fast<LN, true>(env, io, limbs, rows) : launch_fast<LN, false>(env, io, limbs, rows);
+#define HB_CASE_FAST(LN)                                                                                     \
+    case LN:                                                                                                 \
+        return forward ? launch_fast<LN, true>(env, io, limbs, rows) : launch_fast<LN, false>(env, io, limbs, rows);
     switch (logn) {
-        HB_CASE(10) HB_CASE(11) HB_CASE(12) HB_CASE(13) HB_CASE(14) HB_CASE(15)
+        HB_CASE_PIPE(10) HB_CASE_PIPE(11) HB_CASE_PIPE(12) HB_CASE_PIPE(13) HB_CASE_FAST(14) HB_CASE_FAST(15)
     }
-#undef HB_CASE
+#undef HB_CASE_PIPE
+#undef HB_CASE_FAST
     return cudaErrorInvalidValue;
 }
 

@@ -41,6 +41,22 @@ HB_CX NttPlan plan_for(int logn) {
     }
 }
 
+// Persistent double-buffered variant (N <= 8192): same pass structure and tables, its own CTA
+// shape; shared memory per CTA is two padded row buffers.
+struct PipePlan {
+    int threads;
+    int min_blocks;
+};
+constexpr int kPipeLogMax = 13;
+HB_CX PipePlan pipe_plan_for(int logn) {
+    switch (logn) {
+    case 10: return PipePlan{64, 8};    //  2 x  9 KiB
+    case 11: return PipePlan{128, 5};   //  2 x 18 KiB
+    case 12: return PipePlan{256, 3};   //  2 x 36 KiB -> 3 CTAs = 221 KB
+    default: return PipePlan{512, 1};   //  2 x 72 KiB, N = 8192
+    }
+}
+
 // ---- forward layout --------------------------------------------------------------------
 // local levels completed before CTA pass p
 HB_CX int fwd_lambda0(const NttPlan &pl, int p) {

@@ -16,6 +16,8 @@
 
 namespace hb {
 
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 // ------------------------------------------------------------------------------------------
 // tensor product: one pass, 4 loads + 3 stores per coefficient
 // ------------------------------------------------------------------------------------------
@@ -74,9 +76,8 @@ struct ExtInttIO {
     u64 *c; // [batch][L][N]
     int L, logn;
     HB_D int limb(int row) const { return row % L; }
-    HB_D u64 load(int row, int i, const LimbConst &) const {
-        return in[(size_t)(row / L) * in_batch_stride + ((size_t)(row % L) << logn) + i];
-    }
+    HB_D const u64 *src(int row) const { return in + (size_t)(row / L) * in_batch_stride + ((size_t)(row % L) << logn); }
+    HB_D u64 pre(int, int, u64 raw, const LimbConst &) const { return raw; }
     HB_D void store(int row, int i, u64 v, const LimbConst &lc) const { c[((size_t)row << logn) + i] = reduce_strict(v, lc.q); }
     HB_D u64 *raw(int row) const { return c + ((size_t)row << logn); }
 };
@@ -98,11 +99,12 @@ struct ExtFanoutIO {
         split(row, b, p, k);
         return k;
     }
-    HB_D u64 load(int row, int i, const LimbConst &) const {
+    HB_D const u64 *src(int row) const {
         int b, p, k;
         split(row, b, p, k);
-        return c[((size_t)(b * L + p) << logn) + i];
+        return c + ((size_t)(b * L + p) << logn);
     }
+    HB_D u64 pre(int, int, u64 raw, const LimbConst &) const { return raw; }
     HB_D void store(int row, int i, u64 v, const LimbConst &) const {
         int b, p, k;
         split(row, b, p, k);
@@ -141,10 +143,10 @@ static int ext_prod_wave(Context &c, unsigned logn, const LimbConst *limbs, size
                          const u64 *key, u64 *out, size_t batch, u64 *cbuf, u64 *dec) {
     const size_t n = (size_t)1 << logn;
     ExtInttIO io1{in, in_batch_stride, cbuf, (int)L, (int)logn};
-    cudaError_t e = launch_ntt(false, c.stream, logn, io1, limbs, (int)(batch * L), c.force_generic, c.stats);
+    cudaError_t e = launch_ntt(false, c.env(), logn, io1, limbs, (int)(batch * L), aligned16(in) && (in_batch_stride % 2 == 0));
     if (e != cudaSuccess) return c.cuda_fail(e, "ext_prod: intt launch");
     ExtFanoutIO io2{cbuf, dec, (int)L, (int)logn};
-    e = launch_ntt(true, c.stream, logn, io2, limbs, (int)(batch * L * L), c.force_generic, c.stats);
+    e = launch_ntt(true, c.env(), logn, io2, limbs, (int)(batch * L * L), true);
     if (e != cudaSuccess) return c.cuda_fail(e, "ext_prod: ntt launch");
     const size_t total = batch * (L + 1) * n;
     HB_LAUNCH(ext_mac_kernel, (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, in_batch_stride, dec, key, out, limbs,
@@ -197,7 +199,8 @@ struct DropInttIO {
     u64 inv_t, inv_t_h; // 0 for CKKS
     int bgv;
     HB_D int limb(int) const { return L - 1; }
-    HB_D u64 load(int row, int i, const LimbConst &) const { return ct[((size_t)(row * L + L - 1) << logn) + i]; }
+    HB_D const u64 *src(int row) const { return ct + ((size_t)(row * L + L - 1) << logn); }
+    HB_D u64 pre(int, int, u64 raw, const LimbConst &) const { return raw; }
     HB_D void store(int row, int i, u64 v, const LimbConst &lc) const {
         if (bgv) v = harvey_lazy(v, inv_t, inv_t_h, lc.nq);
         z[((size_t)row << logn) + i] = reduce_strict(v, lc.q);
@@ -216,9 +219,9 @@ struct DropFwdIO {
     u64 half_qlast;
     int L, logn, bgv, add_halves;
     HB_D int limb(int row) const { return row % (L - 1); }
-    HB_D u64 load(int row, int i, const LimbConst &lc) const {
-        const int poly = row / (L - 1), k = row - poly * (L - 1);
-        const u64 zz = z[((size_t)poly << logn) + i];
+    HB_D const u64 *src(int row) const { return z + ((size_t)(row / (L - 1)) << logn); }
+    HB_D u64 pre(int row, int, u64 zz, const LimbConst &lc) const {
+        const int k = row % (L - 1);
         u64 r = reduce_strict(barrett_lazy(zz, lc), lc.q);          // rescaling.cpp:58-59
         if (zz >= half_qlast) r += lc.q - dc[k].qlast_mod_q;        // rescaling.cpp:63-68
         if (bgv) r = harvey_lazy(r, dc[k].t_mod_q, dc[k].t_mod_q_h, lc.nq); // mod_switch.cpp:70
@@ -253,11 +256,11 @@ int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, 
     u64 *z = c.get_scratch(2, batch * 2 * n, &err);
     if (!z) return err;
     DropInttIO io1{ct, z, (int)L, (int)logn, ds->inv_t, ds->inv_t_h, t ? 1 : 0};
-    cudaError_t e = launch_ntt(false, c.stream, logn, io1, limbs, (int)(batch * 2), c.force_generic, c.stats);
+    cudaError_t e = launch_ntt(false, c.env(), logn, io1, limbs, (int)(batch * 2), aligned16(ct));
     if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: intt launch");
     DropFwdIO io2{ct, z, out, ds->dev, addend, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, t ? 1 : 0,
                   addend ? add_halves : 0};
-    e = launch_ntt(true, c.stream, logn, io2, limbs, (int)(batch * 2 * (L - 1)), c.force_generic, c.stats);
+    e = launch_ntt(true, c.env(), logn, io2, limbs, (int)(batch * 2 * (L - 1)), true);
     if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: ntt launch");
     return 0;
 }

@@ -108,6 +108,39 @@ def test_generic_path_agrees_with_fast_path(dev, oracle, logn):
     assert np.array_equal(slow_i, dev.intt_lazy(logn, Q59, fast))
 
 
+@pytest.mark.parametrize("logn", [10, 11, 12, 13])
+def test_row_per_cta_kernels_agree_with_persistent_pipeline(dev, oracle, logn):
+    """N <= 8192 has two kernel families (persistent double-buffered / one CTA per row); both must
+    give the reference's words, also when a CTA visits several rows and for unaligned slabs."""
+    n = 1 << logn
+    moduli = [Q59, 65537]
+    batch = 11
+    x = np.stack([np.stack([oracle.lcg_fill(3 + 10 * b + k, q, n) for k, q in enumerate(moduli)]) for b in range(batch)])
+    want = np.stack([oracle.poly_ntt_fwd(logn, moduli, x[b]) for b in range(batch)])
+    want_i = np.stack([oracle.poly_intt(logn, moduli, want[b]) for b in range(batch)])
+    for pipeline in (1, 0):
+        dev.set_option("pipeline", pipeline)
+        try:
+            assert np.array_equal(dev.poly_ntt_fwd(logn, moduli, x), want)
+            assert np.array_equal(dev.poly_intt(logn, moduli, want), want_i)
+        finally:
+            dev.set_option("pipeline", 1)
+    # a slab that starts 8 bytes off a 16-byte boundary takes the row-per-CTA path
+    m = np.ascontiguousarray(np.asarray(moduli, dtype=np.uint64))
+    import ctypes as C
+    p64 = C.POINTER(C.c_uint64)
+    d = dev.slab(x.size + 1)
+    try:
+        dev._call("slab_h2d", d.ptr + 8, x.ctypes.data, x.size)
+        dev._call("ntt_fwd_lazy", logn, m.ctypes.data_as(p64), m.size, d.ptr + 8, batch)
+        got = np.empty_like(x)
+        dev._call("slab_d2h", got.ctypes.data, d.ptr + 8, x.size)
+        dev.synchronize()
+    finally:
+        d.free()
+    assert np.array_equal(got, want)
+
+
 # ------------------------------------------------------------------ coefficient-wise kernels
 @pytest.mark.parametrize("n", [1, 2, 5, 1000, 4096, 4099])
 def test_coefficient_wise_kernels(dev, oracle, n):

@@ -54,7 +54,22 @@ __global__ void k_iadd3(unsigned *out, unsigned a, unsigned b) {
     if (s == 0x12345678) out[0] = s;
 }
 
+__global__ void k_imad_hi(unsigned *out, unsigned a, unsigned b) {
+    unsigned x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = threadIdx.x + i;
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
+    }
+    unsigned s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += x[i];
+    if (s == 0x12345678) out[0] = s;
+}
+
 // 8 values per thread, 3 levels (12 butterflies) per iteration, all in registers
+template <int VARIANT>
 __global__ void k_bfly(u64 *out, ulonglong2 tw, u64 nq, u64 q2) {
     u64 v[8];
 #pragma unroll
@@ -65,7 +80,7 @@ __global__ void k_bfly(u64 *out, ulonglong2 tw, u64 nq, u64 q2) {
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 if (i & lvl) continue;
-                u64 t = harvey_lazy(v[i + lvl], tw.x, tw.y, nq);
+                u64 t = VARIANT ? harvey_lazy_split(v[i + lvl], tw.x, tw.y, nq) : harvey_lazy(v[i + lvl], tw.x, tw.y, nq);
                 v[i + lvl] = v[i] + q2 - t;
                 v[i] = v[i] + t;
             }
@@ -114,14 +129,18 @@ int main() {
     const u64 q = 576460752272228353ull;
     ulonglong2 tw = make_ulonglong2(123456789123456789ull % q, 0);
     tw.y = (u64)(((unsigned __int128)tw.x << 64) / q);
-    t = time_ms([&] { k_bfly<<<blocks, threads>>>((u64 *)out, tw, 0 - q, 2 * q); });
+    t = time_ms([&] { k_bfly<0><<<blocks, threads>>>((u64 *)out, tw, 0 - q, 2 * q); });
     const double bfly = lanes * (ITERS / 4) * 12 / (t * 1e-3);
+    t = time_ms([&] { k_bfly<1><<<blocks, threads>>>((u64 *)out, tw, 0 - q, 2 * q); });
+    const double bfly_split = lanes * (ITERS / 4) * 12 / (t * 1e-3);
+    t = time_ms([&] { k_imad_hi<<<blocks, threads>>>((unsigned *)out, 3, 5); });
+    const double imad_hi = lanes * ITERS * 8 / (t * 1e-3);
     int clk = 0;
     cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz_max\": %d, \"imad_per_s\": %.4g, \"imad_wide_per_s\": %.4g, "
-           "\"alu_ops_per_s\": %.4g, \"harvey_butterflies_per_s\": %.4g, "
+           "\"alu_ops_per_s\": %.4g, \"harvey_butterflies_per_s\": %.4g, \"harvey_butterflies_split_hi_per_s\": %.4g, \"imad_hi_per_s\": %.4g, "
            "\"imad_per_clk_per_sm_at_max_clock\": %.1f, \"imad_wide_per_clk_per_sm_at_max_clock\": %.1f, "
            "\"ntt4096_per_s_alu_ceiling\": %.4g}\n",
-           p.name, sms, clk, imad, wide, alu, bfly, imad / sms / (clk * 1e3), wide / sms / (clk * 1e3), bfly / 24576.0);
+           p.name, sms, clk, imad, wide, alu, bfly, bfly_split, imad_hi, imad / sms / (clk * 1e3), wide / sms / (clk * 1e3), bfly / 24576.0);
     return 0;
 }
