@@ -7,11 +7,11 @@ echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q > $OUT/
 echo "== int_peak"; timeout 120 ./tools/int_peak > $OUT/int_peak.json 2>&1; cat $OUT/int_peak.json
 echo "== bench pipeline=1"; timeout 900 python bench.py --no-cpu > $OUT/bench_pipe1.json 2> $OUT/bench1.err; echo "rc=$?"; tail -2 $OUT/bench1.err
 echo "== bench pipeline=0"; timeout 900 python bench.py --no-cpu --pipeline 0 > $OUT/bench_pipe0.json 2> $OUT/bench0.err; echo "rc=$?"; tail -2 $OUT/bench0.err
-python - <<PY
-import json,sys
+TAG=$TAG python - <<'PY'
+import json,sys,os
 for tag in ("pipe1","pipe0"):
     try:
-        d=json.load(open("gpurun_out/%s/bench_%s.json" % ("'$TAG'", tag)))
+        d=json.load(open("gpurun_out/%s/bench_%s.json" % (os.environ["TAG"], tag)))
     except Exception as e:
         print(tag, "unreadable", e); continue
     print(tag, "value %.3e  frac %.3f  e2e %.3e" % (d["value"], d["roofline"]["frac"], d["e2e"]["value"]))
