@@ -1,0 +1,86 @@
+// rgsw.h / keys.h — key-switch key container and the gadget-decomposition inner product
+// (src/fhe/primitives/rgsw.{h,cpp}:57-156, keys.h:19-32).
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "rlwe.h"
+
+namespace hehub {
+
+using RgswCt = std::vector<RlweCt>;
+
+/// RlweKsk = vector<RlweCt> (keys.h:19-32).  The device kernels read the key as ONE slab laid out
+/// [row p][half][limb k <= L][N]; it is packed from the rows on first use and cached in the object
+/// (keys are reused by every relinearize / rotate).  Key generation is host-side reference code.
+struct RlweKsk : public RgswCt {
+    using RgswCt::RgswCt;
+    RlweKsk() {}
+    RlweKsk(RgswCt &&rgsw) : RgswCt(std::move(rgsw)) {}
+
+    struct Packed {
+        u64 *dev = nullptr;
+        size_t rows = 0, limbs = 0, dimension = 0;
+        std::vector<u64> ext_moduli;
+        ~Packed() {
+            if (dev) hehub_b200_slab_free(b200::context(), dev);
+        }
+    };
+    /// validates the shape like rgsw.cpp:59-89 and returns the packed device copy
+    const Packed &packed(const RlwePt &pt) const {
+        if (empty()) throw std::invalid_argument("Empty RGSW ciphertext.");
+        const size_t L = pt.component_count(), n = pt.dimension();
+        auto ext = (*this)[0][0].modulus_vec();
+        if (ext.size() < L + 1) throw std::invalid_argument("Invalid component number in RGSW ciphertext.");
+        const u64 last = ext.back();
+        ext.resize(L + 1);
+        ext.back() = last;
+        for (size_t k = 0; k < L; k++)
+            if (ext[k] != pt.modulus_at((int)k)) throw std::invalid_argument("Moduli mismatch.");
+        for (const auto &sample : *this)
+            for (const auto &poly : sample) {
+                if (poly.dimension() != n) throw std::invalid_argument("Polynomial lengths mismatch.");
+                if (poly.component_count() != L + 1 || poly.modulus_vec() != ext) throw std::invalid_argument("Inconsistent RGSW ciphertext.");
+            }
+        if (size() < L) throw std::invalid_argument("Inconsistent RGSW ciphertext."); // one row per digit
+        if (cache_ && cache_->rows == L && cache_->dimension == n && cache_->ext_moduli == ext) return *cache_;
+        auto p = std::make_shared<Packed>();
+        p->rows = L;
+        p->limbs = L + 1;
+        p->dimension = n;
+        p->ext_moduli = ext;
+        const size_t poly_words = (L + 1) * n;
+        b200::check(hehub_b200_slab_alloc(b200::context(), L * 2 * poly_words, &p->dev));
+        for (size_t r = 0; r < L; r++)
+            for (size_t h = 0; h < 2; h++)
+                b200::check(hehub_b200_slab_d2d(b200::context(), p->dev + (r * 2 + h) * poly_words, (*this)[r][h].dev(), poly_words));
+        cache_ = p;
+        return *cache_;
+    }
+    /// call after mutating the rows in place
+    void invalidate_packed() { cache_.reset(); }
+
+private:
+    mutable std::shared_ptr<Packed> cache_;
+};
+
+/// rgsw.cpp:57-156 — RNS-digit decomposition of `pt` (NTT form) and inner product with the key,
+/// accumulated in 128 bits and Montgomery-reduced once; result over (q_0..q_{L-1}, P), value form.
+inline RlweCt ext_prod_montgomery(const RlwePt &pt, const RlweKsk &rgsw) {
+    const auto &key = rgsw.packed(pt);
+    const size_t L = pt.component_count();
+    RnsPolyParams ext{pt.dimension(), L + 1, key.ext_moduli};
+    // one slab [2][L+1][N] from the kernel, split into the two polynomials of the result
+    detail::Staged out(2 * (L + 1) * pt.dimension());
+    b200::check(hehub_b200_ext_prod_montgomery(b200::context(), (unsigned)pt.log_dimension(), key.ext_moduli.data(), L, pt.dev(),
+                                               key.dev, out.dev, 1));
+    RlweCt ct{RnsPolynomial(ext), RnsPolynomial(ext)};
+    for (size_t h = 0; h < 2; h++) {
+        b200::check(hehub_b200_slab_d2d(b200::context(), ct[h].dev_mut(), out.dev + h * (L + 1) * pt.dimension(), (L + 1) * pt.dimension()));
+        ct[h].rep_form = PolyRepForm::value;
+    }
+    return ct;
+}
+inline RlweCt ext_prod_montgomery(const RlwePt &pt, const RgswCt &rgsw) { return ext_prod_montgomery(pt, RlweKsk(RgswCt(rgsw))); }
+
+} // namespace hehub

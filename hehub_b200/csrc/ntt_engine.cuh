@@ -30,6 +30,8 @@
 //   u64       *raw(int row)                               -> row-sized exchange area in global memory
 //                                                            (N = 32768 inverse only; may be the output row)
 #pragma once
+#include <type_traits>
+
 #include "modarith.cuh"
 #include "ntt_plan.h"
 
@@ -49,32 +51,50 @@ HB_D void bfly(u64 &lo, u64 &hi, const ulonglong2 tw, u64 nq, u64 q2) {
     lo = lo + t;
 }
 
-// K forward levels on 2^K registers.  Level m pairs registers 2^(K-m) apart; twiddle slot
-// (2^(m-1) - 1 + blk) is read at tw[slot * stride].
-template <int K, int M = 1>
-HB_D void fwd_levels(u64 (&v)[1 << K], const ulonglong2 *__restrict__ tw, int stride, u64 nq, u64 q2) {
+// Where a pass takes its 2^K - 1 twiddle pairs from: the table in global memory (L1/L2), or a
+// register copy the persistent kernels keep across rows for the contiguous pass, whose twiddles
+// are private to the thread and identical for every row of the same limb.
+struct TwTable {
+    const ulonglong2 *p;
+    int stride;
+    HB_D ulonglong2 get(int slot) const { return __ldg(p + slot * stride); }
+};
+template <int K>
+struct TwRegs {
+    ulonglong2 r[(1 << K) - 1];
+    HB_D ulonglong2 get(int slot) const { return r[slot]; }
+    HB_D void fill(const ulonglong2 *__restrict__ p, int stride) {
+#pragma unroll
+        for (int s = 0; s < (1 << K) - 1; s++) r[s] = __ldg(p + s * stride);
+    }
+};
+
+// K forward levels on 2^K registers.  Level m pairs registers 2^(K-m) apart and uses twiddle
+// slot (2^(m-1) - 1 + blk).
+template <int K, int M = 1, class TW>
+HB_D void fwd_levels(u64 (&v)[1 << K], const TW &tw, u64 nq, u64 q2) {
     constexpr int half = 1 << (K - M);
 #pragma unroll
     for (int blk = 0; blk < (1 << (M - 1)); blk++) {
-        const ulonglong2 z = __ldg(tw + ((1 << (M - 1)) - 1 + blk) * stride);
+        const ulonglong2 z = tw.get((1 << (M - 1)) - 1 + blk);
 #pragma unroll
         for (int jj = 0; jj < half; jj++) bfly(v[blk * 2 * half + jj], v[blk * 2 * half + jj + half], z, nq, q2);
     }
-    if constexpr (M < K) fwd_levels<K, M + 1>(v, tw, stride, nq, q2);
+    if constexpr (M < K) fwd_levels<K, M + 1>(v, tw, nq, q2);
 }
 
 // K inverse (folded) stages on 2^K registers.  Stage m pairs registers 2^(m-1) apart; twiddle
 // slot (2^(m-1) - 1 + jj) depends on the register's index modulo 2^(m-1).
-template <int K, int M = 1>
-HB_D void inv_levels(u64 (&v)[1 << K], const ulonglong2 *__restrict__ tw, int stride, u64 nq, u64 q2) {
+template <int K, int M = 1, class TW>
+HB_D void inv_levels(u64 (&v)[1 << K], const TW &tw, u64 nq, u64 q2) {
     constexpr int d = 1 << (M - 1);
 #pragma unroll
     for (int jj = 0; jj < d; jj++) {
-        const ulonglong2 z = __ldg(tw + (d - 1 + jj) * stride);
+        const ulonglong2 z = tw.get(d - 1 + jj);
 #pragma unroll
         for (int blk = 0; blk < (1 << (K - M)); blk++) bfly(v[blk * 2 * d + jj], v[blk * 2 * d + jj + d], z, nq, q2);
     }
-    if constexpr (M < K) inv_levels<K, M + 1>(v, tw, stride, nq, q2);
+    if constexpr (M < K) inv_levels<K, M + 1>(v, tw, nq, q2);
 }
 
 HB_D int sphys(int i) { return i + ((i >> 4) << 1); }
@@ -108,8 +128,10 @@ HB_D void prefetch_row(u64 *sm, const u64 *__restrict__ src) {
 // forward passes.  SRC: 0 = first pass reads global memory, 1 = first pass reads the raw words
 // a prefetch left in shared memory.
 // ------------------------------------------------------------------------------------------
-template <int LOGN, int T, int P, int SRC, class IO>
-HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
+// TWC: register twiddles for the contiguous pass (TwRegs<K>) or NoTw (read the table)
+struct NoTw {};
+template <int LOGN, int T, int P, int SRC, class IO, class TWC>
+HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B, const TWC &twc) {
     constexpr NttPlan pl = plan_for(LOGN);
     constexpr int LOGNC = LOGN - pl.lpre, NC = 1 << LOGNC;
     constexpr int K = pl.k[P], L0 = fwd_lambda0(pl, P), GSL = LOGNC - L0 - K; // log2(smallest gap)
@@ -154,7 +176,12 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
             for (int j = 0; j < (1 << K); j++) v[j] = sm[sphys(base + (j << GSL))];
         }
 
-        fwd_levels<K>(v, tw_pass + ((B << L0) + hb), stride, lc.nq, lc.q2);
+        if constexpr (last && !std::is_same<TWC, NoTw>::value) {
+            static_assert(NG == T, "register twiddles need one contiguous group per thread");
+            fwd_levels<K>(v, twc, lc.nq, lc.q2);
+        } else {
+            fwd_levels<K>(v, TwTable{tw_pass + ((B << L0) + hb), stride}, lc.nq, lc.q2);
+        }
 
         if constexpr (last) {
 #pragma unroll
@@ -167,10 +194,10 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     }
 }
 
-template <int LOGN, int T, int P, int SRC, class IO>
-HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
+template <int LOGN, int T, int P, int SRC, class IO, class TWC>
+HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B, const TWC &twc) {
     constexpr NttPlan pl = plan_for(LOGN);
-    fwd_pass<LOGN, T, P, SRC>(sm, io, lc, row, B);
+    fwd_pass<LOGN, T, P, SRC>(sm, io, lc, row, B, twc);
     if constexpr (P == 0 && pl.lpre == 1) {
         // both CTAs of the row have read all of it: from here on either may overwrite it
         // (in-place transforms store into the words the sibling CTA has just read)
@@ -178,7 +205,7 @@ HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B)
     } else {
         __syncthreads();
     }
-    if constexpr (P + 1 < pl.npass) fwd_passes<LOGN, T, P + 1, SRC>(sm, io, lc, row, B);
+    if constexpr (P + 1 < pl.npass) fwd_passes<LOGN, T, P + 1, SRC>(sm, io, lc, row, B, twc);
 }
 
 // one CTA (or one CTA of a 2-CTA cluster) per row
@@ -190,7 +217,7 @@ ntt_fwd_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     HB_SHARED_U64(sm);
     const int row = blockIdx.x >> pl.lpre, B = blockIdx.x & ((1 << pl.lpre) - 1);
     const LimbConst lc = limbs[io.limb(row)];
-    fwd_passes<LOGN, T, 0, 0>(sm, io, lc, row, B);
+    fwd_passes<LOGN, T, 0, 0>(sm, io, lc, row, B, NoTw{});
     for (int i = threadIdx.x; i < NC; i += T) io.store(row, B * NC + i, sm[sphys(i)], lc);
 }
 
@@ -204,6 +231,13 @@ ntt_fwd_pipe_kernel(const IO io, const LimbConst *__restrict__ limbs, int rows) 
     int row = blockIdx.x;
     if (row >= rows) return;
     prefetch_row<NC, T>(smem, io.src(row));
+    // the last (contiguous) pass uses 15 twiddle pairs private to this thread and identical for
+    // every row of a limb: they stay in registers for as long as the CTA keeps seeing that limb
+    constexpr NttPlan pl = plan_for(LOGN);
+    constexpr int KL = pl.k[pl.npass - 1], L0L = fwd_lambda0(pl, pl.npass - 1);
+    constexpr bool kCache = (NC >> KL) == T;
+    typename std::conditional<kCache, TwRegs<KL>, NoTw>::type twc;
+    int cached_limb = -1;
     int cur = 0;
     for (; row < rows; row += gridDim.x) {
         u64 *sm = smem + cur * BUF;
@@ -211,8 +245,15 @@ ntt_fwd_pipe_kernel(const IO io, const LimbConst *__restrict__ limbs, int rows) 
         __syncthreads(); // this row has landed; every thread is done with the other buffer
         const int next = row + gridDim.x;
         if (next < rows) prefetch_row<NC, T>(smem + (cur ^ 1) * BUF, io.src(next));
-        const LimbConst lc = limbs[io.limb(row)];
-        fwd_passes<LOGN, T, 0, 1>(sm, io, lc, row, 0);
+        const int limb = io.limb(row);
+        const LimbConst lc = limbs[limb];
+        if constexpr (kCache) {
+            if (limb != cached_limb) {
+                twc.fill(lc.fwd + fwd_pass_offset(pl, pl.npass - 1) + threadIdx.x, 1 << L0L);
+                cached_limb = limb;
+            }
+        }
+        fwd_passes<LOGN, T, 0, 1>(sm, io, lc, row, 0, twc);
         for (int i = threadIdx.x; i < NC; i += T) io.store(row, i, sm[sphys(i)], lc);
         cur ^= 1;
     }
@@ -221,8 +262,8 @@ ntt_fwd_pipe_kernel(const IO io, const LimbConst *__restrict__ limbs, int rows) 
 // ------------------------------------------------------------------------------------------
 // inverse passes
 // ------------------------------------------------------------------------------------------
-template <int LOGN, int T, int P, int SRC, class IO>
-HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
+template <int LOGN, int T, int P, int SRC, class IO, class TWC>
+HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B, const TWC &twc) {
     constexpr NttPlan pl = plan_for(LOGN);
     constexpr int LOGNC = LOGN - pl.lpre, NC = 1 << LOGNC;
     constexpr int K = inv_k(pl, P), S0 = inv_s0(pl, P);
@@ -248,7 +289,12 @@ HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
             for (int j = 0; j < (1 << K); j++) v[j] = sm[sphys(base + (j << S0))];
         }
 
-        inv_levels<K>(v, tw_pass + lo, stride, lc.nq, lc.q2);
+        if constexpr (last && !std::is_same<TWC, NoTw>::value) {
+            static_assert(NG == T, "register twiddles need one group per thread");
+            inv_levels<K>(v, twc, lc.nq, lc.q2);
+        } else {
+            inv_levels<K>(v, TwTable{tw_pass + lo, stride}, lc.nq, lc.q2);
+        }
 
         if constexpr (last) {
             if constexpr (pl.lpre == 0) {
@@ -272,13 +318,13 @@ HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     }
 }
 
-template <int LOGN, int T, int P, int SRC, class IO>
-HB_D void inv_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
+template <int LOGN, int T, int P, int SRC, class IO, class TWC>
+HB_D void inv_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B, const TWC &twc) {
     constexpr NttPlan pl = plan_for(LOGN);
-    inv_pass<LOGN, T, P, SRC>(sm, io, lc, row, B);
+    inv_pass<LOGN, T, P, SRC>(sm, io, lc, row, B, twc);
     if constexpr (P + 1 < pl.npass) {
         __syncthreads();
-        inv_passes<LOGN, T, P + 1, SRC>(sm, io, lc, row, B);
+        inv_passes<LOGN, T, P + 1, SRC>(sm, io, lc, row, B, twc);
     }
 }
 
@@ -292,7 +338,7 @@ intt_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     const LimbConst lc = limbs[io.limb(row)];
     for (int i = threadIdx.x; i < NC; i += T) sm[sphys(i)] = io_load(io, row, B * NC + i, lc);
     __syncthreads();
-    inv_passes<LOGN, T, 0, 0>(sm, io, lc, row, B);
+    inv_passes<LOGN, T, 0, 0>(sm, io, lc, row, B, NoTw{});
     if constexpr (pl.lpre == 1) {
         // last stage (gap N/2) pairs word i of CTA 0 with word i of CTA 1.  Exchange the halves
         // through the row's exchange area (L2), combine into shared memory, and only after the
@@ -327,6 +373,13 @@ intt_pipe_kernel(const IO io, const LimbConst *__restrict__ limbs, int rows) {
     int row = blockIdx.x;
     if (row >= rows) return;
     prefetch_row<NC, T>(smem, io.src(row));
+    // the last inverse pass (largest gaps) uses twiddle pairs private to this thread and identical
+    // for every row of a limb: kept in registers while the CTA keeps seeing that limb
+    constexpr NttPlan pl = plan_for(LOGN);
+    constexpr int KL = inv_k(pl, pl.npass - 1), S0L = inv_s0(pl, pl.npass - 1);
+    constexpr bool kCache = (NC >> KL) == T;
+    typename std::conditional<kCache, TwRegs<KL>, NoTw>::type twc;
+    int cached_limb = -1;
     int cur = 0;
     for (; row < rows; row += gridDim.x) {
         u64 *sm = smem + cur * BUF;
@@ -334,8 +387,15 @@ intt_pipe_kernel(const IO io, const LimbConst *__restrict__ limbs, int rows) {
         __syncthreads();
         const int next = row + gridDim.x;
         if (next < rows) prefetch_row<NC, T>(smem + (cur ^ 1) * BUF, io.src(next));
-        const LimbConst lc = limbs[io.limb(row)];
-        inv_passes<LOGN, T, 0, 1>(sm, io, lc, row, 0); // the last pass stores straight from registers
+        const int limb = io.limb(row);
+        const LimbConst lc = limbs[limb];
+        if constexpr (kCache) {
+            if (limb != cached_limb) {
+                twc.fill(lc.inv + inv_pass_offset(pl, pl.npass - 1) + threadIdx.x, 1 << S0L);
+                cached_limb = limb;
+            }
+        }
+        inv_passes<LOGN, T, 0, 1>(sm, io, lc, row, 0, twc); // the last pass stores straight from registers
         cur ^= 1;
     }
 }
@@ -410,10 +470,14 @@ constexpr auto pipe_kernel() {
     else return &intt_pipe_kernel<LOGN, IO>;
 }
 
+// Opt in to `smem` bytes of dynamic shared memory and ask for just enough carveout for `blocks`
+// resident CTAs: whatever is left of the SM's 228 KB stays L1, which the twiddle tables live in.
 template <class K>
-inline cudaError_t configure_smem(K kern, int smem) {
+inline cudaError_t configure_smem(K kern, int smem, int blocks) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    int pct = (int)(((long long)blocks * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     return e;
 }
 
@@ -424,7 +488,7 @@ inline cudaError_t launch_fast(const LaunchEnv &env, const IO &io, const LimbCon
     auto kern = fast_kernel<LOGN, FWD, IO>();
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = configure_smem(kern, smem);
+        cudaError_t e = configure_smem(kern, smem, pl.min_blocks);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -444,7 +508,7 @@ inline cudaError_t launch_pipe(const LaunchEnv &env, const IO &io, const LimbCon
     auto kern = pipe_kernel<LOGN, FWD, IO>();
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = configure_smem(kern, smem);
+        cudaError_t e = configure_smem(kern, smem, pp.min_blocks);
         if (e != cudaSuccess) return e;
         configured = true;
     }

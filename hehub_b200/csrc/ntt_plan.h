@@ -50,9 +50,10 @@ struct PipePlan {
 constexpr int kPipeLogMax = 13;
 HB_CX PipePlan pipe_plan_for(int logn) {
     switch (logn) {
+    // 128 registers per thread: 60 hold the register-resident twiddles of the contiguous pass
     case 10: return PipePlan{64, 8};    //  2 x  9 KiB
-    case 11: return PipePlan{128, 5};   //  2 x 18 KiB
-    case 12: return PipePlan{256, 3};   //  2 x 36 KiB -> 3 CTAs = 221 KB
+    case 11: return PipePlan{128, 4};   //  2 x 18 KiB
+    case 12: return PipePlan{256, 2};   //  2 x 36 KiB -> 2 CTAs = 147 KB, ~79 KB left as L1
     default: return PipePlan{512, 1};   //  2 x 72 KiB, N = 8192
     }
 }

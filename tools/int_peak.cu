@@ -135,12 +135,21 @@ int main() {
     const double bfly_split = lanes * (ITERS / 4) * 12 / (t * 1e-3);
     t = time_ms([&] { k_imad_hi<<<blocks, threads>>>((unsigned *)out, 3, 5); });
     const double imad_hi = lanes * ITERS * 8 / (t * 1e-3);
+    // occupancy sweep: how many resident warps per scheduler the butterfly stream needs to fill the pipe
+    char occ[512];
+    int off = 0;
+    for (int bps : {1, 2, 3, 4, 6, 8}) {
+        const int nb = sms * bps;
+        t = time_ms([&] { k_bfly<0><<<nb, threads>>>((u64 *)out, tw, 0 - q, 2 * q); });
+        const double r = (double)nb * threads * (ITERS / 4) * 12 / (t * 1e-3);
+        off += snprintf(occ + off, sizeof(occ) - off, "%s\"%d\": %.4g", off ? ", " : "", bps * threads / 32 / 4, r);
+    }
     int clk = 0;
     cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz_max\": %d, \"imad_per_s\": %.4g, \"imad_wide_per_s\": %.4g, "
            "\"alu_ops_per_s\": %.4g, \"harvey_butterflies_per_s\": %.4g, \"harvey_butterflies_split_hi_per_s\": %.4g, \"imad_hi_per_s\": %.4g, "
            "\"imad_per_clk_per_sm_at_max_clock\": %.1f, \"imad_wide_per_clk_per_sm_at_max_clock\": %.1f, "
-           "\"ntt4096_per_s_alu_ceiling\": %.4g}\n",
-           p.name, sms, clk, imad, wide, alu, bfly, bfly_split, imad_hi, imad / sms / (clk * 1e3), wide / sms / (clk * 1e3), bfly / 24576.0);
+           "\"ntt4096_per_s_alu_ceiling\": %.4g, \"butterflies_per_s_by_warps_per_scheduler\": {%s}}\n",
+           p.name, sms, clk, imad, wide, alu, bfly, bfly_split, imad_hi, imad / sms / (clk * 1e3), wide / sms / (clk * 1e3), bfly / 24576.0, occ);
     return 0;
 }
