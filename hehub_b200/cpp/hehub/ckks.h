@@ -1,0 +1,206 @@
+// ckks.h — the ciphertext-op part of hehub::ckks (src/fhe/ckks/ckks.h:73-329, arith.cpp, rescaling.cpp)
+// on the B200 back end.  Encoding (fp64 FFT, basics.cpp:68-369), sampling and key generation are
+// host-side reference code outside this back end's path; their outputs (CkksPt, CkksCt, RlweKsk)
+// are consumed here unchanged.
+#pragma once
+#include <cmath>
+
+#include "permutation.h"
+#include "rgsw.h"
+
+namespace hehub {
+namespace ckks {
+
+struct CkksPt : public RlwePt {
+    using RlwePt::RlwePt;
+    CkksPt() {}
+    CkksPt(RlwePt &&other) : RlwePt(std::move(other)) {}
+    double scaling_factor = 1.0;
+};
+
+struct CkksCt : public RlweCt {
+    using RlweCt::RlweCt;
+    CkksCt() {}
+    CkksCt(RlweCt &&other) : RlweCt(std::move(other)) {}
+    double scaling_factor = 1.0;
+};
+
+struct CkksQuadraticCt : public std::array<RnsPolynomial, 3> {
+    using std::array<RnsPolynomial, 3>::array;
+    double scaling_factor = 1.0;
+};
+
+namespace detail {
+inline void check_scaling_factor(double a, double b) {
+    if (std::abs(a - b) > std::pow(2.0, -50)) throw std::invalid_argument("The scaling factors mismatch"); // arith.cpp:7-13
+}
+inline void check_ct(const RlweCt &ct) { // rescaling.cpp:15-29
+    if (ct[0].modulus_vec() != ct[1].modulus_vec()) throw std::invalid_argument("Ill-formed ciphertext: modulus sets mismatch.");
+    if (ct[0].dimension() != ct[1].dimension()) throw std::invalid_argument("Ill-formed ciphertext: polynomial lengths mismatch.");
+    if (ct[0].component_count() != ct[1].component_count()) throw std::invalid_argument("Ill-formed ciphertext: component numbers mismatch.");
+}
+/// contiguous [polys][L][N] device copy of separately stored polynomials (what the C ABI consumes)
+template <size_t K>
+inline void gather(const std::array<RnsPolynomial, K> &polys, u64 *dst) {
+    const size_t words = polys[0].component_count() * polys[0].dimension();
+    for (size_t h = 0; h < K; h++) b200::check(hehub_b200_slab_d2d(b200::context(), dst + h * words, polys[h].dev(), words));
+}
+inline RlweCt scatter(const u64 *src, const RnsPolyParams &params) {
+    RlweCt ct{RnsPolynomial(params), RnsPolynomial(params)};
+    const size_t words = params.component_count * params.dimension;
+    for (size_t h = 0; h < 2; h++) {
+        b200::check(hehub_b200_slab_d2d(b200::context(), ct[h].dev_mut(), src + h * words, words));
+        ct[h].rep_form = PolyRepForm::value;
+    }
+    return ct;
+}
+} // namespace detail
+
+inline CkksCt add(const CkksCt &ct1, const CkksCt &ct2) { // arith.cpp:15-20
+    detail::check_scaling_factor(ct1.scaling_factor, ct2.scaling_factor);
+    CkksCt sum_ct = ::hehub::add(ct1, ct2);
+    sum_ct.scaling_factor = ct1.scaling_factor;
+    return sum_ct;
+}
+inline CkksCt sub(const CkksCt &ct1, const CkksCt &ct2) { // arith.cpp:31-36
+    detail::check_scaling_factor(ct1.scaling_factor, ct2.scaling_factor);
+    CkksCt diff_ct = ::hehub::sub(ct1, ct2);
+    diff_ct.scaling_factor = ct1.scaling_factor;
+    return diff_ct;
+}
+inline CkksCt add_plain(const CkksCt &ct, const CkksPt &pt) { // arith.cpp:22-29
+    detail::check_scaling_factor(ct.scaling_factor, pt.scaling_factor);
+    RnsPolynomial pt_ntt(pt);
+    ntt_negacyclic_inplace_lazy(pt_ntt);
+    CkksCt sum_ct = add_plain_core(ct, pt_ntt);
+    sum_ct.scaling_factor = ct.scaling_factor;
+    return sum_ct;
+}
+inline CkksCt sub_plain(const CkksCt &ct, const CkksPt &pt) { // arith.cpp:38-45
+    detail::check_scaling_factor(ct.scaling_factor, pt.scaling_factor);
+    RnsPolynomial pt_ntt(pt);
+    ntt_negacyclic_inplace_lazy(pt_ntt);
+    CkksCt diff_ct = sub_plain_core(ct, pt_ntt);
+    diff_ct.scaling_factor = ct.scaling_factor;
+    return diff_ct;
+}
+inline CkksCt mult_plain(const CkksCt &ct, const CkksPt &pt) { // arith.cpp:47-53
+    RnsPolynomial pt_ntt(pt);
+    ntt_negacyclic_inplace_lazy(pt_ntt);
+    CkksCt prod_ct = mult_plain_core(ct, pt_ntt);
+    prod_ct.scaling_factor = ct.scaling_factor * pt.scaling_factor;
+    return prod_ct;
+}
+
+/// arith.cpp:55-62 — one fused tensor-product kernel (4 multiplications + 1 lazy addition per coefficient)
+inline CkksQuadraticCt mult_low_level(const CkksCt &ct1, const CkksCt &ct2) {
+    detail::check_ct(ct1);
+    detail::check_ct(ct2);
+    ::hehub::detail::check_same_shape(ct1[0], ct2[0]);
+    for (auto *ct : {&ct1, &ct2})
+        for (const auto &p : *ct)
+            if (p.rep_form != PolyRepForm::value)
+                throw std::invalid_argument("Polynomial multiplication requires NTT form (value representation).");
+    const auto params = ct1[0].params();
+    const size_t words = params.component_count * params.dimension;
+    ::hehub::detail::Staged a(2 * words), b(2 * words), q(3 * words);
+    detail::gather<2>(ct1, a.dev);
+    detail::gather<2>(ct2, b.dev);
+    b200::check(hehub_b200_ckks_tensor(b200::context(), (unsigned)ct1[0].log_dimension(), params.moduli.data(), params.component_count,
+                                       a.dev, b.dev, q.dev, 1));
+    CkksQuadraticCt prod;
+    for (size_t h = 0; h < 3; h++) {
+        prod[h] = RnsPolynomial(params);
+        b200::check(hehub_b200_slab_d2d(b200::context(), prod[h].dev_mut(), q.dev + h * words, words));
+        prod[h].rep_form = PolyRepForm::value;
+    }
+    prod.scaling_factor = ct1.scaling_factor * ct2.scaling_factor;
+    return prod;
+}
+
+/// rescaling.cpp:80-90 → :14-78
+inline void rescale_inplace(CkksCt &ct, size_t dropping_primes = 1) {
+    if (dropping_primes >= 2) throw "under development";
+    if (dropping_primes != 1) throw std::invalid_argument("The number of primes to be dropped is not positive.");
+    detail::check_ct(ct);
+    if (ct[0].component_count() == 1) throw std::invalid_argument("Unable to drop the only one prime.");
+    const auto params = ct[0].params();
+    const size_t L = params.component_count, n = params.dimension;
+    ::hehub::detail::Staged in(2 * L * n), out(2 * (L - 1) * n);
+    detail::gather<2>(ct, in.dev);
+    b200::check(hehub_b200_ckks_rescale(b200::context(), (unsigned)ct[0].log_dimension(), params.moduli.data(), L, in.dev, out.dev, 1));
+    RnsPolyParams dropped{n, L - 1, std::vector<u64>(params.moduli.begin(), params.moduli.end() - 1)};
+    const double sf = ct.scaling_factor / (double)params.moduli[L - 1]; // rescaling.cpp:77
+    static_cast<RlweCt &>(ct) = detail::scatter(out.dev, dropped);
+    ct.scaling_factor = sf;
+}
+
+/// arith.cpp:64-73 — key switch of d2, drop of the special prime and the final additions in one call
+inline CkksCt relinearize(const CkksQuadraticCt &ct, const RlweKsk &relin_key) {
+    const auto &key = relin_key.packed(ct[2]);
+    const auto params = ct[0].params();
+    const size_t L = params.component_count, words = L * params.dimension;
+    ::hehub::detail::Staged q(3 * words), out(2 * words);
+    detail::gather<3>(ct, q.dev);
+    b200::check(hehub_b200_ckks_relinearize(b200::context(), (unsigned)ct[0].log_dimension(), key.ext_moduli.data(), L, q.dev, key.dev,
+                                            out.dev, 1));
+    CkksCt ct_new = detail::scatter(out.dev, params);
+    ct_new.scaling_factor = ct.scaling_factor;
+    return ct_new;
+}
+
+/// ckks.h:270-274 — tensor product + relinearize fused behind one C-ABI call
+inline CkksCt mult(const CkksCt &ct1, const CkksCt &ct2, const RlweKsk &relin_key) {
+    detail::check_ct(ct1);
+    detail::check_ct(ct2);
+    ::hehub::detail::check_same_shape(ct1[0], ct2[0]);
+    const auto &key = relin_key.packed(ct1[1]);
+    const auto params = ct1[0].params();
+    const size_t L = params.component_count, words = L * params.dimension;
+    ::hehub::detail::Staged a(2 * words), b(2 * words), out(2 * words);
+    detail::gather<2>(ct1, a.dev);
+    detail::gather<2>(ct2, b.dev);
+    b200::check(hehub_b200_ckks_mult_relin(b200::context(), (unsigned)ct1[0].log_dimension(), key.ext_moduli.data(), L, a.dev, b.dev,
+                                           key.dev, out.dev, 1));
+    CkksCt prod = detail::scatter(out.dev, params);
+    prod.scaling_factor = ct1.scaling_factor * ct2.scaling_factor;
+    return prod;
+}
+
+/// arith.cpp:75-83
+inline CkksCt conjugate(const CkksCt &ct, const RlweKsk &conj_key) {
+    detail::check_ct(ct);
+    const auto &key = conj_key.packed(ct[1]);
+    const auto params = ct[0].params();
+    const size_t L = params.component_count, words = L * params.dimension;
+    ::hehub::detail::Staged a(2 * words), out(2 * words);
+    detail::gather<2>(ct, a.dev);
+    b200::check(hehub_b200_ckks_conjugate(b200::context(), (unsigned)ct[0].log_dimension(), key.ext_moduli.data(), L, a.dev, key.dev,
+                                          out.dev, 1));
+    CkksCt res = detail::scatter(out.dev, params);
+    res.scaling_factor = ct.scaling_factor;
+    return res;
+}
+
+/// arith.cpp:85-93
+inline CkksCt rotate(const CkksCt &ct, const RlweKsk &rot_key, const size_t step) {
+    detail::check_ct(ct);
+    const auto &key = rot_key.packed(ct[1]);
+    const auto params = ct[0].params();
+    const size_t L = params.component_count, words = L * params.dimension;
+    ::hehub::detail::Staged a(2 * words), out(2 * words);
+    detail::gather<2>(ct, a.dev);
+    b200::check(hehub_b200_ckks_rotate(b200::context(), (unsigned)ct[0].log_dimension(), key.ext_moduli.data(), L, a.dev, key.dev, step,
+                                       out.dev, 1));
+    CkksCt res = detail::scatter(out.dev, params);
+    res.scaling_factor = ct.scaling_factor;
+    return res;
+}
+
+} // namespace ckks
+
+using CkksPt = ckks::CkksPt;
+using CkksCt = ckks::CkksCt;
+using CkksSk = RlweSk;
+
+} // namespace hehub

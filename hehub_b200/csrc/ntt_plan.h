@@ -34,7 +34,19 @@ HB_CX NttPlan plan_for(int logn) {
     switch (logn) {
     case 10: return NttPlan{10, 0, 3, {3, 3, 4, 0, 0}, 64, 8};
     case 11: return NttPlan{11, 0, 3, {4, 3, 4, 0, 0}, 128, 6};
+#if !defined(HB_PLAN12) || HB_PLAN12 == 0
     case 12: return NttPlan{12, 0, 3, {4, 4, 4, 0, 0}, 256, 3};
+#elif HB_PLAN12 == 1
+    case 12: return NttPlan{12, 0, 3, {4, 4, 4, 0, 0}, 256, 4};
+#elif HB_PLAN12 == 2
+    case 12: return NttPlan{12, 0, 4, {3, 3, 3, 3, 0}, 512, 2};
+#elif HB_PLAN12 == 3
+    case 12: return NttPlan{12, 0, 4, {3, 3, 3, 3, 0}, 512, 3};
+#elif HB_PLAN12 == 4
+    case 12: return NttPlan{12, 0, 4, {3, 3, 3, 3, 0}, 256, 4};
+#elif HB_PLAN12 == 5
+    case 12: return NttPlan{12, 0, 4, {3, 3, 3, 3, 0}, 256, 5};
+#endif
     case 13: return NttPlan{13, 0, 4, {3, 3, 3, 4, 0}, 256, 2};
     case 14: return NttPlan{14, 0, 4, {4, 3, 3, 4, 0}, 512, 1};
     default: return NttPlan{15, 1, 4, {4, 3, 3, 4, 0}, 512, 1};

@@ -1,0 +1,338 @@
+// test_hehub_api.cpp — the hehub:: host mirror (hehub_b200/cpp/hehub) exercised the way the
+// reference's own unit tests exercise the reference (tests/ntt_t.cpp, tests/mod_arith_t.cpp,
+// tests/common_t.cpp, tests/ckks_t.cpp:136-175), plus word-for-word comparison of every
+// ciphertext op against the CPU oracle (oracle/hehub_oracle.h; test infrastructure).
+//
+// Linked against hehub_b200/libhehub_b200.so on a GPU box, or against the CTA-emulator build of
+// the same sources for the CPU suite (tests/test_cpp_mirror.py drives both).
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "hehub/hehub.h"
+#include "hehub_oracle.h"
+
+using namespace hehub;
+
+static int g_fail = 0, g_checks = 0;
+#define CHECK(cond)                                                                  \
+    do {                                                                             \
+        g_checks++;                                                                  \
+        if (!(cond)) {                                                               \
+            g_fail++;                                                                \
+            std::fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond);     \
+        }                                                                            \
+    } while (0)
+#define CHECK_THROWS(expr, type)                                                     \
+    do {                                                                             \
+        g_checks++;                                                                  \
+        bool thrown = false;                                                         \
+        try {                                                                        \
+            expr;                                                                    \
+        } catch (const type &) {                                                     \
+            thrown = true;                                                           \
+        } catch (...) {                                                              \
+        }                                                                            \
+        if (!thrown) {                                                               \
+            g_fail++;                                                                \
+            std::fprintf(stderr, "FAIL %s:%d: %s did not throw %s\n", __FILE__, __LINE__, #expr, #type); \
+        }                                                                            \
+    } while (0)
+
+static const u64 Q59 = 576460752272228353ull;
+
+static RnsPolynomial filled(size_t n, const std::vector<u64> &moduli, u64 seed0, PolyRepForm form) {
+    RnsPolynomial p(n, moduli.size(), moduli);
+    for (size_t k = 0; k < moduli.size(); k++) orc_lcg_fill(seed0 + k, moduli[k], n, p[k].data());
+    p.rep_form = form;
+    return p;
+}
+static std::vector<u64> flat(const RnsPolynomial &p) {
+    std::vector<u64> out;
+    for (size_t k = 0; k < p.component_count(); k++) out.insert(out.end(), p[k].begin(), p[k].end());
+    return out;
+}
+template <size_t K>
+static std::vector<u64> flat(const std::array<RnsPolynomial, K> &ct) {
+    std::vector<u64> out;
+    for (const auto &p : ct) {
+        auto f = flat(p);
+        out.insert(out.end(), f.begin(), f.end());
+    }
+    return out;
+}
+
+// tests/ntt_t.cpp:91-181
+static void test_ntt_round_trip() {
+    std::mt19937_64 rng(7);
+    for (size_t logn : {4, 7, 10, 12, 13, 15})
+        for (u64 q : std::vector<u64>{65537ull, 260898817ull, 35184358850561ull, 36028796997599233ull, Q59}) {
+            const size_t n = (size_t)1 << logn;
+            std::vector<std::vector<u64>> cases(3, std::vector<u64>(n, 0));
+            cases[0][0] = 1;
+            cases[1][1] = 1;
+            for (auto &c : cases[2]) c = rng() % q;
+            for (const auto &x : cases) {
+                std::vector<u64> y(x);
+                ntt_negacyclic_inplace_lazy(logn, q, y.data());
+                bool lazy_ok = true;
+                for (u64 v : y) lazy_ok &= v < 2 * q;
+                CHECK(lazy_ok);
+                std::vector<u64> want(x);
+                orc_ntt_fwd_lazy((unsigned)logn, q, want.data());
+                CHECK(y == want);
+                intt_negacyclic_inplace_lazy(logn, q, y.data());
+                for (u64 v : y) lazy_ok &= v < 2 * q;
+                CHECK(lazy_ok);
+                batched_reduce_strict(q, n, y.data());
+                CHECK(y == x);
+            }
+            // on an RnsPolynomial (ntt_t.cpp:148-180)
+            RnsPolynomial poly(n, 2, std::vector<u64>{q, q});
+            for (size_t k = 0; k < 2; k++)
+                for (auto &c : poly[k]) c = rng() % q;
+            RnsPolynomial orig(poly);
+            ntt_negacyclic_inplace_lazy(poly);
+            CHECK(poly.rep_form == PolyRepForm::value);
+            CHECK_THROWS(ntt_negacyclic_inplace_lazy(poly), std::invalid_argument);
+            intt_negacyclic_inplace(poly);
+            CHECK(poly == orig);
+        }
+}
+
+// tests/mod_arith_t.cpp:6-78
+static void test_mod_arith() {
+    const size_t len = 1000;
+    for (u64 q : {65537ull, 33333333ull, 777777777777777ull, 1234567890111111111ull}) {
+        u64 seed = 42;
+        std::vector<u64> vec(len), copy;
+        for (auto &v : vec) v = seed = ((seed ^ 893758435427369ull) * 65536) + 945738773644543ull;
+        copy = vec;
+        batched_barrett_lazy(q, len, vec.data());
+        bool ok = true;
+        for (size_t i = 0; i < len; i++) ok &= vec[i] < 2 * q && (vec[i] % q) == (copy[i] % q);
+        CHECK(ok);
+    }
+    const u64 q = 1234567890111111111ull;
+    u64 seed = 42;
+    std::vector<u64> f(len), g(len), h(len);
+    for (size_t i = 0; i < len; i++) {
+        seed = (seed * 65968279837582827ull) ^ 3948528936546489545ull;
+        f[i] = seed % q;
+        seed = (seed * 43534547657678213ull) ^ 7955436776934235466ull;
+        g[i] = seed % q;
+    }
+    batched_mul_mod_hybrid(q, len, f.data(), g.data(), h.data());
+    bool ok = true;
+    for (size_t i = 0; i < len; i++) ok &= h[i] == (u64)((u128)f[i] * g[i] % q);
+    CHECK(ok);
+    const u64 qm = 38589379749438777ull;
+    std::vector<u128> big(len);
+    std::vector<u64> red(len);
+    std::mt19937_64 rng(3);
+    for (auto &b : big) b = ((u128)(rng() % qm) << 64) | rng();
+    batched_montgomery_128_lazy(qm, len, big.data(), red.data());
+    ok = true;
+    for (size_t i = 0; i < len; i++) ok &= red[i] < 2 * qm && (u64)((((u128)red[i]) << 64) % qm) == (u64)(big[i] % qm);
+    CHECK(ok);
+}
+
+// tests/common_t.cpp:63-166 (container semantics)
+static void test_container() {
+    std::vector<u64> moduli{1099510054913ull, 1073479681ull, 1072496641ull};
+    RnsPolynomial a = filled(64, moduli, 5, PolyRepForm::value);
+    RnsPolynomial b(a); // deep copy
+    CHECK(a == b);
+    b[1][3] ^= 1;
+    CHECK(!(a == b));
+    CHECK(a.component_count() == 3 && a.dimension() == 64 && a.log_dimension() == 6);
+    CHECK_THROWS(RnsPolynomial(48, 1, moduli), std::invalid_argument);
+    CHECK_THROWS(RnsPolynomial(64, 4, moduli), std::invalid_argument);
+    RnsPolynomial c(a);
+    c.remove_components(1);
+    CHECK(c.component_count() == 2 && c.modulus_vec().size() == 2);
+    const auto fa = flat(a);
+    const std::vector<u64> fa2(fa.begin(), fa.begin() + 128);
+    CHECK(flat(c) == fa2);
+    CHECK_THROWS(c.remove_components(3), std::invalid_argument);
+    c.add_components({1072496641ull});
+    CHECK(c.component_count() == 3 && c.modulus_at(2) == 1072496641ull);
+    {
+        const auto fc = flat(c);
+        CHECK(std::vector<u64>(fc.begin(), fc.begin() + 128) == fa2);
+    }
+    c.remove_components(1);
+    CHECK_THROWS(a += c, std::invalid_argument);
+    RnsPolynomial coeff = filled(64, moduli, 9, PolyRepForm::coeff);
+    CHECK_THROWS(a + coeff, std::invalid_argument);
+    CHECK_THROWS(coeff * coeff, std::invalid_argument);
+    // operators against the oracle, limb by limb
+    RnsPolynomial d = filled(64, moduli, 77, PolyRepForm::value);
+    auto sum = a + d, diff = a - d, prod = a * d, scaled = a * (u64)12345;
+    for (size_t k = 0; k < 3; k++) {
+        std::vector<u64> x(a[k].begin(), a[k].end()), y(d[k].begin(), d[k].end()), w(64);
+        auto t = x;
+        orc_add_lazy(moduli[k], 64, t.data(), y.data());
+        CHECK(t == std::vector<u64>(sum[k].begin(), sum[k].end()));
+        t = x;
+        orc_sub_lazy(moduli[k], 64, t.data(), y.data());
+        CHECK(t == std::vector<u64>(diff[k].begin(), diff[k].end()));
+        orc_mul_hybrid_lazy(moduli[k], 64, x.data(), y.data(), w.data());
+        CHECK(w == std::vector<u64>(prod[k].begin(), prod[k].end()));
+        t = x;
+        orc_mul_scalar_lazy(moduli[k], 64, t.data(), 12345);
+        CHECK(t == std::vector<u64>(scaled[k].begin(), scaled[k].end()));
+    }
+    // moved-from objects are empty and destructible
+    RnsPolynomial m(std::move(sum));
+    CHECK(m.component_count() == 3);
+}
+
+// ciphertext ops against the oracle on identical inputs
+static void test_scheme_ops(size_t logn, const std::vector<unsigned> &bits, unsigned pbits) {
+    const size_t n = (size_t)1 << logn, L = bits.size();
+    std::vector<u64> mods(L);
+    u64 P = 0;
+    CHECK(orc_ckks_pick_moduli(bits.data(), L, pbits, mods.data(), &P) == 0);
+    std::vector<u64> ext(mods);
+    ext.push_back(P);
+    ckks::CkksCt ct1(RlweCt{filled(n, mods, 100, PolyRepForm::value), filled(n, mods, 110, PolyRepForm::value)});
+    ckks::CkksCt ct2(RlweCt{filled(n, mods, 200, PolyRepForm::value), filled(n, mods, 210, PolyRepForm::value)});
+    ct1.scaling_factor = ct2.scaling_factor = 1073741824.0;
+    RlweKsk key;
+    for (size_t r = 0; r < L; r++)
+        key.push_back(RlweCt{filled(n, ext, 1000 + 100 * r, PolyRepForm::value), filled(n, ext, 1010 + 100 * r, PolyRepForm::value)});
+    std::vector<u64> fkey;
+    for (auto &row : key) {
+        auto f = flat(row);
+        fkey.insert(fkey.end(), f.begin(), f.end());
+    }
+    const auto f1 = flat(ct1), f2 = flat(ct2);
+
+    auto quad = ckks::mult_low_level(ct1, ct2);
+    std::vector<u64> wq(3 * L * n);
+    orc_ckks_tensor((unsigned)logn, L, mods.data(), f1.data(), f2.data(), wq.data());
+    CHECK(flat(quad) == wq);
+    CHECK(quad.scaling_factor == ct1.scaling_factor * ct2.scaling_factor);
+
+    auto e = ext_prod_montgomery(quad[2], key);
+    std::vector<u64> we(2 * (L + 1) * n);
+    orc_ext_prod((unsigned)logn, L, ext.data(), wq.data() + 2 * L * n, fkey.data(), we.data());
+    CHECK(flat(e) == we);
+    CHECK(e[0].component_count() == L + 1 && e[0].rep_form == PolyRepForm::value);
+
+    auto relin = ckks::relinearize(quad, key);
+    std::vector<u64> wr(2 * L * n);
+    orc_ckks_relinearize((unsigned)logn, L, ext.data(), wq.data(), fkey.data(), wr.data());
+    CHECK(flat(relin) == wr);
+    auto prod = ckks::mult(ct1, ct2, key);
+    CHECK(flat(prod) == wr);
+    CHECK(prod.scaling_factor == quad.scaling_factor);
+
+    if (L >= 2) {
+        ckks::CkksCt rs(prod);
+        rs.scaling_factor = prod.scaling_factor;
+        ckks::rescale_inplace(rs);
+        std::vector<u64> wrs(2 * (L - 1) * n);
+        orc_ckks_rescale((unsigned)logn, L, mods.data(), wr.data(), wrs.data());
+        CHECK(flat(rs) == wrs);
+        CHECK(rs[0].component_count() == L - 1);
+        CHECK(rs.scaling_factor == prod.scaling_factor / (double)mods[L - 1]);
+        CHECK_THROWS(ckks::rescale_inplace(rs, 0), std::invalid_argument);
+        {
+            typedef const char *cstr;
+            CHECK_THROWS(ckks::rescale_inplace(rs, 2), cstr);
+        }
+
+        bgv::BgvCt bct(RlweCt{ct1[0], ct1[1]});
+        bct.plain_modulus = 65537;
+        bgv::mod_switch_inplace(bct);
+        std::vector<u64> wms(2 * (L - 1) * n);
+        orc_bgv_mod_switch((unsigned)logn, L, mods.data(), 65537, f1.data(), wms.data());
+        CHECK(flat(bct) == wms);
+    }
+    {
+        bgv::BgvCt b1(RlweCt{ct1[0], ct1[1]}), b2(RlweCt{ct2[0], ct2[1]});
+        b1.plain_modulus = b2.plain_modulus = 65537;
+        auto bq = bgv::mult_low_level(b1, b2);
+        CHECK(flat(bq) == wq);
+        auto br = bgv::relinearize(bq, key);
+        std::vector<u64> wbr(2 * L * n);
+        orc_bgv_relinearize((unsigned)logn, L, ext.data(), 1, wq.data(), fkey.data(), wbr.data());
+        CHECK(flat(br) == wbr);
+        CHECK(br.plain_modulus == 65537);
+        b2.plain_modulus = 3;
+        CHECK_THROWS(bgv::mult_low_level(b1, b2), std::invalid_argument);
+    }
+    auto rot = ckks::rotate(ct1, key, 3);
+    std::vector<u64> wrot(2 * L * n);
+    orc_ckks_rotate((unsigned)logn, L, ext.data(), f1.data(), fkey.data(), 3, wrot.data());
+    CHECK(flat(rot) == wrot);
+    auto conj = ckks::conjugate(ct1, key);
+    orc_ckks_conjugate((unsigned)logn, L, ext.data(), f1.data(), fkey.data(), wrot.data());
+    CHECK(flat(conj) == wrot);
+    auto cyc = cycle(ct1[0], 5);
+    std::vector<u64> wc(L * n);
+    orc_galois_cycle((unsigned)logn, L, f1.data(), wc.data(), 5);
+    CHECK(flat(cyc) == wc);
+    auto sum = ckks::add(ct1, ct2);
+    CHECK(sum[0] == ct1[0] + ct2[0]);
+    ct2.scaling_factor *= 2;
+    CHECK_THROWS(ckks::add(ct1, ct2), std::invalid_argument);
+    // key of the wrong level: exactly L + 1 limbs are required (rgsw.cpp:84-87)
+    if (L >= 2) {
+        RnsPolynomial shorter(quad[2]);
+        shorter.remove_components(1);
+        CHECK_THROWS(ext_prod_montgomery(shorter, key), std::invalid_argument);
+    }
+}
+
+// tests/ckks_t.cpp:136-175 — exact rounded division by the dropped prime
+static void test_rescale_exactness() {
+    const size_t n = 8;
+    std::vector<u64> mods(3);
+    orc_prime_row(34, 3, mods.data());
+    std::mt19937_64 rng(11);
+    const u128 big_q = (u128)mods[0] * mods[1] * mods[2];
+    std::vector<u128> coeffs(n);
+    for (auto &c : coeffs) c = (((u128)rng() << 64) | rng()) % big_q;
+    RnsPolynomial poly(n, 3, mods);
+    for (size_t k = 0; k < 3; k++)
+        for (size_t i = 0; i < n; i++) poly[k][i] = (u64)(coeffs[i] % mods[k]);
+    ntt_negacyclic_inplace_lazy(poly);
+    ckks::CkksCt ct(RlweCt{poly, poly});
+    ckks::rescale_inplace(ct);
+    intt_negacyclic_inplace(ct[0]);
+    const u128 q01 = (u128)mods[0] * mods[1];
+    const u64 inv = inverse_mod_prime(mods[0] % mods[1], mods[1]);
+    bool ok = true;
+    for (size_t i = 0; i < n; i++) {
+        const u128 want = ((coeffs[i] + mods[2] / 2) / mods[2]) % q01;
+        const u64 r0 = ct[0][0][i], r1 = ct[0][1][i];
+        const u64 d = (u64)((u128)((r1 + mods[1] - r0 % mods[1]) % mods[1]) * inv % mods[1]);
+        ok &= ((u128)r0 + (u128)mods[0] * d) % q01 == want;
+    }
+    CHECK(ok);
+}
+
+int main() {
+    try {
+        test_ntt_round_trip();
+        test_mod_arith();
+        test_container();
+        test_scheme_ops(10, {40, 30, 30}, 40);
+        test_scheme_ops(12, {39}, 39);
+        test_scheme_ops(13, {40, 30, 30, 30}, 40);
+        test_rescale_exactness();
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "unexpected exception: %s\n", e.what());
+        return 2;
+    } catch (const char *msg) {
+        std::fprintf(stderr, "unexpected exception: %s\n", msg);
+        return 2;
+    }
+    std::printf("%d checks, %d failures\n", g_checks, g_fail);
+    return g_fail ? 1 : 0;
+}

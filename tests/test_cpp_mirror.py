@@ -1,0 +1,38 @@
+"""The C++ host mirror of the hehub:: API (hehub_b200/cpp/hehub) — compiled and run as the reference's
+own unit tests would be, against the CUDA library on a GPU box and against the CTA-emulator build of
+the same sources in the CPU suite."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "test_hehub_api.cpp")
+OUT = os.path.join(ROOT, "tests", "cpp", "_build")
+
+
+def _build(kind: str) -> str:
+    import __graft_entry__ as ge
+    from oracle.binding import build_oracle
+    oracle_so = build_oracle()
+    lib = ge.build_sim() if kind == "sim" else ge.CUDA_SO
+    if not os.path.exists(lib):
+        raise FileNotFoundError(f"{lib} missing: run __graft_entry__.build() first (there is no CPU fallback)")
+    os.makedirs(OUT, exist_ok=True)
+    exe = os.path.join(OUT, f"test_hehub_api_{kind}")
+    deps = [SRC, lib, oracle_so] + [os.path.join(ROOT, "hehub_b200", "cpp", "hehub", f)
+                                    for f in os.listdir(os.path.join(ROOT, "hehub_b200", "cpp", "hehub"))]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wno-ignored-qualifiers", "-I" + os.path.join(ROOT, "hehub_b200", "cpp"),
+                               "-I" + os.path.join(ROOT, "oracle"), SRC, lib, oracle_so,
+                               "-Wl,-rpath," + os.path.dirname(lib), "-Wl,-rpath," + os.path.dirname(oracle_so),
+                               "-pthread", "-o", exe])
+    return exe
+
+
+@pytest.mark.parametrize("kind", ["sim", pytest.param("gpu", marks=pytest.mark.gpu)])
+def test_cpp_mirror(kind):
+    exe = _build(kind)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "0 failures" in res.stdout
