@@ -252,7 +252,16 @@ def run_cuda(args):
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                "kernel": "ntt_fwd_fast_kernel<12>", "algorithmic_bytes_per_launch": alg_bytes}
+                "kernel": "ntt_fwd_pipe_kernel<12>" if args.pipeline else "ntt_fwd_fast_kernel<12>",
+                "algorithmic_bytes_per_launch": alg_bytes}
+    # the transforms are bound by the integer (FMA-heavy) pipe, not HBM: report that fraction too
+    try:
+        with open(os.path.join(ROOT, "profiles", "int_peak.json")) as fh:
+            ip = json.load(fh)
+        roofline["int_pipe_ceiling_ntt_per_s"] = ip["ntt4096_per_s_alu_ceiling"]
+        roofline["int_pipe_frac"] = (value / world) / ip["ntt4096_per_s_alu_ceiling"]
+    except Exception:
+        pass
 
     # ---- e2e: host words in, host words out through hehub_b200_ntt_host ---------------------------
     hx = ctx.pinned((POLYS, n))
@@ -410,7 +419,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--extras", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=1, help="0: one-CTA-per-row kernels (A/B of the persistent pipeline)")
+    ap.add_argument("--pipeline", type=int, default=0, help="1: persistent double-buffered kernels for N <= 8192 (A/B against one CTA per row)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "reference":

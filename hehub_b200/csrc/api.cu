@@ -14,16 +14,27 @@ namespace hb {
 // ------------------------------------------------------------------------------------------
 // IO policy of the plain in-place transforms: rows are [batch][L][N], limb = row % L.
 // ------------------------------------------------------------------------------------------
+template <bool STRICT> // STRICT: reduce_strict in the store (intt_negacyclic_inplace, ntt.h:89-92)
 struct RowsIO {
     u64 *x;
     int L;
     int logn;
-    int strict;
+    bool vec;
     HB_D int limb(int row) const { return row % L; }
     HB_D const u64 *src(int row) const { return x + ((size_t)row << logn); }
     HB_D u64 pre(int, int, u64 raw, const LimbConst &) const { return raw; }
     HB_D void store(int row, int i, u64 v, const LimbConst &lc) const {
-        x[((size_t)row << logn) + i] = strict ? reduce_strict(v, lc.q) : v;
+#if defined(HB_ABL_NOSTORE) // ablation builds only: results are (almost) never written
+        if (v != 0x0123456789abcdefull) return;
+#endif
+        x[((size_t)row << logn) + i] = STRICT ? reduce_strict(v, lc.q) : v;
+    }
+    HB_D void store2(int row, int i, u64 v0, u64 v1, const LimbConst &lc) const {
+#if defined(HB_ABL_NOSTORE)
+        if (v0 != 0x0123456789abcdefull) return;
+#endif
+        *reinterpret_cast<ulonglong2 *>(x + ((size_t)row << logn) + i) =
+            STRICT ? make_ulonglong2(reduce_strict(v0, lc.q), reduce_strict(v1, lc.q)) : make_ulonglong2(v0, v1);
     }
     HB_D u64 *raw(int row) const { return x + ((size_t)row << logn); }
 };
@@ -194,8 +205,12 @@ int run_transform(Context &c, bool forward, unsigned logn, const u64 *moduli, si
     int err = 0;
     const LimbConst *limbs = c.get_chain(logn, moduli, L, &err);
     if (!limbs) return err;
-    RowsIO io{x, (int)L, (int)logn, strict};
-    cudaError_t e = launch_ntt(forward, c.env(), logn, io, limbs, (int)(batch * L), aligned16(x));
+    cudaError_t e;
+    if (strict && !forward) {
+        e = launch_ntt(false, c.env(), logn, RowsIO<true>{x, (int)L, (int)logn, aligned16(x)}, limbs, (int)(batch * L), aligned16(x));
+    } else { // the forward transform has no strict variant in the reference
+        e = launch_ntt(forward, c.env(), logn, RowsIO<false>{x, (int)L, (int)logn, aligned16(x)}, limbs, (int)(batch * L), aligned16(x));
+    }
     return e == cudaSuccess ? 0 : c.cuda_fail(e, forward ? "ntt launch" : "intt launch");
 }
 } // namespace hb

@@ -42,7 +42,7 @@ struct Context {
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
     bool force_generic = false;
-    bool pipeline = true; // persistent double-buffered transforms where available
+    bool pipeline = false; // option "pipeline": persistent double-buffered transforms (N <= 8192) instead of one CTA per row
     int sm_count = 148;
     LaunchEnv env() { return LaunchEnv{stream, sm_count, force_generic, pipeline, &stats}; }
     size_t scratch_cap_bytes = (size_t)2 << 30; // bound on the per-call workspace; batches run in waves

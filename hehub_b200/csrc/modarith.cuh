@@ -103,9 +103,32 @@ HB_D u64 harvey_lazy(u64 x, u64 w, u64 wh, u64 nq) {
 }
 HB_D u64 harvey_lazy_split(u64 x, u64 w, u64 wh, u64 nq) { return mul2_lo64(x, w, umul64hi_split(x, wh), nq); }
 
-// the sweep at ntt.cpp:171-175: x -= ((x >> logq) - fix) * q
+// lo64(a*b + c): one wide + two narrow IMADs, the addition rides on the accumulator
+HB_D u64 mad_lo64(u64 a, u64 b, u64 c) {
+#if defined(HB_KERNEL_SIM)
+    return a * b + c;
+#else
+    u64 t;
+    asm("{\n\t"
+        ".reg .u64 acc;\n\t"
+        ".reg .u32 a0, a1, b0, b1, lo, hi;\n\t"
+        "mov.b64 {a0, a1}, %1;\n\t"
+        "mov.b64 {b0, b1}, %2;\n\t"
+        "mad.wide.u32 acc, a0, b0, %3;\n\t"
+        "mov.b64 {lo, hi}, acc;\n\t"
+        "mad.lo.u32 hi, a0, b1, hi;\n\t"
+        "mad.lo.u32 hi, a1, b0, hi;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t"
+        "}"
+        : "=l"(t)
+        : "l"(a), "l"(b), "l"(c));
+    return t;
+#endif
+}
+
+// the sweep at ntt.cpp:171-175: x -= ((x >> logq) - fix) * q, computed as x + m * (-q) mod 2^64
 HB_D u64 approx_reduce(u64 x, const LimbConst &c) {
-    return x - ((x >> c.logq) - (u64)c.fix) * c.q;
+    return mad_lo64((x >> c.logq) - (u64)c.fix, c.nq, x);
 }
 
 // batched_reduce_strict — mod_arith.h:58-63

@@ -29,6 +29,8 @@
 //   void       store(int row, int i, u64 v, LimbConst&)   -> consumes output word i
 //   u64       *raw(int row)                               -> row-sized exchange area in global memory
 //                                                            (N = 32768 inverse only; may be the output row)
+//   bool       vec                                        -> every row pointer is 16-byte aligned
+//   void       store2(int row, int i, u64 v0, u64 v1, LimbConst&) -> words i (even) and i+1, used when vec
 #pragma once
 #include <type_traits>
 
@@ -39,7 +41,11 @@ namespace hb {
 
 template <class IO>
 HB_D u64 io_load(const IO &io, int row, int i, const LimbConst &lc) {
+#if defined(HB_ABL_NOLOAD) // ablation builds only: synthesise the input words, no global reads
+    return io.pre(row, i, (u64)i * 0x9E3779B97F4A7C15ull + (u64)row, lc);
+#else
     return io.pre(row, i, io.src(row)[i], lc);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -57,7 +63,11 @@ HB_D void bfly(u64 &lo, u64 &hi, const ulonglong2 tw, u64 nq, u64 q2) {
 struct TwTable {
     const ulonglong2 *p;
     int stride;
+#if defined(HB_ABL_TWCONST) // ablation builds only (tools/ab_build.sh): one twiddle per pass, no table traffic
+    HB_D ulonglong2 get(int) const { return __ldg(p); }
+#else
     HB_D ulonglong2 get(int slot) const { return __ldg(p + slot * stride); }
+#endif
 };
 template <int K>
 struct TwRegs {
@@ -99,6 +109,10 @@ HB_D void inv_levels(u64 (&v)[1 << K], const TW &tw, u64 nq, u64 q2) {
 
 HB_D int sphys(int i) { return i + ((i >> 4) << 1); }
 
+// padded offset of a stride that is a multiple of 16 words: sphys(b + j * s) == sphys(b) + j * sstride(s),
+// so strided passes address shared memory as one base register plus immediates
+HB_D constexpr int sstride(int s) { return s + (s >> 3); }
+
 // contiguous 2^K-word group at logical index base (aligned to 2^K <= 16): 128-bit accesses
 template <int K>
 HB_D void lds_contig(const u64 *sm, int base, u64 (&v)[1 << K]) {
@@ -120,8 +134,55 @@ HB_D void sts_contig(u64 *sm, int base, const u64 (&v)[1 << K]) {
 // stream a row of NC raw words into the padded shared-memory layout, 16 bytes per cp.async
 template <int NC, int T>
 HB_D void prefetch_row(u64 *sm, const u64 *__restrict__ src) {
-    for (int c = threadIdx.x; c < NC / 2; c += T) hb_cp_async16(sm + sphys(2 * c), src + 2 * c);
+    static_assert((NC / 2) % T == 0 && (2 * T) % 16 == 0, "whole 16-byte chunks per thread");
+    u64 *const d = sm + sphys(2 * threadIdx.x);
+    const u64 *const g = src + 2 * threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < NC / 2 / T; k++) hb_cp_async16(d + k * sstride(2 * T), g + k * 2 * T);
     hb_cp_async_commit();
+}
+
+// the CTA's NC words between shared memory (padded) and the IO policy.  io.vec (uniform): every row
+// pointer of the policy is 16-byte aligned, so rows move as 128-bit words (two coefficients).
+template <int NC, int T, class IO>
+HB_D void store_row(const u64 *sm, const IO &io, const LimbConst &lc, int row, int first_word) {
+    static_assert(NC % (2 * T) == 0 && T % 16 == 0, "whole steps");
+    if (io.vec) {
+        const u64 *const s = sm + sphys(2 * threadIdx.x);
+#pragma unroll
+        for (int k = 0; k < NC / 2 / T; k++) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(s + k * sstride(2 * T));
+            io.store2(row, first_word + 2 * threadIdx.x + k * 2 * T, v.x, v.y, lc);
+        }
+    } else {
+        const u64 *const s = sm + sphys(threadIdx.x);
+#pragma unroll
+        for (int k = 0; k < NC / T; k++) io.store(row, first_word + threadIdx.x + k * T, s[k * sstride(T)], lc);
+    }
+}
+template <int NC, int T, class IO>
+HB_D void load_row(u64 *sm, const IO &io, const LimbConst &lc, int row, int first_word) {
+    static_assert(NC % (2 * T) == 0 && T % 16 == 0, "whole steps");
+    if (io.vec) {
+        u64 *const d = sm + sphys(2 * threadIdx.x);
+        const u64 *const g = io.src(row) + first_word + 2 * threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < NC / 2 / T; k++) {
+            const int i = first_word + 2 * threadIdx.x + k * 2 * T;
+#if defined(HB_ABL_NOLOAD)
+            ulonglong2 v = make_ulonglong2((u64)i * 0x9E3779B97F4A7C15ull + (u64)row, (u64)i);
+#else
+            ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(g + k * 2 * T);
+#endif
+            v.x = io.pre(row, i, v.x, lc);
+            v.y = io.pre(row, i + 1, v.y, lc);
+            *reinterpret_cast<ulonglong2 *>(d + k * sstride(2 * T)) = v;
+        }
+    } else {
+        u64 *const d = sm + sphys(threadIdx.x);
+#pragma unroll
+        for (int k = 0; k < NC / T; k++) d[k * sstride(T)] = io_load(io, row, first_word + threadIdx.x + k * T, lc);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -145,14 +206,14 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B, c
     for (int g = threadIdx.x; g < NG; g += T) {
         const int lo = g & ((1 << GSL) - 1), hb = g >> GSL;
         const int base = (hb << (LOGNC - L0)) + lo;
+        static_assert(last || GSL >= 4, "strided passes step by multiples of 16 words");
+        u64 *const smb = sm + sphys(base); // strided passes: element j lives at smb[j * SJ]
+        constexpr int SJ = sstride(1 << GSL);
         u64 v[1 << K];
         if constexpr (first && SRC == 1) {
             static_assert(pl.lpre == 0, "prefetched rows are whole rows");
 #pragma unroll
-            for (int j = 0; j < (1 << K); j++) {
-                const int i = base + (j << GSL);
-                v[j] = io.pre(row, i, sm[sphys(i)], lc);
-            }
+            for (int j = 0; j < (1 << K); j++) v[j] = io.pre(row, base + (j << GSL), smb[j * SJ], lc);
         } else if constexpr (first) {
             if constexpr (pl.lpre == 0) {
 #pragma unroll
@@ -173,7 +234,7 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B, c
             lds_contig<K>(sm, base, v);
         } else {
 #pragma unroll
-            for (int j = 0; j < (1 << K); j++) v[j] = sm[sphys(base + (j << GSL))];
+            for (int j = 0; j < (1 << K); j++) v[j] = smb[j * SJ];
         }
 
         if constexpr (last && !std::is_same<TWC, NoTw>::value) {
@@ -189,7 +250,7 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B, c
             sts_contig<K>(sm, base, v);
         } else {
 #pragma unroll
-            for (int j = 0; j < (1 << K); j++) sm[sphys(base + (j << GSL))] = v[j];
+            for (int j = 0; j < (1 << K); j++) smb[j * SJ] = v[j];
         }
     }
 }
@@ -218,7 +279,7 @@ ntt_fwd_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     const int row = blockIdx.x >> pl.lpre, B = blockIdx.x & ((1 << pl.lpre) - 1);
     const LimbConst lc = limbs[io.limb(row)];
     fwd_passes<LOGN, T, 0, 0>(sm, io, lc, row, B, NoTw{});
-    for (int i = threadIdx.x; i < NC; i += T) io.store(row, B * NC + i, sm[sphys(i)], lc);
+    store_row<NC, T>(sm, io, lc, row, B * NC);
 }
 
 // persistent, double-buffered: grid = resident CTA slots, rows visited with stride gridDim.x
@@ -254,7 +315,7 @@ ntt_fwd_pipe_kernel(const IO io, const LimbConst *__restrict__ limbs, int rows) 
             }
         }
         fwd_passes<LOGN, T, 0, 1>(sm, io, lc, row, 0, twc);
-        for (int i = threadIdx.x; i < NC; i += T) io.store(row, i, sm[sphys(i)], lc);
+        store_row<NC, T>(sm, io, lc, row, 0);
         cur ^= 1;
     }
 }
@@ -277,6 +338,9 @@ HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B, c
     for (int g = threadIdx.x; g < NG; g += T) {
         const int lo = g & ((1 << S0) - 1), hi = g >> S0;
         const int base = (hi << (S0 + K)) + lo;
+        static_assert(first || S0 >= 4, "strided passes step by multiples of 16 words");
+        u64 *const smb = sm + sphys(base);
+        constexpr int SJ = sstride(1 << S0);
         u64 v[1 << K];
         if constexpr (first) {
             lds_contig<K>(sm, base, v);
@@ -286,7 +350,7 @@ HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B, c
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < (1 << K); j++) v[j] = sm[sphys(base + (j << S0))];
+            for (int j = 0; j < (1 << K); j++) v[j] = smb[j * SJ];
         }
 
         if constexpr (last && !std::is_same<TWC, NoTw>::value) {
@@ -307,13 +371,13 @@ HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B, c
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < (1 << K); j++) sm[sphys(base + (j << S0))] = v[j];
+                for (int j = 0; j < (1 << K); j++) smb[j * SJ] = v[j];
             }
         } else if constexpr (first) {
             sts_contig<K>(sm, base, v);
         } else {
 #pragma unroll
-            for (int j = 0; j < (1 << K); j++) sm[sphys(base + (j << S0))] = v[j];
+            for (int j = 0; j < (1 << K); j++) smb[j * SJ] = v[j];
         }
     }
 }
@@ -336,7 +400,7 @@ intt_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     HB_SHARED_U64(sm);
     const int row = blockIdx.x >> pl.lpre, B = blockIdx.x & ((1 << pl.lpre) - 1);
     const LimbConst lc = limbs[io.limb(row)];
-    for (int i = threadIdx.x; i < NC; i += T) sm[sphys(i)] = io_load(io, row, B * NC + i, lc);
+    load_row<NC, T>(sm, io, lc, row, B * NC);
     __syncthreads();
     inv_passes<LOGN, T, 0, 0>(sm, io, lc, row, B, NoTw{});
     if constexpr (pl.lpre == 1) {

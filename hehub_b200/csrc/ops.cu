@@ -75,10 +75,14 @@ struct ExtInttIO {
     size_t in_batch_stride;
     u64 *c; // [batch][L][N]
     int L, logn;
+    bool vec;
     HB_D int limb(int row) const { return row % L; }
     HB_D const u64 *src(int row) const { return in + (size_t)(row / L) * in_batch_stride + ((size_t)(row % L) << logn); }
     HB_D u64 pre(int, int, u64 raw, const LimbConst &) const { return raw; }
     HB_D void store(int row, int i, u64 v, const LimbConst &lc) const { c[((size_t)row << logn) + i] = reduce_strict(v, lc.q); }
+    HB_D void store2(int row, int i, u64 v0, u64 v1, const LimbConst &lc) const {
+        *reinterpret_cast<ulonglong2 *>(c + ((size_t)row << logn) + i) = make_ulonglong2(reduce_strict(v0, lc.q), reduce_strict(v1, lc.q));
+    }
     HB_D u64 *raw(int row) const { return c + ((size_t)row << logn); }
 };
 
@@ -87,6 +91,7 @@ struct ExtFanoutIO {
     const u64 *c; // [batch][L][N]
     u64 *dec;     // [batch][L][L+1][N]; slot k == p is not written (the diagonal keeps in[p])
     int L, logn;
+    bool vec;
     HB_D void split(int row, int &b, int &p, int &k) const {
         b = row / (L * L);
         const int rem = row - b * L * L;
@@ -109,6 +114,11 @@ struct ExtFanoutIO {
         int b, p, k;
         split(row, b, p, k);
         dec[((size_t)((b * L + p) * (L + 1) + k) << logn) + i] = v;
+    }
+    HB_D void store2(int row, int i, u64 v0, u64 v1, const LimbConst &) const {
+        int b, p, k;
+        split(row, b, p, k);
+        *reinterpret_cast<ulonglong2 *>(dec + ((size_t)((b * L + p) * (L + 1) + k) << logn) + i) = make_ulonglong2(v0, v1);
     }
     HB_D u64 *raw(int) const { return nullptr; }
 };
@@ -142,10 +152,10 @@ ext_mac_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__
 static int ext_prod_wave(Context &c, unsigned logn, const LimbConst *limbs, size_t L, const u64 *in, size_t in_batch_stride,
                          const u64 *key, u64 *out, size_t batch, u64 *cbuf, u64 *dec) {
     const size_t n = (size_t)1 << logn;
-    ExtInttIO io1{in, in_batch_stride, cbuf, (int)L, (int)logn};
+    ExtInttIO io1{in, in_batch_stride, cbuf, (int)L, (int)logn, aligned16(in) && (in_batch_stride % 2 == 0) && aligned16(cbuf)};
     cudaError_t e = launch_ntt(false, c.env(), logn, io1, limbs, (int)(batch * L), aligned16(in) && (in_batch_stride % 2 == 0));
     if (e != cudaSuccess) return c.cuda_fail(e, "ext_prod: intt launch");
-    ExtFanoutIO io2{cbuf, dec, (int)L, (int)logn};
+    ExtFanoutIO io2{cbuf, dec, (int)L, (int)logn, aligned16(cbuf) && aligned16(dec)};
     e = launch_ntt(true, c.env(), logn, io2, limbs, (int)(batch * L * L), true);
     if (e != cudaSuccess) return c.cuda_fail(e, "ext_prod: ntt launch");
     const size_t total = batch * (L + 1) * n;
@@ -198,12 +208,20 @@ struct DropInttIO {
     int L, logn;
     u64 inv_t, inv_t_h; // 0 for CKKS
     int bgv;
+    bool vec;
     HB_D int limb(int) const { return L - 1; }
     HB_D const u64 *src(int row) const { return ct + ((size_t)(row * L + L - 1) << logn); }
     HB_D u64 pre(int, int, u64 raw, const LimbConst &) const { return raw; }
     HB_D void store(int row, int i, u64 v, const LimbConst &lc) const {
         if (bgv) v = harvey_lazy(v, inv_t, inv_t_h, lc.nq);
         z[((size_t)row << logn) + i] = reduce_strict(v, lc.q);
+    }
+    HB_D void store2(int row, int i, u64 v0, u64 v1, const LimbConst &lc) const {
+        if (bgv) {
+            v0 = harvey_lazy(v0, inv_t, inv_t_h, lc.nq);
+            v1 = harvey_lazy(v1, inv_t, inv_t_h, lc.nq);
+        }
+        *reinterpret_cast<ulonglong2 *>(z + ((size_t)row << logn) + i) = make_ulonglong2(reduce_strict(v0, lc.q), reduce_strict(v1, lc.q));
     }
     HB_D u64 *raw(int row) const { return z + ((size_t)row << logn); }
 };
@@ -218,6 +236,7 @@ struct DropFwdIO {
     size_t add_batch_stride, add_poly_stride;
     u64 half_qlast;
     int L, logn, bgv, add_halves;
+    bool vec;
     HB_D int limb(int row) const { return row % (L - 1); }
     HB_D const u64 *src(int row) const { return z + ((size_t)(row / (L - 1)) << logn); }
     HB_D u64 pre(int row, int, u64 zz, const LimbConst &lc) const {
@@ -230,14 +249,31 @@ struct DropFwdIO {
     HB_D void store(int row, int i, u64 v, const LimbConst &lc) const {
         const int poly = row / (L - 1), k = row - poly * (L - 1);
         const DropConst d = dc[k];
-        u64 x = ct[((size_t)(poly * L + k) << logn) + i];
-        x = sub_lazy(x, v, lc.q2);                                   // rescaling.cpp:73
-        x = harvey_lazy(x, d.inv_qlast, d.inv_qlast_h, lc.nq);       // rescaling.cpp:74
-        if (bgv) x = harvey_lazy(x, d.qlt_mod_q, d.qlt_mod_q_h, lc.nq); // mod_switch.cpp:76
+        u64 x = finish(ct[((size_t)(poly * L + k) << logn) + i], v, d, lc);
         const int h = poly & 1, b = poly >> 1;
         if (h < add_halves) // ckks/arith.cpp:70-71, 84, 91
             x = add_lazy(x, addend[(size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn) + i], lc.q2);
         out[((size_t)row << logn) + i] = x;
+    }
+    HB_D u64 finish(u64 x, u64 v, const DropConst &d, const LimbConst &lc) const {
+        x = sub_lazy(x, v, lc.q2);                                   // rescaling.cpp:73
+        x = harvey_lazy(x, d.inv_qlast, d.inv_qlast_h, lc.nq);       // rescaling.cpp:74
+        if (bgv) x = harvey_lazy(x, d.qlt_mod_q, d.qlt_mod_q_h, lc.nq); // mod_switch.cpp:76
+        return x;
+    }
+    HB_D void store2(int row, int i, u64 v0, u64 v1, const LimbConst &lc) const {
+        const int poly = row / (L - 1), k = row - poly * (L - 1);
+        const DropConst d = dc[k];
+        const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(ct + ((size_t)(poly * L + k) << logn) + i);
+        ulonglong2 r = make_ulonglong2(finish(x.x, v0, d, lc), finish(x.y, v1, d, lc));
+        const int h = poly & 1, b = poly >> 1;
+        if (h < add_halves) { // ckks/arith.cpp:70-71, 84, 91
+            const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(
+                addend + (size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn) + i);
+            r.x = add_lazy(r.x, a.x, lc.q2);
+            r.y = add_lazy(r.y, a.y, lc.q2);
+        }
+        *reinterpret_cast<ulonglong2 *>(out + ((size_t)row << logn) + i) = r;
     }
     HB_D u64 *raw(int) const { return nullptr; }
 };
@@ -255,11 +291,13 @@ int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, 
     const size_t n = (size_t)1 << logn;
     u64 *z = c.get_scratch(2, batch * 2 * n, &err);
     if (!z) return err;
-    DropInttIO io1{ct, z, (int)L, (int)logn, ds->inv_t, ds->inv_t_h, t ? 1 : 0};
+    DropInttIO io1{ct, z, (int)L, (int)logn, ds->inv_t, ds->inv_t_h, t ? 1 : 0, aligned16(ct) && aligned16(z)};
     cudaError_t e = launch_ntt(false, c.env(), logn, io1, limbs, (int)(batch * 2), aligned16(ct));
     if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: intt launch");
+    const bool vec = aligned16(ct) && aligned16(z) && aligned16(out) &&
+                     (!addend || (aligned16(addend) && add_batch_stride % 2 == 0 && add_poly_stride % 2 == 0));
     DropFwdIO io2{ct, z, out, ds->dev, addend, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, t ? 1 : 0,
-                  addend ? add_halves : 0};
+                  addend ? add_halves : 0, vec};
     e = launch_ntt(true, c.env(), logn, io2, limbs, (int)(batch * 2 * (L - 1)), true);
     if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: ntt launch");
     return 0;

@@ -124,7 +124,7 @@ def test_row_per_cta_kernels_agree_with_persistent_pipeline(dev, oracle, logn):
             assert np.array_equal(dev.poly_ntt_fwd(logn, moduli, x), want)
             assert np.array_equal(dev.poly_intt(logn, moduli, want), want_i)
         finally:
-            dev.set_option("pipeline", 1)
+            dev.set_option("pipeline", 0)
     # a slab that starts 8 bytes off a 16-byte boundary takes the row-per-CTA path
     m = np.ascontiguousarray(np.asarray(moduli, dtype=np.uint64))
     import ctypes as C
