@@ -281,12 +281,12 @@ def run_cuda(args):
     e2e_elapsed = max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": world * POLYS * e2e_steps / e2e_elapsed, "unit": UNIT, "h2d_bytes_per_step": POLYS * n * 8,
            "d2h_bytes_per_step": POLYS * n * 8, "steps": e2e_steps,
-           "call": "hehub_b200_ntt_host (pinned host buffers, 3-stage chunked pipeline)"}
+           "call": "hehub_b200_ntt_host (pinned host buffers, chunked H2D | kernel | D2H pipeline on three streams)"}
 
     # ---- extras: the other BASELINE configs -------------------------------------------------------
     extras = {}
     if args.extras:
-        extras = run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist if world > 1 else None)
+        extras = run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist if world > 1 else None, args.sweep_cts)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------------
     cpu = None
@@ -320,7 +320,7 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
-def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist):
+def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, sweep_cts=0):
     """Other BASELINE configs, device-resident, same timing discipline; values are whole-job."""
     import numpy as np
     from hehub_b200.binding import _mod
@@ -408,6 +408,50 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist):
     ct_bench("c3_ckks_mult_relin_N8192_L4", 13, [40, 30, 30, 30], 40, 256, 4, ("mult", "tensor"))
     ct_bench("c4_rescale_N16384_L8", 14, [50] + [40] * 7, 50, 128, 4, ("rescale",))
     ct_bench("c5_ckks_mult_relin_N32768_L12", 15, [50] * 12, 55, 16, 2, ("mult", "tensor"))
+
+    # config 5 as a sweep: `sweep_cts` independent ciphertext pairs (65 536 in BASELINE; bounded by default so the
+    # whole bench stays within minutes) cut into contiguous per-rank ranges, processed in waves, inputs generated
+    # on the device; NCCL only broadcasts the key and gathers one checksum per ciphertext (hehub_b200/sweep.py)
+    if sweep_cts > 0:
+        from hehub_b200.sweep import CtSweep
+        mods, p = orc.ckks_pick_moduli([50] * 12, 55)
+        sw = CtSweep(ctx, f"cuda:{torch.cuda.current_device()}", 15, [int(m) for m in mods], int(p), seed=42)
+        with torch.cuda.stream(stream):
+            sw.make_key(dist, rank)
+
+            def ev_timer(fn):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+                e1.synchronize()
+                return e0.elapsed_time(e1) * 1e-3
+
+            sw.run(min(sweep_cts, 64 * world), 32, rank, world, dist)  # warm-up (tables, workspaces)
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            res = sw.run(sweep_cts, 32, rank, world, dist, timer=ev_timer)
+            torch.cuda.synchronize()
+            barrier()
+            wall = time.perf_counter() - t0
+        t = torch.tensor([res["op_seconds"], wall], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        op_s, wall_s = float(t[0].item()), float(t[1].item())
+        r = {"cts_total": sweep_cts, "scaling": "strong", "wave": 32, "mult_relin_per_s_device_time": sweep_cts / op_s,
+             "mult_relin_per_s_wall_incl_input_generation_and_checksums": sweep_cts / wall_s,
+             "gbs_algorithmic": 48 * 12 * 32768 * sweep_cts / op_s / 1e9}
+        r["frac_hbm_per_gpu"] = r["gbs_algorithmic"] / world / hbm
+        if "all_checksums" in res:
+            import numpy as np
+            r["checksums_gathered"] = int(res["all_checksums"].size)
+            r["checksum_of_checksums"] = int(np.bitwise_xor.reduce(res["all_checksums"])) if res["all_checksums"].size else 0
+        elif dist is None:
+            import numpy as np
+            r["checksums_gathered"] = int(res["checksums"].size)
+            r["checksum_of_checksums"] = int(np.bitwise_xor.reduce(res["checksums"]))
+        out["c5_sweep_N32768_L12"] = r
     return out
 
 
@@ -419,6 +463,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--extras", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sweep-cts", type=int, default=2048,
+                    help="ciphertext pairs in the config-5 sweep extra, whole job (BASELINE: 65536; 0 disables)")
     ap.add_argument("--pipeline", type=int, default=0, help="1: persistent double-buffered kernels for N <= 8192 (A/B against one CTA per row)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup

@@ -286,6 +286,9 @@ int hehub_b200_ctx_set_option(hehub_b200_ctx *ctx, const char *name, int64_t val
         c.force_generic = value != 0;
     } else if (!std::strcmp(name, "pipeline")) {
         c.pipeline = value != 0;
+    } else if (!std::strcmp(name, "host_chunk_kib")) {
+        if (value < 1) return c.fail(HEHUB_B200_ERR_INVALID, "host_chunk_kib must be positive");
+        c.host_chunk_bytes = (size_t)value << 10;
     } else if (!std::strcmp(name, "scratch_cap_mib")) {
         if (value < 1) return c.fail(HEHUB_B200_ERR_INVALID, "scratch_cap_mib must be positive");
         c.scratch_cap_bytes = (size_t)value << 20;

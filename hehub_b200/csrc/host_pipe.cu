@@ -3,7 +3,7 @@
 // src/fhe/common/rns.cpp:25-27).
 //
 // A batch is cut into chunks; chunk c is copied in on the copy-in stream, transformed on the
-// context's compute stream and copied out on the copy-out stream, three chunks in flight, so
+// context's compute stream and copied out on the copy-out stream, up to four chunks in flight, so
 // PCIe traffic in both directions overlaps the kernels.  The calls return once the results are
 // in host memory.  Host buffers should come from hehub_b200_host_alloc (pinned); pageable
 // memory works but serialises the copies.
@@ -99,7 +99,7 @@ int hehub_b200_ntt_host(hehub_b200_ctx *ctx, int forward, unsigned logn, const u
         if (!c.get_chain(logn, reinterpret_cast<const u64 *>(moduli), L, &err)) return err;
     }
     const size_t words = L << logn; // one unit = one polynomial of L limbs
-    const size_t chunk = pick_chunk(batch, words, (size_t)16 << 20);
+    const size_t chunk = pick_chunk(batch, words, c.host_chunk_bytes);
     const u64 *ins[1] = {reinterpret_cast<const u64 *>(host_in)};
     return run_pipeline(c, batch, chunk, 1, ins, words, reinterpret_cast<u64 *>(host_out), words, 8, true,
                         [&](u64 *a, u64 *, u64 *, size_t cnt) -> int {
@@ -119,7 +119,7 @@ int hehub_b200_ckks_mult_relin_host(hehub_b200_ctx *ctx, unsigned logn, const ui
         if (!c.get_chain(logn, reinterpret_cast<const u64 *>(ext_moduli), L + 1, &err)) return err;
     }
     const size_t words = (2 * L) << logn; // one ciphertext
-    const size_t chunk = pick_chunk(batch, words, (size_t)16 << 20);
+    const size_t chunk = pick_chunk(batch, words, c.host_chunk_bytes);
     const u64 *ins[2] = {reinterpret_cast<const u64 *>(host_ct1), reinterpret_cast<const u64 *>(host_ct2)};
     return run_pipeline(c, batch, chunk, 2, ins, words, reinterpret_cast<u64 *>(host_out), words, 8, false,
                         [&](u64 *a, u64 *b, u64 *out, size_t cnt) -> int {
