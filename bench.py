@@ -180,6 +180,7 @@ def run_cuda(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -195,7 +196,6 @@ def run_cuda(args):
 
     stream = torch.cuda.Stream()
     ctx = Context(device=local, stream=stream.cuda_stream)
-    ctx.set_option("pipeline", args.pipeline)
     n = 1 << LOGN
     mod1, mod1p = _mod([Q59])
 
@@ -252,7 +252,7 @@ def run_cuda(args):
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                "kernel": "ntt_fwd_pipe_kernel<12>" if args.pipeline else "ntt_fwd_fast_kernel<12>",
+                "kernel": "ntt_fwd_fast_kernel<12, RowsIO<0>>",
                 "algorithmic_bytes_per_launch": alg_bytes}
     # the transforms are bound by the integer (FMA-heavy) pipe, not HBM: report that fraction too
     try:
@@ -286,7 +286,8 @@ def run_cuda(args):
     # ---- extras: the other BASELINE configs -------------------------------------------------------
     extras = {}
     if args.extras:
-        extras = run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist if world > 1 else None, args.sweep_cts)
+        extras = run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist if world > 1 else None, args.sweep_cts,
+                            cpu_ok=(rank == 0 and world == 1 and not args.no_cpu))
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------------
     cpu = None
@@ -320,7 +321,7 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
-def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, sweep_cts=0):
+def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, sweep_cts=0, cpu_ok=False):
     """Other BASELINE configs, device-resident, same timing discipline; values are whole-job."""
     import numpy as np
     from hehub_b200.binding import _mod
@@ -397,6 +398,46 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
             per = el / steps / batch
             gbs = 56 * L * n / per / 1e9
             r["tensor"] = {"per_s": world / per, "us_per_ct": per * 1e6, "gbs_algorithmic": gbs, "frac_hbm": gbs / hbm}
+        if "e2e" in what:
+            # the same op through the host-buffer entry point: ciphertexts in pinned host memory, key resident on the device
+            h1, h2, ho = (ctx.pinned((batch, 2, L, n)) for _ in range(3))
+            rng = np.random.default_rng(5 + rank)
+            for k, q in enumerate(mods):
+                h1[:, :, k, :] = rng.integers(0, q, (batch, 2, n), dtype=np.uint64)
+                h2[:, :, k, :] = rng.integers(0, q, (batch, 2, n), dtype=np.uint64)
+
+            class _Key:  # ckks_mult_relin_host takes a Slab-like object
+                ptr = key.data_ptr()
+            for _ in range(2):
+                ctx.ckks_mult_relin_host(logn, ext, h1, h2, _Key, ho)
+            torch.cuda.synchronize()
+            barrier()
+            reps, t0 = 5, time.perf_counter()
+            for _ in range(reps):
+                ctx.ckks_mult_relin_host(logn, ext, h1, h2, _Key, ho)
+            torch.cuda.synchronize()
+            barrier()
+            dt = time.perf_counter() - t0
+            if dist is not None:
+                tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            r["mult_relin_e2e_host_buffers"] = {"per_s": world * batch * reps / dt, "h2d_bytes_per_ct": 2 * 16 * L * n,
+                                                "d2h_bytes_per_ct": 16 * L * n, "frac_hbm": 48 * L * n * world * batch * reps / dt / 1e9 / hbm / world}
+            if cpu_ok:
+                lib, kind = _cpu_lib()
+                keyh = key.cpu().numpy().view(np.uint64).reshape(L, 2, L + 1, n)
+                lib.ckks_mult_relin(logn, ext, h1[0], h2[0], keyh)
+                cr, t0 = 0, time.perf_counter()
+                while time.perf_counter() - t0 < 3.0:
+                    got = lib.ckks_mult_relin(logn, ext, h1[cr % batch], h2[cr % batch], keyh)
+                    cr += 1
+                cdt = time.perf_counter() - t0
+                ctx.ckks_mult_relin_host(logn, ext, h1, h2, _Key, ho)
+                r["cpu_mult_relin"] = {"per_s": cr / cdt, "cores": 1, "kind": kind, "sample": f"{cr} ciphertext pairs, {cdt:.1f} s, one core",
+                                       "last_sample_bit_exact_vs_gpu": bool(np.array_equal(got, ho[(cr - 1) % batch]))}
+                r["speedup_e2e_vs_one_cpu_core"] = r["mult_relin_e2e_host_buffers"]["per_s"] / (cr / cdt)
+                r["speedup_device_resident_vs_one_cpu_core"] = r["mult_relin"]["per_s"] / (cr / cdt)
         if dist is not None and "mult" in what:  # result checksums gathered over NCCL
             chk = res.view(torch.int64)[:: max(1, res.numel() // 4096)].sum().reshape(1)
             allc = [torch.empty_like(chk) for _ in range(world)]
@@ -405,7 +446,7 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
         r["shape"] = {"N": n, "L": L, "batch_per_gpu": batch}
         out[tag] = r
 
-    ct_bench("c3_ckks_mult_relin_N8192_L4", 13, [40, 30, 30, 30], 40, 256, 4, ("mult", "tensor"))
+    ct_bench("c3_ckks_mult_relin_N8192_L4", 13, [40, 30, 30, 30], 40, 256, 4, ("mult", "tensor", "e2e"))
     ct_bench("c4_rescale_N16384_L8", 14, [50] + [40] * 7, 50, 128, 4, ("rescale",))
     ct_bench("c5_ckks_mult_relin_N32768_L12", 15, [50] * 12, 55, 16, 2, ("mult", "tensor"))
 
@@ -465,7 +506,6 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--sweep-cts", type=int, default=2048,
                     help="ciphertext pairs in the config-5 sweep extra, whole job (BASELINE: 65536; 0 disables)")
-    ap.add_argument("--pipeline", type=int, default=0, help="1: persistent double-buffered kernels for N <= 8192 (A/B against one CTA per row)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "reference":

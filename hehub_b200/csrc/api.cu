@@ -207,9 +207,9 @@ int run_transform(Context &c, bool forward, unsigned logn, const u64 *moduli, si
     if (!limbs) return err;
     cudaError_t e;
     if (strict && !forward) {
-        e = launch_ntt(false, c.env(), logn, RowsIO<true>{x, (int)L, (int)logn, aligned16(x)}, limbs, (int)(batch * L), aligned16(x));
+        e = launch_ntt(false, c.env(), logn, RowsIO<true>{x, (int)L, (int)logn, aligned16(x)}, limbs, (int)(batch * L));
     } else { // the forward transform has no strict variant in the reference
-        e = launch_ntt(forward, c.env(), logn, RowsIO<false>{x, (int)L, (int)logn, aligned16(x)}, limbs, (int)(batch * L), aligned16(x));
+        e = launch_ntt(forward, c.env(), logn, RowsIO<false>{x, (int)L, (int)logn, aligned16(x)}, limbs, (int)(batch * L));
     }
     return e == cudaSuccess ? 0 : c.cuda_fail(e, forward ? "ntt launch" : "intt launch");
 }
@@ -284,8 +284,6 @@ int hehub_b200_ctx_set_option(hehub_b200_ctx *ctx, const char *name, int64_t val
     if (!name) return c.fail(HEHUB_B200_ERR_INVALID, "null option name");
     if (!std::strcmp(name, "force_generic")) {
         c.force_generic = value != 0;
-    } else if (!std::strcmp(name, "pipeline")) {
-        c.pipeline = value != 0;
     } else if (!std::strcmp(name, "host_chunk_kib")) {
         if (value < 1) return c.fail(HEHUB_B200_ERR_INVALID, "host_chunk_kib must be positive");
         c.host_chunk_bytes = (size_t)value << 10;

@@ -22,6 +22,7 @@
 #define HB_LAUNCH_CLUSTER(kern, grid, block, smem, stream, cluster, ...) \
     (::hbsim::launch((grid), (block), (smem), 1, [&]() { kern(__VA_ARGS__); }, (cluster)), cudaSuccess)
 inline void hb_cluster_sync() { ::hbsim::cluster_sync(); }
+inline void hb_syncwarp() { __syncthreads(); } // the emulator has no warps: a CTA barrier is a superset
 template <class T>
 inline T hb_ldcg(const T *p) { return *p; }
 inline void hb_cp_async16(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 16); }
@@ -58,6 +59,7 @@ inline cudaError_t hb_launch_cluster(void (*kern)(KArgs...), unsigned grid, unsi
 __device__ __forceinline__ void hb_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void hb_syncwarp() { __syncwarp(); }
 template <class T>
 __device__ __forceinline__ T hb_ldcg(const T *p) { return __ldcg(p); }
 // 16-byte asynchronous global -> shared copy (LDGSTS), bypassing L1: the words are streamed once

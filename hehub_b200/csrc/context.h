@@ -42,9 +42,8 @@ struct Context {
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
     bool force_generic = false;
-    bool pipeline = false; // option "pipeline": persistent double-buffered transforms (N <= 8192) instead of one CTA per row
     int sm_count = 148;
-    LaunchEnv env() { return LaunchEnv{stream, sm_count, force_generic, pipeline, &stats}; }
+    LaunchEnv env() { return LaunchEnv{stream, sm_count, force_generic, &stats}; }
     size_t scratch_cap_bytes = (size_t)2 << 30; // bound on the per-call workspace; batches run in waves
     std::string last_error;
     LaunchStats stats;

@@ -10,10 +10,11 @@
 //     16 coefficients in registers and runs 3-4 levels on them ("pass"), so the row crosses
 //     shared memory 2-3 times instead of log2(N) times;
 //   * the inverse uses the folded form (no bit-reversal permutations);
-//   * N <= 8192: PERSISTENT kernel, one CTA per resident slot looping over rows; the next row's
-//     words are streamed into a second shared-memory buffer with cp.async while the current row
-//     is being transformed, so HBM latency and the copy-in never stall the integer pipes;
-//   * N = 16384: one CTA per row; N = 32768 (256 KiB, more than one SM holds): a 2-CTA
+//   * the contiguous pass moves the row between global and shared memory warp by warp (each warp
+//     owns 32 << K adjacent words), and when the neighbouring pass keeps the same number of words
+//     per thread the exchange between the two stays inside a warp: N = 4096 needs ONE CTA barrier
+//     per transform;
+//   * N <= 16384: one CTA per row; N = 32768 (256 KiB, more than one SM holds): a 2-CTA
 //     thread-block cluster per row, half a row each; the single cross-CTA level (gap N/2) is
 //     computed from global/L2 reads on the way in (forward) or exchanged through the row's own
 //     global words between two cluster barriers (inverse).
@@ -69,16 +70,6 @@ struct TwTable {
     HB_D ulonglong2 get(int slot) const { return __ldg(p + slot * stride); }
 #endif
 };
-template <int K>
-struct TwRegs {
-    ulonglong2 r[(1 << K) - 1];
-    HB_D ulonglong2 get(int slot) const { return r[slot]; }
-    HB_D void fill(const ulonglong2 *__restrict__ p, int stride) {
-#pragma unroll
-        for (int s = 0; s < (1 << K) - 1; s++) r[s] = __ldg(p + s * stride);
-    }
-};
-
 // K forward levels on 2^K registers.  Level m pairs registers 2^(K-m) apart and uses twiddle
 // slot (2^(m-1) - 1 + blk).
 template <int K, int M = 1, class TW>
@@ -131,90 +122,81 @@ HB_D void sts_contig(u64 *sm, int base, const u64 (&v)[1 << K]) {
     for (int c = 0; c < (1 << K) / 2; c++) p[c] = make_ulonglong2(v[2 * c], v[2 * c + 1]);
 }
 
-// stream a row of NC raw words into the padded shared-memory layout, 16 bytes per cp.async
-template <int NC, int T>
-HB_D void prefetch_row(u64 *sm, const u64 *__restrict__ src) {
-    static_assert((NC / 2) % T == 0 && (2 * T) % 16 == 0, "whole 16-byte chunks per thread");
-    u64 *const d = sm + sphys(2 * threadIdx.x);
-    const u64 *const g = src + 2 * threadIdx.x;
-#pragma unroll
-    for (int k = 0; k < NC / 2 / T; k++) hb_cp_async16(d + k * sstride(2 * T), g + k * 2 * T);
-    hb_cp_async_commit();
-}
-
-// the CTA's NC words between shared memory (padded) and the IO policy.  io.vec (uniform): every row
-// pointer of the policy is 16-byte aligned, so rows move as 128-bit words (two coefficients).
-template <int NC, int T, class IO>
-HB_D void store_row(const u64 *sm, const IO &io, const LimbConst &lc, int row, int first_word) {
-    static_assert(NC % (2 * T) == 0 && T % 16 == 0, "whole steps");
+// ------------------------------------------------------------------------------------------
+// warp-local row movement.  In the contiguous pass every thread owns 2^K adjacent words, so a warp
+// owns the 32 << K adjacent words of its lanes: those move between global and shared memory with
+// coalesced 128-bit accesses of the warp itself and only a warp barrier, no CTA barrier.
+// ------------------------------------------------------------------------------------------
+template <int K, class IO>
+HB_D void warp_store(const u64 *sm, const IO &io, const LimbConst &lc, int row, int first_word, int wbase) {
+    const int lane = threadIdx.x & 31;
     if (io.vec) {
-        const u64 *const s = sm + sphys(2 * threadIdx.x);
+        const u64 *const s = sm + sphys(wbase + 2 * lane);
 #pragma unroll
-        for (int k = 0; k < NC / 2 / T; k++) {
-            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(s + k * sstride(2 * T));
-            io.store2(row, first_word + 2 * threadIdx.x + k * 2 * T, v.x, v.y, lc);
+        for (int k = 0; k < (1 << K) / 2; k++) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(s + k * sstride(64));
+            io.store2(row, first_word + wbase + 2 * lane + 64 * k, v.x, v.y, lc);
         }
     } else {
-        const u64 *const s = sm + sphys(threadIdx.x);
+        const u64 *const s = sm + sphys(wbase + lane);
 #pragma unroll
-        for (int k = 0; k < NC / T; k++) io.store(row, first_word + threadIdx.x + k * T, s[k * sstride(T)], lc);
+        for (int k = 0; k < (1 << K); k++) io.store(row, first_word + wbase + lane + 32 * k, s[k * sstride(32)], lc);
     }
 }
-template <int NC, int T, class IO>
-HB_D void load_row(u64 *sm, const IO &io, const LimbConst &lc, int row, int first_word) {
-    static_assert(NC % (2 * T) == 0 && T % 16 == 0, "whole steps");
+template <int K, class IO>
+HB_D void warp_load(u64 *sm, const IO &io, const LimbConst &lc, int row, int first_word, int wbase) {
+    const int lane = threadIdx.x & 31;
     if (io.vec) {
-        u64 *const d = sm + sphys(2 * threadIdx.x);
-        const u64 *const g = io.src(row) + first_word + 2 * threadIdx.x;
+        u64 *const d = sm + sphys(wbase + 2 * lane);
+        const u64 *const g = io.src(row) + first_word + wbase + 2 * lane;
 #pragma unroll
-        for (int k = 0; k < NC / 2 / T; k++) {
-            const int i = first_word + 2 * threadIdx.x + k * 2 * T;
+        for (int k = 0; k < (1 << K) / 2; k++) {
+            const int i = first_word + wbase + 2 * lane + 64 * k;
 #if defined(HB_ABL_NOLOAD)
             ulonglong2 v = make_ulonglong2((u64)i * 0x9E3779B97F4A7C15ull + (u64)row, (u64)i);
 #else
-            ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(g + k * 2 * T);
+            ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(g + 64 * k);
 #endif
             v.x = io.pre(row, i, v.x, lc);
             v.y = io.pre(row, i + 1, v.y, lc);
-            *reinterpret_cast<ulonglong2 *>(d + k * sstride(2 * T)) = v;
+            *reinterpret_cast<ulonglong2 *>(d + k * sstride(64)) = v;
         }
     } else {
-        u64 *const d = sm + sphys(threadIdx.x);
+        u64 *const d = sm + sphys(wbase + lane);
 #pragma unroll
-        for (int k = 0; k < NC / T; k++) d[k * sstride(T)] = io_load(io, row, first_word + threadIdx.x + k * T, lc);
+        for (int k = 0; k < (1 << K); k++) d[k * sstride(32)] = io_load(io, row, first_word + wbase + lane + 32 * k, lc);
     }
 }
 
+// Two consecutive passes that keep the same number of words per thread, one of them the contiguous
+// pass, exchange data only inside groups of 2^K consecutive threads (K <= 5: inside a warp), so
+// the barrier between them is a warp barrier.
+HB_CX bool warp_local_pair(int ka, int kb) { return ka == kb && ka <= 5; }
+
 // ------------------------------------------------------------------------------------------
-// forward passes.  SRC: 0 = first pass reads global memory, 1 = first pass reads the raw words
-// a prefetch left in shared memory.
+// forward passes: gaps shrink, the last pass is contiguous and stores the row
 // ------------------------------------------------------------------------------------------
-// TWC: register twiddles for the contiguous pass (TwRegs<K>) or NoTw (read the table)
-struct NoTw {};
-template <int LOGN, int T, int P, int SRC, class IO, class TWC>
-HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B, const TWC &twc) {
+template <int LOGN, int T, int P, class IO>
+HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     constexpr NttPlan pl = plan_for(LOGN);
     constexpr int LOGNC = LOGN - pl.lpre, NC = 1 << LOGNC;
     constexpr int K = pl.k[P], L0 = fwd_lambda0(pl, P), GSL = LOGNC - L0 - K; // log2(smallest gap)
     constexpr int NG = NC >> K;
     constexpr bool first = (P == 0), last = (P == pl.npass - 1);
     static_assert(!last || GSL == 0, "last forward pass must be contiguous");
+    static_assert(last || GSL >= 4, "strided passes step by multiples of 16 words");
+    static_assert(NG % T == 0 && T % 32 == 0, "whole warps in every step");
     const ulonglong2 *tw_pass = lc.fwd + fwd_pass_offset(pl, P);
     constexpr int stride = 1 << (pl.lpre + L0);
+    constexpr int SJ = sstride(1 << GSL);
 
 #pragma unroll 1
     for (int g = threadIdx.x; g < NG; g += T) {
         const int lo = g & ((1 << GSL) - 1), hb = g >> GSL;
         const int base = (hb << (LOGNC - L0)) + lo;
-        static_assert(last || GSL >= 4, "strided passes step by multiples of 16 words");
         u64 *const smb = sm + sphys(base); // strided passes: element j lives at smb[j * SJ]
-        constexpr int SJ = sstride(1 << GSL);
         u64 v[1 << K];
-        if constexpr (first && SRC == 1) {
-            static_assert(pl.lpre == 0, "prefetched rows are whole rows");
-#pragma unroll
-            for (int j = 0; j < (1 << K); j++) v[j] = io.pre(row, base + (j << GSL), smb[j * SJ], lc);
-        } else if constexpr (first) {
+        if constexpr (first) {
             if constexpr (pl.lpre == 0) {
 #pragma unroll
                 for (int j = 0; j < (1 << K); j++) v[j] = io_load(io, row, base + (j << GSL), lc);
@@ -237,17 +219,14 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B, c
             for (int j = 0; j < (1 << K); j++) v[j] = smb[j * SJ];
         }
 
-        if constexpr (last && !std::is_same<TWC, NoTw>::value) {
-            static_assert(NG == T, "register twiddles need one contiguous group per thread");
-            fwd_levels<K>(v, twc, lc.nq, lc.q2);
-        } else {
-            fwd_levels<K>(v, TwTable{tw_pass + ((B << L0) + hb), stride}, lc.nq, lc.q2);
-        }
+        fwd_levels<K>(v, TwTable{tw_pass + ((B << L0) + hb), stride}, lc.nq, lc.q2);
 
         if constexpr (last) {
 #pragma unroll
             for (int j = 0; j < (1 << K); j++) v[j] = approx_reduce(v[j], lc); // ntt.cpp:171-175
-            sts_contig<K>(sm, base, v);
+            sts_contig<K>(sm, base, v); // own words only
+            hb_syncwarp();
+            warp_store<K>(sm, io, lc, row, B * NC, (g - (int)(threadIdx.x & 31)) << K);
         } else {
 #pragma unroll
             for (int j = 0; j < (1 << K); j++) smb[j * SJ] = v[j];
@@ -255,18 +234,22 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B, c
     }
 }
 
-template <int LOGN, int T, int P, int SRC, class IO, class TWC>
-HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B, const TWC &twc) {
+template <int LOGN, int T, int P, class IO>
+HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     constexpr NttPlan pl = plan_for(LOGN);
-    fwd_pass<LOGN, T, P, SRC>(sm, io, lc, row, B, twc);
-    if constexpr (P == 0 && pl.lpre == 1) {
-        // both CTAs of the row have read all of it: from here on either may overwrite it
-        // (in-place transforms store into the words the sibling CTA has just read)
-        hb_cluster_sync();
-    } else {
-        __syncthreads();
+    fwd_pass<LOGN, T, P>(sm, io, lc, row, B);
+    if constexpr (P + 1 < pl.npass) {
+        if constexpr (P == 0 && pl.lpre == 1) {
+            // both CTAs of the row have read all of it: from here on either may overwrite it
+            // (in-place transforms store into the words the sibling CTA has just read)
+            hb_cluster_sync();
+        } else if constexpr (P + 2 == pl.npass && warp_local_pair(pl.k[P], pl.k[P + 1])) {
+            hb_syncwarp();
+        } else {
+            __syncthreads();
+        }
+        fwd_passes<LOGN, T, P + 1>(sm, io, lc, row, B);
     }
-    if constexpr (P + 1 < pl.npass) fwd_passes<LOGN, T, P + 1, SRC>(sm, io, lc, row, B, twc);
 }
 
 // one CTA (or one CTA of a 2-CTA cluster) per row
@@ -274,104 +257,54 @@ template <int LOGN, class IO>
 HB_GLOBAL(plan_for(LOGN).threads, plan_for(LOGN).min_blocks)
 ntt_fwd_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     constexpr NttPlan pl = plan_for(LOGN);
-    constexpr int NC = 1 << (LOGN - pl.lpre), T = pl.threads;
+    constexpr int T = pl.threads;
     HB_SHARED_U64(sm);
     const int row = blockIdx.x >> pl.lpre, B = blockIdx.x & ((1 << pl.lpre) - 1);
     const LimbConst lc = limbs[io.limb(row)];
-    fwd_passes<LOGN, T, 0, 0>(sm, io, lc, row, B, NoTw{});
-    store_row<NC, T>(sm, io, lc, row, B * NC);
-}
-
-// persistent, double-buffered: grid = resident CTA slots, rows visited with stride gridDim.x
-template <int LOGN, class IO>
-HB_GLOBAL(pipe_plan_for(LOGN).threads, pipe_plan_for(LOGN).min_blocks)
-ntt_fwd_pipe_kernel(const IO io, const LimbConst *__restrict__ limbs, int rows) {
-    constexpr PipePlan pp = pipe_plan_for(LOGN);
-    constexpr int NC = 1 << LOGN, T = pp.threads, BUF = smem_words(NC);
-    HB_SHARED_U64(smem);
-    int row = blockIdx.x;
-    if (row >= rows) return;
-    prefetch_row<NC, T>(smem, io.src(row));
-    // the last (contiguous) pass uses 15 twiddle pairs private to this thread and identical for
-    // every row of a limb: they stay in registers for as long as the CTA keeps seeing that limb
-    constexpr NttPlan pl = plan_for(LOGN);
-    constexpr int KL = pl.k[pl.npass - 1], L0L = fwd_lambda0(pl, pl.npass - 1);
-    constexpr bool kCache = (NC >> KL) == T;
-    typename std::conditional<kCache, TwRegs<KL>, NoTw>::type twc;
-    int cached_limb = -1;
-    int cur = 0;
-    for (; row < rows; row += gridDim.x) {
-        u64 *sm = smem + cur * BUF;
-        hb_cp_async_wait_all();
-        __syncthreads(); // this row has landed; every thread is done with the other buffer
-        const int next = row + gridDim.x;
-        if (next < rows) prefetch_row<NC, T>(smem + (cur ^ 1) * BUF, io.src(next));
-        const int limb = io.limb(row);
-        const LimbConst lc = limbs[limb];
-        if constexpr (kCache) {
-            if (limb != cached_limb) {
-                twc.fill(lc.fwd + fwd_pass_offset(pl, pl.npass - 1) + threadIdx.x, 1 << L0L);
-                cached_limb = limb;
-            }
-        }
-        fwd_passes<LOGN, T, 0, 1>(sm, io, lc, row, 0, twc);
-        store_row<NC, T>(sm, io, lc, row, 0);
-        cur ^= 1;
-    }
+    fwd_passes<LOGN, T, 0>(sm, io, lc, row, B);
 }
 
 // ------------------------------------------------------------------------------------------
-// inverse passes
+// inverse passes: the first pass is contiguous and loads the row, gaps grow
 // ------------------------------------------------------------------------------------------
-template <int LOGN, int T, int P, int SRC, class IO, class TWC>
-HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B, const TWC &twc) {
+template <int LOGN, int T, int P, class IO>
+HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     constexpr NttPlan pl = plan_for(LOGN);
     constexpr int LOGNC = LOGN - pl.lpre, NC = 1 << LOGNC;
     constexpr int K = inv_k(pl, P), S0 = inv_s0(pl, P);
     constexpr int NG = NC >> K;
     constexpr bool first = (P == 0), last = (P == pl.npass - 1);
     static_assert(!first || S0 == 0, "first inverse pass must be contiguous");
+    static_assert(first || S0 >= 4, "strided passes step by multiples of 16 words");
+    static_assert(NG % T == 0 && T % 32 == 0, "whole warps in every step");
     const ulonglong2 *tw_pass = lc.inv + inv_pass_offset(pl, P);
     constexpr int stride = 1 << S0;
+    constexpr int SJ = sstride(1 << S0);
 
 #pragma unroll 1
     for (int g = threadIdx.x; g < NG; g += T) {
         const int lo = g & ((1 << S0) - 1), hi = g >> S0;
         const int base = (hi << (S0 + K)) + lo;
-        static_assert(first || S0 >= 4, "strided passes step by multiples of 16 words");
         u64 *const smb = sm + sphys(base);
-        constexpr int SJ = sstride(1 << S0);
         u64 v[1 << K];
         if constexpr (first) {
+            warp_load<K>(sm, io, lc, row, B * NC, (g - (int)(threadIdx.x & 31)) << K);
+            hb_syncwarp();
             lds_contig<K>(sm, base, v);
-            if constexpr (SRC == 1) { // raw prefetched words: apply the policy's input map
-#pragma unroll
-                for (int j = 0; j < (1 << K); j++) v[j] = io.pre(row, base + j, v[j], lc);
-            }
         } else {
 #pragma unroll
             for (int j = 0; j < (1 << K); j++) v[j] = smb[j * SJ];
         }
 
-        if constexpr (last && !std::is_same<TWC, NoTw>::value) {
-            static_assert(NG == T, "register twiddles need one group per thread");
-            inv_levels<K>(v, twc, lc.nq, lc.q2);
-        } else {
-            inv_levels<K>(v, TwTable{tw_pass + lo, stride}, lc.nq, lc.q2);
-        }
+        inv_levels<K>(v, TwTable{tw_pass + lo, stride}, lc.nq, lc.q2);
 
-        if constexpr (last) {
-            if constexpr (pl.lpre == 0) {
+        if constexpr (last && pl.lpre == 0) {
 #pragma unroll
-                for (int j = 0; j < (1 << K); j++) {
-                    const int i = base + (j << S0);
-                    u64 x = approx_reduce(v[j], lc);                 // ntt.cpp:218
-                    const ulonglong2 s = __ldg(lc.inv_scale + i);    // psi^{-i}/N, ntt.cpp:219-221
-                    io.store(row, i, harvey_lazy(x, s.x, s.y, lc.nq), lc);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < (1 << K); j++) smb[j * SJ] = v[j];
+            for (int j = 0; j < (1 << K); j++) {
+                const int i = base + (j << S0);
+                u64 x = approx_reduce(v[j], lc);                 // ntt.cpp:218
+                const ulonglong2 s = __ldg(lc.inv_scale + i);    // psi^{-i}/N, ntt.cpp:219-221
+                io.store(row, i, harvey_lazy(x, s.x, s.y, lc.nq), lc);
             }
         } else if constexpr (first) {
             sts_contig<K>(sm, base, v);
@@ -382,13 +315,17 @@ HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B, c
     }
 }
 
-template <int LOGN, int T, int P, int SRC, class IO, class TWC>
-HB_D void inv_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B, const TWC &twc) {
+template <int LOGN, int T, int P, class IO>
+HB_D void inv_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     constexpr NttPlan pl = plan_for(LOGN);
-    inv_pass<LOGN, T, P, SRC>(sm, io, lc, row, B, twc);
+    inv_pass<LOGN, T, P>(sm, io, lc, row, B);
     if constexpr (P + 1 < pl.npass) {
-        __syncthreads();
-        inv_passes<LOGN, T, P + 1, SRC>(sm, io, lc, row, B, twc);
+        if constexpr (P == 0 && warp_local_pair(inv_k(pl, 0), inv_k(pl, 1))) {
+            hb_syncwarp();
+        } else {
+            __syncthreads();
+        }
+        inv_passes<LOGN, T, P + 1>(sm, io, lc, row, B);
     }
 }
 
@@ -400,9 +337,7 @@ intt_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     HB_SHARED_U64(sm);
     const int row = blockIdx.x >> pl.lpre, B = blockIdx.x & ((1 << pl.lpre) - 1);
     const LimbConst lc = limbs[io.limb(row)];
-    load_row<NC, T>(sm, io, lc, row, B * NC);
-    __syncthreads();
-    inv_passes<LOGN, T, 0, 0>(sm, io, lc, row, B, NoTw{});
+    inv_passes<LOGN, T, 0>(sm, io, lc, row, B);
     if constexpr (pl.lpre == 1) {
         // last stage (gap N/2) pairs word i of CTA 0 with word i of CTA 1.  Exchange the halves
         // through the row's exchange area (L2), combine into shared memory, and only after the
@@ -425,42 +360,6 @@ intt_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
             const ulonglong2 s = __ldg(lc.inv_scale + gi);
             io.store(row, gi, harvey_lazy(approx_reduce(sm[sphys(i)], lc), s.x, s.y, lc.nq), lc);
         }
-    }
-}
-
-template <int LOGN, class IO>
-HB_GLOBAL(pipe_plan_for(LOGN).threads, pipe_plan_for(LOGN).min_blocks)
-intt_pipe_kernel(const IO io, const LimbConst *__restrict__ limbs, int rows) {
-    constexpr PipePlan pp = pipe_plan_for(LOGN);
-    constexpr int NC = 1 << LOGN, T = pp.threads, BUF = smem_words(NC);
-    HB_SHARED_U64(smem);
-    int row = blockIdx.x;
-    if (row >= rows) return;
-    prefetch_row<NC, T>(smem, io.src(row));
-    // the last inverse pass (largest gaps) uses twiddle pairs private to this thread and identical
-    // for every row of a limb: kept in registers while the CTA keeps seeing that limb
-    constexpr NttPlan pl = plan_for(LOGN);
-    constexpr int KL = inv_k(pl, pl.npass - 1), S0L = inv_s0(pl, pl.npass - 1);
-    constexpr bool kCache = (NC >> KL) == T;
-    typename std::conditional<kCache, TwRegs<KL>, NoTw>::type twc;
-    int cached_limb = -1;
-    int cur = 0;
-    for (; row < rows; row += gridDim.x) {
-        u64 *sm = smem + cur * BUF;
-        hb_cp_async_wait_all();
-        __syncthreads();
-        const int next = row + gridDim.x;
-        if (next < rows) prefetch_row<NC, T>(smem + (cur ^ 1) * BUF, io.src(next));
-        const int limb = io.limb(row);
-        const LimbConst lc = limbs[limb];
-        if constexpr (kCache) {
-            if (limb != cached_limb) {
-                twc.fill(lc.inv + inv_pass_offset(pl, pl.npass - 1) + threadIdx.x, 1 << S0L);
-                cached_limb = limb;
-            }
-        }
-        inv_passes<LOGN, T, 0, 1>(sm, io, lc, row, 0, twc); // the last pass stores straight from registers
-        cur ^= 1;
     }
 }
 
@@ -519,7 +418,6 @@ struct LaunchEnv {
     cudaStream_t stream;
     int sm_count;       // persistent grids are sized from it
     bool force_generic; // parity cross-check path
-    bool pipeline;      // use the persistent double-buffered kernels where they exist
     LaunchStats *stats;
 };
 
@@ -528,12 +426,6 @@ constexpr auto fast_kernel() {
     if constexpr (FWD) return &ntt_fwd_fast_kernel<LOGN, IO>;
     else return &intt_fast_kernel<LOGN, IO>;
 }
-template <int LOGN, bool FWD, class IO>
-constexpr auto pipe_kernel() {
-    if constexpr (FWD) return &ntt_fwd_pipe_kernel<LOGN, IO>;
-    else return &intt_pipe_kernel<LOGN, IO>;
-}
-
 // Opt in to `smem` bytes of dynamic shared memory and ask for just enough carveout for `blocks`
 // resident CTAs: whatever is left of the SM's 228 KB stays L1, which the twiddle tables live in.
 template <class K>
@@ -565,26 +457,6 @@ inline cudaError_t launch_fast(const LaunchEnv &env, const IO &io, const LimbCon
     }
 }
 
-template <int LOGN, bool FWD, class IO>
-inline cudaError_t launch_pipe(const LaunchEnv &env, const IO &io, const LimbConst *limbs, int rows) {
-    constexpr PipePlan pp = pipe_plan_for(LOGN);
-    constexpr int smem = 2 * smem_words(1 << LOGN) * 8;
-    auto kern = pipe_kernel<LOGN, FWD, IO>();
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = configure_smem(kern, smem, pp.min_blocks);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    // balanced persistent grid: every CTA visits ceil(rows / slots) rows or one fewer
-    const int slots = env.sm_count * pp.min_blocks;
-    const int per = (rows + slots - 1) / slots;
-    const int grid = (rows + per - 1) / per;
-    env.stats->launches++;
-    HB_LAUNCH(kern, grid, pp.threads, smem, env.stream, 1, io, limbs, rows);
-    return cudaGetLastError();
-}
-
 template <class IO>
 inline cudaError_t launch_generic(bool forward, const LaunchEnv &env, unsigned logn, const IO &io, const LimbConst *limbs,
                                   int rows) {
@@ -614,25 +486,18 @@ inline cudaError_t launch_generic(bool forward, const LaunchEnv &env, unsigned l
     return cudaGetLastError();
 }
 
-// Dispatch on ring size.  `aligned16`: every src(row) is 16-byte aligned (cp.async granularity).
+// Dispatch on ring size (the policy's `vec` flag says whether rows move as 128-bit words).
 template <class IO>
-inline cudaError_t launch_ntt(bool forward, const LaunchEnv &env, unsigned logn, const IO &io, const LimbConst *limbs, int rows,
-                              bool aligned16) {
+inline cudaError_t launch_ntt(bool forward, const LaunchEnv &env, unsigned logn, const IO &io, const LimbConst *limbs, int rows) {
     if (rows <= 0) return cudaSuccess;
     if (logn < 1 || logn > kFastLogMax) return cudaErrorInvalidValue;
     if (logn < kFastLogMin || (env.force_generic && logn <= kGenericLogMax)) return launch_generic(forward, env, logn, io, limbs, rows);
-    const bool pipe = env.pipeline && aligned16 && logn <= (unsigned)kPipeLogMax;
-#define HB_CASE_PIPE(LN)                                                                                     \
-    case LN:                                                                                                 \
-        if (pipe) return forward ? launch_pipe<LN, true>(env, io, limbs, rows) : launch_pipe<LN, false>(env, io, limbs, rows); \
-        return forward ? launch_fast<LN, true>(env, io, limbs, rows) : launch_fast<LN, false>(env, io, limbs, rows);
 #define HB_CASE_FAST(LN)                                                                                     \
     case LN:                                                                                                 \
         return forward ? launch_fast<LN, true>(env, io, limbs, rows) : launch_fast<LN, false>(env, io, limbs, rows);
     switch (logn) {
-        HB_CASE_PIPE(10) HB_CASE_PIPE(11) HB_CASE_PIPE(12) HB_CASE_PIPE(13) HB_CASE_FAST(14) HB_CASE_FAST(15)
+        HB_CASE_FAST(10) HB_CASE_FAST(11) HB_CASE_FAST(12) HB_CASE_FAST(13) HB_CASE_FAST(14) HB_CASE_FAST(15)
     }
-#undef HB_CASE_PIPE
 #undef HB_CASE_FAST
     return cudaErrorInvalidValue;
 }

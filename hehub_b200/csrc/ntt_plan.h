@@ -31,42 +31,19 @@ constexpr int kFastLogMax = 15;
 constexpr int kGenericLogMax = 14; // one row must fit one CTA's shared memory
 
 HB_CX NttPlan plan_for(int logn) {
+    // Measured on B200 (profiles/r1_plan_sweep.md).  Passes of 4-5 levels keep 16-32 words per thread
+    // in registers; ending with two passes of equal width keeps their exchange inside a warp.
     switch (logn) {
     case 10: return NttPlan{10, 0, 3, {3, 3, 4, 0, 0}, 64, 8};
+#if defined(HB_PLAN11) && HB_PLAN11 == 1
     case 11: return NttPlan{11, 0, 3, {4, 3, 4, 0, 0}, 128, 6};
-#if !defined(HB_PLAN12) || HB_PLAN12 == 0
-    case 12: return NttPlan{12, 0, 3, {4, 4, 4, 0, 0}, 256, 3};
-#elif HB_PLAN12 == 1
-    case 12: return NttPlan{12, 0, 3, {4, 4, 4, 0, 0}, 256, 4};
-#elif HB_PLAN12 == 2
-    case 12: return NttPlan{12, 0, 4, {3, 3, 3, 3, 0}, 512, 2};
-#elif HB_PLAN12 == 3
-    case 12: return NttPlan{12, 0, 4, {3, 3, 3, 3, 0}, 512, 3};
-#elif HB_PLAN12 == 4
-    case 12: return NttPlan{12, 0, 4, {3, 3, 3, 3, 0}, 256, 4};
-#elif HB_PLAN12 == 5
-    case 12: return NttPlan{12, 0, 4, {3, 3, 3, 3, 0}, 256, 5};
+#else
+    case 11: return NttPlan{11, 0, 3, {3, 4, 4, 0, 0}, 128, 6};
 #endif
-    case 13: return NttPlan{13, 0, 4, {3, 3, 3, 4, 0}, 256, 2};
-    case 14: return NttPlan{14, 0, 4, {4, 3, 3, 4, 0}, 512, 1};
+    case 12: return NttPlan{12, 0, 3, {4, 4, 4, 0, 0}, 256, 3};
+    case 13: return NttPlan{13, 0, 3, {5, 4, 4, 0, 0}, 256, 2};
+    case 14: return NttPlan{14, 0, 3, {5, 5, 4, 0, 0}, 512, 1};
     default: return NttPlan{15, 1, 4, {4, 3, 3, 4, 0}, 512, 1};
-    }
-}
-
-// Persistent double-buffered variant (N <= 8192): same pass structure and tables, its own CTA
-// shape; shared memory per CTA is two padded row buffers.
-struct PipePlan {
-    int threads;
-    int min_blocks;
-};
-constexpr int kPipeLogMax = 13;
-HB_CX PipePlan pipe_plan_for(int logn) {
-    switch (logn) {
-    // 128 registers per thread: 60 hold the register-resident twiddles of the contiguous pass
-    case 10: return PipePlan{64, 8};    //  2 x  9 KiB
-    case 11: return PipePlan{128, 4};   //  2 x 18 KiB
-    case 12: return PipePlan{256, 2};   //  2 x 36 KiB -> 2 CTAs = 147 KB, ~79 KB left as L1
-    default: return PipePlan{512, 1};   //  2 x 72 KiB, N = 8192
     }
 }
 

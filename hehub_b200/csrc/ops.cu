@@ -124,9 +124,58 @@ struct ExtFanoutIO {
 };
 
 // step 3: out[b][h][k][i] = Mont128_{q_k}( sum_p dec[p][k][i] * key[p][h][k][i] )   rgsw.cpp:126-153
+// One thread owns two adjacent coefficients of one (ciphertext, limb): 128-bit loads, the L rows
+// consumed four at a time so a dozen independent loads are in flight before the multiplies start.
+// The sum is exact in 128 bits and reduced once, like the reference (reducing per term would
+// change the representative).
 HB_GLOBAL(256, 1)
 ext_mac_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
-               u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, int logn, size_t total) {
+               u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, int logn, size_t total_pairs) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // (b, k, i / 2)
+    if (gid >= total_pairs) return;
+    const int L1 = L + 1;
+    const size_t i = (gid & (((size_t)1 << (logn - 1)) - 1)) * 2;
+    const size_t bk = gid >> (logn - 1);
+    const int k = (int)(bk % L1);
+    const size_t b = bk / L1;
+    const LimbConst lc = limbs[k];
+    u64 lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0}; // [half][coefficient]
+    const u64 *const in_b = in + b * in_batch_stride + i;
+    const u64 *const dec_b = dec + (((size_t)b * L * L1 + k) << logn) + i;
+    const u64 *const key_k = key + ((size_t)k << logn) + i;
+    const size_t dec_row = (size_t)L1 << logn, key_row = (size_t)(2 * L1) << logn, key_half = (size_t)L1 << logn;
+    constexpr int U = 4;
+    for (int p0 = 0; p0 < L; p0 += U) {
+        ulonglong2 d[U], k0[U], k1[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int p = p0 + u;
+            if (p < L) {
+                const u64 *src = (p == k) ? in_b + ((size_t)p << logn) : dec_b + p * dec_row; // the diagonal keeps in[p], rgsw.cpp:99-101
+                d[u] = *reinterpret_cast<const ulonglong2 *>(src);
+                k0[u] = __ldg(reinterpret_cast<const ulonglong2 *>(key_k + p * key_row));
+                k1[u] = __ldg(reinterpret_cast<const ulonglong2 *>(key_k + p * key_row + key_half));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (p0 + u < L) {
+                mac128(lo[0], hi[0], d[u].x, k0[u].x);
+                mac128(lo[1], hi[1], d[u].y, k0[u].y);
+                mac128(lo[2], hi[2], d[u].x, k1[u].x);
+                mac128(lo[3], hi[3], d[u].y, k1[u].y);
+            }
+        }
+    }
+    u64 *const o = out + (((b * 2) * L1 + k) << logn) + i;
+    *reinterpret_cast<ulonglong2 *>(o) = make_ulonglong2(montgomery128(lo[0], hi[0], lc), montgomery128(lo[1], hi[1], lc));
+    *reinterpret_cast<ulonglong2 *>(o + key_half) = make_ulonglong2(montgomery128(lo[2], hi[2], lc), montgomery128(lo[3], hi[3], lc));
+}
+
+// unaligned operands (a slab that starts 8 bytes off a 16-byte boundary): one coefficient per thread
+HB_GLOBAL(256, 1)
+ext_mac_scalar_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
+                      u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, int logn, size_t total) {
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // (b, k, i)
     if (gid >= total) return;
     const int L1 = L + 1;
@@ -153,14 +202,20 @@ static int ext_prod_wave(Context &c, unsigned logn, const LimbConst *limbs, size
                          const u64 *key, u64 *out, size_t batch, u64 *cbuf, u64 *dec) {
     const size_t n = (size_t)1 << logn;
     ExtInttIO io1{in, in_batch_stride, cbuf, (int)L, (int)logn, aligned16(in) && (in_batch_stride % 2 == 0) && aligned16(cbuf)};
-    cudaError_t e = launch_ntt(false, c.env(), logn, io1, limbs, (int)(batch * L), aligned16(in) && (in_batch_stride % 2 == 0));
+    cudaError_t e = launch_ntt(false, c.env(), logn, io1, limbs, (int)(batch * L));
     if (e != cudaSuccess) return c.cuda_fail(e, "ext_prod: intt launch");
     ExtFanoutIO io2{cbuf, dec, (int)L, (int)logn, aligned16(cbuf) && aligned16(dec)};
-    e = launch_ntt(true, c.env(), logn, io2, limbs, (int)(batch * L * L), true);
+    e = launch_ntt(true, c.env(), logn, io2, limbs, (int)(batch * L * L));
     if (e != cudaSuccess) return c.cuda_fail(e, "ext_prod: ntt launch");
-    const size_t total = batch * (L + 1) * n;
-    HB_LAUNCH(ext_mac_kernel, (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, in_batch_stride, dec, key, out, limbs,
-              (int)L, (int)logn, total);
+    if (aligned16(in) && in_batch_stride % 2 == 0 && aligned16(dec) && aligned16(key) && aligned16(out) && n >= 2) {
+        const size_t total = batch * (L + 1) * (n / 2);
+        HB_LAUNCH(ext_mac_kernel, (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, in_batch_stride, dec, key, out, limbs,
+                  (int)L, (int)logn, total);
+    } else {
+        const size_t total = batch * (L + 1) * n;
+        HB_LAUNCH(ext_mac_scalar_kernel, (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, in_batch_stride, dec, key, out,
+                  limbs, (int)L, (int)logn, total);
+    }
     c.stats.launches++;
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : c.cuda_fail(e, "ext_prod: mac launch");
@@ -202,22 +257,22 @@ int op_ext_prod(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, cons
 // drop the last prime (CKKS rescale / BGV mod-switch)
 // ------------------------------------------------------------------------------------------
 // step 1: z[b][h] = strict( [H(., t^{-1})] INTT_{q_last}(ct[b][h][L-1]) )   rescaling.cpp:47-50, mod_switch.cpp:48-51
+template <bool BGV>
 struct DropInttIO {
     const u64 *ct;
     u64 *z; // [batch][2][N]
     int L, logn;
     u64 inv_t, inv_t_h; // 0 for CKKS
-    int bgv;
     bool vec;
     HB_D int limb(int) const { return L - 1; }
     HB_D const u64 *src(int row) const { return ct + ((size_t)(row * L + L - 1) << logn); }
     HB_D u64 pre(int, int, u64 raw, const LimbConst &) const { return raw; }
     HB_D void store(int row, int i, u64 v, const LimbConst &lc) const {
-        if (bgv) v = harvey_lazy(v, inv_t, inv_t_h, lc.nq);
+        if (BGV) v = harvey_lazy(v, inv_t, inv_t_h, lc.nq);
         z[((size_t)row << logn) + i] = reduce_strict(v, lc.q);
     }
     HB_D void store2(int row, int i, u64 v0, u64 v1, const LimbConst &lc) const {
-        if (bgv) {
+        if (BGV) {
             v0 = harvey_lazy(v0, inv_t, inv_t_h, lc.nq);
             v1 = harvey_lazy(v1, inv_t, inv_t_h, lc.nq);
         }
@@ -227,6 +282,7 @@ struct DropInttIO {
 };
 
 // step 2: per remaining limb k: r = centre(barrett(z)); NTT; out = H(lazy_sub(ct, r), q_last^{-1}) [...]
+template <bool BGV>
 struct DropFwdIO {
     const u64 *ct;
     const u64 *z;
@@ -235,35 +291,35 @@ struct DropFwdIO {
     const u64 *addend; // optional, lazy-added to the first add_halves polynomials
     size_t add_batch_stride, add_poly_stride;
     u64 half_qlast;
-    int L, logn, bgv, add_halves;
+    int L, logn, add_halves;
     bool vec;
     HB_D int limb(int row) const { return row % (L - 1); }
     HB_D const u64 *src(int row) const { return z + ((size_t)(row / (L - 1)) << logn); }
     HB_D u64 pre(int row, int, u64 zz, const LimbConst &lc) const {
         const int k = row % (L - 1);
         u64 r = reduce_strict(barrett_lazy(zz, lc), lc.q);          // rescaling.cpp:58-59
-        if (zz >= half_qlast) r += lc.q - dc[k].qlast_mod_q;        // rescaling.cpp:63-68
-        if (bgv) r = harvey_lazy(r, dc[k].t_mod_q, dc[k].t_mod_q_h, lc.nq); // mod_switch.cpp:70
+        if (zz >= half_qlast) r += lc.q - __ldg(&dc[k].qlast_mod_q); // rescaling.cpp:63-68
+        if (BGV) r = harvey_lazy(r, __ldg(&dc[k].t_mod_q), __ldg(&dc[k].t_mod_q_h), lc.nq); // mod_switch.cpp:70
         return r;
     }
     HB_D void store(int row, int i, u64 v, const LimbConst &lc) const {
         const int poly = row / (L - 1), k = row - poly * (L - 1);
-        const DropConst d = dc[k];
+        const DropConst *d = dc + k;
         u64 x = finish(ct[((size_t)(poly * L + k) << logn) + i], v, d, lc);
         const int h = poly & 1, b = poly >> 1;
         if (h < add_halves) // ckks/arith.cpp:70-71, 84, 91
             x = add_lazy(x, addend[(size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn) + i], lc.q2);
         out[((size_t)row << logn) + i] = x;
     }
-    HB_D u64 finish(u64 x, u64 v, const DropConst &d, const LimbConst &lc) const {
-        x = sub_lazy(x, v, lc.q2);                                   // rescaling.cpp:73
-        x = harvey_lazy(x, d.inv_qlast, d.inv_qlast_h, lc.nq);       // rescaling.cpp:74
-        if (bgv) x = harvey_lazy(x, d.qlt_mod_q, d.qlt_mod_q_h, lc.nq); // mod_switch.cpp:76
+    HB_D u64 finish(u64 x, u64 v, const DropConst *d, const LimbConst &lc) const {
+        x = sub_lazy(x, v, lc.q2);                                                         // rescaling.cpp:73
+        x = harvey_lazy(x, __ldg(&d->inv_qlast), __ldg(&d->inv_qlast_h), lc.nq);          // rescaling.cpp:74
+        if (BGV) x = harvey_lazy(x, __ldg(&d->qlt_mod_q), __ldg(&d->qlt_mod_q_h), lc.nq); // mod_switch.cpp:76
         return x;
     }
     HB_D void store2(int row, int i, u64 v0, u64 v1, const LimbConst &lc) const {
         const int poly = row / (L - 1), k = row - poly * (L - 1);
-        const DropConst d = dc[k];
+        const DropConst *d = dc + k;
         const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(ct + ((size_t)(poly * L + k) << logn) + i);
         ulonglong2 r = make_ulonglong2(finish(x.x, v0, d, lc), finish(x.y, v1, d, lc));
         const int h = poly & 1, b = poly >> 1;
@@ -291,14 +347,23 @@ int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, 
     const size_t n = (size_t)1 << logn;
     u64 *z = c.get_scratch(2, batch * 2 * n, &err);
     if (!z) return err;
-    DropInttIO io1{ct, z, (int)L, (int)logn, ds->inv_t, ds->inv_t_h, t ? 1 : 0, aligned16(ct) && aligned16(z)};
-    cudaError_t e = launch_ntt(false, c.env(), logn, io1, limbs, (int)(batch * 2), aligned16(ct));
-    if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: intt launch");
     const bool vec = aligned16(ct) && aligned16(z) && aligned16(out) &&
                      (!addend || (aligned16(addend) && add_batch_stride % 2 == 0 && add_poly_stride % 2 == 0));
-    DropFwdIO io2{ct, z, out, ds->dev, addend, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, t ? 1 : 0,
-                  addend ? add_halves : 0, vec};
-    e = launch_ntt(true, c.env(), logn, io2, limbs, (int)(batch * 2 * (L - 1)), true);
+    const int halves = addend ? add_halves : 0;
+    cudaError_t e;
+    if (t) {
+        DropInttIO<true> io1{ct, z, (int)L, (int)logn, ds->inv_t, ds->inv_t_h, aligned16(ct) && aligned16(z)};
+        e = launch_ntt(false, c.env(), logn, io1, limbs, (int)(batch * 2));
+        if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: intt launch");
+        DropFwdIO<true> io2{ct, z, out, ds->dev, addend, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, halves, vec};
+        e = launch_ntt(true, c.env(), logn, io2, limbs, (int)(batch * 2 * (L - 1)));
+    } else {
+        DropInttIO<false> io1{ct, z, (int)L, (int)logn, 0, 0, aligned16(ct) && aligned16(z)};
+        e = launch_ntt(false, c.env(), logn, io1, limbs, (int)(batch * 2));
+        if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: intt launch");
+        DropFwdIO<false> io2{ct, z, out, ds->dev, addend, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, halves, vec};
+        e = launch_ntt(true, c.env(), logn, io2, limbs, (int)(batch * 2 * (L - 1)));
+    }
     if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: ntt launch");
     return 0;
 }

@@ -50,8 +50,7 @@ int hehub_b200_ctx_synchronize(hehub_b200_ctx *ctx);
 const char *hehub_b200_last_error(const hehub_b200_ctx *ctx);
 /* options: "force_generic" (0/1) routes transforms through the one-level-per-sweep kernels
  * (an on-device cross-check of the fast path); "scratch_cap_mib" bounds the workspace a
- * batched call may use (large batches are processed in waves); "pipeline" (0/1) selects the
- * persistent double-buffered transform kernels for N <= 8192 instead of one CTA per row;
+ * batched call may use (large batches are processed in waves);
  * "host_chunk_kib" sets the chunk size of the host-buffer pipeline (default 16384; measured best on PCIe Gen5, profiles/r1d_e2e_chunk_sweep.log). */
 int hehub_b200_ctx_set_option(hehub_b200_ctx *ctx, const char *name, int64_t value);
 /* number of kernels this context has launched since creation (bench bookkeeping) */

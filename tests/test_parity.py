@@ -109,23 +109,18 @@ def test_generic_path_agrees_with_fast_path(dev, oracle, logn):
 
 
 @pytest.mark.parametrize("logn", [10, 11, 12, 13])
-def test_row_per_cta_kernels_agree_with_persistent_pipeline(dev, oracle, logn):
-    """N <= 8192 has two kernel families (persistent double-buffered / one CTA per row); both must
-    give the reference's words, also when a CTA visits several rows and for unaligned slabs."""
+def test_multi_row_batches_and_unaligned_slabs(dev, oracle, logn):
+    """Batches whose row count is not a multiple of anything convenient, mixed moduli per row, and a
+    slab that is only 8-byte aligned (rows then move as 64-bit words instead of 128-bit)."""
     n = 1 << logn
     moduli = [Q59, 65537]
     batch = 11
     x = np.stack([np.stack([oracle.lcg_fill(3 + 10 * b + k, q, n) for k, q in enumerate(moduli)]) for b in range(batch)])
     want = np.stack([oracle.poly_ntt_fwd(logn, moduli, x[b]) for b in range(batch)])
     want_i = np.stack([oracle.poly_intt(logn, moduli, want[b]) for b in range(batch)])
-    for pipeline in (1, 0):
-        dev.set_option("pipeline", pipeline)
-        try:
-            assert np.array_equal(dev.poly_ntt_fwd(logn, moduli, x), want)
-            assert np.array_equal(dev.poly_intt(logn, moduli, want), want_i)
-        finally:
-            dev.set_option("pipeline", 0)
-    # a slab that starts 8 bytes off a 16-byte boundary takes the row-per-CTA path
+    assert np.array_equal(dev.poly_ntt_fwd(logn, moduli, x), want)
+    assert np.array_equal(dev.poly_intt(logn, moduli, want), want_i)
+    # a slab that starts 8 bytes off a 16-byte boundary
     m = np.ascontiguousarray(np.asarray(moduli, dtype=np.uint64))
     import ctypes as C
     p64 = C.POINTER(C.c_uint64)
@@ -135,10 +130,14 @@ def test_row_per_cta_kernels_agree_with_persistent_pipeline(dev, oracle, logn):
         dev._call("ntt_fwd_lazy", logn, m.ctypes.data_as(p64), m.size, d.ptr + 8, batch)
         got = np.empty_like(x)
         dev._call("slab_d2h", got.ctypes.data, d.ptr + 8, x.size)
+        dev._call("intt_lazy", logn, m.ctypes.data_as(p64), m.size, d.ptr + 8, batch, 0)
+        got_i = np.empty_like(x)
+        dev._call("slab_d2h", got_i.ctypes.data, d.ptr + 8, x.size)
         dev.synchronize()
     finally:
         d.free()
     assert np.array_equal(got, want)
+    assert np.array_equal(got_i, want_i)
 
 
 # ------------------------------------------------------------------ coefficient-wise kernels
