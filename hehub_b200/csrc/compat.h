@@ -23,6 +23,8 @@
     (::hbsim::launch((grid), (block), (smem), 1, [&]() { kern(__VA_ARGS__); }, (cluster)), cudaSuccess)
 inline void hb_cluster_sync() { ::hbsim::cluster_sync(); }
 inline void hb_syncwarp() { __syncthreads(); } // the emulator has no warps: a CTA barrier is a superset
+inline unsigned long long hb_ld_stream(const unsigned long long *p) { return *p; }
+inline ulonglong2 hb_ld_stream2(const unsigned long long *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
 template <class T>
 inline T hb_ldcg(const T *p) { return *p; }
 inline void hb_cp_async16(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 16); }
@@ -60,6 +62,22 @@ __device__ __forceinline__ void hb_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void hb_syncwarp() { __syncwarp(); }
+// row words are read once: keep them out of L1, which holds the twiddle tables
+#if defined(HB_NO_STREAM_LD) // A/B builds only
+__device__ __forceinline__ unsigned long long hb_ld_stream(const unsigned long long *p) { return *p; }
+__device__ __forceinline__ ulonglong2 hb_ld_stream2(const unsigned long long *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
+#else
+__device__ __forceinline__ unsigned long long hb_ld_stream(const unsigned long long *p) {
+    unsigned long long v;
+    asm("ld.global.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ ulonglong2 hb_ld_stream2(const unsigned long long *p) {
+    ulonglong2 v;
+    asm("ld.global.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+    return v;
+}
+#endif
 template <class T>
 __device__ __forceinline__ T hb_ldcg(const T *p) { return __ldcg(p); }
 // 16-byte asynchronous global -> shared copy (LDGSTS), bypassing L1: the words are streamed once

@@ -45,7 +45,7 @@ HB_D u64 io_load(const IO &io, int row, int i, const LimbConst &lc) {
 #if defined(HB_ABL_NOLOAD) // ablation builds only: synthesise the input words, no global reads
     return io.pre(row, i, (u64)i * 0x9E3779B97F4A7C15ull + (u64)row, lc);
 #else
-    return io.pre(row, i, io.src(row)[i], lc);
+    return io.pre(row, i, hb_ld_stream(io.src(row) + i), lc);
 #endif
 }
 
@@ -155,7 +155,7 @@ HB_D void warp_load(u64 *sm, const IO &io, const LimbConst &lc, int row, int fir
 #if defined(HB_ABL_NOLOAD)
             ulonglong2 v = make_ulonglong2((u64)i * 0x9E3779B97F4A7C15ull + (u64)row, (u64)i);
 #else
-            ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(g + 64 * k);
+            ulonglong2 v = hb_ld_stream2(g + 64 * k);
 #endif
             v.x = io.pre(row, i, v.x, lc);
             v.y = io.pre(row, i + 1, v.y, lc);
@@ -256,6 +256,9 @@ HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B)
 template <int LOGN, class IO>
 HB_GLOBAL(plan_for(LOGN).threads, plan_for(LOGN).min_blocks)
 ntt_fwd_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
+    // One row per CTA on purpose: resident CTAs walking several rows each (with or without a start
+    // skew between the CTAs of an SM) measured 15-20 % slower than letting the block scheduler hand
+    // out rows (profiles/r1_plan_sweep.md).
     constexpr NttPlan pl = plan_for(LOGN);
     constexpr int T = pl.threads;
     HB_SHARED_U64(sm);

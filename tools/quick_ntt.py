@@ -14,6 +14,7 @@ ap.add_argument("--nocheck", action="store_true")
 ap.add_argument("--pipeline", type=int, nargs="*", default=[0])  # kept for old logs; the option is gone
 ap.add_argument("--slab-mib", type=int, default=512)
 ap.add_argument("--reps", type=int, default=60)
+ap.add_argument("--persistent", type=int, nargs="*", default=[0])
 a = ap.parse_args()
 Q = 576460752272228353
 ctx = Context(lib_path=a.lib)
@@ -26,7 +27,7 @@ if not a.nocheck:
         for pipeline in a.pipeline:
             assert np.array_equal(ctx.ntt_fwd_lazy(logn, Q, x), y), "NTT mismatch"
             assert np.array_equal(ctx.intt_lazy(logn, Q, y), orc.intt_lazy(logn, Q, y)), "INTT mismatch"
-for pipeline in a.pipeline:
+for pipeline in a.persistent:
     for logn in a.logn:
         n, polys = 1 << logn, a.polys
         m, mp = _mod([Q])
@@ -46,6 +47,6 @@ for pipeline in a.pipeline:
             ctx.synchronize()
             dt = (time.perf_counter() - t0) / reps
             out.append(polys / dt)
-        print(f"{os.path.basename(a.lib):28s} pipeline={pipeline} N={n:6d} polys={polys} slabs={len(slabs)} ntt {out[0]:.3e}/s intt {out[1]:.3e}/s", flush=True)
+        print(f"{os.path.basename(a.lib):28s} persistent={pipeline} N={n:6d} polys={polys} slabs={len(slabs)} ntt {out[0]:.3e}/s intt {out[1]:.3e}/s", flush=True)
         for s in slabs: s.free()
 ctx.close()
