@@ -25,6 +25,8 @@ inline void hb_cluster_sync() { ::hbsim::cluster_sync(); }
 inline void hb_syncwarp() { __syncthreads(); } // the emulator has no warps: a CTA barrier is a superset
 inline unsigned long long hb_ld_stream(const unsigned long long *p) { return *p; }
 inline ulonglong2 hb_ld_stream2(const unsigned long long *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
+inline unsigned long long hb_ld_ro(const unsigned long long *p) { return *p; }
+inline ulonglong2 hb_ld_ro2(const unsigned long long *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
 template <class T>
 inline T hb_ldcg(const T *p) { return *p; }
 inline void hb_cp_async16(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 16); }
@@ -56,6 +58,18 @@ inline cudaError_t hb_launch_cluster(void (*kern)(KArgs...), unsigned grid, unsi
     cfg.attrs = at;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+// read-only operands that never alias the kernel's outputs (non-coherent path: the compiler may
+// hoist these above stores), read once: no L1 allocation
+__device__ __forceinline__ unsigned long long hb_ld_ro(const unsigned long long *p) {
+    unsigned long long v;
+    asm("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ ulonglong2 hb_ld_ro2(const unsigned long long *p) {
+    ulonglong2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+    return v;
 }
 // barrier over the thread-block cluster with release/acquire ordering of global and shared writes
 __device__ __forceinline__ void hb_cluster_sync() {

@@ -21,7 +21,19 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 // ------------------------------------------------------------------------------------------
 // tensor product: one pass, 4 loads + 3 stores per coefficient
 // ------------------------------------------------------------------------------------------
-HB_GLOBAL(256, 1)
+#ifndef HB_TENSOR_MINB
+#define HB_TENSOR_MINB 4
+#endif
+#ifndef HB_MAC_MINB
+#define HB_MAC_MINB 3
+#endif
+#ifndef HB_MAC_U
+#define HB_MAC_U 2
+#endif
+#ifndef HB_MAC_CPT
+#define HB_MAC_CPT 2
+#endif
+HB_GLOBAL(256, HB_TENSOR_MINB)
 tensor_kernel(const u64 *__restrict__ ct1, const u64 *__restrict__ ct2, u64 *__restrict__ quad,
               const LimbConst *__restrict__ limbs, int L, int logn, size_t pairs_total) {
     // one thread per pair of adjacent coefficients of one (ct, limb)
@@ -124,77 +136,99 @@ struct ExtFanoutIO {
 };
 
 // step 3: out[b][h][k][i] = Mont128_{q_k}( sum_p dec[p][k][i] * key[p][h][k][i] )   rgsw.cpp:126-153
-// One thread owns two adjacent coefficients of one (ciphertext, limb): 128-bit loads, the L rows
-// consumed four at a time so a dozen independent loads are in flight before the multiplies start.
 // The sum is exact in 128 bits and reduced once, like the reference (reducing per term would
-// change the representative).
-HB_GLOBAL(256, 1)
+// change the representative).  One thread owns W adjacent coefficients (W = 2: 128-bit accesses;
+// W = 1 for slabs that are only 8-byte aligned) of one limb of CPT consecutive ciphertexts, so a
+// key word fetched from L2 feeds CPT products: the key stream (2 L (L+1) N words per ciphertext,
+// more than every other operand together) is what bounds this kernel.
+template <int W>
+HB_D void ld_words(u64 (&dst)[W], const u64 *p, bool read_only) {
+    if constexpr (W == 2) {
+        const ulonglong2 v = read_only ? __ldg(reinterpret_cast<const ulonglong2 *>(p)) : hb_ld_stream2(p);
+        dst[0] = v.x;
+        dst[1] = v.y;
+    } else {
+        dst[0] = read_only ? __ldg(p) : hb_ld_stream(p);
+    }
+}
+template <int W>
+HB_D void st_words(u64 *p, const u64 (&src)[W]) {
+    if constexpr (W == 2) *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(src[0], src[1]);
+    else p[0] = src[0];
+}
+
+template <int CPT, int W>
+HB_GLOBAL(256, HB_MAC_MINB)
 ext_mac_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
-               u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, int logn, size_t total_pairs) {
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // (b, k, i / 2)
-    if (gid >= total_pairs) return;
+               u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, int logn, size_t batch, size_t total) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // (b / CPT, k, i / W)
+    if (gid >= total) return;
     const int L1 = L + 1;
-    const size_t i = (gid & (((size_t)1 << (logn - 1)) - 1)) * 2;
-    const size_t bk = gid >> (logn - 1);
+    constexpr int LW = (W == 2) ? 1 : 0;
+    const size_t i = (gid & (((size_t)1 << (logn - LW)) - 1)) * W;
+    const size_t bk = gid >> (logn - LW);
     const int k = (int)(bk % L1);
-    const size_t b = bk / L1;
+    const size_t b0 = (bk / L1) * CPT;
     const LimbConst lc = limbs[k];
-    u64 lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0}; // [half][coefficient]
-    const u64 *const in_b = in + b * in_batch_stride + i;
-    const u64 *const dec_b = dec + (((size_t)b * L * L1 + k) << logn) + i;
+    u64 lo[CPT][2][W], hi[CPT][2][W];
+#pragma unroll
+    for (int c = 0; c < CPT; c++)
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int w = 0; w < W; w++) lo[c][h][w] = hi[c][h][w] = 0;
+    const size_t dec_ct = ((size_t)L * L1) << logn, dec_row = (size_t)L1 << logn;
+    const size_t key_row = (size_t)(2 * L1) << logn, key_half = (size_t)L1 << logn;
+    const u64 *const dec_k = dec + b0 * dec_ct + ((size_t)k << logn) + i;
+    const u64 *const in_b = in + b0 * in_batch_stride + i;
     const u64 *const key_k = key + ((size_t)k << logn) + i;
-    const size_t dec_row = (size_t)L1 << logn, key_row = (size_t)(2 * L1) << logn, key_half = (size_t)L1 << logn;
-    constexpr int U = 4;
+    constexpr int U = HB_MAC_U;
     for (int p0 = 0; p0 < L; p0 += U) {
-        ulonglong2 d[U], k0[U], k1[U];
+        u64 d[U][CPT][W], k0[U][W], k1[U][W];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int p = p0 + u;
             if (p < L) {
-                const u64 *src = (p == k) ? in_b + ((size_t)p << logn) : dec_b + p * dec_row; // the diagonal keeps in[p], rgsw.cpp:99-101
-                d[u] = *reinterpret_cast<const ulonglong2 *>(src);
-                k0[u] = __ldg(reinterpret_cast<const ulonglong2 *>(key_k + p * key_row));
-                k1[u] = __ldg(reinterpret_cast<const ulonglong2 *>(key_k + p * key_row + key_half));
+                ld_words<W>(k0[u], key_k + p * key_row, true);
+                ld_words<W>(k1[u], key_k + p * key_row + key_half, true);
+#pragma unroll
+                for (int c = 0; c < CPT; c++) {
+                    if (b0 + c < batch) { // the diagonal keeps in[p], rgsw.cpp:99-101
+                        const u64 *src = (p == k) ? in_b + c * in_batch_stride + ((size_t)p << logn) : dec_k + c * dec_ct + p * dec_row;
+                        ld_words<W>(d[u][c], src, false);
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < W; w++) d[u][c][w] = 0;
+                    }
+                }
             }
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             if (p0 + u < L) {
-                mac128(lo[0], hi[0], d[u].x, k0[u].x);
-                mac128(lo[1], hi[1], d[u].y, k0[u].y);
-                mac128(lo[2], hi[2], d[u].x, k1[u].x);
-                mac128(lo[3], hi[3], d[u].y, k1[u].y);
+#pragma unroll
+                for (int c = 0; c < CPT; c++)
+#pragma unroll
+                    for (int w = 0; w < W; w++) {
+                        mac128(lo[c][0][w], hi[c][0][w], d[u][c][w], k0[u][w]);
+                        mac128(lo[c][1][w], hi[c][1][w], d[u][c][w], k1[u][w]);
+                    }
             }
         }
     }
-    u64 *const o = out + (((b * 2) * L1 + k) << logn) + i;
-    *reinterpret_cast<ulonglong2 *>(o) = make_ulonglong2(montgomery128(lo[0], hi[0], lc), montgomery128(lo[1], hi[1], lc));
-    *reinterpret_cast<ulonglong2 *>(o + key_half) = make_ulonglong2(montgomery128(lo[2], hi[2], lc), montgomery128(lo[3], hi[3], lc));
-}
-
-// unaligned operands (a slab that starts 8 bytes off a 16-byte boundary): one coefficient per thread
-HB_GLOBAL(256, 1)
-ext_mac_scalar_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
-                      u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, int logn, size_t total) {
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // (b, k, i)
-    if (gid >= total) return;
-    const int L1 = L + 1;
-    const size_t i = gid & (((size_t)1 << logn) - 1);
-    const size_t bk = gid >> logn;
-    const int k = (int)(bk % L1);
-    const size_t b = bk / L1;
-    const LimbConst lc = limbs[k];
-    u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
-    for (int p = 0; p < L; p++) {
-        const u64 d = (p == k) ? in[b * in_batch_stride + ((size_t)p << logn) + i]
-                               : dec[((size_t)((b * L + p) * L1 + k) << logn) + i];
-        const size_t kb = ((size_t)(p * 2) * L1 + k) << logn; // key[p][0][k]
-        mac128(lo0, hi0, d, __ldg(key + kb + i));
-        mac128(lo1, hi1, d, __ldg(key + kb + ((size_t)L1 << logn) + i));
+#pragma unroll
+    for (int c = 0; c < CPT; c++) {
+        if (b0 + c < batch) {
+            u64 *const o = out + ((((b0 + c) * 2) * L1 + k) << logn) + i;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                u64 r[W];
+#pragma unroll
+                for (int w = 0; w < W; w++) r[w] = montgomery128(lo[c][h][w], hi[c][h][w], lc);
+                st_words<W>(o + h * key_half, r);
+            }
+        }
     }
-    const size_t ob = ((b * 2) * L1 + k) << logn;
-    out[ob + i] = montgomery128(lo0, hi0, lc);
-    out[ob + ((size_t)L1 << logn) + i] = montgomery128(lo1, hi1, lc);
 }
 
 // one wave of at most `wave` ciphertexts; scratch slots 0 (c) and 1 (dec)
@@ -207,14 +241,16 @@ static int ext_prod_wave(Context &c, unsigned logn, const LimbConst *limbs, size
     ExtFanoutIO io2{cbuf, dec, (int)L, (int)logn, aligned16(cbuf) && aligned16(dec)};
     e = launch_ntt(true, c.env(), logn, io2, limbs, (int)(batch * L * L));
     if (e != cudaSuccess) return c.cuda_fail(e, "ext_prod: ntt launch");
+    constexpr int CPT = HB_MAC_CPT;
+    const size_t groups = (batch + CPT - 1) / CPT;
     if (aligned16(in) && in_batch_stride % 2 == 0 && aligned16(dec) && aligned16(key) && aligned16(out) && n >= 2) {
-        const size_t total = batch * (L + 1) * (n / 2);
-        HB_LAUNCH(ext_mac_kernel, (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, in_batch_stride, dec, key, out, limbs,
-                  (int)L, (int)logn, total);
+        const size_t total = groups * (L + 1) * (n / 2);
+        HB_LAUNCH((ext_mac_kernel<CPT, 2>), (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, in_batch_stride, dec, key, out,
+                  limbs, (int)L, (int)logn, batch, total);
     } else {
-        const size_t total = batch * (L + 1) * n;
-        HB_LAUNCH(ext_mac_scalar_kernel, (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, in_batch_stride, dec, key, out,
-                  limbs, (int)L, (int)logn, total);
+        const size_t total = groups * (L + 1) * n;
+        HB_LAUNCH((ext_mac_kernel<CPT, 1>), (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, in_batch_stride, dec, key, out,
+                  limbs, (int)L, (int)logn, batch, total);
     }
     c.stats.launches++;
     e = cudaGetLastError();
@@ -305,10 +341,10 @@ struct DropFwdIO {
     HB_D void store(int row, int i, u64 v, const LimbConst &lc) const {
         const int poly = row / (L - 1), k = row - poly * (L - 1);
         const DropConst *d = dc + k;
-        u64 x = finish(ct[((size_t)(poly * L + k) << logn) + i], v, d, lc);
+        u64 x = finish(hb_ld_ro(ct + ((size_t)(poly * L + k) << logn) + i), v, d, lc);
         const int h = poly & 1, b = poly >> 1;
         if (h < add_halves) // ckks/arith.cpp:70-71, 84, 91
-            x = add_lazy(x, addend[(size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn) + i], lc.q2);
+            x = add_lazy(x, hb_ld_ro(addend + (size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn) + i), lc.q2);
         out[((size_t)row << logn) + i] = x;
     }
     HB_D u64 finish(u64 x, u64 v, const DropConst *d, const LimbConst &lc) const {
@@ -320,12 +356,11 @@ struct DropFwdIO {
     HB_D void store2(int row, int i, u64 v0, u64 v1, const LimbConst &lc) const {
         const int poly = row / (L - 1), k = row - poly * (L - 1);
         const DropConst *d = dc + k;
-        const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(ct + ((size_t)(poly * L + k) << logn) + i);
+        const ulonglong2 x = hb_ld_ro2(ct + ((size_t)(poly * L + k) << logn) + i);
         ulonglong2 r = make_ulonglong2(finish(x.x, v0, d, lc), finish(x.y, v1, d, lc));
         const int h = poly & 1, b = poly >> 1;
         if (h < add_halves) { // ckks/arith.cpp:70-71, 84, 91
-            const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(
-                addend + (size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn) + i);
+            const ulonglong2 a = hb_ld_ro2(addend + (size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn) + i);
             r.x = add_lazy(r.x, a.x, lc.q2);
             r.y = add_lazy(r.y, a.y, lc.q2);
         }

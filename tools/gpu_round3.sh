@@ -6,7 +6,6 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.csv 2>&1
 echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "rc=$?"; tail -4 $OUT/pytest_gpu.log
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "rc=$?"; tail -2 $OUT/smoke.log
-echo "== e2e chunk sweep"; timeout 300 python tools/e2e_sweep.py 2>&1 | tee $OUT/e2e_sweep.log
 echo "== bench"; timeout 1200 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "rc=$?"; tail -3 $OUT/bench.err
 echo "== bench reference"; timeout 300 python bench.py --impl reference --steps 10 --warmup 2 > $OUT/bench_ref.json 2>&1; tail -c 400 $OUT/bench_ref.json
 echo "== ncu launch list"
@@ -15,6 +14,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 echo "== ncu full (ntt fwd N=4096)"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ntt_fwd_fast_kernel -s 3 -c 1 -o $OUT/prof_ntt_fwd -f \
     python bench.py --steps 3 --warmup 3 --no-cpu --extras 0 > $OUT/ncu_full.log 2>&1; echo "rc=$?"
+echo "== ncu full (key-switch MAC, drop-last forward, tensor; C3 shapes)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"ext_mac_kernel|tensor_kernel|DropFwdIO|ExtFanoutIO" -s 12 -c 4 -o $OUT/prof_c3 -f \
+    python bench.py --steps 3 --warmup 3 --no-cpu --sweep-cts 0 > $OUT/ncu_c3.log 2>&1; echo "rc=$?"
+ncu -i $OUT/prof_c3.ncu-rep --page raw --csv > $OUT/raw_c3.csv 2>/dev/null
 ncu -i $OUT/prof_ntt_fwd.ncu-rep --page raw --csv > $OUT/raw.csv 2>/dev/null
 ncu -i $OUT/prof_ntt_fwd.ncu-rep --page source --csv > $OUT/src.csv 2>/dev/null
 python - <<PY

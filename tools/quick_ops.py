@@ -1,0 +1,44 @@
+"""Quick timing of the scheme-level ops for one library build (host-timed, device-resident operands).
+usage: python tools/quick_ops.py <lib.so> [--shape c3|c4|c5]"""
+import argparse, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from hehub_b200.binding import Context, _mod
+from oracle.binding import Oracle
+ap = argparse.ArgumentParser()
+ap.add_argument("lib")
+ap.add_argument("--shape", nargs="*", default=["c3"])
+a = ap.parse_args()
+SHAPES = {"c3": (13, [40, 30, 30, 30], 40, 256), "c4": (14, [50] + [40] * 7, 50, 128), "c5": (15, [50] * 12, 55, 16)}
+orc = Oracle()
+ctx = Context(lib_path=a.lib)
+for name in a.shape:
+    logn, bits, pbits, batch = SHAPES[name]
+    mods, p = orc.ckks_pick_moduli(bits, pbits)
+    mods = [int(m) for m in mods]; ext = mods + [int(p)]
+    L, n = len(mods), 1 << logn
+    em, ep = _mod(ext); mm, mp = _mod(mods)
+    key = ctx.slab(L * 2 * (L + 1) * n); ct1 = ctx.slab(batch * 2 * L * n); ct2 = ctx.slab(batch * 2 * L * n)
+    res = ctx.slab(batch * 2 * L * n); quad = ctx.slab(batch * 3 * L * n); ext_out = ctx.slab(batch * 2 * (L + 1) * n)
+    ctx._call("lcg_fill", n, ep, L + 1, key.ptr, L * 2 * (L + 1), 1000, 1)
+    ctx._call("lcg_fill", n, mp, L, ct1.ptr, batch * 2 * L, 100, 1)
+    ctx._call("lcg_fill", n, mp, L, ct2.ptr, batch * 2 * L, 200, 1)
+    ops = {
+        "tensor": lambda: ctx._call("ckks_tensor", logn, mp, L, ct1.ptr, ct2.ptr, quad.ptr, batch),
+        "ext_prod": lambda: ctx._call("ext_prod_montgomery", logn, ep, L, ct1.ptr, key.ptr, ext_out.ptr, batch),
+        "rescale": lambda: ctx._call("ckks_rescale", logn, mp, L, ct1.ptr, res.ptr, batch),
+        "mult_relin": lambda: ctx._call("ckks_mult_relin", logn, ep, L, ct1.ptr, ct2.ptr, key.ptr, res.ptr, batch),
+    }
+    out = []
+    for k, fn in ops.items():
+        for _ in range(3): fn()
+        ctx.synchronize()
+        reps = 20
+        t0 = time.perf_counter()
+        for _ in range(reps): fn()
+        ctx.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        out.append(f"{k} {dt * 1e6 / batch:.3f} us/ct")
+    print(f"{os.path.basename(a.lib):26s} {name}: " + " | ".join(out), flush=True)
+    for s in (key, ct1, ct2, res, quad, ext_out): s.free()
+ctx.close()
