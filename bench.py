@@ -285,9 +285,11 @@ def run_cuda(args):
 
     # ---- extras: the other BASELINE configs -------------------------------------------------------
     extras = {}
+    if args.extras and args.rows:
+        extras["rows_c3_shape"] = run_rows(ctx, torch, timed, world, rank, peaks, cpu_ok=(rank == 0 and world == 1 and not args.no_cpu))
     if args.extras:
-        extras = run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist if world > 1 else None, args.sweep_cts,
-                            cpu_ok=(rank == 0 and world == 1 and not args.no_cpu))
+        extras.update(run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist if world > 1 else None, args.sweep_cts,
+                                 cpu_ok=(rank == 0 and world == 1 and not args.no_cpu)))
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------------
     cpu = None
@@ -496,6 +498,152 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
     return out
 
 
+def run_rows(ctx, torch, timed, world, rank, peaks, cpu_ok):
+    """One line per SURVEY §8(a) row: the C-ABI entry point timed on the device (CUDA events, operands
+    resident in HBM and larger than L2 for the coefficient-wise rows) and the reference's CPU function
+    for the same row timed beside it on one host core (bounded sample).  Shape: BASELINE config C3
+    (N = 8192, L = 4, {40,30,30,30}+P40)."""
+    import ctypes as C
+    import numpy as np
+    from hehub_b200.binding import _mod
+    from oracle.binding import Oracle, build_oracle
+    build_oracle()
+    orc = Oracle()
+    hbm = peaks["hbm_gbs"]
+    logn, n = 13, 8192
+    mods, p = orc.ckks_pick_moduli([40, 30, 30, 30], 40)
+    mods = [int(m) for m in mods]
+    ext = mods + [int(p)]
+    L = len(mods)
+    mm, mp = _mod(mods)
+    em, ep = _mod(ext)
+    t_plain = 65537
+    EW, CT = 512, 256  # polynomials per launch (coefficient-wise rows: 3 x 128 MiB operands), ciphertexts per launch
+    u64p = C.POINTER(C.c_uint64)
+
+    def buf(words):
+        return torch.empty(words, dtype=torch.int64, device="cuda")
+
+    # two operand sets visited alternately: 2 x 3 x 128 MiB, so a launch never finds its operands in the 126 MB L2
+    sets = []
+    for s_ in range(2):
+        a_, b_, c_ = buf(EW * L * n), buf(EW * L * n), buf(EW * L * n)
+        ctx._call("lcg_fill", n, mp, L, a_.data_ptr(), EW * L, 11 + rank + 1000 * s_, 1)
+        ctx._call("lcg_fill", n, mp, L, b_.data_ptr(), EW * L, 77 + rank + 1000 * s_, 1)
+        ctx._call("lcg_fill", n, mp, L, c_.data_ptr(), EW * L, 99 + rank + 1000 * s_, 1)
+        sets.append((a_, b_, c_))
+    A = lambda i: sets[i & 1][0].data_ptr()
+    B = lambda i: sets[i & 1][1].data_ptr()
+    Cc = lambda i: sets[i & 1][2].data_ptr()
+    pairs = buf(2 * EW * n)  # (lo, hi) pairs for montgomery128
+    ctx._call("lcg_fill", 2 * EW * n, mp, 1, pairs.data_ptr(), 1, 5, 1)
+    key = buf(L * 2 * (L + 1) * n)
+    ctx._call("lcg_fill", n, ep, L + 1, key.data_ptr(), L * 2 * (L + 1), 1000, 1)
+    ct1, ct2, res = buf(CT * 2 * L * n), buf(CT * 2 * L * n), buf(CT * 2 * L * n)
+    ctx._call("lcg_fill", n, mp, L, ct1.data_ptr(), CT * 2 * L, 100, 1)
+    ctx._call("lcg_fill", n, mp, L, ct2.data_ptr(), CT * 2 * L, 200, 1)
+    quad, extout = buf(CT * 3 * L * n), buf(CT * 2 * (L + 1) * n)
+    scal = np.array([3, 5, 7, 11], dtype=np.uint64)
+    ctx._call("ckks_tensor", logn, mp, L, ct1.data_ptr(), ct2.data_ptr(), quad.data_ptr(), CT)
+    ctx.synchronize()
+
+    W = EW * L * n  # words per coefficient-wise operand
+    gpu = {  # row: (call, units per launch, algorithmic bytes per unit, unit name)
+        "a3 ntt_negacyclic_inplace_lazy (poly, L limbs)": (lambda i: ctx._call("ntt_fwd_lazy", logn, mp, L, A(i), EW), EW, 16 * L * n, "poly"),
+        "a4 intt_negacyclic_inplace_lazy (poly, L limbs)": (lambda i: ctx._call("intt_lazy", logn, mp, L, A(i), EW, 0), EW, 16 * L * n, "poly"),
+        "a5 batched_mul_mod_hybrid_lazy": (lambda i: ctx._call("mulmod_hybrid_lazy", n, mp, L, A(i), B(i), Cc(i), EW), W, 24, "word"),
+        "a6 operator+= (lazy add)": (lambda i: ctx._call("add_lazy", n, mp, L, Cc(i), B(i), EW), W, 24, "word"),
+        "a6 operator-= (lazy sub)": (lambda i: ctx._call("sub_lazy", n, mp, L, Cc(i), B(i), EW), W, 24, "word"),
+        "a6 operator*= (scalar)": (lambda i: ctx._call("mul_scalar_lazy", n, mp, L, Cc(i), scal.ctypes.data_as(u64p), EW), W, 16, "word"),
+        "a6 batched_reduce_strict": (lambda i: ctx._call("reduce_strict", n, mp, L, Cc(i), EW), W, 16, "word"),
+        "a7 batched_barrett_lazy": (lambda i: ctx._call("barrett_lazy", n, mp, L, Cc(i), EW), W, 16, "word"),
+        "a8 batched_montgomery_128_lazy": (lambda i: ctx._call("montgomery128_lazy", mods[0], EW * n, pairs.data_ptr(), Cc(i)), EW * n, 24, "word"),
+        "a9 ckks::mult_low_level": (lambda i: ctx._call("ckks_tensor", logn, mp, L, ct1.data_ptr(), ct2.data_ptr(), quad.data_ptr(), CT), CT, 56 * L * n, "ct"),
+        "a10 ext_prod_montgomery": (lambda i: ctx._call("ext_prod_montgomery", logn, ep, L, ct1.data_ptr(), key.data_ptr(), extout.data_ptr(), CT), CT, 8 * n * (L + 2 * (L + 1)), "poly"),
+        "a11 ckks::rescale_inplace": (lambda i: ctx._call("ckks_rescale", logn, mp, L, ct1.data_ptr(), res.data_ptr(), CT), CT, 16 * n * (2 * L - 1), "ct"),
+        "a12 bgv::mod_switch_inplace": (lambda i: ctx._call("bgv_mod_switch", logn, mp, L, t_plain, ct1.data_ptr(), res.data_ptr(), CT), CT, 16 * n * (2 * L - 1), "ct"),
+        "a13 ckks::relinearize": (lambda i: ctx._call("ckks_relinearize", logn, ep, L, quad.data_ptr(), key.data_ptr(), res.data_ptr(), CT), CT, 40 * L * n, "ct"),
+        "a13 ckks::mult (tensor + relinearize)": (lambda i: ctx._call("ckks_mult_relin", logn, ep, L, ct1.data_ptr(), ct2.data_ptr(), key.data_ptr(), res.data_ptr(), CT), CT, 48 * L * n, "ct"),
+        "f1 ckks::rotate": (lambda i: ctx._call("ckks_rotate", logn, ep, L, ct1.data_ptr(), key.data_ptr(), 1, res.data_ptr(), CT), CT, 32 * L * n, "ct"),
+    }
+    out = {}
+    for name, (fn, units, bytes_per_unit, unit) in gpu.items():
+        el = timed(fn, 6, 3) / 6
+        gbs = units * bytes_per_unit / el / 1e9
+        out[name] = {"unit": unit, "gpu_per_s": world * units / el, "us_per_launch": el * 1e6, "units_per_launch": units,
+                     "algorithmic_bytes_per_unit": bytes_per_unit, "gbs_algorithmic": gbs, "frac_hbm": gbs / hbm}
+    if cpu_ok:
+        rows_cpu(out, logn, mods, ext, key.cpu().numpy().view(np.uint64).reshape(L, 2, L + 1, n), t_plain, world)
+    return {"shape": {"N": n, "L": L, "moduli_bits": [40, 30, 30, 30], "special_bits": 40},
+            "note": "gpu: device-resident operands, CUDA-event time; cpu: the reference's function on one host core, same shape", "rows": out}
+
+
+def rows_cpu(out, logn, mods, ext, hkey, t_plain, world=1, budget_s=0.4):
+    """The reference's own functions for the rows of run_rows, one host core, bounded samples."""
+    import ctypes as C
+    import numpy as np
+    u64p = C.POINTER(C.c_uint64)
+    n, L = 1 << logn, len(mods)
+    lib, kind = _cpu_lib()
+    rng = np.random.default_rng(3)
+    ha = np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in mods])   # one polynomial [L][N]
+    hb_ = np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in mods])
+    hc1 = np.stack([ha, hb_])                                              # one ciphertext [2][L][N]
+    hc2 = np.stack([hb_, ha])
+    hquad = lib.ckks_tensor(logn, mods, hc1, hc2)
+    hpairs = rng.integers(0, mods[0], 2 * n, dtype=np.uint64)
+    word = lambda name, *sig: lib._fn(name, None, *sig)
+    f_bar = word("barrett_lazy", C.c_uint64, C.c_size_t, u64p)
+    f_str = word("reduce_strict", C.c_uint64, C.c_size_t, u64p)
+    f_hyb = word("mul_hybrid_lazy", C.c_uint64, C.c_size_t, u64p, u64p, u64p)
+    f_mont = word("montgomery128_lazy", C.c_uint64, C.c_size_t, u64p, u64p)
+    wa, wb, wc = ha.copy(), hb_.copy(), np.empty_like(ha)
+    ptr = lambda arr, k=None: (arr[k] if k is not None else arr).ctypes.data_as(u64p)
+    mod_arr = np.array(mods, dtype=np.uint64)
+
+    def per_limb(f):
+        def run():
+            for k, q in enumerate(mods):
+                f(k, q)
+        return run
+
+    cpu = {
+        "a3 ntt_negacyclic_inplace_lazy (poly, L limbs)": (lambda: lib.poly_ntt_fwd(logn, mods, ha), 1),
+        "a4 intt_negacyclic_inplace_lazy (poly, L limbs)": (lambda: lib.poly_intt(logn, mods, ha), 1),
+        "a5 batched_mul_mod_hybrid_lazy": (per_limb(lambda k, q: f_hyb(q, n, ptr(wa, k), ptr(wb, k), ptr(wc, k))), L * n),
+        "a7 batched_barrett_lazy": (per_limb(lambda k, q: f_bar(q, n, ptr(wc, k))), L * n),
+        "a6 batched_reduce_strict": (per_limb(lambda k, q: f_str(q, n, ptr(wc, k))), L * n),
+        "a8 batched_montgomery_128_lazy": (lambda: f_mont(mods[0], n, ptr(hpairs), ptr(wc, 0)), n),
+        "a9 ckks::mult_low_level": (lambda: lib.ckks_tensor(logn, mods, hc1, hc2), 1),
+        "a10 ext_prod_montgomery": (lambda: lib.ext_prod(logn, ext, ha, hkey), 1),
+        "a11 ckks::rescale_inplace": (lambda: lib.ckks_rescale(logn, mods, hc1), 1),
+        "a12 bgv::mod_switch_inplace": (lambda: lib.bgv_mod_switch(logn, mods, t_plain, hc1), 1),
+        "a13 ckks::relinearize": (lambda: lib.ckks_relinearize(logn, ext, hquad, hkey), 1),
+        "a13 ckks::mult (tensor + relinearize)": (lambda: lib.ckks_mult_relin(logn, ext, hc1, hc2, hkey), 1),
+        "f1 ckks::rotate": (lambda: lib.ckks_rotate(logn, ext, hc1, hkey, 1), 1),
+    }
+    if kind == "reference":  # the reference's RnsPolynomial operators (rns.cpp:58-171) through the shim
+        f_add = lib._fn("poly_add", C.c_int, C.c_uint, C.c_size_t, u64p, u64p, u64p)
+        f_sub = lib._fn("poly_sub", C.c_int, C.c_uint, C.c_size_t, u64p, u64p, u64p)
+        f_scl = lib._fn("poly_mul_scalar", C.c_int, C.c_uint, C.c_size_t, u64p, u64p, C.c_uint64)
+        cpu["a6 operator+= (lazy add)"] = (lambda: f_add(logn, L, ptr(mod_arr), ptr(wa), ptr(wb)), L * n)
+        cpu["a6 operator-= (lazy sub)"] = (lambda: f_sub(logn, L, ptr(mod_arr), ptr(wa), ptr(wb)), L * n)
+        cpu["a6 operator*= (scalar)"] = (lambda: f_scl(logn, L, ptr(mod_arr), ptr(wa), 3), L * n)
+    for name, (fn, units) in cpu.items():
+        fn()
+        reps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < budget_s:
+            fn()
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        r = out.setdefault(name, {"unit": "?", "gpu_per_s": float("nan")})
+        r["cpu_per_s"] = units / dt
+        r["cpu_cores"] = 1
+        r["cpu_kind"] = kind
+        r["cpu_sample"] = f"{reps} calls of {units} {r['unit']}(s)"
+        r["gpu_over_one_core"] = r["gpu_per_s"] / world / r["cpu_per_s"]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -504,6 +652,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--extras", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--rows", type=int, default=1, help="0: skip the per-row table (SURVEY 8(a) rows, GPU and CPU side by side)")
     ap.add_argument("--sweep-cts", type=int, default=2048,
                     help="ciphertext pairs in the config-5 sweep extra, whole job (BASELINE: 65536; 0 disables)")
     args = ap.parse_args()
