@@ -565,6 +565,10 @@ def run_rows(ctx, torch, timed, world, rank, peaks, cpu_ok):
         "a13 ckks::relinearize": (lambda i: ctx._call("ckks_relinearize", logn, ep, L, quad.data_ptr(), key.data_ptr(), res.data_ptr(), CT), CT, 40 * L * n, "ct"),
         "a13 ckks::mult (tensor + relinearize)": (lambda i: ctx._call("ckks_mult_relin", logn, ep, L, ct1.data_ptr(), ct2.data_ptr(), key.data_ptr(), res.data_ptr(), CT), CT, 48 * L * n, "ct"),
         "f1 ckks::rotate": (lambda i: ctx._call("ckks_rotate", logn, ep, L, ct1.data_ptr(), key.data_ptr(), 1, res.data_ptr(), CT), CT, 32 * L * n, "ct"),
+        # sk = one polynomial of the key slab; plaintexts / masks / errors = halves of the ciphertext slabs
+        "f3 decrypt_core": (lambda i: ctx._call("rlwe_decrypt_core", logn, mp, L, ct1.data_ptr(), key.data_ptr(), res.data_ptr(), CT), CT, 24 * L * n, "ct"),
+        "f3 encrypt_core (samples supplied)": (lambda i: ctx._call("rlwe_encrypt_core", logn, mp, L, ct1.data_ptr(), key.data_ptr(), ct2.data_ptr(),
+                                                                    ct2.data_ptr() + 8 * CT * L * n, res.data_ptr(), CT), CT, 40 * L * n, "ct"),
     }
     out = {}
     for name, (fn, units, bytes_per_unit, unit) in gpu.items():
@@ -621,6 +625,8 @@ def rows_cpu(out, logn, mods, ext, hkey, t_plain, world=1, budget_s=0.4):
         "a13 ckks::relinearize": (lambda: lib.ckks_relinearize(logn, ext, hquad, hkey), 1),
         "a13 ckks::mult (tensor + relinearize)": (lambda: lib.ckks_mult_relin(logn, ext, hc1, hc2, hkey), 1),
         "f1 ckks::rotate": (lambda: lib.ckks_rotate(logn, ext, hc1, hkey, 1), 1),
+        "f3 decrypt_core": (lambda: lib.rlwe_decrypt_core(logn, mods, hc1, ha), 1),
+        "f3 encrypt_core (samples supplied)": (lambda: lib.rlwe_encrypt_core(logn, mods, ha, hb_, hc2[0], hc2[1]), 1),
     }
     if kind == "reference":  # the reference's RnsPolynomial operators (rns.cpp:58-171) through the shim
         f_add = lib._fn("poly_add", C.c_int, C.c_uint, C.c_size_t, u64p, u64p, u64p)

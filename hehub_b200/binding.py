@@ -69,6 +69,8 @@ _SIGS = {
     "ckks_mult_relin": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, sz],
     "ckks_rotate": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, sz, C.c_void_p, sz],
     "ckks_conjugate": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, C.c_void_p, sz],
+    "rlwe_decrypt_core": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, C.c_void_p, sz],
+    "rlwe_encrypt_core": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, sz],
     "lcg_fill": [sz, p64, sz, C.c_void_p, sz, u64, u64],
     "ntt_host": [C.c_int, C.c_uint, p64, sz, C.c_void_p, C.c_void_p, sz, C.c_int],
     "ckks_mult_relin_host": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, sz],
@@ -400,6 +402,33 @@ class Context:
         L, n = len(ext_moduli) - 1, 1 << logn
         ct, batch = self._batch_of(ct, (2, L, n))
         return self._op("ckks_conjugate", logn, ext_moduli, [ct, key], ct.shape, L, batch=batch)
+
+    def rlwe_decrypt_core(self, logn, moduli, ct, sk):
+        L, n = len(moduli), 1 << logn
+        ct, batch = self._batch_of(ct, (2, L, n))
+        m, mp = _mod(moduli)
+        dct, dsk, out = self.to_device(ct), self.to_device(sk), self.slab(batch * L * n)
+        try:
+            self._call("rlwe_decrypt_core", logn, mp, L, dct.ptr, dsk.ptr, out.ptr, batch)
+            return out.download(ct.shape[:-3] + (L, n))
+        finally:
+            dct.free()
+            dsk.free()
+            out.free()
+
+    def rlwe_encrypt_core(self, logn, moduli, pt, sk, c1, e):
+        L, n = len(moduli), 1 << logn
+        pt, batch = self._batch_of(pt, (L, n))
+        m, mp = _mod(moduli)
+        d = [self.to_device(a) for a in (pt, sk, c1, e)]
+        out = self.slab(batch * 2 * L * n)
+        try:
+            self._call("rlwe_encrypt_core", logn, mp, L, d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, out.ptr, batch)
+            return out.download(pt.shape[:-2] + (2, L, n))
+        finally:
+            for x in d:
+                x.free()
+            out.free()
 
     def galois_cycle(self, logn, poly, step):
         poly = _arr(poly)

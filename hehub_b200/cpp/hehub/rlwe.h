@@ -33,4 +33,17 @@ inline RlwePt decrypt_core(const RlweCt &ct, const RlweSk &sk) {
     return pt;
 }
 
+/// rlwe.cpp:34-61 with the samples supplied by the caller: the reference draws `mask` (uniform, NTT
+/// form) and `error` (small coefficients, coefficient form) from a process-global RNG
+/// (sampling.cpp:12-69), which this back end does not replicate.  Same statements, same operators.
+inline RlweCt encrypt_core(const RlwePt &pt, const RlweSk &sk, const RnsPolynomial &mask, RnsPolynomial error) {
+    if (pt.rep_form == PolyRepForm::value) throw std::invalid_argument("Plaintext not in coeff representation."); // rlwe.cpp:51-53
+    ntt_negacyclic_inplace_lazy(error);                                   // sampling.cpp:66
+    auto c0 = error - mask * static_cast<const RnsPolynomial &>(sk);      // rlwe.cpp:50
+    auto pt_ntt(pt);
+    ntt_negacyclic_inplace_lazy(pt_ntt);                                  // rlwe.cpp:54-55
+    c0 += pt_ntt;                                                         // rlwe.cpp:58
+    return RlweCt{std::move(c0), mask};
+}
+
 } // namespace hehub

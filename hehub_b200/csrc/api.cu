@@ -562,6 +562,21 @@ int hehub_b200_ckks_mult_relin(hehub_b200_ctx *ctx, unsigned logn, const uint64_
                          (u64 *)out, batch);
 }
 
+int hehub_b200_rlwe_decrypt_core(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *moduli, size_t L, const uint64_t *ct,
+                                 const uint64_t *sk, uint64_t *pt, size_t batch) {
+    CTX_GUARD(ctx);
+    if (int rc = check_ring(c, logn, L, batch)) return rc;
+    return op_rlwe_decrypt_core(c, logn, (const u64 *)moduli, L, (const u64 *)ct, (const u64 *)sk, (u64 *)pt, batch);
+}
+
+int hehub_b200_rlwe_encrypt_core(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *moduli, size_t L, const uint64_t *pt,
+                                 const uint64_t *sk, const uint64_t *c1, const uint64_t *e, uint64_t *out, size_t batch) {
+    CTX_GUARD(ctx);
+    if (int rc = check_ring(c, logn, L, batch)) return rc;
+    return op_rlwe_encrypt_core(c, logn, (const u64 *)moduli, L, (const u64 *)pt, (const u64 *)sk, (const u64 *)c1,
+                                (const u64 *)e, (u64 *)out, batch);
+}
+
 int hehub_b200_ckks_rotate(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli, size_t L, const uint64_t *ct,
                            const uint64_t *key, size_t step, uint64_t *out, size_t batch) {
     CTX_GUARD(ctx);

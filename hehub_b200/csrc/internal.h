@@ -33,6 +33,10 @@ int op_relinearize(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u
                    const u64 *key, u64 *out, size_t batch);
 int op_mult_relin(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *ct1, const u64 *ct2,
                   const u64 *key, u64 *out, size_t batch);
+int op_rlwe_decrypt_core(Context &c, unsigned logn, const u64 *moduli, size_t L, const u64 *ct, const u64 *sk, u64 *pt,
+                         size_t batch);
+int op_rlwe_encrypt_core(Context &c, unsigned logn, const u64 *moduli, size_t L, const u64 *pt, const u64 *sk, const u64 *c1,
+                         const u64 *e, u64 *out, size_t batch);
 int op_galois(Context &c, unsigned logn, size_t L, const u64 *in, u64 *out, bool conj, size_t step, size_t batch);
 int op_galois_keyswitch(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *ct, const u64 *key,
                         bool conj, size_t step, u64 *out, size_t batch);

@@ -447,6 +447,116 @@ int op_mult_relin(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, co
 }
 
 // ------------------------------------------------------------------------------------------
+// RLWE decrypt / encrypt cores — src/fhe/primitives/rlwe.cpp:34-71.
+// The products with the secret key and the lazy additions ride in the transforms' load / store.
+// ------------------------------------------------------------------------------------------
+// pt[b] = strict( INTT( c0 + c1 * sk ) )                                   rlwe.cpp:63-71
+struct DecryptIO {
+    const u64 *ct; // [batch][2][L][N], NTT form
+    const u64 *sk; // [L][N], NTT form, shared by the batch
+    u64 *pt;       // [batch][L][N]
+    int L, logn;
+    bool vec;
+    HB_D int limb(int row) const { return row % L; }
+    HB_D const u64 *src(int row) const { return ct + ((size_t)((row / L) * 2 * L + row % L) << logn); }
+    HB_D u64 pre(int row, int i, u64 c0, const LimbConst &lc) const {
+        const int k = row % L;
+        const u64 c1 = hb_ld_ro(src(row) + ((size_t)L << logn) + i), s = __ldg(sk + ((size_t)k << logn) + i);
+        return add_lazy(c0, mul_hybrid_lazy(c1, s, lc), lc.q2); // rns.cpp:120-140, 58-86
+    }
+    HB_D void store(int row, int i, u64 v, const LimbConst &lc) const { pt[((size_t)row << logn) + i] = reduce_strict(v, lc.q); }
+    HB_D void store2(int row, int i, u64 v0, u64 v1, const LimbConst &lc) const {
+        *reinterpret_cast<ulonglong2 *>(pt + ((size_t)row << logn) + i) = make_ulonglong2(reduce_strict(v0, lc.q), reduce_strict(v1, lc.q));
+    }
+    HB_D u64 *raw(int row) const { return pt + ((size_t)row << logn); }
+};
+
+// encrypt, step 1: out[b][0] = NTT(e) - c1 * sk, out[b][1] = c1       sampling.cpp:66, rlwe.cpp:50
+struct EncryptErrIO {
+    const u64 *e, *c1; // [batch][L][N]: error coefficients, NTT-form mask
+    const u64 *sk;     // [L][N]
+    u64 *out;          // [batch][2][L][N]
+    int L, logn;
+    bool vec;
+    HB_D int limb(int row) const { return row % L; }
+    HB_D const u64 *src(int row) const { return e + ((size_t)row << logn); }
+    HB_D u64 pre(int, int, u64 raw, const LimbConst &) const { return raw; }
+    HB_D void store(int row, int i, u64 v, const LimbConst &lc) const {
+        const int b = row / L, k = row - b * L;
+        const u64 m = hb_ld_ro(c1 + ((size_t)row << logn) + i), s = __ldg(sk + ((size_t)k << logn) + i);
+        u64 *o = out + ((size_t)(b * 2 * L + k) << logn) + i;
+        o[0] = sub_lazy(v, mul_hybrid_lazy(m, s, lc), lc.q2);
+        o[(size_t)L << logn] = m;
+    }
+    HB_D void store2(int row, int i, u64 v0, u64 v1, const LimbConst &lc) const {
+        const int b = row / L, k = row - b * L;
+        const ulonglong2 m = hb_ld_ro2(c1 + ((size_t)row << logn) + i);
+        const ulonglong2 s = __ldg(reinterpret_cast<const ulonglong2 *>(sk + ((size_t)k << logn) + i));
+        u64 *o = out + ((size_t)(b * 2 * L + k) << logn) + i;
+        *reinterpret_cast<ulonglong2 *>(o) =
+            make_ulonglong2(sub_lazy(v0, mul_hybrid_lazy(m.x, s.x, lc), lc.q2), sub_lazy(v1, mul_hybrid_lazy(m.y, s.y, lc), lc.q2));
+        *reinterpret_cast<ulonglong2 *>(o + ((size_t)L << logn)) = m;
+    }
+    HB_D u64 *raw(int) const { return nullptr; }
+};
+
+// encrypt, step 2: out[b][0] += NTT(pt)                                  rlwe.cpp:54-58
+struct EncryptAddIO {
+    const u64 *pt; // [batch][L][N] coefficients
+    u64 *out;
+    int L, logn;
+    bool vec;
+    HB_D int limb(int row) const { return row % L; }
+    HB_D const u64 *src(int row) const { return pt + ((size_t)row << logn); }
+    HB_D u64 pre(int, int, u64 raw, const LimbConst &) const { return raw; }
+    HB_D u64 *slot(int row, int i) const {
+        const int b = row / L, k = row - b * L;
+        return out + ((size_t)(b * 2 * L + k) << logn) + i;
+    }
+    HB_D void store(int row, int i, u64 v, const LimbConst &lc) const {
+        u64 *o = slot(row, i);
+        *o = add_lazy(*o, v, lc.q2);
+    }
+    HB_D void store2(int row, int i, u64 v0, u64 v1, const LimbConst &lc) const {
+        ulonglong2 *o = reinterpret_cast<ulonglong2 *>(slot(row, i));
+        const ulonglong2 c = *o;
+        *o = make_ulonglong2(add_lazy(c.x, v0, lc.q2), add_lazy(c.y, v1, lc.q2));
+    }
+    HB_D u64 *raw(int) const { return nullptr; }
+};
+
+int op_rlwe_decrypt_core(Context &c, unsigned logn, const u64 *moduli, size_t L, const u64 *ct, const u64 *sk, u64 *pt,
+                         size_t batch) {
+    if (!moduli || !ct || !sk || !pt) return c.fail(1, "null operand");
+    if (batch == 0) return 0;
+    for (size_t k = 0; k < L; k++)
+        if (!(moduli[k] & 1)) return c.fail(1, "Montgomery multiplication needs odd moduli");
+    int err = 0;
+    const LimbConst *limbs = c.get_chain(logn, moduli, L, &err);
+    if (!limbs) return err;
+    DecryptIO io{ct, sk, pt, (int)L, (int)logn, aligned16(ct) && aligned16(pt)};
+    cudaError_t e = launch_ntt(false, c.env(), logn, io, limbs, (int)(batch * L));
+    return e == cudaSuccess ? 0 : c.cuda_fail(e, "decrypt_core: intt launch");
+}
+
+int op_rlwe_encrypt_core(Context &c, unsigned logn, const u64 *moduli, size_t L, const u64 *pt, const u64 *sk, const u64 *c1,
+                         const u64 *e, u64 *out, size_t batch) {
+    if (!moduli || !pt || !sk || !c1 || !e || !out) return c.fail(1, "null operand");
+    if (batch == 0) return 0;
+    for (size_t k = 0; k < L; k++)
+        if (!(moduli[k] & 1)) return c.fail(1, "Montgomery multiplication needs odd moduli");
+    int err = 0;
+    const LimbConst *limbs = c.get_chain(logn, moduli, L, &err);
+    if (!limbs) return err;
+    EncryptErrIO io1{e, c1, sk, out, (int)L, (int)logn, aligned16(e) && aligned16(c1) && aligned16(sk) && aligned16(out)};
+    cudaError_t rc = launch_ntt(true, c.env(), logn, io1, limbs, (int)(batch * L));
+    if (rc != cudaSuccess) return c.cuda_fail(rc, "encrypt_core: error ntt launch");
+    EncryptAddIO io2{pt, out, (int)L, (int)logn, aligned16(pt) && aligned16(out)};
+    rc = launch_ntt(true, c.env(), logn, io2, limbs, (int)(batch * L));
+    return rc == cudaSuccess ? 0 : c.cuda_fail(rc, "encrypt_core: plaintext ntt launch");
+}
+
+// ------------------------------------------------------------------------------------------
 // Galois permutations on NTT-form polynomials.  Slot j holds the evaluation at psi^(2*brev(j)+1);
 // the automorphism X -> X^g moves root index e to e*g, so output slot j gathers from the slot whose
 // root index is e_j * g^{-1} (mod 2N).  cycle: g = 3^step (permutation.cpp:42-58); involution:

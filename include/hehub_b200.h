@@ -154,6 +154,19 @@ int hehub_b200_ckks_rotate(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *e
 int hehub_b200_ckks_conjugate(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli, size_t L,
                               const uint64_t *ct, const uint64_t *key, uint64_t *out, size_t batch);
 
+/* ---- RLWE cores (next row §8(f).3) — src/fhe/primitives/rlwe.cpp:34-71 ---------------
+ * decrypt_core: pt = reduce_strict(INTT(c0 + c1 * sk)); ct [batch][2][L][N] and sk [L][N] in NTT
+ *   form, pt [batch][L][N] coefficients < q.
+ * encrypt_core: ct = (NTT(e) - c1 * sk + NTT(pt), c1).  The reference draws the mask c1 (uniform,
+ *   NTT form) and the error e (small coefficients, reduced mod each q) from a process-global RNG
+ *   (sampling.cpp:12-69); here the caller supplies them, so the op is deterministic.
+ *   pt, e, c1: [batch][L][N]; out: [batch][2][L][N]. */
+int hehub_b200_rlwe_decrypt_core(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *moduli, size_t L,
+                                 const uint64_t *ct, const uint64_t *sk, uint64_t *pt, size_t batch);
+int hehub_b200_rlwe_encrypt_core(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *moduli, size_t L,
+                                 const uint64_t *pt, const uint64_t *sk, const uint64_t *c1, const uint64_t *e,
+                                 uint64_t *out, size_t batch);
+
 /* ---- host-buffer variants --------------------------------------------------------
  * The reference keeps every RnsPolynomial in host memory (rns.cpp:25-27), so a caller that has
  * not moved its data to device slabs calls these: operands are HOST pointers (pinned memory from

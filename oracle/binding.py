@@ -208,6 +208,24 @@ class _CpuLib:
             raise ValueError(f"ckks_mult_relin rc={rc}")
         return out
 
+    def rlwe_decrypt_core(self, logn, moduli, ct, sk):
+        m, ct, sk = _arr(moduli), _arr(ct), _arr(sk)
+        out = np.empty((m.size, 1 << logn), dtype=np.uint64)
+        rc = self._fn("rlwe_decrypt_core", C.c_int, C.c_uint, C.c_size_t, p64, p64, p64, p64)(
+            logn, m.size, _ptr(m), _ptr(ct), _ptr(sk), _ptr(out))
+        if rc:
+            raise ValueError(f"rlwe_decrypt_core rc={rc}")
+        return out
+
+    def rlwe_encrypt_core(self, logn, moduli, pt, sk, c1, e):
+        m, pt, sk, c1, e = _arr(moduli), _arr(pt), _arr(sk), _arr(c1), _arr(e)
+        out = np.empty((2, m.size, 1 << logn), dtype=np.uint64)
+        rc = self._fn("rlwe_encrypt_core", C.c_int, C.c_uint, C.c_size_t, p64, p64, p64, p64, p64, p64)(
+            logn, m.size, _ptr(m), _ptr(pt), _ptr(sk), _ptr(c1), _ptr(e), _ptr(out))
+        if rc:
+            raise ValueError(f"rlwe_encrypt_core rc={rc}")
+        return out
+
     def galois_cycle(self, logn, poly, step):
         a = _arr(poly)
         L = a.size >> logn

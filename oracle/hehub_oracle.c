@@ -578,6 +578,51 @@ int orc_ckks_conjugate(unsigned logn, size_t L, const u64 *ext_moduli, const u64
 }
 
 /* ------------------------------------------------------------------ */
+/* RLWE encrypt / decrypt cores                   */
+/* ------------------------------------------------------------------ */
+
+/* decrypt_core — src/fhe/primitives/rlwe.cpp:63-71: pt = c0 + c1 * sk (hybrid mulmod, lazy add),
+ * INTT, reduce_strict.  ct: [2][L][N] NTT form; sk: [L][N] NTT form; pt: [L][N] coefficients < q. */
+int orc_rlwe_decrypt_core(unsigned logn, size_t L, const u64 *moduli, const u64 *ct, const u64 *sk, u64 *pt) {
+    const size_t n = (size_t)1 << logn;
+    u64 *prod = malloc(n * sizeof(u64));
+    for (size_t k = 0; k < L; k++) {
+        const u64 q = moduli[k];
+        orc_mul_hybrid_lazy(q, n, ct + (L + k) * n, sk + k * n, prod); /* c1 * sk, rns.cpp:120-140 */
+        memcpy(pt + k * n, ct + k * n, n * sizeof(u64));               /* c0 + ..., rns.cpp:58-86   */
+        orc_add_lazy(q, n, pt + k * n, prod);
+    }
+    free(prod);
+    return orc_poly_intt(logn, L, moduli, pt, 1);
+}
+
+/* encrypt_core with the samples supplied by the caller — rlwe.cpp:34-61 and sampling.cpp:47-69:
+ * ex = NTT(e) for the error coefficients e (already reduced mod each q), c0 = ex - c1 * sk,
+ * c0 += NTT(pt).  pt, e: [L][N] coefficient form; c1: [L][N] uniform NTT-form mask; out: [2][L][N]. */
+int orc_rlwe_encrypt_core(unsigned logn, size_t L, const u64 *moduli, const u64 *pt, const u64 *sk, const u64 *c1,
+                          const u64 *e, u64 *out) {
+    const size_t n = (size_t)1 << logn;
+    u64 *prod = malloc(n * sizeof(u64));
+    u64 *ptn = malloc(L * n * sizeof(u64));
+    int rc = 0;
+    memcpy(out, e, L * n * sizeof(u64));
+    memcpy(ptn, pt, L * n * sizeof(u64));
+    if (orc_poly_ntt_fwd(logn, L, moduli, out)) { rc = 1; goto done; }  /* sampling.cpp:66 */
+    if (orc_poly_ntt_fwd(logn, L, moduli, ptn)) { rc = 1; goto done; }  /* rlwe.cpp:54-55   */
+    for (size_t k = 0; k < L; k++) {
+        const u64 q = moduli[k];
+        orc_mul_hybrid_lazy(q, n, c1 + k * n, sk + k * n, prod);
+        orc_sub_lazy(q, n, out + k * n, prod);                          /* rlwe.cpp:50      */
+        orc_add_lazy(q, n, out + k * n, ptn + k * n);                   /* rlwe.cpp:58      */
+    }
+    memcpy(out + L * n, c1, L * n * sizeof(u64));
+done:
+    free(prod);
+    free(ptn);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ */
 /* harness helpers                                                     */
 /* ------------------------------------------------------------------ */
 

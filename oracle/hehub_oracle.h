@@ -81,6 +81,11 @@ int orc_bgv_relinearize(unsigned logn, size_t L, const orc_u64 *ext_moduli, orc_
 int orc_ckks_mult_relin(unsigned logn, size_t L, const orc_u64 *ext_moduli,
                         const orc_u64 *ct1, const orc_u64 *ct2, const orc_u64 *key,
                         orc_u64 *out);
+/* RLWE cores (rlwe.cpp:34-71); encrypt takes the samples (mask c1 in NTT form, error e in
+ * coefficient form) from the caller so it is deterministic */
+int orc_rlwe_decrypt_core(unsigned logn, size_t L, const orc_u64 *moduli, const orc_u64 *ct, const orc_u64 *sk, orc_u64 *pt);
+int orc_rlwe_encrypt_core(unsigned logn, size_t L, const orc_u64 *moduli, const orc_u64 *pt, const orc_u64 *sk,
+                          const orc_u64 *c1, const orc_u64 *e, orc_u64 *out);
 int orc_galois_cycle(unsigned logn, size_t L, const orc_u64 *in, orc_u64 *out, size_t step);
 int orc_galois_involution(unsigned logn, size_t L, const orc_u64 *in, orc_u64 *out);
 /* rotate / conjugate = permutation + ext_prod + rescale + add (ckks/arith.cpp:75-93) */

@@ -154,6 +154,20 @@ def main():
     mm = ref.ckks_mult_relin(logn, ext, ct1, ct2, key)
     kat["c5"] = {"logn": logn, "moduli": mods, "P": P, "mult": [hx(mm[h]) for h in range(2)]}
 
+    # ---- RLWE cores (rlwe.cpp:34-71), C3 moduli, LCG-filled operands -------------------------
+    mods, P = ref.ckks_pick_moduli([40, 30, 30, 30], 40)
+    logn, n = 13, 8192
+    L = len(mods)
+    sk = np.stack([lcg(4000 + k, mods[k], n) for k in range(L)])
+    c1 = np.stack([lcg(4100 + k, mods[k], n) for k in range(L)])
+    pt = np.stack([lcg(4200 + k, mods[k], n) for k in range(L)])
+    small = (lcg(4300, 39, n).astype(np.int64) - 19)       # error coefficients in [-19, 19]
+    err = np.stack([np.where(small < 0, mods[k] + small, small).astype(np.uint64) for k in range(L)])
+    ct = fill_ct(4400, mods, n)
+    dec = ref.rlwe_decrypt_core(logn, mods, ct, sk)
+    enc = ref.rlwe_encrypt_core(logn, mods, pt, sk, c1, err)
+    kat["rlwe"] = {"logn": logn, "moduli": mods, "decrypt": hx(dec), "encrypt": [hx(enc[h]) for h in range(2)]}
+
     # ---- small raw fixtures: N=16, L=3 ({34,34,34} + P 34) ------------------
     mods, P = ref.ckks_pick_moduli([34, 34, 34], 34)
     ext, logn, n = mods + [P], 4, 16

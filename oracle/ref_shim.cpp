@@ -266,6 +266,37 @@ int ref_ckks_conjugate(unsigned logn, size_t L, const u64 *ext_moduli, const u64
     });
 }
 
+/* decrypt_core is the reference's own function; encrypt_core draws its samples from a global RNG,
+ * so the shim repeats its three statements (rlwe.cpp:50, 54-58) with the reference's own operators
+ * on caller-supplied samples. */
+int ref_rlwe_decrypt_core(unsigned logn, size_t L, const u64 *moduli, const u64 *ct, const u64 *sk, u64 *pt) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        RlweCt c;
+        for (int h = 0; h < 2; h++) c[h] = load_poly(n, L, moduli, ct + h * L * n, true);
+        RlweSk s(load_poly(n, L, moduli, sk, true));
+        auto r = decrypt_core(c, s);
+        store_poly(r, pt);
+    });
+}
+
+int ref_rlwe_encrypt_core(unsigned logn, size_t L, const u64 *moduli, const u64 *pt, const u64 *sk, const u64 *c1,
+                          const u64 *e, u64 *out) {
+    return guarded([&] {
+        size_t n = (size_t)1 << logn;
+        RlweSk s(load_poly(n, L, moduli, sk, true));
+        auto mask = load_poly(n, L, moduli, c1, true);
+        auto ex = load_poly(n, L, moduli, e, false);
+        ntt_negacyclic_inplace_lazy(ex);          // sampling.cpp:66
+        auto c0 = ex - mask * s;                  // rlwe.cpp:50
+        auto pt_ntt = load_poly(n, L, moduli, pt, false);
+        ntt_negacyclic_inplace_lazy(pt_ntt);      // rlwe.cpp:54-55
+        c0 += pt_ntt;                             // rlwe.cpp:58
+        store_poly(c0, out);
+        store_poly(mask, out + L * n);
+    });
+}
+
 /* the raw prime table, for checking the restated selection rule */
 int ref_prime_row(unsigned bits, size_t count, u64 *out) {
     if (bits >= prime_lists.size()) return 0;

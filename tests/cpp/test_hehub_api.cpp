@@ -317,6 +317,43 @@ static void test_rescale_exactness() {
     CHECK(ok);
 }
 
+// encrypt_core / decrypt_core (rlwe.cpp:34-71) through the hehub:: mirror, word for word against the oracle
+static void test_rlwe_cores(size_t logn, const std::vector<unsigned> &bits) {
+    const size_t n = (size_t)1 << logn, L = bits.size();
+    std::vector<u64> mods(L);
+    u64 p = 0;
+    orc_ckks_pick_moduli(bits.data(), L, 55, mods.data(), &p);
+    auto sk_poly = filled(n, mods, 4000, PolyRepForm::value);
+    RlweSk sk(std::move(sk_poly));
+    auto mask = filled(n, mods, 4100, PolyRepForm::value);
+    auto pt = filled(n, mods, 4200, PolyRepForm::coeff);
+    RnsPolynomial err(n, L, mods);
+    std::vector<u64> small(n);
+    orc_lcg_fill(4300, 39, n, small.data());
+    for (size_t k = 0; k < L; k++)
+        for (size_t i = 0; i < n; i++) err[k][i] = small[i] < 19 ? mods[k] + small[i] - 19 : small[i] - 19;
+    err.rep_form = PolyRepForm::coeff;
+
+    auto ct = encrypt_core(pt, sk, mask, err);
+    std::vector<u64> want(2 * L * n);
+    orc_rlwe_encrypt_core((unsigned)logn, L, mods.data(), flat(pt).data(), flat(sk).data(), flat(mask).data(), flat(err).data(), want.data());
+    CHECK(flat(ct) == want);
+    CHECK(ct[0].rep_form == PolyRepForm::value);
+
+    auto back = decrypt_core(ct, sk);
+    std::vector<u64> want_pt(L * n);
+    orc_rlwe_decrypt_core((unsigned)logn, L, mods.data(), want.data(), flat(sk).data(), want_pt.data());
+    CHECK(flat(back) == want_pt);
+    CHECK(back.rep_form == PolyRepForm::coeff);
+    bool sum_ok = true; // decrypt(encrypt(pt)) == pt + e (mod q)
+    for (size_t k = 0; k < L; k++)
+        for (size_t i = 0; i < n; i++) sum_ok &= back[k][i] == (u64)(((unsigned __int128)pt[k][i] + err[k][i]) % mods[k]);
+    CHECK(sum_ok);
+    auto pt_ntt(pt);
+    ntt_negacyclic_inplace_lazy(pt_ntt);
+    CHECK_THROWS(encrypt_core(pt_ntt, sk, mask, err), std::invalid_argument); // rlwe.cpp:51-53
+}
+
 int main() {
     try {
         test_ntt_round_trip();
@@ -326,6 +363,8 @@ int main() {
         test_scheme_ops(12, {39}, 39);
         test_scheme_ops(13, {40, 30, 30, 30}, 40);
         test_rescale_exactness();
+        test_rlwe_cores(10, {40, 30});
+        test_rlwe_cores(13, {40, 30, 30, 30});
     } catch (const std::exception &e) {
         std::fprintf(stderr, "unexpected exception: %s\n", e.what());
         return 2;

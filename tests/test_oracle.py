@@ -288,3 +288,27 @@ def test_differential_against_reference_library(oracle, reference):
             assert (oracle.bgv_mod_switch(logn, mods, t, ct1) == reference.bgv_mod_switch(logn, mods, t, ct1)).all()
         assert (oracle.ckks_rotate(logn, ext, ct1, key, 3) == reference.ckks_rotate(logn, ext, ct1, key, 3)).all()
         assert (oracle.ckks_conjugate(logn, ext, ct1, key) == reference.ckks_conjugate(logn, ext, ct1, key)).all()
+
+
+def test_rlwe_cores_against_reference_library(oracle, reference):
+    """decrypt_core is the reference's own function; encrypt_core is its three statements on supplied samples."""
+    for logn, bits in ((4, [30]), (10, [40, 30]), (12, [50, 40, 40])):
+        mods, _ = oracle.ckks_pick_moduli(bits, 50)
+        mods = [int(m) for m in mods]
+        n = 1 << logn
+        rng = np.random.default_rng(100 + logn)
+        uni = lambda: np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in mods])
+        sk, c1, pt, ct = uni(), uni(), uni(), np.stack([uni(), uni()])
+        small = rng.integers(-19, 20, n)
+        e = np.stack([np.where(small < 0, q + small, small).astype(np.uint64) for q in mods])
+        assert np.array_equal(oracle.rlwe_decrypt_core(logn, mods, ct, sk), reference.rlwe_decrypt_core(logn, mods, ct, sk))
+        assert np.array_equal(oracle.rlwe_encrypt_core(logn, mods, pt, sk, c1, e), reference.rlwe_encrypt_core(logn, mods, pt, sk, c1, e))
+
+
+def test_rlwe_cores_golden(oracle, kat):
+    from test_parity import _rlwe_golden_inputs, hx
+    g = kat["rlwe"]
+    sk, c1, pt, err, ct = _rlwe_golden_inputs(oracle, g)
+    assert hx(oracle.rlwe_decrypt_core(g["logn"], g["moduli"], ct, sk)) == g["decrypt"]
+    enc = oracle.rlwe_encrypt_core(g["logn"], g["moduli"], pt, sk, c1, err)
+    assert [hx(enc[h]) for h in range(2)] == g["encrypt"]

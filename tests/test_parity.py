@@ -297,6 +297,62 @@ def test_scheme_ops_match_oracle(dev, oracle, logn, bits, pbits):
     assert np.array_equal(dev.ckks_conjugate(logn, ext, ct1, key), oracle.ckks_conjugate(logn, ext, ct1, key))
 
 
+# ------------------------------------------------------------------ RLWE cores
+def _rlwe_inputs(oracle, logn, mods, seed, batch):
+    n = 1 << logn
+    rng = np.random.default_rng(seed)
+    uni = lambda: np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in mods])
+    sk = uni()
+    pts, c1s, es, cts = [], [], [], []
+    for _ in range(batch):
+        small = rng.integers(-19, 20, n)  # the reference's Gaussian is bounded by 6 sigma = 19.2 (sampling.cpp:49-58)
+        es.append(np.stack([np.where(small < 0, q + small, small).astype(np.uint64) for q in mods]))
+        pts.append(uni())
+        c1s.append(uni())
+        cts.append(np.stack([uni(), uni()]))
+    return sk, np.stack(pts), np.stack(c1s), np.stack(es), np.stack(cts)
+
+
+@pytest.mark.parametrize("logn,bits", [(5, [30, 30]), (10, [40, 30, 30]), (12, [59]), (13, [40, 30, 30, 30]), (15, [50, 50])])
+def test_rlwe_encrypt_decrypt_cores_match_oracle(dev, oracle, logn, bits):
+    """decrypt_core / encrypt_core (rlwe.cpp:34-71) with caller-supplied samples: raw words equal the
+    oracle's (itself pinned on the reference, tests/test_oracle.py), and decrypt(encrypt(pt)) = pt + e."""
+    mods, _ = _shape(oracle, logn, bits, 55)
+    if bits == [59]:
+        mods = [Q59]
+    L, batch = len(mods), 3
+    sk, pt, c1, e, ct = _rlwe_inputs(oracle, logn, mods, logn, batch)
+    got_d = dev.rlwe_decrypt_core(logn, mods, ct, sk)
+    got_e = dev.rlwe_encrypt_core(logn, mods, pt, sk, c1, e)
+    for b in range(batch):
+        assert np.array_equal(got_d[b], oracle.rlwe_decrypt_core(logn, mods, ct[b], sk))
+        assert np.array_equal(got_e[b], oracle.rlwe_encrypt_core(logn, mods, pt[b], sk, c1[b], e[b]))
+    back = dev.rlwe_decrypt_core(logn, mods, got_e, sk)
+    for k, q in enumerate(mods):
+        want = (pt[:, k].astype(object) + e[:, k].astype(object)) % q
+        assert np.array_equal(back[:, k], want.astype(np.uint64))
+
+
+def _rlwe_golden_inputs(oracle, g):
+    mods, n = g["moduli"], 1 << g["logn"]
+    L = len(mods)
+    sk = np.stack([oracle.lcg_fill(4000 + k, mods[k], n) for k in range(L)])
+    c1 = np.stack([oracle.lcg_fill(4100 + k, mods[k], n) for k in range(L)])
+    pt = np.stack([oracle.lcg_fill(4200 + k, mods[k], n) for k in range(L)])
+    small = oracle.lcg_fill(4300, 39, n).astype(np.int64) - 19
+    err = np.stack([np.where(small < 0, mods[k] + small, small).astype(np.uint64) for k in range(L)])
+    return sk, c1, pt, err, fill_ct(oracle, 4400, mods, n)
+
+
+def test_rlwe_cores_reference_golden(dev, oracle, kat):
+    """Hashes recorded from the unmodified reference (oracle/make_golden.py), N = 8192, L = 4."""
+    g = kat["rlwe"]
+    sk, c1, pt, err, ct = _rlwe_golden_inputs(oracle, g)
+    assert hx(dev.rlwe_decrypt_core(g["logn"], g["moduli"], ct, sk)) == g["decrypt"]
+    enc = dev.rlwe_encrypt_core(g["logn"], g["moduli"], pt, sk, c1, err)
+    assert [hx(enc[h]) for h in range(2)] == g["encrypt"]
+
+
 def test_single_limb_key_switch(dev, oracle):
     """L = 1: the decomposition has one row; rescale of the (q0, P) result leaves one limb."""
     logn = 10
