@@ -544,6 +544,9 @@ def run_rows(ctx, torch, timed, world, rank, peaks, cpu_ok):
     ctx._call("lcg_fill", n, mp, L, ct2.data_ptr(), CT * 2 * L, 200, 1)
     quad, extout = buf(CT * 3 * L * n), buf(CT * 2 * (L + 1) * n)
     scal = np.array([3, 5, 7, 11], dtype=np.uint64)
+    tern = np.random.default_rng(3).integers(-1, 2, n)  # key generation needs a small (ternary) secret, NTT form
+    sk_host = ctx.poly_ntt_fwd(logn, mods, np.stack([np.where(tern < 0, q + tern, tern).astype(np.uint64) for q in mods]))
+    sk_dev = torch.from_numpy(sk_host.view(np.int64).copy()).cuda()
     ctx._call("ckks_tensor", logn, mp, L, ct1.data_ptr(), ct2.data_ptr(), quad.data_ptr(), CT)
     ctx.synchronize()
 
@@ -565,6 +568,9 @@ def run_rows(ctx, torch, timed, world, rank, peaks, cpu_ok):
         "a13 ckks::relinearize": (lambda i: ctx._call("ckks_relinearize", logn, ep, L, quad.data_ptr(), key.data_ptr(), res.data_ptr(), CT), CT, 40 * L * n, "ct"),
         "a13 ckks::mult (tensor + relinearize)": (lambda i: ctx._call("ckks_mult_relin", logn, ep, L, ct1.data_ptr(), ct2.data_ptr(), key.data_ptr(), res.data_ptr(), CT), CT, 48 * L * n, "ct"),
         "f1 ckks::rotate": (lambda i: ctx._call("ckks_rotate", logn, ep, L, ct1.data_ptr(), key.data_ptr(), 1, res.data_ptr(), CT), CT, 32 * L * n, "ct"),
+        "f2 rns_base_transform (1 -> L moduli)": (lambda i: ctx._call("rns_base_transform_from_single", ext[L], mp, L, B(i), Cc(i), n, EW), EW, 8 * n * (1 + L), "poly"),
+        "f2 RlweKsk::RlweKsk (samples supplied)": (lambda i: ctx._call("ksk_generate", logn, ep, L, sk_dev.data_ptr(), sk_dev.data_ptr(), ct1.data_ptr(),
+                                                                          ct2.data_ptr(), extout.data_ptr()), 1, 8 * n * (2 * L + 4 * L * (L + 1)), "key"),
         # sk = one polynomial of the key slab; plaintexts / masks / errors = halves of the ciphertext slabs
         "f3 decrypt_core": (lambda i: ctx._call("rlwe_decrypt_core", logn, mp, L, ct1.data_ptr(), key.data_ptr(), res.data_ptr(), CT), CT, 24 * L * n, "ct"),
         "f3 encrypt_core (samples supplied)": (lambda i: ctx._call("rlwe_encrypt_core", logn, mp, L, ct1.data_ptr(), key.data_ptr(), ct2.data_ptr(),
@@ -595,6 +601,10 @@ def rows_cpu(out, logn, mods, ext, hkey, t_plain, world=1, budget_s=0.4):
     hc1 = np.stack([ha, hb_])                                              # one ciphertext [2][L][N]
     hc2 = np.stack([hb_, ha])
     hquad = lib.ckks_tensor(logn, mods, hc1, hc2)
+    tern = rng.integers(-1, 2, n)  # a ternary secret in NTT form (key generation needs small coefficients)
+    hsk = lib.poly_ntt_fwd(logn, mods, np.stack([np.where(tern < 0, q + tern, tern).astype(np.uint64) for q in mods]))
+    hmasks = np.stack([np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in ext]) for _ in range(L)])
+    herrs = np.stack([np.stack([rng.integers(0, 9, n).astype(np.uint64) for _ in ext]) for _ in range(L)])
     hpairs = rng.integers(0, mods[0], 2 * n, dtype=np.uint64)
     word = lambda name, *sig: lib._fn(name, None, *sig)
     f_bar = word("barrett_lazy", C.c_uint64, C.c_size_t, u64p)
@@ -625,6 +635,8 @@ def rows_cpu(out, logn, mods, ext, hkey, t_plain, world=1, budget_s=0.4):
         "a13 ckks::relinearize": (lambda: lib.ckks_relinearize(logn, ext, hquad, hkey), 1),
         "a13 ckks::mult (tensor + relinearize)": (lambda: lib.ckks_mult_relin(logn, ext, hc1, hc2, hkey), 1),
         "f1 ckks::rotate": (lambda: lib.ckks_rotate(logn, ext, hc1, hkey, 1), 1),
+        "f2 rns_base_transform (1 -> L moduli)": (lambda: lib.base_transform_from_single(ext[L], hpairs[:n], mods), 1),
+        "f2 RlweKsk::RlweKsk (samples supplied)": (lambda: lib.ksk_generate(logn, ext, hsk, hsk, hmasks, herrs), 1),
         "f3 decrypt_core": (lambda: lib.rlwe_decrypt_core(logn, mods, hc1, ha), 1),
         "f3 encrypt_core (samples supplied)": (lambda: lib.rlwe_encrypt_core(logn, mods, ha, hb_, hc2[0], hc2[1]), 1),
     }

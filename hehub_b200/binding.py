@@ -71,6 +71,9 @@ _SIGS = {
     "ckks_conjugate": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, C.c_void_p, sz],
     "rlwe_decrypt_core": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, C.c_void_p, sz],
     "rlwe_encrypt_core": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, sz],
+    "rns_base_transform_from_single": [u64, p64, sz, C.c_void_p, C.c_void_p, sz, sz],
+    "rns_base_transform_to_single": [p64, sz, u64, C.c_void_p, C.c_void_p, sz, sz],
+    "ksk_generate": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "lcg_fill": [sz, p64, sz, C.c_void_p, sz, u64, u64],
     "ntt_host": [C.c_int, C.c_uint, p64, sz, C.c_void_p, C.c_void_p, sz, C.c_int],
     "ckks_mult_relin_host": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, sz],
@@ -425,6 +428,45 @@ class Context:
         try:
             self._call("rlwe_encrypt_core", logn, mp, L, d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, out.ptr, batch)
             return out.download(pt.shape[:-2] + (2, L, n))
+        finally:
+            for x in d:
+                x.free()
+            out.free()
+
+    def base_transform_from_single(self, q_old, x, new_moduli):
+        x = _arr(x)
+        n = x.shape[-1]
+        batch = x.size // n
+        m, mp = _mod(new_moduli)
+        din, out = self.to_device(x), self.slab(batch * m.size * n)
+        try:
+            self._call("rns_base_transform_from_single", q_old, mp, m.size, din.ptr, out.ptr, n, batch)
+            return out.download(x.shape[:-1] + (m.size, n))
+        finally:
+            din.free()
+            out.free()
+
+    def base_transform_to_single(self, old_moduli, x, new_modulus):
+        x = _arr(x)
+        m, mp = _mod(old_moduli)
+        n = x.shape[-1]
+        batch = x.size // (n * m.size)
+        din, out = self.to_device(x), self.slab(batch * n)
+        try:
+            self._call("rns_base_transform_to_single", mp, m.size, new_modulus, din.ptr, out.ptr, n, batch)
+            return out.download(x.shape[:-2] + (n,))
+        finally:
+            din.free()
+            out.free()
+
+    def ksk_generate(self, logn, ext_moduli, sk_curr, sk_orig, masks, errors):
+        m, mp = _mod(ext_moduli)
+        L, n = m.size - 1, 1 << logn
+        d = [self.to_device(a) for a in (sk_curr, sk_orig, masks, errors)]
+        out = self.slab(L * 2 * (L + 1) * n)
+        try:
+            self._call("ksk_generate", logn, mp, L, d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, out.ptr)
+            return out.download((L, 2, L + 1, n))
         finally:
             for x in d:
                 x.free()

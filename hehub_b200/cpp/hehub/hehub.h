@@ -8,3 +8,4 @@
 #include "rgsw.h"
 #include "rlwe.h"
 #include "rns.h"
+#include "rns_transform.h"

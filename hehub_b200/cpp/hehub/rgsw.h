@@ -18,6 +18,37 @@ struct RlweKsk : public RgswCt {
     RlweKsk() {}
     RlweKsk(RgswCt &&rgsw) : RgswCt(std::move(rgsw)) {}
 
+    /// keys.cpp:8-36 on the device, with the RLWE samples supplied by the caller: the reference draws
+    /// them from a process-global RNG inside rgsw_encrypt (rgsw.cpp:21-23), which this back end does
+    /// not replicate.  masks[p]: uniform, NTT form; errors[p]: small coefficients, coefficient form;
+    /// both over (q_0..q_{L-1}, additional_mod), one per row p < L.
+    RlweKsk(const RlweSk &sk_curr, const RlweSk &sk_orig, const u64 additional_mod, const std::vector<RnsPolynomial> &masks,
+            const std::vector<RnsPolynomial> &errors) {
+        const size_t L = sk_orig.component_count(), n = sk_orig.dimension();
+        if (masks.size() != L || errors.size() != L) throw std::invalid_argument("One RLWE sample per RNS component is needed.");
+        auto ext = sk_orig.modulus_vec();
+        ext.push_back(additional_mod);
+        const size_t poly_words = (L + 1) * n;
+        detail::Staged m(L * poly_words), e(L * poly_words), key(L * 2 * poly_words);
+        for (size_t p = 0; p < L; p++) {
+            if (masks[p].modulus_vec() != ext || errors[p].modulus_vec() != ext || masks[p].dimension() != n || errors[p].dimension() != n)
+                throw std::invalid_argument("Samples do not match the extended modulus chain.");
+            b200::check(hehub_b200_slab_d2d(b200::context(), m.dev + p * poly_words, masks[p].dev(), poly_words));
+            b200::check(hehub_b200_slab_d2d(b200::context(), e.dev + p * poly_words, errors[p].dev(), poly_words));
+        }
+        b200::check(hehub_b200_ksk_generate(b200::context(), (unsigned)sk_orig.log_dimension(), ext.data(), L, sk_curr.dev(), sk_orig.dev(),
+                                            m.dev, e.dev, key.dev));
+        RnsPolyParams params{n, L + 1, ext};
+        for (size_t p = 0; p < L; p++) {
+            RlweCt row{RnsPolynomial(params), RnsPolynomial(params)};
+            for (size_t h = 0; h < 2; h++) {
+                b200::check(hehub_b200_slab_d2d(b200::context(), row[h].dev_mut(), key.dev + (p * 2 + h) * poly_words, poly_words));
+                row[h].rep_form = PolyRepForm::value;
+            }
+            push_back(std::move(row));
+        }
+    }
+
     struct Packed {
         u64 *dev = nullptr;
         size_t rows = 0, limbs = 0, dimension = 0;

@@ -577,6 +577,26 @@ int hehub_b200_rlwe_encrypt_core(hehub_b200_ctx *ctx, unsigned logn, const uint6
                                 (const u64 *)e, (u64 *)out, batch);
 }
 
+int hehub_b200_rns_base_transform_from_single(hehub_b200_ctx *ctx, uint64_t q_old, const uint64_t *new_moduli, size_t Lnew,
+                                              const uint64_t *in, uint64_t *out, size_t n, size_t batch) {
+    CTX_GUARD(ctx);
+    return op_base_from_single(c, q_old, (const u64 *)new_moduli, Lnew, (const u64 *)in, (u64 *)out, n, batch);
+}
+
+int hehub_b200_rns_base_transform_to_single(hehub_b200_ctx *ctx, const uint64_t *old_moduli, size_t L, uint64_t new_modulus,
+                                            const uint64_t *in, uint64_t *out, size_t n, size_t batch) {
+    CTX_GUARD(ctx);
+    return op_base_to_single(c, (const u64 *)old_moduli, L, new_modulus, (const u64 *)in, (u64 *)out, n, batch);
+}
+
+int hehub_b200_ksk_generate(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli, size_t L, const uint64_t *sk_curr,
+                            const uint64_t *sk_orig, const uint64_t *masks, const uint64_t *errors, uint64_t *key) {
+    CTX_GUARD(ctx);
+    if (int rc = check_ring(c, logn, L + 1, 1)) return rc;
+    return op_ksk_generate(c, logn, (const u64 *)ext_moduli, L, (const u64 *)sk_curr, (const u64 *)sk_orig, (const u64 *)masks,
+                           (const u64 *)errors, (u64 *)key);
+}
+
 int hehub_b200_ckks_rotate(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli, size_t L, const uint64_t *ct,
                            const uint64_t *key, size_t step, uint64_t *out, size_t batch) {
     CTX_GUARD(ctx);

@@ -12,6 +12,8 @@
 // rescale, lazy subtract + q_last^{-1} multiply + addend after them, strict reduction after
 // the inverse transforms) lives in the IO policies of the transform kernels, so those values
 // never make a separate trip through HBM.
+#include <vector>
+
 #include "internal.h"
 
 namespace hb {
@@ -554,6 +556,150 @@ int op_rlwe_encrypt_core(Context &c, unsigned logn, const u64 *moduli, size_t L,
     EncryptAddIO io2{pt, out, (int)L, (int)logn, aligned16(pt) && aligned16(out)};
     rc = launch_ntt(true, c.env(), logn, io2, limbs, (int)(batch * L));
     return rc == cudaSuccess ? 0 : c.cuda_fail(rc, "encrypt_core: plaintext ntt launch");
+}
+
+// ------------------------------------------------------------------------------------------
+// RNS base transform and key-switch key generation
+//   rns_base_transform            src/fhe/common/rns_transform.cpp:11-126
+//   RlweKsk::RlweKsk              src/fhe/primitives/keys.cpp:8-36 (+ rgsw.cpp:11-55, rlwe.cpp:34-51)
+// ------------------------------------------------------------------------------------------
+// one modulus -> many: out[b][k][i] from in[b][i]                       rns_transform.cpp:11-37, :116
+HB_GLOBAL(256, 1)
+base_from_single_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const LimbConst *__restrict__ limbs, u64 q_old, int Lnew,
+                        size_t n, size_t total) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // (b, k, i)
+    if (gid >= total) return;
+    const size_t i = gid % n, bk = gid / n;
+    const int k = (int)(bk % Lnew);
+    const size_t b = bk / Lnew;
+    const LimbConst lc = limbs[k];
+    u64 x = reduce_strict(in[b * n + i], q_old);
+    if (x >= q_old / 2) x = (q_old / lc.q + 1) * lc.q - q_old + x;
+    if (lc.q < q_old) x = barrett_lazy(x, lc);
+    out[gid] = x;
+}
+
+// many -> one modulus, small-coefficient path; *not_small is set when some coefficient is not the same
+// small signed value under every old modulus (the reference then composes big integers)   :39-84, :116
+HB_GLOBAL(256, 1)
+base_to_single_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const LimbConst *__restrict__ old_limbs, int L,
+                      LimbConst new_lc, size_t n, size_t total, int *not_small) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // (b, i)
+    if (gid >= total) return;
+    const size_t i = gid % n, b = gid / n;
+    const u64 q0 = old_limbs[0].q, half = q0 / 2;
+    const u64 x0 = reduce_strict(in[(b * L) * n + i], q0);
+    bool small = true;
+    for (int k = 1; k < L; k++) {
+        const u64 qk = old_limbs[k].q, xk = reduce_strict(in[(b * L + k) * n + i], qk);
+        small &= (x0 < half) ? (xk == x0) : (qk - xk == q0 - x0);
+    }
+    if (!small) *not_small = 1;
+    u64 r = (x0 < half) ? x0 : (q0 / new_lc.q + 1) * new_lc.q - q0 + x0;
+    out[gid] = reduce_strict(barrett_lazy(r, new_lc), new_lc.q);
+}
+
+int op_base_from_single(Context &c, u64 q_old, const u64 *new_moduli, size_t Lnew, const u64 *in, u64 *out, size_t n, size_t batch) {
+    if (!new_moduli || !in || !out) return c.fail(1, "null operand");
+    if (q_old < 2 || Lnew == 0) return c.fail(1, "bad moduli");
+    const size_t total = batch * Lnew * n;
+    if (total == 0) return 0;
+    int err = 0;
+    const LimbConst *limbs = c.get_chain(0, new_moduli, Lnew, &err);
+    if (!limbs) return err;
+    HB_LAUNCH(base_from_single_kernel, (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, out, limbs, q_old, (int)Lnew, n, total);
+    c.stats.launches++;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : c.cuda_fail(e, "base transform launch");
+}
+
+int op_base_to_single(Context &c, const u64 *old_moduli, size_t L, u64 new_modulus, const u64 *in, u64 *out, size_t n, size_t batch) {
+    if (!old_moduli || !in || !out) return c.fail(1, "null operand");
+    if (L == 0 || new_modulus < 2) return c.fail(1, "bad moduli");
+    const size_t total = batch * n;
+    if (total == 0) return 0;
+    int err = 0;
+    const LimbConst *limbs = c.get_chain(0, old_moduli, L, &err);
+    if (!limbs) return err;
+    const ModTables *nt = c.get_tables(new_modulus, 0, &err);
+    if (!nt) return err;
+    int *flag = reinterpret_cast<int *>(c.get_scratch(6, 2, &err));
+    if (!flag) return err;
+    cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), c.stream);
+    if (e != cudaSuccess) return c.cuda_fail(e, "base transform: flag");
+    HB_LAUNCH(base_to_single_kernel, (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, out, limbs, (int)L, nt->lc, n, total, flag);
+    c.stats.launches++;
+    int host_flag = 0;
+    e = cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+    if (e != cudaSuccess) return c.cuda_fail(e, "base transform to single");
+    if (host_flag) return c.fail(3, "under development: CRT composition of large coefficients (rns_transform.cpp:86-105) is not built");
+    return 0;
+}
+
+// one row of the key: (c0, c1) = ( (NTT(e) - mask * sk_ext + [k == p] sk_curr * (P mod q_p)) * R, mask * R ), R = 2^64 mod q_k
+struct KskRowIO {
+    const u64 *errors, *masks; // [L][L+1][N]
+    const u64 *sk_ext;         // [L+1][N], NTT form (sk_orig_extended)
+    const u64 *sk_curr;        // [L][N], NTT form
+    const ulonglong2 *pmod;    // [L]: (P mod q_p, Harvey companion)
+    u64 *key;                  // [L][2][L+1][N]
+    int L, logn;
+    bool vec;
+    HB_D int limb(int row) const { return row % (L + 1); }
+    HB_D const u64 *src(int row) const { return errors + ((size_t)row << logn); }
+    HB_D u64 pre(int, int, u64 raw, const LimbConst &) const { return raw; }
+    HB_D void store(int row, int i, u64 v, const LimbConst &lc) const {
+        const int p = row / (L + 1), k = row - p * (L + 1);
+        const u64 m = hb_ld_ro(masks + ((size_t)row << logn) + i);
+        u64 c0 = sub_lazy(v, mul_hybrid_lazy(m, __ldg(sk_ext + ((size_t)k << logn) + i), lc), lc.q2); // rlwe.cpp:50
+        // + pt_ntt * basis_p (rgsw.cpp:27): Harvey multiple of sk_curr at k == p, of anything by 0 elsewhere (= 0)
+        u64 term = 0;
+        if (k == p) {
+            const ulonglong2 s = __ldg(pmod + p);
+            term = harvey_lazy(__ldg(sk_curr + ((size_t)k << logn) + i), s.x, s.y, lc.nq);
+        }
+        c0 = add_lazy(c0, term, lc.q2);
+        u64 *o = key + ((size_t)((p * 2) * (L + 1) + k) << logn) + i;
+        o[0] = harvey_lazy(c0, lc.r, lc.r_h, lc.nq);                      // rgsw.cpp:47-51
+        o[(size_t)(L + 1) << logn] = harvey_lazy(m, lc.r, lc.r_h, lc.nq);
+    }
+    HB_D void store2(int row, int i, u64 v0, u64 v1, const LimbConst &lc) const {
+        store(row, i, v0, lc);
+        store(row, i + 1, v1, lc);
+    }
+    HB_D u64 *raw(int) const { return nullptr; }
+};
+
+int op_ksk_generate(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *sk_curr, const u64 *sk_orig,
+                    const u64 *masks, const u64 *errors, u64 *key) {
+    if (!ext_moduli || !sk_curr || !sk_orig || !masks || !errors || !key) return c.fail(1, "null operand");
+    if (L == 0) return c.fail(1, "no RNS components");
+    for (size_t k = 0; k <= L; k++)
+        if (!(ext_moduli[k] & 1)) return c.fail(1, "Montgomery multiplication needs odd moduli");
+    const size_t n = (size_t)1 << logn, L1 = L + 1;
+    int err = 0;
+    const LimbConst *limbs = c.get_chain(logn, ext_moduli, L1, &err);
+    if (!limbs) return err;
+    u64 *sk_ext = c.get_scratch(7, L1 * n + 2 * L, &err); // sk_orig_extended, then the (P mod q_p) pairs
+    if (!sk_ext) return err;
+    cudaError_t e = cudaMemcpyAsync(sk_ext, sk_orig, L * n * 8, cudaMemcpyDeviceToDevice, c.stream);
+    if (e != cudaSuccess) return c.cuda_fail(e, "ksk: copy");
+    if (int rc = run_transform(c, false, logn, ext_moduli, L, sk_ext, 1, 0)) return rc;                       // keys.cpp:22
+    if (int rc = op_base_to_single(c, ext_moduli, L, ext_moduli[L], sk_ext, sk_ext + L * n, n, 1)) return rc; // keys.cpp:23-25
+    if (int rc = run_transform(c, true, logn, ext_moduli, L1, sk_ext, 1, 0)) return rc;                       // keys.cpp:26
+    std::vector<u64> pm(2 * L);
+    for (size_t p = 0; p < L; p++) { // keys.cpp:28-33, rns.cpp:162-164
+        pm[2 * p] = ext_moduli[L] % ext_moduli[p];
+        pm[2 * p + 1] = host_harvey_quotient(pm[2 * p], ext_moduli[p]);
+    }
+    u64 *pmod = sk_ext + L1 * n;
+    e = cudaMemcpyAsync(pmod, pm.data(), pm.size() * 8, cudaMemcpyHostToDevice, c.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream); // pm is a host temporary
+    if (e != cudaSuccess) return c.cuda_fail(e, "ksk: constants");
+    KskRowIO io{errors, masks, sk_ext, sk_curr, reinterpret_cast<const ulonglong2 *>(pmod), key, (int)L, (int)logn, aligned16(errors)};
+    e = launch_ntt(true, c.env(), logn, io, limbs, (int)(L * L1));
+    return e == cudaSuccess ? 0 : c.cuda_fail(e, "ksk: row launch");
 }
 
 // ------------------------------------------------------------------------------------------

@@ -167,6 +167,27 @@ int hehub_b200_rlwe_encrypt_core(hehub_b200_ctx *ctx, unsigned logn, const uint6
                                  const uint64_t *pt, const uint64_t *sk, const uint64_t *c1, const uint64_t *e,
                                  uint64_t *out, size_t batch);
 
+/* ---- RNS base transform and key generation (next row §8(f).2) ----------------------------
+ * rns_base_transform — src/fhe/common/rns_transform.cpp:11-126 on coefficient-form words (the
+ *   strict reduction of :116 included).  from_single: in [batch][n] under q_old -> out
+ *   [batch][Lnew][n].  to_single: in [batch][L][n] -> out [batch][n]; only the reference's
+ *   small-coefficient path (:47-84) is built: ERR_UNSUPPORTED when some coefficient is not the same
+ *   small signed value under every old modulus (the reference then composes big integers).
+ *   to_single synchronises the stream (it has to read the verdict).
+ * ksk_generate — RlweKsk::RlweKsk, src/fhe/primitives/keys.cpp:8-36 with rgsw_encrypt_montgomery
+ *   (rgsw.cpp:11-55).  The reference draws one RLWE sample per row from a process-global RNG; here
+ *   the caller supplies them: masks [L][L+1][N] (uniform, NTT form), errors [L][L+1][N] (small
+ *   coefficients reduced mod each modulus).  sk_curr, sk_orig: [L][N] NTT form; key: [L][2][L+1][N]
+ *   (the layout ext_prod_montgomery takes). */
+int hehub_b200_rns_base_transform_from_single(hehub_b200_ctx *ctx, uint64_t q_old, const uint64_t *new_moduli,
+                                              size_t Lnew, const uint64_t *in, uint64_t *out, size_t n, size_t batch);
+int hehub_b200_rns_base_transform_to_single(hehub_b200_ctx *ctx, const uint64_t *old_moduli, size_t L,
+                                            uint64_t new_modulus, const uint64_t *in, uint64_t *out, size_t n,
+                                            size_t batch);
+int hehub_b200_ksk_generate(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli, size_t L,
+                            const uint64_t *sk_curr, const uint64_t *sk_orig, const uint64_t *masks,
+                            const uint64_t *errors, uint64_t *key);
+
 /* ---- host-buffer variants --------------------------------------------------------
  * The reference keeps every RnsPolynomial in host memory (rns.cpp:25-27), so a caller that has
  * not moved its data to device slabs calls these: operands are HOST pointers (pinned memory from

@@ -226,6 +226,35 @@ class _CpuLib:
             raise ValueError(f"rlwe_encrypt_core rc={rc}")
         return out
 
+    def base_transform_from_single(self, q_old, x, new_moduli):
+        x, m = _arr(x), _arr(new_moduli)
+        out = np.empty((m.size, x.size), dtype=np.uint64)
+        rc = self._fn("base_transform_from_single", C.c_int, u64, C.c_size_t, p64, p64, C.c_size_t, p64)(
+            q_old, x.size, _ptr(x), _ptr(m), m.size, _ptr(out))
+        if rc:
+            raise ValueError(f"base_transform_from_single rc={rc}")
+        return out
+
+    def base_transform_to_single(self, old_moduli, x, new_modulus):
+        m, x = _arr(old_moduli), _arr(x)
+        n = x.size // m.size
+        out = np.empty(n, dtype=np.uint64)
+        rc = self._fn("base_transform_to_single", C.c_int, C.c_size_t, C.c_size_t, p64, p64, u64, p64)(
+            n, m.size, _ptr(m), _ptr(x), new_modulus, _ptr(out))
+        if rc:
+            raise ValueError(f"base_transform_to_single rc={rc}")
+        return out
+
+    def ksk_generate(self, logn, ext_moduli, sk_curr, sk_orig, masks, errors):
+        m = _arr(ext_moduli)
+        L, n = m.size - 1, 1 << logn
+        key = np.empty((L, 2, L + 1, n), dtype=np.uint64)
+        rc = self._fn("ksk_generate", C.c_int, C.c_uint, C.c_size_t, p64, p64, p64, p64, p64, p64)(
+            logn, L, _ptr(m), _ptr(_arr(sk_curr)), _ptr(_arr(sk_orig)), _ptr(_arr(masks)), _ptr(_arr(errors)), _ptr(key))
+        if rc:
+            raise ValueError(f"ksk_generate rc={rc}")
+        return key
+
     def galois_cycle(self, logn, poly, step):
         a = _arr(poly)
         L = a.size >> logn

@@ -623,6 +623,94 @@ done:
 }
 
 /* ------------------------------------------------------------------ */
+/* RNS base transform and key-switch key generation */
+/* ------------------------------------------------------------------ */
+
+/* rns_base_transform, one modulus -> many — src/fhe/common/rns_transform.cpp:11-37 (after the strict
+ * reduction at :116).  in: [N] coefficients (any lazy value); out: [Lnew][N]. */
+int orc_base_transform_from_single(u64 q_old, size_t n, const u64 *in, const u64 *new_moduli, size_t Lnew, u64 *out) {
+    const u64 half = q_old / 2;
+    for (size_t k = 0; k < Lnew; k++) {
+        const u64 q = new_moduli[k], multiple = (q_old / q + 1) * q;
+        for (size_t i = 0; i < n; i++) {
+            u64 x = in[i];
+            x -= (x >= q_old) ? q_old : 0; /* reduce_strict of the by-value argument, :116 */
+            out[k * n + i] = (x < half) ? x : multiple - q_old + x;
+        }
+        if (q < q_old) orc_barrett_lazy(q, n, out + k * n);
+    }
+    return 0;
+}
+
+/* rns_base_transform, many -> one modulus, small-coefficient path — rns_transform.cpp:39-84.
+ * Returns 3 when the coefficients are not all small (the reference then composes big integers). */
+int orc_base_transform_to_single(size_t n, size_t L, const u64 *old_moduli, const u64 *in, u64 new_modulus, u64 *out) {
+    u64 *x = malloc(L * n * sizeof(u64));
+    memcpy(x, in, L * n * sizeof(u64));
+    for (size_t k = 0; k < L; k++) orc_reduce_strict(old_moduli[k], n, x + k * n); /* :116 */
+    const u64 q0 = old_moduli[0], half = q0 / 2;
+    int small = 1;
+    for (size_t i = 0; i < n && small; i++)
+        for (size_t k = 1; k < L; k++) {
+            if (x[i] < half && x[k * n + i] != x[i]) small = 0;
+            if (x[i] >= half && old_moduli[k] - x[k * n + i] != q0 - x[i]) small = 0;
+        }
+    if (!small) {
+        free(x);
+        return 3;
+    }
+    const u64 multiple = (q0 / new_modulus + 1) * new_modulus;
+    for (size_t i = 0; i < n; i++) out[i] = (x[i] < half) ? x[i] : multiple - q0 + x[i];
+    orc_barrett(new_modulus, n, out);
+    free(x);
+    return 0;
+}
+
+/* RlweKsk::RlweKsk — src/fhe/primitives/keys.cpp:8-36, with rgsw_encrypt_montgomery (rgsw.cpp:11-55)
+ * and get_rlwe_sample (rlwe.cpp:34-51) on caller-supplied samples.
+ *   sk_curr, sk_orig: [L][N] NTT form; masks: [L][L+1][N] uniform NTT-form c1 per row;
+ *   errors: [L][L+1][N] error coefficients per row; key: [L][2][L+1][N]. */
+int orc_ksk_generate(unsigned logn, size_t L, const u64 *ext_moduli, const u64 *sk_curr, const u64 *sk_orig,
+                     const u64 *masks, const u64 *errors, u64 *key) {
+    const size_t n = (size_t)1 << logn, L1 = L + 1;
+    const u64 P = ext_moduli[L];
+    int rc = 0;
+    u64 *sk_ext = malloc(L1 * n * sizeof(u64)); /* sk_orig_extended */
+    u64 *prod = malloc(n * sizeof(u64));
+    u64 *term = malloc(n * sizeof(u64));
+    memcpy(sk_ext, sk_orig, L * n * sizeof(u64));
+    if (orc_poly_intt(logn, L, ext_moduli, sk_ext, 0)) { rc = 1; goto done; }                       /* keys.cpp:22 */
+    rc = orc_base_transform_to_single(n, L, ext_moduli, sk_ext, P, sk_ext + L * n);               /* :23-25     */
+    if (rc) goto done;
+    if (orc_poly_ntt_fwd(logn, L1, ext_moduli, sk_ext)) { rc = 1; goto done; }                     /* :26        */
+    for (size_t p = 0; p < L; p++) {
+        u64 *c0 = key + (p * 2 + 0) * L1 * n, *c1 = key + (p * 2 + 1) * L1 * n;
+        memcpy(c0, errors + p * L1 * n, L1 * n * sizeof(u64));
+        memcpy(c1, masks + p * L1 * n, L1 * n * sizeof(u64));
+        if (orc_poly_ntt_fwd(logn, L1, ext_moduli, c0)) { rc = 1; goto done; }                     /* sampling.cpp:66 */
+        for (size_t k = 0; k < L1; k++) {
+            const u64 q = ext_moduli[k];
+            orc_mul_hybrid_lazy(q, n, c1 + k * n, sk_ext + k * n, prod);
+            orc_sub_lazy(q, n, c0 + k * n, prod);                                                    /* rlwe.cpp:50 */
+            /* pt_ntt * basis_p (rgsw.cpp:27, rns.cpp:155-171): basis_p[k] = P mod q_p at k == p, else 0.  The
+             * extra limb of sk_curr_extended is uninitialised in the reference but multiplied by 0. */
+            if (k < L) memcpy(term, sk_curr + k * n, n * sizeof(u64));
+            else memset(term, 0, n * sizeof(u64));
+            orc_mul_scalar_lazy(q, n, term, (k == p) ? P % q : 0);
+            orc_add_lazy(q, n, c0 + k * n, term);
+            const u64 r = ((u64)(-1LL) % q) + 1;                                                     /* rgsw.cpp:36-39 */
+            orc_mul_scalar_lazy(q, n, c0 + k * n, r);                                               /* rgsw.cpp:47-51 */
+            orc_mul_scalar_lazy(q, n, c1 + k * n, r);
+        }
+    }
+done:
+    free(sk_ext);
+    free(prod);
+    free(term);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ */
 /* harness helpers                                                     */
 /* ------------------------------------------------------------------ */
 

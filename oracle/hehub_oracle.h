@@ -86,6 +86,12 @@ int orc_ckks_mult_relin(unsigned logn, size_t L, const orc_u64 *ext_moduli,
 int orc_rlwe_decrypt_core(unsigned logn, size_t L, const orc_u64 *moduli, const orc_u64 *ct, const orc_u64 *sk, orc_u64 *pt);
 int orc_rlwe_encrypt_core(unsigned logn, size_t L, const orc_u64 *moduli, const orc_u64 *pt, const orc_u64 *sk,
                           const orc_u64 *c1, const orc_u64 *e, orc_u64 *out);
+/* rns_base_transform (rns_transform.cpp:11-84; many->one: small-coefficient path, rc 3 otherwise) and
+ * RlweKsk construction (keys.cpp:8-36) on caller-supplied samples */
+int orc_base_transform_from_single(orc_u64 q_old, size_t n, const orc_u64 *in, const orc_u64 *new_moduli, size_t Lnew, orc_u64 *out);
+int orc_base_transform_to_single(size_t n, size_t L, const orc_u64 *old_moduli, const orc_u64 *in, orc_u64 new_modulus, orc_u64 *out);
+int orc_ksk_generate(unsigned logn, size_t L, const orc_u64 *ext_moduli, const orc_u64 *sk_curr, const orc_u64 *sk_orig,
+                     const orc_u64 *masks, const orc_u64 *errors, orc_u64 *key);
 int orc_galois_cycle(unsigned logn, size_t L, const orc_u64 *in, orc_u64 *out, size_t step);
 int orc_galois_involution(unsigned logn, size_t L, const orc_u64 *in, orc_u64 *out);
 /* rotate / conjugate = permutation + ext_prod + rescale + add (ckks/arith.cpp:75-93) */

@@ -168,6 +168,30 @@ def main():
     enc = ref.rlwe_encrypt_core(logn, mods, pt, sk, c1, err)
     kat["rlwe"] = {"logn": logn, "moduli": mods, "decrypt": hx(dec), "encrypt": [hx(enc[h]) for h in range(2)]}
 
+    # ---- base transform + key generation (rns_transform.cpp:11-126, keys.cpp:8-36), C3 chain ----
+    mods, P = ref.ckks_pick_moduli([40, 30, 30, 30], 40)
+    ext, logn, n = mods + [P], 13, 8192
+    L = len(mods)
+
+    def ternary(seed):
+        t = lcg(seed, 3, n).astype(np.int64) - 1
+        return np.stack([np.where(t < 0, q + t, t).astype(np.uint64) for q in mods])
+
+    sk_o_coeff, sk_c_coeff = ternary(5000), ternary(5001)
+    sk_o, sk_c = ref.poly_ntt_fwd(logn, mods, sk_o_coeff), ref.poly_ntt_fwd(logn, mods, sk_c_coeff)
+    masks = np.stack([np.stack([lcg(5200 + 10 * p + k, ext[k], n) for k in range(L + 1)]) for p in range(L)])
+    errs = []
+    for p in range(L):
+        sm = lcg(5300 + p, 39, n).astype(np.int64) - 19
+        errs.append(np.stack([np.where(sm < 0, q + sm, sm).astype(np.uint64) for q in ext]))
+    errs = np.stack(errs)
+    ksk = ref.ksk_generate(logn, ext, sk_c, sk_o, masks, errs)
+    single = ref.base_transform_to_single(mods, sk_o_coeff, P)
+    lazy = lcg(5400, 2 * mods[0], n)
+    fan = ref.base_transform_from_single(mods[0], lazy, ext[1:])
+    kat["keygen"] = {"logn": logn, "moduli": mods, "P": P, "ksk_rows": [hx(ksk[p]) for p in range(L)],
+                     "to_single": hx(single), "from_single": hx(fan)}
+
     # ---- small raw fixtures: N=16, L=3 ({34,34,34} + P 34) ------------------
     mods, P = ref.ckks_pick_moduli([34, 34, 34], 34)
     ext, logn, n = mods + [P], 4, 16

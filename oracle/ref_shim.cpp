@@ -14,6 +14,7 @@
 #include "fhe/common/ntt.h"
 #include "fhe/common/permutation.h"
 #include "fhe/common/primelists.h"
+#include "fhe/common/rns_transform.h"
 #include "fhe/primitives/keys.h"
 #include "fhe/primitives/rgsw.h"
 
@@ -294,6 +295,59 @@ int ref_rlwe_encrypt_core(unsigned logn, size_t L, const u64 *moduli, const u64 
         c0 += pt_ntt;                             // rlwe.cpp:58
         store_poly(c0, out);
         store_poly(mask, out + L * n);
+    });
+}
+
+/* rns_base_transform is the reference's own function (both directions). */
+int ref_base_transform_from_single(u64 q_old, size_t n, const u64 *in, const u64 *new_moduli, size_t Lnew, u64 *out) {
+    return guarded([&] {
+        auto p = load_poly(n, 1, &q_old, in, false);
+        auto r = rns_base_transform(p, std::vector<u64>(new_moduli, new_moduli + Lnew));
+        store_poly(r, out);
+    });
+}
+
+int ref_base_transform_to_single(size_t n, size_t L, const u64 *old_moduli, const u64 *in, u64 new_modulus, u64 *out) {
+    return guarded([&] {
+        auto p = load_poly(n, L, old_moduli, in, false);
+        auto r = rns_base_transform(p, std::vector<u64>{new_modulus});
+        store_poly(r, out);
+    });
+}
+
+/* RlweKsk::RlweKsk (keys.cpp:8-36) draws its RLWE samples from the global RNG inside rgsw_encrypt; the shim
+ * repeats the constructor's statements with the reference's own operators, taking the samples from the caller
+ * (mask = c1 of get_rlwe_sample, error = the Gaussian coefficients before their NTT). */
+int ref_ksk_generate(unsigned logn, size_t L, const u64 *ext_moduli, const u64 *sk_curr, const u64 *sk_orig,
+                     const u64 *masks, const u64 *errors, u64 *key) {
+    return guarded([&] {
+        const size_t n = (size_t)1 << logn, L1 = L + 1;
+        const u64 P = ext_moduli[L];
+        RlweSk sk_c(load_poly(n, L, ext_moduli, sk_curr, true)), sk_o(load_poly(n, L, ext_moduli, sk_orig, true));
+        auto sk_curr_extended = sk_c;                                   // keys.cpp:10-11
+        sk_curr_extended.add_components({P});
+        std::fill(sk_curr_extended.last()->begin(), sk_curr_extended.last()->end(), (u64)0); // keys.cpp:13-16 (x0 anyway)
+        auto sk_orig_extended(sk_o);                                    // keys.cpp:21-26
+        intt_negacyclic_inplace_lazy(sk_orig_extended);
+        auto extended_part = rns_base_transform(sk_orig_extended, {P});
+        sk_orig_extended.add_components({P});
+        *sk_orig_extended.last() = std::move(extended_part[0]);
+        ntt_negacyclic_inplace_lazy(sk_orig_extended);
+        std::vector<u64> mont_consts;                                   // rgsw.cpp:36-45
+        for (size_t k = 0; k < L1; k++) mont_consts.push_back(((u64)(-1LL) % ext_moduli[k]) + 1);
+        for (size_t p = 0; p < L; p++) {
+            std::vector<u64> basis(L1, 0);                              // keys.cpp:28-33
+            basis[p] = P % ext_moduli[p];
+            auto c1 = load_poly(n, L1, ext_moduli, masks + p * L1 * n, true);      // rlwe.cpp:41
+            auto ex = load_poly(n, L1, ext_moduli, errors + p * L1 * n, false);    // sampling.cpp:47-66
+            ntt_negacyclic_inplace_lazy(ex);
+            auto c0 = ex - c1 * sk_orig_extended;                       // rlwe.cpp:50
+            c0 += sk_curr_extended * basis;                             // rgsw.cpp:27
+            c0 *= mont_consts;                                          // rgsw.cpp:47-51
+            c1 *= mont_consts;
+            store_poly(c0, key + (p * 2 + 0) * L1 * n);
+            store_poly(c1, key + (p * 2 + 1) * L1 * n);
+        }
     });
 }
 

@@ -354,6 +354,72 @@ static void test_rlwe_cores(size_t logn, const std::vector<unsigned> &bits) {
     CHECK_THROWS(encrypt_core(pt_ntt, sk, mask, err), std::invalid_argument); // rlwe.cpp:51-53
 }
 
+// rns_base_transform (rns_transform.cpp:11-126) and RlweKsk construction (keys.cpp:8-36) through the mirror
+static void test_base_transform_and_ksk(size_t logn, const std::vector<unsigned> &bits, unsigned pbits) {
+    const size_t n = (size_t)1 << logn, L = bits.size();
+    std::vector<u64> mods(L);
+    u64 P = 0;
+    orc_ckks_pick_moduli(bits.data(), L, pbits, mods.data(), &P);
+    std::vector<u64> ext(mods);
+    ext.push_back(P);
+    // ternary secrets in NTT form
+    auto ternary = [&](u64 seed) {
+        std::vector<u64> t(n);
+        orc_lcg_fill(seed, 3, n, t.data());
+        RnsPolynomial s(n, L, mods);
+        for (size_t k = 0; k < L; k++)
+            for (size_t i = 0; i < n; i++) s[k][i] = t[i] == 2 ? mods[k] - 1 : t[i];
+        s.rep_form = PolyRepForm::coeff;
+        return s;
+    };
+    auto so_coeff = ternary(5000), sc_coeff = ternary(5001);
+    // many -> one on the small secret, one -> many on a lazy single-modulus polynomial
+    auto single = rns_base_transform(so_coeff, {P});
+    std::vector<u64> want1(n);
+    CHECK(orc_base_transform_to_single(n, L, mods.data(), flat(so_coeff).data(), P, want1.data()) == 0);
+    CHECK(flat(single) == want1);
+    auto fan = rns_base_transform(single, mods);
+    std::vector<u64> want2(L * n);
+    orc_base_transform_from_single(P, n, want1.data(), mods.data(), L, want2.data());
+    CHECK(flat(fan) == want2);
+    auto as_values(so_coeff);
+    ntt_negacyclic_inplace_lazy(as_values);
+    CHECK_THROWS(rns_base_transform(as_values, {P}), std::logic_error);              // rns_transform.cpp:109-112
+    typedef const char *cstr_t;
+    CHECK_THROWS(rns_base_transform(so_coeff, std::vector<u64>{P, mods[0]}), cstr_t); // :123
+    auto large = filled(n, mods, 5100, PolyRepForm::coeff);
+    CHECK_THROWS(rns_base_transform(large, {P}), cstr_t);                      // CRT composition path not built
+
+    RlweSk sk_o(std::move(as_values));
+    auto sc_values(sc_coeff);
+    ntt_negacyclic_inplace_lazy(sc_values);
+    RlweSk sk_c(std::move(sc_values));
+    std::vector<RnsPolynomial> masks, errors;
+    std::vector<u64> small(n);
+    for (size_t p = 0; p < L; p++) {
+        masks.push_back(filled(n, ext, 5200 + 10 * p, PolyRepForm::value));
+        orc_lcg_fill(5300 + p, 39, n, small.data());
+        RnsPolynomial e(n, L + 1, ext);
+        for (size_t k = 0; k <= L; k++)
+            for (size_t i = 0; i < n; i++) e[k][i] = small[i] < 19 ? ext[k] + small[i] - 19 : small[i] - 19;
+        e.rep_form = PolyRepForm::coeff;
+        errors.push_back(std::move(e));
+    }
+    RlweKsk ksk(sk_c, sk_o, P, masks, errors);
+    std::vector<u64> fm, fe, got;
+    for (size_t p = 0; p < L; p++) {
+        auto a = flat(masks[p]), b = flat(errors[p]);
+        fm.insert(fm.end(), a.begin(), a.end());
+        fe.insert(fe.end(), b.begin(), b.end());
+        auto r = flat(ksk[p]);
+        got.insert(got.end(), r.begin(), r.end());
+    }
+    std::vector<u64> want(L * 2 * (L + 1) * n);
+    CHECK(orc_ksk_generate((unsigned)logn, L, ext.data(), flat(sk_c).data(), flat(sk_o).data(), fm.data(), fe.data(), want.data()) == 0);
+    CHECK(got == want);
+    CHECK(ksk.size() == L && ksk[0][0].rep_form == PolyRepForm::value);
+}
+
 int main() {
     try {
         test_ntt_round_trip();
@@ -365,6 +431,8 @@ int main() {
         test_rescale_exactness();
         test_rlwe_cores(10, {40, 30});
         test_rlwe_cores(13, {40, 30, 30, 30});
+        test_base_transform_and_ksk(8, {40, 30}, 45);
+        test_base_transform_and_ksk(12, {40, 30, 30}, 45);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "unexpected exception: %s\n", e.what());
         return 2;

@@ -312,3 +312,31 @@ def test_rlwe_cores_golden(oracle, kat):
     assert hx(oracle.rlwe_decrypt_core(g["logn"], g["moduli"], ct, sk)) == g["decrypt"]
     enc = oracle.rlwe_encrypt_core(g["logn"], g["moduli"], pt, sk, c1, err)
     assert [hx(enc[h]) for h in range(2)] == g["encrypt"]
+
+
+def test_keygen_golden_and_reference(oracle, reference, kat):
+    from test_parity import _keygen_golden_inputs, hx
+    g = kat["keygen"]
+    ext, so, sc, masks, errs, lazy = _keygen_golden_inputs(oracle, g)
+    mods, logn = g["moduli"], g["logn"]
+    sk_o, sk_c = oracle.poly_ntt_fwd(logn, mods, so), oracle.poly_ntt_fwd(logn, mods, sc)
+    ksk = oracle.ksk_generate(logn, ext, sk_c, sk_o, masks, errs)
+    assert [hx(ksk[p]) for p in range(len(mods))] == g["ksk_rows"]
+    assert hx(oracle.base_transform_to_single(mods, so, g["P"])) == g["to_single"]
+    assert hx(oracle.base_transform_from_single(mods[0], lazy, ext[1:])) == g["from_single"]
+    # randomized differential check against the reference library itself
+    rng = np.random.default_rng(12)
+    for q_old, news in ((1099507695617, [1073479681, 1099510054913]), (65537, [260898817, 65537])):
+        x = rng.integers(0, 2 * q_old, 128, dtype=np.uint64)
+        assert np.array_equal(oracle.base_transform_from_single(q_old, x, news), reference.base_transform_from_single(q_old, x, news))
+    small_logn = 6
+    sm, P = oracle.ckks_pick_moduli([30, 30], 40)
+    sm, ext2 = [int(m) for m in sm], [int(m) for m in sm] + [int(P)]
+    n = 1 << small_logn
+    t = rng.integers(-1, 2, n)
+    so2 = np.stack([np.where(t < 0, q + t, t).astype(np.uint64) for q in sm])
+    sk2 = oracle.poly_ntt_fwd(small_logn, sm, so2)
+    masks2 = np.stack([np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in ext2]) for _ in range(2)])
+    errs2 = np.stack([np.stack([rng.integers(0, 5, n).astype(np.uint64) for _ in ext2]) for _ in range(2)])
+    assert np.array_equal(oracle.ksk_generate(small_logn, ext2, sk2, sk2, masks2, errs2),
+                          reference.ksk_generate(small_logn, ext2, sk2, sk2, masks2, errs2))

@@ -353,6 +353,116 @@ def test_rlwe_cores_reference_golden(dev, oracle, kat):
     assert [hx(enc[h]) for h in range(2)] == g["encrypt"]
 
 
+# ------------------------------------------------------------------ base transform + key generation
+def _ternary_ntt(oracle, rng, logn, mods):
+    t = rng.integers(-1, 2, 1 << logn)
+    coeff = np.stack([np.where(t < 0, q + t, t).astype(np.uint64) for q in mods])
+    return oracle.poly_ntt_fwd(logn, mods, coeff), coeff, t
+
+
+def _small_errors(rng, n, mods, rows):
+    out = []
+    for _ in range(rows):
+        sm = rng.integers(-19, 20, n)
+        out.append(np.stack([np.where(sm < 0, q + sm, sm).astype(np.uint64) for q in mods]))
+    return np.stack(out)
+
+
+def test_rns_base_transform(dev, oracle):
+    """rns_base_transform (rns_transform.cpp:11-126): one modulus -> many on lazy inputs, and the
+    small-coefficient many -> one path; large coefficients are refused like the oracle refuses them."""
+    rng = np.random.default_rng(9)
+    for q_old, news in ((1099507695617, [1073479681, 1099510054913, Q59]), (65537, [260898817]), (Q59, [65537, 1099507695617])):
+        x = rng.integers(0, 2 * q_old, (3, 257), dtype=np.uint64)
+        got = dev.base_transform_from_single(q_old, x, news)
+        for b in range(3):
+            assert np.array_equal(got[b], oracle.base_transform_from_single(q_old, x[b], news))
+    mods, P = oracle.ckks_pick_moduli([40, 30, 30], 45)
+    mods, P = [int(m) for m in mods], int(P)
+    small = np.stack([_ternary_ntt(oracle, rng, 8, mods)[1] for _ in range(4)])
+    small[1] += np.array(mods, dtype=np.uint64)[:, None]  # lazy representatives: + q per limb
+    got = dev.base_transform_to_single(mods, small, P)
+    for b in range(4):
+        assert np.array_equal(got[b], oracle.base_transform_to_single(mods, small[b], P))
+    big = np.stack([rng.integers(0, q, 256, dtype=np.uint64) for q in mods])
+    with pytest.raises(ValueError):
+        oracle.base_transform_to_single(mods, big, P)
+    from hehub_b200.binding import Unsupported
+    with pytest.raises(Unsupported):
+        dev.base_transform_to_single(mods, big, P)
+
+
+@pytest.mark.parametrize("logn,bits,pbits", [(5, [30, 30], 40), (10, [40, 30, 30], 45), (12, [50], 55), (13, [40, 30, 30, 30], 40)])
+def test_ksk_generate_matches_oracle(dev, oracle, logn, bits, pbits):
+    """RlweKsk::RlweKsk (keys.cpp:8-36) on supplied samples: raw key words equal the oracle's."""
+    mods, ext = _shape(oracle, logn, bits, pbits)
+    L, n = len(mods), 1 << logn
+    rng = np.random.default_rng(40 + logn)
+    sk_o = _ternary_ntt(oracle, rng, logn, mods)[0]
+    sk_c = _ternary_ntt(oracle, rng, logn, mods)[0]
+    masks = np.stack([np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in ext]) for _ in range(L)])
+    errs = _small_errors(rng, n, ext, L)
+    assert np.array_equal(dev.ksk_generate(logn, ext, sk_c, sk_o, masks, errs), oracle.ksk_generate(logn, ext, sk_c, sk_o, masks, errs))
+
+
+def test_generated_relin_key_relinearizes(dev, oracle):
+    """End to end on the device: encrypt two plaintexts, multiply, relinearize with a key generated by
+    ksk_generate(s*s, s, P), decrypt: the result is the negacyclic product plus small noise."""
+    logn, n = 8, 256
+    mods, ext = _shape(oracle, logn, [50, 50], 55)
+    L = len(mods)
+    rng = np.random.default_rng(77)
+    sk, _, s_int = _ternary_ntt(oracle, rng, logn, mods)
+    sk2 = dev.mul_hybrid_lazy(mods, sk, sk)  # s*s in NTT form (keys.h:43)
+    masks = np.stack([np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in ext]) for _ in range(L)])
+    key = dev.ksk_generate(logn, ext, sk2, sk, masks, _small_errors(rng, n, ext, L))
+    m = [rng.integers(-50, 51, n) for _ in range(2)]
+    cts = []
+    for mi in m:
+        pt = np.stack([np.where(mi < 0, q + mi, mi).astype(np.uint64) for q in mods])
+        c1 = np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in mods])
+        cts.append(dev.rlwe_encrypt_core(logn, mods, pt, sk, c1, _small_errors(rng, n, mods, 1)[0]))
+    prod = dev.ckks_mult_relin(logn, ext, cts[0], cts[1], key)
+    dec = dev.rlwe_decrypt_core(logn, mods, prod, sk)
+    # expected: (m0 + e0) * (m1 + e1) in Z[X]/(X^n + 1), up to relinearisation noise
+    full = np.convolve(m[0].astype(object), m[1].astype(object))
+    want = full[:n].copy()
+    want[: n - 1] -= full[n:]
+    q0 = mods[0]
+    centred = np.array([int(v) if int(v) < q0 // 2 else int(v) - q0 for v in dec[0]], dtype=object)
+    assert max(abs(int(a) - int(b)) for a, b in zip(centred, want)) < 2 ** 22  # noise ~ n * 50 * 19 * few
+
+
+def _keygen_golden_inputs(oracle, g):
+    mods, P, logn = g["moduli"], g["P"], g["logn"]
+    ext, n, L = mods + [P], 1 << logn, len(mods)
+
+    def ternary(seed):
+        t = oracle.lcg_fill(seed, 3, n).astype(np.int64) - 1
+        return np.stack([np.where(t < 0, q + t, t).astype(np.uint64) for q in mods])
+
+    so, sc = ternary(5000), ternary(5001)
+    masks = np.stack([np.stack([oracle.lcg_fill(5200 + 10 * p + k, ext[k], n) for k in range(L + 1)]) for p in range(L)])
+    errs = []
+    for p in range(L):
+        sm = oracle.lcg_fill(5300 + p, 39, n).astype(np.int64) - 19
+        errs.append(np.stack([np.where(sm < 0, q + sm, sm).astype(np.uint64) for q in ext]))
+    return ext, so, sc, masks, np.stack(errs), oracle.lcg_fill(5400, 2 * mods[0], n)
+
+
+def test_keygen_reference_golden(dev, oracle, kat):
+    """Hashes recorded from the unmodified reference (oracle/make_golden.py): key-switch key rows and
+    both base-transform directions at N = 8192, L = 4."""
+    g = kat["keygen"]
+    ext, so, sc, masks, errs, lazy = _keygen_golden_inputs(oracle, g)
+    mods, logn = g["moduli"], g["logn"]
+    sk_o, sk_c = dev.poly_ntt_fwd(logn, mods, so), dev.poly_ntt_fwd(logn, mods, sc)
+    ksk = dev.ksk_generate(logn, ext, sk_c, sk_o, masks, errs)
+    assert [hx(ksk[p]) for p in range(len(mods))] == g["ksk_rows"]
+    assert hx(dev.base_transform_to_single(mods, so, g["P"])) == g["to_single"]
+    assert hx(dev.base_transform_from_single(mods[0], lazy, ext[1:])) == g["from_single"]
+
+
 def test_single_limb_key_switch(dev, oracle):
     """L = 1: the decomposition has one row; rescale of the (q0, P) result leaves one limb."""
     logn = 10
