@@ -9,3 +9,4 @@
 #include "rlwe.h"
 #include "rns.h"
 #include "rns_transform.h"
+#include "serialize.h"

@@ -564,19 +564,26 @@ int op_rlwe_encrypt_core(Context &c, unsigned logn, const u64 *moduli, size_t L,
 //   RlweKsk::RlweKsk              src/fhe/primitives/keys.cpp:8-36 (+ rgsw.cpp:11-55, rlwe.cpp:34-51)
 // ------------------------------------------------------------------------------------------
 // one modulus -> many: out[b][k][i] from in[b][i]                       rns_transform.cpp:11-37, :116
+// blocks tile one (b, k) row, so the modulus — and the 64-bit division behind `modulus_multiple` — is per block
 HB_GLOBAL(256, 1)
 base_from_single_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const LimbConst *__restrict__ limbs, u64 q_old, int Lnew,
-                        size_t n, size_t total) {
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // (b, k, i)
-    if (gid >= total) return;
-    const size_t i = gid % n, bk = gid / n;
+                        size_t n, unsigned blocks_per_row) {
+    const size_t bk = blockIdx.x / blocks_per_row;
     const int k = (int)(bk % Lnew);
     const size_t b = bk / Lnew;
     const LimbConst lc = limbs[k];
-    u64 x = reduce_strict(in[b * n + i], q_old);
-    if (x >= q_old / 2) x = (q_old / lc.q + 1) * lc.q - q_old + x;
-    if (lc.q < q_old) x = barrett_lazy(x, lc);
-    out[gid] = x;
+    const u64 lift = (q_old / lc.q + 1) * lc.q - q_old; // uniform across the block
+    const size_t i0 = (size_t)(blockIdx.x % blocks_per_row) * 1024 + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const size_t i = i0 + (size_t)u * 256;
+        if (i < n) {
+            u64 x = reduce_strict(in[b * n + i], q_old);
+            if (x >= q_old / 2) x += lift;
+            if (lc.q < q_old) x = barrett_lazy(x, lc);
+            out[bk * n + i] = x;
+        }
+    }
 }
 
 // many -> one modulus, small-coefficient path; *not_small is set when some coefficient is not the same
@@ -607,7 +614,9 @@ int op_base_from_single(Context &c, u64 q_old, const u64 *new_moduli, size_t Lne
     int err = 0;
     const LimbConst *limbs = c.get_chain(0, new_moduli, Lnew, &err);
     if (!limbs) return err;
-    HB_LAUNCH(base_from_single_kernel, (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, out, limbs, q_old, (int)Lnew, n, total);
+    const size_t bpr = (n + 1023) / 1024, blocks = batch * Lnew * bpr;
+    if (blocks > 0x7fffffffull) return c.fail(1, "operand too large for one launch");
+    HB_LAUNCH(base_from_single_kernel, (unsigned)blocks, 256, 0, c.stream, 0, in, out, limbs, q_old, (int)Lnew, n, (unsigned)bpr);
     c.stats.launches++;
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : c.cuda_fail(e, "base transform launch");

@@ -420,7 +420,28 @@ static void test_base_transform_and_ksk(size_t logn, const std::vector<unsigned>
     CHECK(ksk.size() == L && ksk[0][0].rep_form == PolyRepForm::value);
 }
 
-int main() {
+// raw-slab files (hehub_b200/cpp/hehub/serialize.h): round trip, and a file for the Python side to read
+static void test_serialize(const char *dir) {
+    const size_t n = 64;
+    const std::vector<u64> mods{65537ull, 260898817ull, Q59};
+    auto poly = filled(n, mods, 6000, PolyRepForm::coeff);
+    RlweCt ct{filled(n, mods, 6100, PolyRepForm::value), filled(n, mods, 6200, PolyRepForm::value)};
+    RlweKsk key(RgswCt{ct, RlweCt{ct[1], ct[0]}});
+    const std::string base = std::string(dir) + "/";
+    b200::save(base + "poly.slab", poly);
+    b200::save(base + "ct.slab", ct);
+    b200::save(base + "ksk.slab", key);
+    auto p2 = b200::load_polynomial(base + "poly.slab");
+    CHECK(p2 == poly && p2.rep_form == PolyRepForm::coeff && p2.modulus_vec() == mods);
+    auto c2 = b200::load_ciphertext(base + "ct.slab");
+    CHECK(flat(c2) == flat(ct) && c2[0].rep_form == PolyRepForm::value);
+    auto k2 = b200::load_key_switch_key(base + "ksk.slab");
+    CHECK(k2.size() == 2 && flat(k2[1]) == flat(key[1]));
+    CHECK_THROWS(b200::load_ciphertext(base + "poly.slab"), std::invalid_argument);
+    CHECK_THROWS(b200::load_polynomial(base + "missing.slab"), std::runtime_error);
+}
+
+int main(int argc, char **argv) {
     try {
         test_ntt_round_trip();
         test_mod_arith();
@@ -433,6 +454,7 @@ int main() {
         test_rlwe_cores(13, {40, 30, 30, 30});
         test_base_transform_and_ksk(8, {40, 30}, 45);
         test_base_transform_and_ksk(12, {40, 30, 30}, 45);
+        if (argc > 1) test_serialize(argv[1]);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "unexpected exception: %s\n", e.what());
         return 2;

@@ -31,8 +31,21 @@ def _build(kind: str) -> str:
 
 
 @pytest.mark.parametrize("kind", ["sim", pytest.param("gpu", marks=pytest.mark.gpu)])
-def test_cpp_mirror(kind):
+def test_cpp_mirror(kind, tmp_path_factory):
     exe = _build(kind)
-    res = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    out_dir = tmp_path_factory.mktemp(f"slabs_{kind}")
+    res = subprocess.run([exe, str(out_dir)], capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "0 failures" in res.stdout
+    # the slab files the C++ mirror wrote are read back by the Python side (same layout, hehub_b200/slabio.py)
+    import numpy as np
+    from hehub_b200 import slabio
+    from oracle.binding import Oracle
+    orc = Oracle()
+    mods = [65537, 260898817, 576460752272228353]
+    words, moduli, kind_tag, value_form = slabio.load(str(out_dir / "poly.slab"))
+    assert moduli == mods and kind_tag == slabio.KIND_POLY and not value_form
+    assert np.array_equal(words[0], np.stack([orc.lcg_fill(6000 + k, q, 64) for k, q in enumerate(mods)]))
+    words, moduli, kind_tag, value_form = slabio.load(str(out_dir / "ksk.slab"))
+    assert words.shape == (4, 3, 64) and kind_tag == slabio.KIND_KSK and value_form
+    assert slabio.dumps(words, moduli, kind_tag, value_form) == open(out_dir / "ksk.slab", "rb").read()
