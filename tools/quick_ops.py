@@ -8,6 +8,9 @@ from oracle.binding import Oracle
 ap = argparse.ArgumentParser()
 ap.add_argument("lib")
 ap.add_argument("--shape", nargs="*", default=["c3"])
+ap.add_argument("--only", nargs="*", default=None, help="subset of tensor ext_prod rescale mult_relin")
+ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--warmup", type=int, default=3)
 a = ap.parse_args()
 SHAPES = {"c3": (13, [40, 30, 30, 30], 40, 256), "c4": (14, [50] + [40] * 7, 50, 128), "c5": (15, [50] * 12, 55, 16)}
 orc = Oracle()
@@ -31,9 +34,10 @@ for name in a.shape:
     }
     out = []
     for k, fn in ops.items():
-        for _ in range(3): fn()
+        if a.only and k not in a.only: continue
+        for _ in range(a.warmup): fn()
         ctx.synchronize()
-        reps = 20
+        reps = a.reps
         t0 = time.perf_counter()
         for _ in range(reps): fn()
         ctx.synchronize()
