@@ -31,6 +31,7 @@ Q59 = 576460752272228353
 LOGN = 12
 POLYS = 4096
 SLABS = 4
+SWEEP_WAVE = 37  # ciphertexts per wave of the config-5 sweep: 2 x 37 rows = one CTA pair per SM pair on 148 SMs
 METRIC = "NTT/s (N=4096, one 59-bit modulus, batch 4096)"
 UNIT = "NTT/s"
 
@@ -448,9 +449,11 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
         r["shape"] = {"N": n, "L": L, "batch_per_gpu": batch}
         out[tag] = r
 
-    ct_bench("c3_ckks_mult_relin_N8192_L4", 13, [40, 30, 30, 30], 40, 256, 4, ("mult", "tensor", "e2e"))
-    ct_bench("c4_rescale_N16384_L8", 14, [50] + [40] * 7, 50, 128, 4, ("rescale",))
-    ct_bench("c5_ckks_mult_relin_N32768_L12", 15, [50] * 12, 55, 16, 2, ("mult", "tensor"))
+    # batch sizes are multiples of the rows one wave of CTAs covers on 148 SMs (N=8192: 2 CTAs per SM, N=16384: one,
+    # N=32768: one CTA pair per row), so every transform launch of the composite ops ends on a full wave
+    ct_bench("c3_ckks_mult_relin_N8192_L4", 13, [40, 30, 30, 30], 40, 296, 4, ("mult", "tensor", "e2e"))
+    ct_bench("c4_rescale_N16384_L8", 14, [50] + [40] * 7, 50, 148, 4, ("rescale",))
+    ct_bench("c5_ckks_mult_relin_N32768_L12", 15, [50] * 12, 55, 37, 2, ("mult", "tensor"))
 
     # config 5 as a sweep: `sweep_cts` independent ciphertext pairs (65 536 in BASELINE; bounded by default so the
     # whole bench stays within minutes) cut into contiguous per-rank ranges, processed in waves, inputs generated
@@ -470,11 +473,11 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
                 e1.synchronize()
                 return e0.elapsed_time(e1) * 1e-3
 
-            sw.run(min(sweep_cts, 64 * world), 32, rank, world, dist)  # warm-up (tables, workspaces)
+            sw.run(min(sweep_cts, 74 * world), SWEEP_WAVE, rank, world, dist)  # warm-up (tables, workspaces)
             torch.cuda.synchronize()
             barrier()
             t0 = time.perf_counter()
-            res = sw.run(sweep_cts, 32, rank, world, dist, timer=ev_timer)
+            res = sw.run(sweep_cts, SWEEP_WAVE, rank, world, dist, timer=ev_timer)
             torch.cuda.synchronize()
             barrier()
             wall = time.perf_counter() - t0
@@ -482,7 +485,7 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         op_s, wall_s = float(t[0].item()), float(t[1].item())
-        r = {"cts_total": sweep_cts, "scaling": "strong", "wave": 32, "mult_relin_per_s_device_time": sweep_cts / op_s,
+        r = {"cts_total": sweep_cts, "scaling": "strong", "wave": SWEEP_WAVE, "mult_relin_per_s_device_time": sweep_cts / op_s,
              "mult_relin_per_s_wall_incl_input_generation_and_checksums": sweep_cts / wall_s,
              "gbs_algorithmic": 48 * 12 * 32768 * sweep_cts / op_s / 1e9}
         r["frac_hbm_per_gpu"] = r["gbs_algorithmic"] / world / hbm
@@ -671,7 +674,7 @@ def main():
     ap.add_argument("--extras", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--rows", type=int, default=1, help="0: skip the per-row table (SURVEY 8(a) rows, GPU and CPU side by side)")
-    ap.add_argument("--sweep-cts", type=int, default=2048,
+    ap.add_argument("--sweep-cts", type=int, default=2072,
                     help="ciphertext pairs in the config-5 sweep extra, whole job (BASELINE: 65536; 0 disables)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup

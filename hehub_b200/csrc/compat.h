@@ -22,6 +22,11 @@
 #define HB_LAUNCH_CLUSTER(kern, grid, block, smem, stream, cluster, ...) \
     (::hbsim::launch((grid), (block), (smem), 1, [&]() { kern(__VA_ARGS__); }, (cluster)), cudaSuccess)
 inline void hb_cluster_sync() { ::hbsim::cluster_sync(); }
+// two adjacent words of CTA `rank`'s shared memory at the offset `p` has in this CTA's (DSMEM)
+inline ulonglong2 hb_ld_dsmem2(const unsigned long long *p, unsigned rank) {
+    return *reinterpret_cast<const ulonglong2 *>(::hbsim::shared_u64_of(rank) + (p - ::hbsim::shared_u64()));
+}
+inline void hb_prefetch_l2(const void *) {}
 inline void hb_syncwarp() { __syncthreads(); } // the emulator has no warps: a CTA barrier is a superset
 inline unsigned long long hb_ld_stream(const unsigned long long *p) { return *p; }
 inline ulonglong2 hb_ld_stream2(const unsigned long long *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
@@ -75,6 +80,16 @@ __device__ __forceinline__ ulonglong2 hb_ld_ro2(const unsigned long long *p) {
 __device__ __forceinline__ void hb_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// two adjacent words of CTA `rank`'s shared memory at the offset `p` has in this CTA's (distributed shared memory)
+__device__ __forceinline__ ulonglong2 hb_ld_dsmem2(const unsigned long long *p, unsigned rank) {
+    unsigned local = (unsigned)__cvta_generic_to_shared(p), remote;
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    ulonglong2 v;
+    asm volatile("ld.shared::cluster.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(remote) : "memory");
+    return v;
+}
+// ask L2 for a line the CTA will read much later (epilogue operands of the fused transforms)
+__device__ __forceinline__ void hb_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void hb_syncwarp() { __syncwarp(); }
 // row words are read once: keep them out of L1, which holds the twiddle tables
 #if defined(HB_NO_STREAM_LD) // A/B builds only

@@ -29,6 +29,7 @@ struct DropConst {
     u64 inv_qlast, inv_qlast_h; // q_last^{-1} mod q_i and Harvey companion
     u64 t_mod_q, t_mod_q_h;     // BGV: t mod q_i
     u64 qlt_mod_q, qlt_mod_q_h; // BGV: (q_last mod t) mod q_i
+    u64 z_below_q;              // q_last <= q_i: every strictly reduced z is already < q_i
 };
 
 struct DropSet {

@@ -149,31 +149,59 @@ HB_D u64 sub_lazy(u64 x, u64 y, u64 q2) {
     return x - ((x >= q2) ? q2 : 0ull);
 }
 
+// 128-bit accumulate acc += a*b (exact; rgsw.cpp:131-134).  Written as one carry chain over the four
+// 32x32 partial products so that ptxas emits exactly four IMAD.WIDE (separate lo64 / hi64 multiplies
+// cost five wide and two narrow IMADs on the multiplier pipe that bounds these kernels).
+HB_D void mac128(u64 &lo, u64 &hi, u64 a, u64 b) {
+#if defined(HB_KERNEL_SIM)
+    u64 plo = a * b;
+    u64 phi = __umul64hi(a, b);
+    lo += plo;
+    hi += phi + ((lo < plo) ? 1ull : 0ull);
+#else
+    u32 l0 = (u32)lo, l1 = (u32)(lo >> 32), h0 = (u32)hi, h1 = (u32)(hi >> 32);
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    asm("mad.lo.cc.u32 %0, %4, %6, %0;\n\t"
+        "madc.hi.cc.u32 %1, %4, %6, %1;\n\t"
+        "madc.lo.cc.u32 %2, %5, %7, %2;\n\t"
+        "madc.hi.u32 %3, %5, %7, %3;\n\t"
+        "mad.lo.cc.u32 %1, %4, %7, %1;\n\t"
+        "madc.hi.cc.u32 %2, %4, %7, %2;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        "mad.lo.cc.u32 %1, %5, %6, %1;\n\t"
+        "madc.hi.cc.u32 %2, %5, %6, %2;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        : "+r"(l0), "+r"(l1), "+r"(h0), "+r"(h1)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    lo = ((u64)l1 << 32) | l0;
+    hi = ((u64)h1 << 32) | h0;
+#endif
+}
+
+// full 128-bit product (lo, hi) = a * b with four IMAD.WIDE
+HB_D void mul_full(u64 a, u64 b, u64 &lo, u64 &hi) {
+    lo = 0;
+    hi = 0;
+    mac128(lo, hi, a, b);
+}
+
 // 128-bit a = (hi, lo);  Montgomery reduce: (a + (lo*minus_qinv mod 2^64)*q) >> 64
 // — mod_arith.cpp:126-133 (also the first half of the hybrid mulmod, :80-87).
 HB_D u64 montgomery128(u64 lo, u64 hi, const LimbConst &c) {
     u64 u = lo * c.minus_qinv;
-    u64 plo = u * c.q;
     u64 phi = __umul64hi(u, c.q);
-    // lo + plo == 0 mod 2^64 by construction; the carry is (lo != 0)
-    u64 carry = (lo + plo < lo) ? 1ull : 0ull;
+    // lo + lo64(u*q) == 0 mod 2^64 by construction, so that addition carries exactly when lo != 0:
+    // the low product itself is never needed
+    u64 carry = (lo != 0) ? 1ull : 0ull;
     return hi + phi + carry;
 }
 
 // batched_mul_mod_hybrid_lazy — mod_arith.cpp:64-92
 HB_D u64 mul_hybrid_lazy(u64 a, u64 b, const LimbConst &c) {
-    u64 lo = a * b;
-    u64 hi = __umul64hi(a, b);
+    u64 lo, hi;
+    mul_full(a, b, lo, hi);
     u64 t = montgomery128(lo, hi, c);
     return harvey_lazy(t, c.r, c.r_h, c.nq);
-}
-
-// 128-bit accumulate acc += a*b (exact; rgsw.cpp:131-134)
-HB_D void mac128(u64 &lo, u64 &hi, u64 a, u64 b) {
-    u64 plo = a * b;
-    u64 phi = __umul64hi(a, b);
-    lo += plo;
-    hi += phi + ((lo < plo) ? 1ull : 0ull);
 }
 
 } // namespace hb

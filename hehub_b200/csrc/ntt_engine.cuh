@@ -34,6 +34,7 @@
 //   void       store2(int row, int i, u64 v0, u64 v1, LimbConst&) -> words i (even) and i+1, used when vec
 #pragma once
 #include <type_traits>
+#include <utility>
 
 #include "modarith.cuh"
 #include "ntt_plan.h"
@@ -48,6 +49,12 @@ HB_D u64 io_load(const IO &io, int row, int i, const LimbConst &lc) {
     return io.pre(row, i, hb_ld_stream(io.src(row) + i), lc);
 #endif
 }
+
+// optional policy hook: prefetch(row, first_word, nwords) is called once per CTA before the first pass
+template <class IO, class = void>
+struct io_has_prefetch : std::false_type {};
+template <class IO>
+struct io_has_prefetch<IO, std::void_t<decltype(std::declval<const IO &>().prefetch(0, 0, 0))>> : std::true_type {};
 
 // ------------------------------------------------------------------------------------------
 // butterfly — ntt.cpp:161-167 (identical for both directions)
@@ -264,6 +271,7 @@ ntt_fwd_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     HB_SHARED_U64(sm);
     const int row = blockIdx.x >> pl.lpre, B = blockIdx.x & ((1 << pl.lpre) - 1);
     const LimbConst lc = limbs[io.limb(row)];
+    if constexpr (io_has_prefetch<IO>::value) io.prefetch(row, B << (LOGN - pl.lpre), 1 << (LOGN - pl.lpre));
     fwd_passes<LOGN, T, 0>(sm, io, lc, row, B);
 }
 
@@ -342,27 +350,38 @@ intt_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     const LimbConst lc = limbs[io.limb(row)];
     inv_passes<LOGN, T, 0>(sm, io, lc, row, B);
     if constexpr (pl.lpre == 1) {
-        // last stage (gap N/2) pairs word i of CTA 0 with word i of CTA 1.  Exchange the halves
-        // through the row's exchange area (L2), combine into shared memory, and only after the
-        // sibling has also finished reading write the final words (the area may be the output).
-        __syncthreads();
-        u64 *raw = io.raw(row);
-        for (int i = threadIdx.x; i < NC; i += T) raw[B * NC + i] = sm[sphys(i)];
+        // Last stage (gap N/2) pairs word i of CTA 0 with word i of CTA 1 — ntt.cpp:199-206.  Each CTA
+        // takes half of the offsets, reads its own words from shared memory and the sibling's through
+        // distributed shared memory, and finishes BOTH outputs of every pair (approximate reduction and
+        // psi^{-i}/N scaling, ntt.cpp:214-221): no butterfly is computed twice and the row never makes
+        // a round trip through L2.
         hb_cluster_sync();
         const ulonglong2 *tw = lc.inv + inv_pass_offset(pl, pl.npass);
-        for (int i = threadIdx.x; i < NC; i += T) {
-            const u64 mine = sm[sphys(i)], other = hb_ldcg(raw + (1 - B) * NC + i);
-            const u64 lo = B ? other : mine, hi = B ? mine : other;
-            const ulonglong2 z = __ldg(tw + i);
-            const u64 t = harvey_lazy(hi, z.x, z.y, lc.nq);
-            sm[sphys(i)] = B ? (lo + lc.q2 - t) : (lo + t); // ntt.cpp:199-206, own half only
+        for (int i = B * (NC / 2) + 2 * (int)threadIdx.x; i < (B + 1) * (NC / 2); i += 2 * T) {
+            const u64 *p = sm + sphys(i); // i even: words i, i+1 are adjacent
+            const ulonglong2 mine = *reinterpret_cast<const ulonglong2 *>(p), other = hb_ld_dsmem2(p, 1 - B);
+            const ulonglong2 lo = B ? other : mine, hi = B ? mine : other;
+            u64 out_lo[2], out_hi[2];
+#pragma unroll
+            for (int w = 0; w < 2; w++) {
+                const ulonglong2 z = __ldg(tw + i + w);
+                const u64 l = w ? lo.y : lo.x, h = w ? hi.y : hi.x;
+                const u64 t = harvey_lazy(h, z.x, z.y, lc.nq);
+                const ulonglong2 s0 = __ldg(lc.inv_scale + i + w), s1 = __ldg(lc.inv_scale + NC + i + w);
+                out_lo[w] = harvey_lazy(approx_reduce(l + t, lc), s0.x, s0.y, lc.nq);
+                out_hi[w] = harvey_lazy(approx_reduce(l + lc.q2 - t, lc), s1.x, s1.y, lc.nq);
+            }
+            if (io.vec) {
+                io.store2(row, i, out_lo[0], out_lo[1], lc);
+                io.store2(row, NC + i, out_hi[0], out_hi[1], lc);
+            } else {
+                io.store(row, i, out_lo[0], lc);
+                io.store(row, i + 1, out_lo[1], lc);
+                io.store(row, NC + i, out_hi[0], lc);
+                io.store(row, NC + i + 1, out_hi[1], lc);
+            }
         }
-        hb_cluster_sync();
-        for (int i = threadIdx.x; i < NC; i += T) {
-            const int gi = B * NC + i;
-            const ulonglong2 s = __ldg(lc.inv_scale + gi);
-            io.store(row, gi, harvey_lazy(approx_reduce(sm[sphys(i)], lc), s.x, s.y, lc.nq), lc);
-        }
+        hb_cluster_sync(); // the sibling may still be reading this CTA's shared memory
     }
 }
 

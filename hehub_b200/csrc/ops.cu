@@ -162,8 +162,14 @@ HB_D void st_words(u64 *p, const u64 (&src)[W]) {
 template <int CPT, int W>
 HB_GLOBAL(256, HB_MAC_MINB)
 ext_mac_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
-               u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, int logn, size_t batch, size_t total) {
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // (b / CPT, k, i / W)
+               u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, int logn, size_t batch, size_t total,
+               unsigned groups, unsigned chunks_per_group) {
+    // gid = (b / CPT, k, i / W).  With `groups` != 0 consecutive CTAs take the SAME 256-thread slice of
+    // (k, i) for consecutive ciphertext groups, so CTAs resident together share their key words in L2
+    // (the key is read once per group: 8-18 times per wave) instead of streaming it from HBM each time.
+    size_t gid;
+    if (groups) gid = ((size_t)(blockIdx.x % groups) * chunks_per_group + blockIdx.x / groups) * 256 + threadIdx.x;
+    else gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
     const int L1 = L + 1;
     constexpr int LW = (W == 2) ? 1 : 0;
@@ -246,13 +252,15 @@ static int ext_prod_wave(Context &c, unsigned logn, const LimbConst *limbs, size
     constexpr int CPT = HB_MAC_CPT;
     const size_t groups = (batch + CPT - 1) / CPT;
     if (aligned16(in) && in_batch_stride % 2 == 0 && aligned16(dec) && aligned16(key) && aligned16(out) && n >= 2) {
-        const size_t total = groups * (L + 1) * (n / 2);
+        const size_t total = groups * (L + 1) * (n / 2), per_group = (L + 1) * (n / 2);
+        const bool inter = per_group % 256 == 0 && groups > 1;
         HB_LAUNCH((ext_mac_kernel<CPT, 2>), (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, in_batch_stride, dec, key, out,
-                  limbs, (int)L, (int)logn, batch, total);
+                  limbs, (int)L, (int)logn, batch, total, inter ? (unsigned)groups : 0u, (unsigned)(per_group / 256));
     } else {
-        const size_t total = groups * (L + 1) * n;
+        const size_t total = groups * (L + 1) * n, per_group = (L + 1) * n;
+        const bool inter = per_group % 256 == 0 && groups > 1;
         HB_LAUNCH((ext_mac_kernel<CPT, 1>), (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, in_batch_stride, dec, key, out,
-                  limbs, (int)L, (int)logn, batch, total);
+                  limbs, (int)L, (int)logn, batch, total, inter ? (unsigned)groups : 0u, (unsigned)(per_group / 256));
     }
     c.stats.launches++;
     e = cudaGetLastError();
@@ -335,7 +343,10 @@ struct DropFwdIO {
     HB_D const u64 *src(int row) const { return z + ((size_t)(row / (L - 1)) << logn); }
     HB_D u64 pre(int row, int, u64 zz, const LimbConst &lc) const {
         const int k = row % (L - 1);
-        u64 r = reduce_strict(barrett_lazy(zz, lc), lc.q);          // rescaling.cpp:58-59
+        // rescaling.cpp:58-59.  z < q_last; when q_last <= q_k the Barrett quotient hi64(z * floor((2^64-1)/q_k)) is 0
+        // and the strict reduction is the identity, so the reference's result is z itself.
+        u64 r = zz;
+        if (!__ldg(&dc[k].z_below_q)) r = reduce_strict(barrett_lazy(zz, lc), lc.q);
         if (zz >= half_qlast) r += lc.q - __ldg(&dc[k].qlast_mod_q); // rescaling.cpp:63-68
         if (BGV) r = harvey_lazy(r, __ldg(&dc[k].t_mod_q), __ldg(&dc[k].t_mod_q_h), lc.nq); // mod_switch.cpp:70
         return r;
@@ -348,6 +359,18 @@ struct DropFwdIO {
         if (h < add_halves) // ckks/arith.cpp:70-71, 84, 91
             x = add_lazy(x, hb_ld_ro(addend + (size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn) + i), lc.q2);
         out[((size_t)row << logn) + i] = x;
+    }
+    // the epilogue's operands (this row of ct and of the addend) are first touched ~10 us after the CTA
+    // starts: ask L2 for them now so the stores at the end do not wait on HBM
+    HB_D void prefetch(int row, int first_word, int nwords) const {
+        const int poly = row / (L - 1), k = row - poly * (L - 1);
+        const u64 *c = ct + ((size_t)(poly * L + k) << logn) + first_word;
+        for (int w = (int)threadIdx.x * 16; w < nwords; w += (int)blockDim.x * 16) hb_prefetch_l2(c + w);
+        const int h = poly & 1, b = poly >> 1;
+        if (h < add_halves) {
+            const u64 *a = addend + (size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn) + first_word;
+            for (int w = (int)threadIdx.x * 16; w < nwords; w += (int)blockDim.x * 16) hb_prefetch_l2(a + w);
+        }
     }
     HB_D u64 finish(u64 x, u64 v, const DropConst *d, const LimbConst &lc) const {
         x = sub_lazy(x, v, lc.q2);                                                         // rescaling.cpp:73

@@ -251,6 +251,7 @@ const DropSet *Context::get_drop(unsigned logn, const u64 *moduli, size_t L, u64
         d.t_mod_q_h = host_harvey_quotient(d.t_mod_q, q);
         d.qlt_mod_q = t ? (q_last % t) % q : 0;
         d.qlt_mod_q_h = host_harvey_quotient(d.qlt_mod_q, q);
+        d.z_below_q = q_last <= q ? 1 : 0;
     }
     DropSet ds;
     ds.half_qlast = q_last / 2;

@@ -12,6 +12,7 @@ constexpr size_t kMaxCluster = 2;
 static std::vector<hbsim_u64> g_shared[kMaxCluster];
 static thread_local size_t t_rank = 0; // CTA rank within its cluster
 hbsim_u64 *shared_u64() { return g_shared[t_rank].data(); }
+hbsim_u64 *shared_u64_of(size_t cluster_rank) { return g_shared[cluster_rank].data(); }
 
 // A reusable sense-reversing barrier.
 struct Barrier {

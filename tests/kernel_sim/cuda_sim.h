@@ -31,6 +31,7 @@ struct hbsim_dim3 {
 namespace hbsim {
 extern thread_local hbsim_dim3 t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
 hbsim_u64 *shared_u64();
+hbsim_u64 *shared_u64_of(size_t cluster_rank);
 void sync_threads();
 void cluster_sync();
 void launch(size_t grid, size_t block, size_t smem_bytes, int sync, const std::function<void()> &body, size_t cluster = 1);

@@ -12,7 +12,7 @@ ap.add_argument("--only", nargs="*", default=None, help="subset of tensor ext_pr
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--warmup", type=int, default=3)
 a = ap.parse_args()
-SHAPES = {"c3": (13, [40, 30, 30, 30], 40, 256), "c4": (14, [50] + [40] * 7, 50, 128), "c5": (15, [50] * 12, 55, 16)}
+SHAPES = {"c3": (13, [40, 30, 30, 30], 40, 296), "c4": (14, [50] + [40] * 7, 50, 148), "c5": (15, [50] * 12, 55, 37)}
 orc = Oracle()
 ctx = Context(lib_path=a.lib)
 for name in a.shape:
