@@ -42,7 +42,11 @@ HB_CX NttPlan plan_for(int logn) {
 #endif
     case 12: return NttPlan{12, 0, 3, {4, 4, 4, 0, 0}, 256, 3};
     case 13: return NttPlan{13, 0, 3, {5, 4, 4, 0, 0}, 256, 2};
+#if defined(HB_PLAN14) && HB_PLAN14 == 0 // one CTA per row: nothing else shares the SM, load/compute/store phases do not overlap
     case 14: return NttPlan{14, 0, 3, {5, 5, 4, 0, 0}, 512, 1};
+#else // 2-CTA cluster per row, half a row per CTA, so CTAs of two different rows share an SM (+5 %, profiles/r1_plan_sweep.md)
+    case 14: return NttPlan{14, 1, 3, {5, 4, 4, 0, 0}, 256, 2};
+#endif
     default: return NttPlan{15, 1, 4, {4, 3, 3, 4, 0}, 512, 1};
     }
 }
