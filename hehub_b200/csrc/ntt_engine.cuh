@@ -14,10 +14,10 @@
 //     owns 32 << K adjacent words), and when the neighbouring pass keeps the same number of words
 //     per thread the exchange between the two stays inside a warp: N = 4096 needs ONE CTA barrier
 //     per transform;
-//   * N <= 16384: one CTA per row; N = 32768 (256 KiB, more than one SM holds): a 2-CTA
+//   * N <= 8192: one CTA per row; N = 16384 and N = 32768 (256 KiB, more than one SM holds): a 2-CTA
 //     thread-block cluster per row, half a row each; the single cross-CTA level (gap N/2) is
-//     computed from global/L2 reads on the way in (forward) or exchanged through the row's own
-//     global words between two cluster barriers (inverse).
+//     computed from global/L2 reads on the way in (forward) or finished from the sibling's shared
+//     memory (distributed shared memory) on the way out (inverse).
 //
 // Kernels are parameterised by an IO policy; the fused rescale / key-switch kernels (ops.cu)
 // are instantiations with prologue/epilogue arithmetic inside the policy, so those values are
@@ -28,8 +28,9 @@
 //   const u64 *src(int row)                               -> the row's N contiguous input words
 //   u64        pre(int row, int i, u64 raw, LimbConst&)   -> input word i from the raw word read at src(row)[i]
 //   void       store(int row, int i, u64 v, LimbConst&)   -> consumes output word i
-//   u64       *raw(int row)                               -> row-sized exchange area in global memory
-//                                                            (N = 32768 inverse only; may be the output row)
+//   u64       *raw(int row)                               -> row-sized scratch in global memory (unused since the
+//                                                            cluster inverse exchanges through shared memory)
+//   void       prefetch(int row, int first, int nwords)   -> optional: called once per CTA before the first pass
 //   bool       vec                                        -> every row pointer is 16-byte aligned
 //   void       store2(int row, int i, u64 v0, u64 v1, LimbConst&) -> words i (even) and i+1, used when vec
 #pragma once
