@@ -8,6 +8,8 @@
 // in host memory.  Host buffers should come from hehub_b200_host_alloc (pinned); pageable
 // memory works but serialises the copies.
 #include "../../include/hehub_b200.h"
+#include <vector>
+
 #include "internal.h"
 
 using namespace hb;
@@ -47,9 +49,35 @@ static int run_pipeline(Context &c, size_t units, size_t chunk, int n_in, const 
     if (!dout) return err;
     // everything queued earlier on the compute stream precedes the first kernel anyway; the copy
     // streams only touch the staging slabs
-    size_t idx = 0;
-    for (size_t first = 0; first < units; first += chunk, idx++) {
-        const size_t cnt = (units - first < chunk) ? units - first : chunk;
+    // Chunk schedule: the first copy-in and the last copy-out overlap nothing, so the pipeline starts
+    // and ends with small chunks (chunk/8, chunk/4, chunk/2) and runs full-size chunks in between.
+    std::vector<size_t> sched;
+    {
+        std::vector<size_t> ramp;
+        size_t used = 0;
+        for (size_t cc = chunk / 8 ? chunk / 8 : 1; cc < chunk; cc *= 2) {
+            ramp.push_back(cc);
+            used += 2 * cc;
+        }
+        if (used + chunk <= units) {
+            sched = ramp;
+            for (size_t left = units - used; left > 0;) {
+                const size_t cc = left < chunk ? left : chunk;
+                sched.push_back(cc);
+                left -= cc;
+            }
+            sched.insert(sched.end(), ramp.rbegin(), ramp.rend());
+        } else {
+            for (size_t left = units; left > 0;) {
+                const size_t cc = left < chunk ? left : chunk;
+                sched.push_back(cc);
+                left -= cc;
+            }
+        }
+    }
+    size_t idx = 0, first = 0;
+    for (; idx < sched.size(); first += sched[idx], idx++) {
+        const size_t cnt = sched[idx];
         const int slot = (int)(idx % S);
         cudaError_t e = cudaSuccess;
         if (idx >= (size_t)S) e = cudaStreamWaitEvent(c.s_in, c.ev_out[slot], 0); // slot drained

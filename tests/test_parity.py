@@ -571,6 +571,18 @@ def test_host_buffer_pipeline(dev, oracle):
     assert np.array_equal(y, want)
     dev.ntt_host(False, logn, moduli, y, y, strict=True)  # in place on the host buffer
     assert np.array_equal(y, x)
+    # a long batch with a small chunk: ramp-up chunks (1, 2, 4 units), full chunks of 8, a ragged one, ramp-down
+    big = 41
+    xb, yb = dev.pinned((big, 2, n)), dev.pinned((big, 2, n))
+    for b in range(big):
+        for k, q in enumerate(moduli):
+            xb[b, k] = oracle.lcg_fill(1000 + 10 * b + k, q, n)
+    dev.set_option("host_chunk_kib", 128)
+    try:
+        dev.ntt_host(True, logn, moduli, xb, yb)
+    finally:
+        dev.set_option("host_chunk_kib", 16384)
+    assert np.array_equal(yb, np.stack([oracle.poly_ntt_fwd(logn, moduli, xb[b]) for b in range(big)]))
     mods, ext = _shape(oracle, logn, [40, 30], 40)
     ct1, ct2 = dev.pinned((batch, 2, 2, n)), dev.pinned((batch, 2, 2, n))
     for b in range(batch):
