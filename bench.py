@@ -388,6 +388,10 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
             gbs = 48 * L * n / per / 1e9
             r["mult_relin"] = {"per_s": world / per, "us_per_ct": per * 1e6, "gbs_algorithmic": gbs, "frac_hbm": gbs / hbm,
                                "transforms_per_ct": L * L + 3 * L + 2}
+        if "latency" in what:  # one ciphertext pair per call: the launch-bound end of the same path
+            fn = lambda i: ctx._call("ckks_mult_relin", logn, extp, L, ct1.data_ptr(), ct2.data_ptr(), key.data_ptr(), res.data_ptr(), 1)
+            el = timed(fn, 50, 5)
+            r["mult_relin_single_ct"] = {"us_per_call": el / 50 * 1e6, "per_s": world * 50 / el, "kernel_launches_per_call": 6}
         if "rescale" in what:
             fn = lambda i: ctx._call("ckks_rescale", logn, modp, L, ct1.data_ptr(), res.data_ptr(), batch)
             el = timed(fn, steps, 2)
@@ -451,9 +455,9 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
 
     # batch sizes are multiples of the rows one wave of CTAs covers on 148 SMs (N=8192: 2 CTAs per SM, N=16384: one,
     # N=32768: one CTA pair per row), so every transform launch of the composite ops ends on a full wave
-    ct_bench("c3_ckks_mult_relin_N8192_L4", 13, [40, 30, 30, 30], 40, 296, 4, ("mult", "tensor", "e2e"))
+    ct_bench("c3_ckks_mult_relin_N8192_L4", 13, [40, 30, 30, 30], 40, 296, 4, ("mult", "tensor", "e2e", "latency"))
     ct_bench("c4_rescale_N16384_L8", 14, [50] + [40] * 7, 50, 148, 4, ("rescale",))
-    ct_bench("c5_ckks_mult_relin_N32768_L12", 15, [50] * 12, 55, 37, 2, ("mult", "tensor"))
+    ct_bench("c5_ckks_mult_relin_N32768_L12", 15, [50] * 12, 55, 37, 2, ("mult", "tensor", "latency"))
 
     # config 5 as a sweep: `sweep_cts` independent ciphertext pairs (65 536 in BASELINE; bounded by default so the
     # whole bench stays within minutes) cut into contiguous per-rank ranges, processed in waves, inputs generated
