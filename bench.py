@@ -501,6 +501,23 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
             import numpy as np
             r["checksums_gathered"] = int(res["checksums"].size)
             r["checksum_of_checksums"] = int(np.bitwise_xor.reduce(res["checksums"]))
+        if cpu_ok and rank == 0:
+            # sampled parity at the full config-5 size: this rank's first, middle and last ciphertext pairs
+            # recomputed by the reference's CPU path and compared through the per-ciphertext checksum; the same calls
+            # give the CPU side of the config-5 speed-up
+            from hehub_b200.sweep import ct_checksum_numpy
+            lib, kind = _cpu_lib()
+            keyh = sw.key_host()
+            picks = sorted({res["first"], res["first"] + res["count"] // 2, res["first"] + res["count"] - 1})
+            okc, t0 = 0, time.perf_counter()
+            for idx in picks:
+                a, b = sw.one_ct_inputs_host(idx)
+                okc += int(ct_checksum_numpy(lib.ckks_mult_relin(15, sw.ext, a, b, keyh)) == int(res["checksums"][idx - res["first"]]))
+            cdt = (time.perf_counter() - t0) / len(picks)
+            r["parity_sample"] = {"ciphertexts_checked": len(picks), "bit_exact": okc == len(picks), "checker": kind}
+            r["cpu_mult_relin"] = {"per_s": 1.0 / cdt, "cores": 1, "kind": kind,
+                                   "sample": f"{len(picks)} ciphertext pairs (incl. regenerating their inputs), one core"}
+            r["speedup_device_resident_vs_one_cpu_core"] = r["mult_relin_per_s_device_time"] / (1.0 / cdt)
         out["c5_sweep_N32768_L12"] = r
     return out
 
@@ -678,7 +695,7 @@ def main():
     ap.add_argument("--extras", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--rows", type=int, default=1, help="0: skip the per-row table (SURVEY 8(a) rows, GPU and CPU side by side)")
-    ap.add_argument("--sweep-cts", type=int, default=2072,
+    ap.add_argument("--sweep-cts", type=int, default=65536,
                     help="ciphertext pairs in the config-5 sweep extra, whole job (BASELINE: 65536; 0 disables)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
