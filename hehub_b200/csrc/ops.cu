@@ -267,10 +267,16 @@ static int ext_prod_wave(Context &c, unsigned logn, const LimbConst *limbs, size
     return e == cudaSuccess ? 0 : c.cuda_fail(e, "ext_prod: mac launch");
 }
 
+// Ciphertexts per wave: what the scratch cap allows, rounded down to a multiple of a quarter of the SM count
+// when the batch has to be cut anyway — the transform launches of a wave run 2, L, L^2 or 2(L-1) rows per
+// ciphertext on 1-2 CTAs per row, and with such a wave all of them end on (nearly) full waves of CTAs.
 static size_t wave_size(const Context &c, size_t words_per_ct, size_t batch) {
     size_t w = c.scratch_cap_bytes / (words_per_ct * 8);
     if (w < 1) w = 1;
-    return w < batch ? w : batch;
+    if (w >= batch) return batch;
+    const size_t quantum = (size_t)(c.sm_count > 4 ? c.sm_count / 4 : 1);
+    if (w >= quantum) w -= w % quantum;
+    return w;
 }
 
 int op_ext_prod(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *in, size_t in_batch_stride,
