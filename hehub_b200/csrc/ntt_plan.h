@@ -41,13 +41,23 @@ HB_CX NttPlan plan_for(int logn) {
     case 11: return NttPlan{11, 0, 3, {3, 4, 4, 0, 0}, 128, 6};
 #endif
     case 12: return NttPlan{12, 0, 3, {4, 4, 4, 0, 0}, 256, 3};
+#if defined(HB_PLAN13) && HB_PLAN13 == 1 // A/B: four narrower passes, three CTAs per SM
+    case 13: return NttPlan{13, 0, 4, {3, 3, 3, 4, 0}, 256, 3};
+#else
     case 13: return NttPlan{13, 0, 3, {5, 4, 4, 0, 0}, 256, 2};
+#endif
 #if defined(HB_PLAN14) && HB_PLAN14 == 0 // one CTA per row: nothing else shares the SM, load/compute/store phases do not overlap
     case 14: return NttPlan{14, 0, 3, {5, 5, 4, 0, 0}, 512, 1};
-#else // 2-CTA cluster per row, half a row per CTA, so CTAs of two different rows share an SM (+5 %, profiles/r1_plan_sweep.md)
+#elif defined(HB_PLAN14) && HB_PLAN14 == 1 // 2-CTA cluster per row, half a row per CTA, two CTAs per SM (+5 % over one CTA per row)
     case 14: return NttPlan{14, 1, 3, {5, 4, 4, 0, 0}, 256, 2};
+#else // cluster form with four narrower passes: three CTAs (of up to three different rows) per SM, another +2-4 %
+    case 14: return NttPlan{14, 1, 4, {3, 3, 3, 4, 0}, 256, 3};
 #endif
+#if defined(HB_PLAN15) && HB_PLAN15 == 0 // 16 warps per CTA (one CTA per SM): too few to hide the fused epilogues' loads
     default: return NttPlan{15, 1, 4, {4, 3, 3, 4, 0}, 512, 1};
+#else // 32 warps per CTA at 64 registers: C5 rescale -11 %, mult+relin -1.6 % (profiles/r1_plan_sweep.md)
+    default: return NttPlan{15, 1, 4, {3, 3, 4, 4, 0}, 1024, 1};
+#endif
     }
 }
 
