@@ -186,7 +186,7 @@ HB_CX bool warp_local_pair(int ka, int kb) { return ka == kb && ka <= 5; }
 // ------------------------------------------------------------------------------------------
 template <int LOGN, int T, int P, class IO>
 HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
-    constexpr NttPlan pl = plan_for(LOGN);
+    constexpr NttPlan pl = plan_for(LOGN, true);
     constexpr int LOGNC = LOGN - pl.lpre, NC = 1 << LOGNC;
     constexpr int K = pl.k[P], L0 = fwd_lambda0(pl, P), GSL = LOGNC - L0 - K; // log2(smallest gap)
     constexpr int NG = NC >> K;
@@ -244,7 +244,7 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
 
 template <int LOGN, int T, int P, class IO>
 HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
-    constexpr NttPlan pl = plan_for(LOGN);
+    constexpr NttPlan pl = plan_for(LOGN, true);
     fwd_pass<LOGN, T, P>(sm, io, lc, row, B);
     if constexpr (P + 1 < pl.npass) {
         if constexpr (P == 0 && pl.lpre == 1) {
@@ -262,12 +262,12 @@ HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B)
 
 // one CTA (or one CTA of a 2-CTA cluster) per row
 template <int LOGN, class IO>
-HB_GLOBAL(plan_for(LOGN).threads, plan_for(LOGN).min_blocks)
+HB_GLOBAL(plan_for(LOGN, true).threads, plan_for(LOGN, true).min_blocks)
 ntt_fwd_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     // One row per CTA on purpose: resident CTAs walking several rows each (with or without a start
     // skew between the CTAs of an SM) measured 15-20 % slower than letting the block scheduler hand
     // out rows (profiles/r1_plan_sweep.md).
-    constexpr NttPlan pl = plan_for(LOGN);
+    constexpr NttPlan pl = plan_for(LOGN, true);
     constexpr int T = pl.threads;
     HB_SHARED_U64(sm);
     const int row = blockIdx.x >> pl.lpre, B = blockIdx.x & ((1 << pl.lpre) - 1);
@@ -281,7 +281,7 @@ ntt_fwd_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
 // ------------------------------------------------------------------------------------------
 template <int LOGN, int T, int P, class IO>
 HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
-    constexpr NttPlan pl = plan_for(LOGN);
+    constexpr NttPlan pl = plan_for(LOGN, false);
     constexpr int LOGNC = LOGN - pl.lpre, NC = 1 << LOGNC;
     constexpr int K = inv_k(pl, P), S0 = inv_s0(pl, P);
     constexpr int NG = NC >> K;
@@ -329,7 +329,7 @@ HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
 
 template <int LOGN, int T, int P, class IO>
 HB_D void inv_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
-    constexpr NttPlan pl = plan_for(LOGN);
+    constexpr NttPlan pl = plan_for(LOGN, false);
     inv_pass<LOGN, T, P>(sm, io, lc, row, B);
     if constexpr (P + 1 < pl.npass) {
         if constexpr (P == 0 && warp_local_pair(inv_k(pl, 0), inv_k(pl, 1))) {
@@ -342,9 +342,9 @@ HB_D void inv_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B)
 }
 
 template <int LOGN, class IO>
-HB_GLOBAL(plan_for(LOGN).threads, plan_for(LOGN).min_blocks)
+HB_GLOBAL(plan_for(LOGN, false).threads, plan_for(LOGN, false).min_blocks)
 intt_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
-    constexpr NttPlan pl = plan_for(LOGN);
+    constexpr NttPlan pl = plan_for(LOGN, false);
     constexpr int NC = 1 << (LOGN - pl.lpre), T = pl.threads;
     HB_SHARED_U64(sm);
     const int row = blockIdx.x >> pl.lpre, B = blockIdx.x & ((1 << pl.lpre) - 1);
@@ -462,7 +462,7 @@ inline cudaError_t configure_smem(K kern, int smem, int blocks) {
 
 template <int LOGN, bool FWD, class IO>
 inline cudaError_t launch_fast(const LaunchEnv &env, const IO &io, const LimbConst *limbs, int rows) {
-    constexpr NttPlan pl = plan_for(LOGN);
+    constexpr NttPlan pl = plan_for(LOGN, FWD);
     constexpr int smem = smem_words(1 << (LOGN - pl.lpre)) * 8;
     auto kern = fast_kernel<LOGN, FWD, IO>();
     static bool configured = false;

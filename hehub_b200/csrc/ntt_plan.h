@@ -6,7 +6,8 @@
 // `npass` passes; in pass p every thread keeps 2^k[p] coefficients in registers and runs k[p]
 // levels on them before the CTA exchanges through shared memory.  The forward transform runs
 // the passes in the listed order (gaps shrink N/2 -> 1, last pass touches contiguous
-// coefficients); the inverse transform runs the mirrored list (gaps grow 1 -> N/2).
+// coefficients); the inverse transform runs the mirrored list (gaps grow 1 -> N/2).  The two directions
+// have separate tables and may use different plans.
 //
 // The twiddle tables are laid out per pass as [slot][block] so that the lanes of a warp read
 // consecutive 16-byte (w, w') pairs in every pass (see tables.cu).
@@ -30,7 +31,7 @@ constexpr int kFastLogMin = 10;
 constexpr int kFastLogMax = 15;
 constexpr int kGenericLogMax = 14; // one row must fit one CTA's shared memory
 
-HB_CX NttPlan plan_for(int logn) {
+HB_CX NttPlan plan_for(int logn, bool fwd) {
     // Measured on B200 (profiles/r1_plan_sweep.md).  Passes of 4-5 levels keep 16-32 words per thread
     // in registers; ending with two passes of equal width keeps their exchange inside a warp.
     switch (logn) {
@@ -41,10 +42,10 @@ HB_CX NttPlan plan_for(int logn) {
     case 11: return NttPlan{11, 0, 3, {3, 4, 4, 0, 0}, 128, 6};
 #endif
     case 12: return NttPlan{12, 0, 3, {4, 4, 4, 0, 0}, 256, 3};
-#if defined(HB_PLAN13) && HB_PLAN13 == 1 // A/B: four narrower passes, three CTAs per SM
-    case 13: return NttPlan{13, 0, 4, {3, 3, 3, 4, 0}, 256, 3};
-#else
+#if defined(HB_PLAN13) && HB_PLAN13 == 0
     case 13: return NttPlan{13, 0, 3, {5, 4, 4, 0, 0}, 256, 2};
+#else // forward: four narrower passes and three CTAs per SM (+2 %, more for the fused kernels); the inverse loses 3 % with it
+    case 13: return fwd ? NttPlan{13, 0, 4, {3, 3, 3, 4, 0}, 256, 3} : NttPlan{13, 0, 3, {5, 4, 4, 0, 0}, 256, 2};
 #endif
 #if defined(HB_PLAN14) && HB_PLAN14 == 0 // one CTA per row: nothing else shares the SM, load/compute/store phases do not overlap
     case 14: return NttPlan{14, 0, 3, {5, 5, 4, 0, 0}, 512, 1};

@@ -149,8 +149,8 @@ const ModTables *Context::get_tables(u64 q, unsigned logn, int *err) {
         inv_scale[i] = pair_of(mulmod(pw[i], n_inv, q));
 
     if (fast) {
-        const NttPlan pl = plan_for((int)logn);
         ulonglong2 *ff = inv_scale + n, *fi = ff + n;
+        NttPlan pl = plan_for((int)logn, true);
         if (pl.lpre) ff[0] = fwd_nat[1];
         for (int p = 0; p < pl.npass; p++) {
             const int K = pl.k[p], l0g = pl.lpre + fwd_lambda0(pl, p), off = fwd_pass_offset(pl, p);
@@ -161,6 +161,7 @@ const ModTables *Context::get_tables(u64 q, unsigned logn, int *err) {
                         ff[off + (slot << l0g) + hb] = fwd_nat[((size_t)1 << (l0g + m - 1)) + ((size_t)hb << (m - 1)) + blk];
                 }
         }
+        pl = plan_for((int)logn, false);
         for (int p = 0; p <= pl.npass; p++) {
             if (p == pl.npass && !pl.lpre) break;
             const int K = (p == pl.npass) ? 1 : inv_k(pl, p);
