@@ -67,6 +67,7 @@ _SIGS = {
     "ckks_relinearize": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, C.c_void_p, sz],
     "bgv_relinearize": [C.c_uint, p64, sz, u64, C.c_void_p, C.c_void_p, C.c_void_p, sz],
     "ckks_mult_relin": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, sz],
+    "bgv_mult_relin": [C.c_uint, p64, sz, u64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, sz],
     "ckks_rotate": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, sz, C.c_void_p, sz],
     "ckks_conjugate": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, C.c_void_p, sz],
     "rlwe_decrypt_core": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, C.c_void_p, sz],
@@ -387,6 +388,11 @@ class Context:
         L, n = len(ext_moduli) - 1, 1 << logn
         ct1, batch = self._batch_of(ct1, (2, L, n))
         return self._op("ckks_mult_relin", logn, ext_moduli, [ct1, ct2, key], ct1.shape[:-3] + (2, L, n), L, batch=batch)
+
+    def bgv_mult_relin(self, logn, ext_moduli, t, ct1, ct2, key):
+        L, n = len(ext_moduli) - 1, 1 << logn
+        ct1, batch = self._batch_of(ct1, (2, L, n))
+        return self._op("bgv_mult_relin", logn, ext_moduli, [ct1, ct2, key], ct1.shape[:-3] + (2, L, n), L, u64(t), batch=batch)
 
     def ckks_rotate(self, logn, ext_moduli, ct, key, step):
         L, n = len(ext_moduli) - 1, 1 << logn

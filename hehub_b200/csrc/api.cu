@@ -558,7 +558,16 @@ int hehub_b200_ckks_mult_relin(hehub_b200_ctx *ctx, unsigned logn, const uint64_
                                const uint64_t *ct1, const uint64_t *ct2, const uint64_t *key, uint64_t *out, size_t batch) {
     CTX_GUARD(ctx);
     if (int rc = check_ring(c, logn, L + 1, batch)) return rc;
-    return op_mult_relin(c, logn, (const u64 *)ext_moduli, L, (const u64 *)ct1, (const u64 *)ct2, (const u64 *)key,
+    return op_mult_relin(c, logn, (const u64 *)ext_moduli, L, 0, (const u64 *)ct1, (const u64 *)ct2, (const u64 *)key,
+                         (u64 *)out, batch);
+}
+
+int hehub_b200_bgv_mult_relin(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli, size_t L, uint64_t t,
+                              const uint64_t *ct1, const uint64_t *ct2, const uint64_t *key, uint64_t *out, size_t batch) {
+    CTX_GUARD(ctx);
+    if (int rc = check_ring(c, logn, L + 1, batch)) return rc;
+    if (t == 0) return c.fail(HEHUB_B200_ERR_INVALID, "plain modulus must be positive");
+    return op_mult_relin(c, logn, (const u64 *)ext_moduli, L, t, (const u64 *)ct1, (const u64 *)ct2, (const u64 *)key,
                          (u64 *)out, batch);
 }
 

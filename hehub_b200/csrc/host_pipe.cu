@@ -151,7 +151,7 @@ int hehub_b200_ckks_mult_relin_host(hehub_b200_ctx *ctx, unsigned logn, const ui
     const u64 *ins[2] = {reinterpret_cast<const u64 *>(host_ct1), reinterpret_cast<const u64 *>(host_ct2)};
     return run_pipeline(c, batch, chunk, 2, ins, words, reinterpret_cast<u64 *>(host_out), words, 8, false,
                         [&](u64 *a, u64 *b, u64 *out, size_t cnt) -> int {
-                            return op_mult_relin(c, logn, reinterpret_cast<const u64 *>(ext_moduli), L, a, b,
+                            return op_mult_relin(c, logn, reinterpret_cast<const u64 *>(ext_moduli), L, 0, a, b,
                                                  reinterpret_cast<const u64 *>(dev_key), out, cnt);
                         });
 }

@@ -31,7 +31,7 @@ int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, 
                  size_t batch, const u64 *addend, size_t add_batch_stride, size_t add_poly_stride, int add_halves);
 int op_relinearize(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u64 t, const u64 *quad,
                    const u64 *key, u64 *out, size_t batch);
-int op_mult_relin(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *ct1, const u64 *ct2,
+int op_mult_relin(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u64 t, const u64 *ct1, const u64 *ct2,
                   const u64 *key, u64 *out, size_t batch);
 int op_rlwe_decrypt_core(Context &c, unsigned logn, const u64 *moduli, size_t L, const u64 *ct, const u64 *sk, u64 *pt,
                          size_t batch);

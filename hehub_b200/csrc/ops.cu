@@ -458,8 +458,8 @@ int op_relinearize(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u
     return 0;
 }
 
-int op_mult_relin(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *ct1, const u64 *ct2, const u64 *key,
-                  u64 *out, size_t batch) {
+int op_mult_relin(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u64 t, const u64 *ct1, const u64 *ct2,
+                  const u64 *key, u64 *out, size_t batch) {
     if (!ext_moduli || !ct1 || !ct2 || !key || !out) return c.fail(1, "null operand");
     if (L == 0) return c.fail(1, "Empty RGSW ciphertext.");
     if (batch == 0) return 0;
@@ -472,7 +472,7 @@ int op_mult_relin(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, co
     for (size_t b0 = 0; b0 < batch; b0 += wave) {
         const size_t nb = (batch - b0 < wave) ? batch - b0 : wave;
         if (int rc = op_ckks_tensor(c, logn, ext_moduli, L, ct1 + b0 * 2 * L * n, ct2 + b0 * 2 * L * n, quad, nb)) return rc;
-        if (int rc = op_relinearize(c, logn, ext_moduli, L, 0, quad, key, out + b0 * 2 * L * n, nb)) return rc;
+        if (int rc = op_relinearize(c, logn, ext_moduli, L, t, quad, key, out + b0 * 2 * L * n, nb)) return rc;
     }
     return 0;
 }

@@ -130,6 +130,8 @@ int hehub_b200_galois_involution(hehub_b200_ctx *ctx, unsigned logn, size_t L, c
  *   mod-switch (the reference always runs it with the default t = 1).
  * ckks_mult_relin: ckks::mult, src/fhe/ckks/ckks.h:270-274 = tensor + relinearize,
  *   fused so the degree-2 ciphertext never round-trips through host code.
+ * bgv_mult_relin: bgv::mult, src/fhe/bgv/bgv.h (mult_low_level, bgv/arith.cpp:59-69, then
+ *   relinearize, :71-79) with plain modulus t for the internal mod-switch (the reference: t = 1).
  * ckks_rotate / ckks_conjugate: src/fhe/ckks/arith.cpp:75-93 (next row §8(f).1). */
 int hehub_b200_ckks_tensor(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *moduli, size_t L,
                            const uint64_t *ct1, const uint64_t *ct2, uint64_t *quad, size_t batch);
@@ -148,6 +150,9 @@ int hehub_b200_bgv_relinearize(hehub_b200_ctx *ctx, unsigned logn, const uint64_
 int hehub_b200_ckks_mult_relin(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli, size_t L,
                                const uint64_t *ct1, const uint64_t *ct2, const uint64_t *key,
                                uint64_t *out, size_t batch);
+int hehub_b200_bgv_mult_relin(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli, size_t L,
+                              uint64_t plain_modulus, const uint64_t *ct1, const uint64_t *ct2,
+                              const uint64_t *key, uint64_t *out, size_t batch);
 int hehub_b200_ckks_rotate(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli, size_t L,
                            const uint64_t *ct, const uint64_t *key, size_t step, uint64_t *out,
                            size_t batch);

@@ -290,6 +290,8 @@ def test_scheme_ops_match_oracle(dev, oracle, logn, bits, pbits):
     assert np.array_equal(dev.ckks_relinearize(logn, ext, quad, key), oracle.ckks_relinearize(logn, ext, quad, key))
     assert np.array_equal(dev.bgv_relinearize(logn, ext, 1, quad, key), oracle.bgv_relinearize(logn, ext, 1, quad, key))
     assert np.array_equal(dev.ckks_mult_relin(logn, ext, ct1, ct2, key), oracle.ckks_mult_relin(logn, ext, ct1, ct2, key))
+    for t in (1, 65537):  # bgv::mult_low_level + bgv::relinearize behind one call
+        assert np.array_equal(dev.bgv_mult_relin(logn, ext, t, ct1, ct2, key), oracle.bgv_relinearize(logn, ext, t, quad, key))
     for step in (0, 1, 5, n // 2 - 1):
         assert np.array_equal(dev.galois_cycle(logn, ct1[0], step), oracle.galois_cycle(logn, ct1[0], step))
     assert np.array_equal(dev.galois_involution(logn, ct1[1]), oracle.galois_involution(logn, ct1[1]))
