@@ -261,6 +261,12 @@ def run_cuda(args):
             ip = json.load(fh)
         roofline["int_pipe_ceiling_ntt_per_s"] = ip["ntt4096_per_s_alu_ceiling"]
         roofline["int_pipe_frac"] = (value / world) / ip["ntt4096_per_s_alu_ceiling"]
+        # the same butterfly loop with twiddles and modulus constants in per-thread registers, as a transform holds
+        # them (tools/uniform_tw.cu): the ceiling a kernel of this design can actually reach
+        with open(os.path.join(ROOT, "profiles", "r1w_uniform_tw.json")) as fh:
+            ut = json.load(fh)
+        roofline["int_pipe_ceiling_register_operands_ntt_per_s"] = ut["ntt4096_per_s_ceiling"]["all_per_thread"]
+        roofline["int_pipe_frac_register_operands"] = (value / world) / ut["ntt4096_per_s_ceiling"]["all_per_thread"]
     except Exception:
         pass
 
