@@ -207,9 +207,10 @@ int run_transform(Context &c, bool forward, unsigned logn, const u64 *moduli, si
     if (!limbs) return err;
     cudaError_t e;
     if (strict && !forward) {
-        e = launch_ntt(false, c.env(), logn, RowsIO<true>{x, (int)L, (int)logn, aligned16(x)}, limbs, (int)(batch * L));
+        e = launch_ntt<false>(c.env(), logn, RowsIO<true>{x, (int)L, (int)logn, aligned16(x)}, limbs, (int)(batch * L));
     } else { // the forward transform has no strict variant in the reference
-        e = launch_ntt(forward, c.env(), logn, RowsIO<false>{x, (int)L, (int)logn, aligned16(x)}, limbs, (int)(batch * L));
+        const RowsIO<false> io{x, (int)L, (int)logn, aligned16(x)};
+        e = forward ? launch_ntt<true>(c.env(), logn, io, limbs, (int)(batch * L)) : launch_ntt<false>(c.env(), logn, io, limbs, (int)(batch * L));
     }
     return e == cudaSuccess ? 0 : c.cuda_fail(e, forward ? "ntt launch" : "intt launch");
 }

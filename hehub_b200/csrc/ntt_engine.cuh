@@ -480,44 +480,35 @@ inline cudaError_t launch_fast(const LaunchEnv &env, const IO &io, const LimbCon
     }
 }
 
-template <class IO>
-inline cudaError_t launch_generic(bool forward, const LaunchEnv &env, unsigned logn, const IO &io, const LimbConst *limbs,
-                                  int rows) {
+template <bool FWD, class IO>
+inline cudaError_t launch_generic(const LaunchEnv &env, unsigned logn, const IO &io, const LimbConst *limbs, int rows) {
     const int smem = (1 << logn) * 8;
     int threads = (1 << logn) / 2;
     threads = threads < 32 ? 32 : (threads > 256 ? 256 : threads);
-    if (forward) {
-        auto kern = ntt_fwd_generic_kernel<IO>;
-        static int configured = 0;
-        if (smem > configured) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return e;
-            configured = smem;
-        }
-        HB_LAUNCH(kern, rows, threads, smem, env.stream, 1, io, limbs, (int)logn);
-    } else {
-        auto kern = intt_generic_kernel<IO>;
-        static int configured = 0;
-        if (smem > configured) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return e;
-            configured = smem;
-        }
-        HB_LAUNCH(kern, rows, threads, smem, env.stream, 1, io, limbs, (int)logn);
+    auto kern = [] {
+        if constexpr (FWD) return &ntt_fwd_generic_kernel<IO>;
+        else return &intt_generic_kernel<IO>;
+    }();
+    static int configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
     }
+    HB_LAUNCH(kern, rows, threads, smem, env.stream, 1, io, limbs, (int)logn);
     env.stats->launches++;
     return cudaGetLastError();
 }
 
-// Dispatch on ring size (the policy's `vec` flag says whether rows move as 128-bit words).
-template <class IO>
-inline cudaError_t launch_ntt(bool forward, const LaunchEnv &env, unsigned logn, const IO &io, const LimbConst *limbs, int rows) {
+// Dispatch on ring size (the policy's `vec` flag says whether rows move as 128-bit words).  The direction is a
+// template parameter so that a policy is only instantiated for the direction it is used in.
+template <bool FWD, class IO>
+inline cudaError_t launch_ntt(const LaunchEnv &env, unsigned logn, const IO &io, const LimbConst *limbs, int rows) {
     if (rows <= 0) return cudaSuccess;
     if (logn < 1 || logn > kFastLogMax) return cudaErrorInvalidValue;
-    if (logn < kFastLogMin || (env.force_generic && logn <= kGenericLogMax)) return launch_generic(forward, env, logn, io, limbs, rows);
-#define HB_CASE_FAST(LN)                                                                                     \
-    case LN:                                                                                                 \
-        return forward ? launch_fast<LN, true>(env, io, limbs, rows) : launch_fast<LN, false>(env, io, limbs, rows);
+    if (logn < kFastLogMin || (env.force_generic && logn <= kGenericLogMax)) return launch_generic<FWD>(env, logn, io, limbs, rows);
+#define HB_CASE_FAST(LN) \
+    case LN: return launch_fast<LN, FWD>(env, io, limbs, rows);
     switch (logn) {
         HB_CASE_FAST(10) HB_CASE_FAST(11) HB_CASE_FAST(12) HB_CASE_FAST(13) HB_CASE_FAST(14) HB_CASE_FAST(15)
     }

@@ -244,10 +244,10 @@ static int ext_prod_wave(Context &c, unsigned logn, const LimbConst *limbs, size
                          const u64 *key, u64 *out, size_t batch, u64 *cbuf, u64 *dec) {
     const size_t n = (size_t)1 << logn;
     ExtInttIO io1{in, in_batch_stride, cbuf, (int)L, (int)logn, aligned16(in) && (in_batch_stride % 2 == 0) && aligned16(cbuf)};
-    cudaError_t e = launch_ntt(false, c.env(), logn, io1, limbs, (int)(batch * L));
+    cudaError_t e = launch_ntt<false>(c.env(), logn, io1, limbs, (int)(batch * L));
     if (e != cudaSuccess) return c.cuda_fail(e, "ext_prod: intt launch");
     ExtFanoutIO io2{cbuf, dec, (int)L, (int)logn, aligned16(cbuf) && aligned16(dec)};
-    e = launch_ntt(true, c.env(), logn, io2, limbs, (int)(batch * L * L));
+    e = launch_ntt<true>(c.env(), logn, io2, limbs, (int)(batch * L * L));
     if (e != cudaSuccess) return c.cuda_fail(e, "ext_prod: ntt launch");
     constexpr int CPT = HB_MAC_CPT;
     const size_t groups = (batch + CPT - 1) / CPT;
@@ -419,16 +419,16 @@ int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, 
     cudaError_t e;
     if (t) {
         DropInttIO<true> io1{ct, z, (int)L, (int)logn, ds->inv_t, ds->inv_t_h, aligned16(ct) && aligned16(z)};
-        e = launch_ntt(false, c.env(), logn, io1, limbs, (int)(batch * 2));
+        e = launch_ntt<false>(c.env(), logn, io1, limbs, (int)(batch * 2));
         if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: intt launch");
         DropFwdIO<true> io2{ct, z, out, ds->dev, addend, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, halves, vec};
-        e = launch_ntt(true, c.env(), logn, io2, limbs, (int)(batch * 2 * (L - 1)));
+        e = launch_ntt<true>(c.env(), logn, io2, limbs, (int)(batch * 2 * (L - 1)));
     } else {
         DropInttIO<false> io1{ct, z, (int)L, (int)logn, 0, 0, aligned16(ct) && aligned16(z)};
-        e = launch_ntt(false, c.env(), logn, io1, limbs, (int)(batch * 2));
+        e = launch_ntt<false>(c.env(), logn, io1, limbs, (int)(batch * 2));
         if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: intt launch");
         DropFwdIO<false> io2{ct, z, out, ds->dev, addend, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, halves, vec};
-        e = launch_ntt(true, c.env(), logn, io2, limbs, (int)(batch * 2 * (L - 1)));
+        e = launch_ntt<true>(c.env(), logn, io2, limbs, (int)(batch * 2 * (L - 1)));
     }
     if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: ntt launch");
     return 0;
@@ -566,7 +566,7 @@ int op_rlwe_decrypt_core(Context &c, unsigned logn, const u64 *moduli, size_t L,
     const LimbConst *limbs = c.get_chain(logn, moduli, L, &err);
     if (!limbs) return err;
     DecryptIO io{ct, sk, pt, (int)L, (int)logn, aligned16(ct) && aligned16(pt)};
-    cudaError_t e = launch_ntt(false, c.env(), logn, io, limbs, (int)(batch * L));
+    cudaError_t e = launch_ntt<false>(c.env(), logn, io, limbs, (int)(batch * L));
     return e == cudaSuccess ? 0 : c.cuda_fail(e, "decrypt_core: intt launch");
 }
 
@@ -580,10 +580,10 @@ int op_rlwe_encrypt_core(Context &c, unsigned logn, const u64 *moduli, size_t L,
     const LimbConst *limbs = c.get_chain(logn, moduli, L, &err);
     if (!limbs) return err;
     EncryptErrIO io1{e, c1, sk, out, (int)L, (int)logn, aligned16(e) && aligned16(c1) && aligned16(sk) && aligned16(out)};
-    cudaError_t rc = launch_ntt(true, c.env(), logn, io1, limbs, (int)(batch * L));
+    cudaError_t rc = launch_ntt<true>(c.env(), logn, io1, limbs, (int)(batch * L));
     if (rc != cudaSuccess) return c.cuda_fail(rc, "encrypt_core: error ntt launch");
     EncryptAddIO io2{pt, out, (int)L, (int)logn, aligned16(pt) && aligned16(out)};
-    rc = launch_ntt(true, c.env(), logn, io2, limbs, (int)(batch * L));
+    rc = launch_ntt<true>(c.env(), logn, io2, limbs, (int)(batch * L));
     return rc == cudaSuccess ? 0 : c.cuda_fail(rc, "encrypt_core: plaintext ntt launch");
 }
 
@@ -736,7 +736,7 @@ int op_ksk_generate(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, 
     if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream); // pm is a host temporary
     if (e != cudaSuccess) return c.cuda_fail(e, "ksk: constants");
     KskRowIO io{errors, masks, sk_ext, sk_curr, reinterpret_cast<const ulonglong2 *>(pmod), key, (int)L, (int)logn, aligned16(errors)};
-    e = launch_ntt(true, c.env(), logn, io, limbs, (int)(L * L1));
+    e = launch_ntt<true>(c.env(), logn, io, limbs, (int)(L * L1));
     return e == cudaSuccess ? 0 : c.cuda_fail(e, "ksk: row launch");
 }
 
