@@ -290,6 +290,32 @@ def test_differential_against_reference_library(oracle, reference):
         assert (oracle.ckks_conjugate(logn, ext, ct1, key) == reference.ckks_conjugate(logn, ext, ct1, key)).all()
 
 
+def test_full_range_words_wrap_like_the_reference(oracle, reference):
+    """Inputs beyond the growth bound: the reference's u64 arithmetic wraps; the restatement must wrap identically."""
+    rng = np.random.default_rng(77)
+    for q in NTT_MODULI:
+        for logn in [2, 9, 12]:
+            if (q - 1) % (2 << logn):
+                continue
+            n = 1 << logn
+            x = rng.integers(0, 1 << 63, n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, n, dtype=np.uint64)
+            x[: n // 2] = np.uint64((1 << 64) - 1)
+            assert (oracle.ntt_fwd_lazy(logn, q, x) == reference.ntt_fwd_lazy(logn, q, x)).all()
+            assert (oracle.intt_lazy(logn, q, x) == reference.intt_lazy(logn, q, x)).all()
+
+
+def test_scheme_ops_on_full_range_words_against_reference_library(oracle, reference):
+    rng = np.random.default_rng(78)
+    wild = lambda *shape: rng.integers(0, 1 << 63, shape, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, shape, dtype=np.uint64)
+    for bits, pbits, logn in [([40, 30, 30], 40, 5), ([59, 59], 59, 6)]:
+        mods, P = oracle.ckks_pick_moduli(bits, pbits)
+        ext, n, L = mods + [P], 1 << logn, len(mods)
+        ct1, ct2, key, wide = wild(2, L, n), wild(2, L, n), wild(L, 2, L + 1, n), wild(2, L + 1, n)
+        assert (oracle.ckks_mult_relin(logn, ext, ct1, ct2, key) == reference.ckks_mult_relin(logn, ext, ct1, ct2, key)).all()
+        assert (oracle.ckks_rescale(logn, ext, wide) == reference.ckks_rescale(logn, ext, wide)).all()
+        assert (oracle.bgv_mod_switch(logn, ext, 65537, wide) == reference.bgv_mod_switch(logn, ext, 65537, wide)).all()
+
+
 def test_rlwe_cores_against_reference_library(oracle, reference):
     """decrypt_core is the reference's own function; encrypt_core is its three statements on supplied samples."""
     for logn, bits in ((4, [30]), (10, [40, 30]), (12, [50, 40, 40])):

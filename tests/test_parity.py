@@ -57,6 +57,21 @@ def test_ntt_intt_raw_words_match_oracle(dev, oracle, logn):
             assert np.array_equal(dev.poly_ntt_fwd(logn, [q], wild), oracle.ntt_fwd_lazy(logn, q, wild))
 
 
+@pytest.mark.parametrize("logn", [3, 10, 12, 13, 14, 15])
+def test_transforms_wrap_like_the_reference_on_full_range_words(dev, oracle, logn):
+    """Words anywhere in [0, 2^64): the reference's growth bound (ntt.cpp:152-175) does not hold, its u64 arithmetic
+    wraps — and so must ours, word for word (the kernels run the same u64 operations per butterfly)."""
+    n = 1 << logn
+    rng = np.random.default_rng(900 + logn)
+    for q in (Q59, 36028796997599233, 65537):
+        x = rng.integers(0, 1 << 63, (2, n), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, (2, n), dtype=np.uint64)
+        x[1, : n // 2] = np.uint64((1 << 64) - 1)
+        want = np.stack([oracle.ntt_fwd_lazy(logn, q, r) for r in x])
+        assert np.array_equal(dev.poly_ntt_fwd(logn, [q], x), want), (logn, q)
+        want = np.stack([oracle.intt_lazy(logn, q, r) for r in x])
+        assert np.array_equal(dev.poly_intt(logn, [q], x), want), (logn, q)
+
+
 def test_ntt_hashes_match_reference_golden(dev, oracle, kat):
     """SURVEY Appendix B / tests/golden: hashes recorded from the unmodified reference."""
     for row in kat["ntt_hashes"]:
@@ -297,6 +312,25 @@ def test_scheme_ops_match_oracle(dev, oracle, logn, bits, pbits):
     assert np.array_equal(dev.galois_involution(logn, ct1[1]), oracle.galois_involution(logn, ct1[1]))
     assert np.array_equal(dev.ckks_rotate(logn, ext, ct1, key, 3), oracle.ckks_rotate(logn, ext, ct1, key, 3))
     assert np.array_equal(dev.ckks_conjugate(logn, ext, ct1, key), oracle.ckks_conjugate(logn, ext, ct1, key))
+
+
+@pytest.mark.parametrize("logn,bits,pbits", [(5, [30, 30], 40), (10, [40, 30, 30], 40), (13, [59, 59], 59)])
+def test_scheme_ops_on_full_range_words(dev, oracle, logn, bits, pbits):
+    """Operands anywhere in [0, 2^64) (not residues): every product, reduction and lazy add of the reference is plain
+    u64 / u128 arithmetic, so the outputs are still defined — and must still agree word for word."""
+    mods, ext = _shape(oracle, logn, bits, pbits)
+    n, L = 1 << logn, len(mods)
+    rng = np.random.default_rng(4000 + logn)
+    wild = lambda *shape: rng.integers(0, 1 << 63, shape, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, shape, dtype=np.uint64)
+    ct1, ct2, key = wild(2, L, n), wild(2, L, n), wild(L, 2, L + 1, n)
+    quad = oracle.ckks_tensor(logn, mods, ct1, ct2)
+    assert np.array_equal(dev.ckks_tensor(logn, mods, ct1, ct2), quad)
+    e = oracle.ext_prod(logn, ext, ct1[0], key)
+    assert np.array_equal(dev.ext_prod(logn, ext, ct1[0], key), e)
+    wide = wild(2, L + 1, n)
+    assert np.array_equal(dev.ckks_rescale(logn, ext, wide), oracle.ckks_rescale(logn, ext, wide))
+    assert np.array_equal(dev.bgv_mod_switch(logn, ext, 65537, wide), oracle.bgv_mod_switch(logn, ext, 65537, wide))
+    assert np.array_equal(dev.ckks_mult_relin(logn, ext, ct1, ct2, key), oracle.ckks_mult_relin(logn, ext, ct1, ct2, key))
 
 
 # ------------------------------------------------------------------ RLWE cores (SURVEY 8(f) rank 3)
