@@ -49,6 +49,7 @@ constexpr int kEwWordsPerBlock = kEwThreads * 4;
 template <class Op>
 HB_GLOBAL(kEwThreads, 1) ew_kernel(const Op op, const LimbConst *__restrict__ limbs, int L, size_t n,
                                                         unsigned blocks_per_row) {
+    hb_pdl_wait();
     const size_t row = blockIdx.x / blocks_per_row;
     const unsigned chunk = blockIdx.x % blocks_per_row;
     const LimbConst lc = limbs[row % L];
@@ -162,6 +163,7 @@ static int launch_ew(Context &c, const Op &op, const LimbConst *limbs, size_t L,
 // SURVEY Appendix B generator, parallelised by jumping the LCG ahead per 64-word chunk.
 HB_GLOBAL(128, 1) lcg_fill_kernel(u64 *x, const LimbConst *__restrict__ limbs, int L, size_t n, size_t rows, u64 seed0,
                                 u64 seed_stride) {
+    hb_pdl_wait();
     constexpr u64 A = 6364136223846793005ull, C = 1442695040888963407ull;
     constexpr int CH = 64;
     const size_t chunks_per_row = (n + CH - 1) / CH;

@@ -27,6 +27,7 @@ inline ulonglong2 hb_ld_dsmem2(const unsigned long long *p, unsigned rank) {
     return *reinterpret_cast<const ulonglong2 *>(::hbsim::shared_u64_of(rank) + (p - ::hbsim::shared_u64()));
 }
 inline void hb_prefetch_l2(const void *) {}
+inline void hb_pdl_wait() {}
 inline void hb_syncwarp() { __syncthreads(); } // the emulator has no warps: a CTA barrier is a superset
 inline unsigned long long hb_ld_stream(const unsigned long long *p) { return *p; }
 inline ulonglong2 hb_ld_stream2(const unsigned long long *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
@@ -43,27 +44,52 @@ inline void hb_cp_async_wait_all() {}
 #define HB_CX __host__ __device__ constexpr
 #define HB_GLOBAL(threads, minblocks) __global__ void __launch_bounds__(threads, minblocks)
 #define HB_SHARED_U64(name) extern __shared__ __align__(16) unsigned long long name[]
-#define HB_LAUNCH(kern, grid, block, smem, stream, sync, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// Every launch goes through cudaLaunchKernelEx with programmatic stream serialization: the next kernel of the
+// stream may be scheduled while this one drains, and runs its prologue (index arithmetic, per-limb constants) up
+// to hb_pdl_wait(), which returns once every earlier grid has completed and its writes are visible.  The
+// transforms of one ciphertext are six launches on nearly empty grids: launch latency is most of that case.
+#define HB_LAUNCH(kern, grid, block, smem, stream, sync, ...) \
+    ((void)::hb_launch_ex(kern, (unsigned)(grid), (unsigned)(block), (smem), (stream), 1u, __VA_ARGS__))
 #define HB_LAUNCH_CLUSTER(kern, grid, block, smem, stream, cluster, ...) \
-    ::hb_launch_cluster(kern, (grid), (block), (smem), (stream), (cluster), __VA_ARGS__)
+    ::hb_launch_ex(kern, (unsigned)(grid), (unsigned)(block), (smem), (stream), (unsigned)(cluster), __VA_ARGS__)
+#include <cstdlib>
 #include <utility>
+inline bool hb_pdl_enabled() {
+    static const bool on = [] {
+        const char *e = std::getenv("HEHUB_B200_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
 template <class... KArgs, class... Args>
-inline cudaError_t hb_launch_cluster(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
-                                     unsigned cluster, Args &&...args) {
+inline cudaError_t hb_launch_ex(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                                unsigned cluster, Args &&...args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(block);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = cluster;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute at[2];
+    unsigned na = 0;
+    if (cluster > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = cluster;
+        at[na].val.clusterDim.y = 1;
+        at[na].val.clusterDim.z = 1;
+        na++;
+    }
+    if (hb_pdl_enabled()) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
+// returns once all grids launched earlier on the stream have completed and flushed (no-op without the attribute)
+// (an explicit early griddepcontrol.launch_dependents measured no better: profiles/r2c_pdl_ab.log)
+__device__ __forceinline__ void hb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // read-only operands that never alias the kernel's outputs (non-coherent path: the compiler may
 // hoist these above stores), read once: no L1 allocation
 __device__ __forceinline__ unsigned long long hb_ld_ro(const unsigned long long *p) {

@@ -271,7 +271,8 @@ ntt_fwd_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     constexpr int T = pl.threads;
     HB_SHARED_U64(sm);
     const int row = blockIdx.x >> pl.lpre, B = blockIdx.x & ((1 << pl.lpre) - 1);
-    const LimbConst lc = limbs[io.limb(row)];
+    const LimbConst lc = limbs[io.limb(row)]; // uploaded when the chain was built: safe to read before the wait
+    hb_pdl_wait();
     if constexpr (io_has_prefetch<IO>::value) io.prefetch(row, B << (LOGN - pl.lpre), 1 << (LOGN - pl.lpre));
     fwd_passes<LOGN, T, 0>(sm, io, lc, row, B);
 }
@@ -349,6 +350,7 @@ intt_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     HB_SHARED_U64(sm);
     const int row = blockIdx.x >> pl.lpre, B = blockIdx.x & ((1 << pl.lpre) - 1);
     const LimbConst lc = limbs[io.limb(row)];
+    hb_pdl_wait();
     inv_passes<LOGN, T, 0>(sm, io, lc, row, B);
     if constexpr (pl.lpre == 1) {
         // Last stage (gap N/2) pairs word i of CTA 0 with word i of CTA 1 — ntt.cpp:199-206.  Each CTA
@@ -395,6 +397,7 @@ HB_GLOBAL(256, 1) ntt_fwd_generic_kernel(const IO io, const LimbConst *__restric
     HB_SHARED_U64(sm);
     const int n = 1 << logn, row = blockIdx.x;
     const LimbConst lc = limbs[io.limb(row)];
+    hb_pdl_wait();
     for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = io_load(io, row, i, lc);
     __syncthreads();
     for (int level = 1; level <= logn; level++) { // ntt.cpp:155-169
@@ -413,6 +416,7 @@ HB_GLOBAL(256, 1) intt_generic_kernel(const IO io, const LimbConst *__restrict__
     HB_SHARED_U64(sm);
     const int n = 1 << logn, row = blockIdx.x;
     const LimbConst lc = limbs[io.limb(row)];
+    hb_pdl_wait();
     for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = io_load(io, row, i, lc);
     __syncthreads();
     for (int s = 1; s <= logn; s++) { // folded form of ntt.cpp:185-212

@@ -38,6 +38,7 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 HB_GLOBAL(256, HB_TENSOR_MINB)
 tensor_kernel(const u64 *__restrict__ ct1, const u64 *__restrict__ ct2, u64 *__restrict__ quad,
               const LimbConst *__restrict__ limbs, int L, int logn, size_t pairs_total) {
+    hb_pdl_wait();
     // one thread per pair of adjacent coefficients of one (ct, limb)
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= pairs_total) return;
@@ -164,6 +165,7 @@ HB_GLOBAL(256, HB_MAC_MINB)
 ext_mac_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
                u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, int logn, size_t batch, size_t total,
                unsigned groups, unsigned chunks_per_group) {
+    hb_pdl_wait();
     // gid = (b / CPT, k, i / W).  With `groups` != 0 consecutive CTAs take the SAME 256-thread slice of
     // (k, i) for consecutive ciphertext groups, so CTAs resident together share their key words in L2
     // (the key is read once per group: 8-18 times per wave) instead of streaming it from HBM each time.
@@ -597,6 +599,7 @@ int op_rlwe_encrypt_core(Context &c, unsigned logn, const u64 *moduli, size_t L,
 HB_GLOBAL(256, 1)
 base_from_single_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const LimbConst *__restrict__ limbs, u64 q_old, int Lnew,
                         size_t n, unsigned blocks_per_row) {
+    hb_pdl_wait();
     const size_t bk = blockIdx.x / blocks_per_row;
     const int k = (int)(bk % Lnew);
     const size_t b = bk / Lnew;
@@ -620,6 +623,7 @@ base_from_single_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const
 HB_GLOBAL(256, 1)
 base_to_single_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const LimbConst *__restrict__ old_limbs, int L,
                       LimbConst new_lc, size_t n, size_t total, int *not_small) {
+    hb_pdl_wait();
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // (b, i)
     if (gid >= total) return;
     const size_t i = gid % n, b = gid / n;
@@ -748,6 +752,7 @@ int op_ksk_generate(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, 
 // ------------------------------------------------------------------------------------------
 HB_GLOBAL(256, 1)
 galois_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, int logn, unsigned ginv, size_t total) {
+    hb_pdl_wait();
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
     const unsigned n = 1u << logn, j = (unsigned)(gid & (n - 1));

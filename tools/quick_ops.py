@@ -10,6 +10,7 @@ ap.add_argument("lib")
 ap.add_argument("--shape", nargs="*", default=["c3"])
 ap.add_argument("--only", nargs="*", default=None, help="subset of tensor ext_prod rescale mult_relin")
 ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--batch", type=int, default=0, help="override the shape's batch (1: single-ciphertext calls)")
 ap.add_argument("--warmup", type=int, default=3)
 a = ap.parse_args()
 SHAPES = {"c3": (13, [40, 30, 30, 30], 40, 296), "c4": (14, [50] + [40] * 7, 50, 148), "c5": (15, [50] * 12, 55, 37)}
@@ -17,6 +18,7 @@ orc = Oracle()
 ctx = Context(lib_path=a.lib)
 for name in a.shape:
     logn, bits, pbits, batch = SHAPES[name]
+    batch = a.batch or batch
     mods, p = orc.ckks_pick_moduli(bits, pbits)
     mods = [int(m) for m in mods]; ext = mods + [int(p)]
     L, n = len(mods), 1 << logn
