@@ -280,14 +280,20 @@ def run_cuda(args):
         ctx.ntt_host(True, LOGN, [Q59], hx, hy)
     torch.cuda.synchronize()
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ctx.ntt_host(True, LOGN, [Q59], hx, hy)  # returns when hy holds the result
-    torch.cuda.synchronize()
-    barrier()
-    e2e_elapsed = max_over_ranks(time.perf_counter() - t0)
+    # three trials of e2e_steps steps each, the median trial is reported: the host link is shared with whatever
+    # else the box is doing, and a single disturbed trial would otherwise stand for the path
+    trials = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.ntt_host(True, LOGN, [Q59], hx, hy)  # returns when hy holds the result
+        torch.cuda.synchronize()
+        barrier()
+        trials.append(max_over_ranks(time.perf_counter() - t0))
+    e2e_elapsed = sorted(trials)[1]
     e2e = {"value": world * POLYS * e2e_steps / e2e_elapsed, "unit": UNIT, "h2d_bytes_per_step": POLYS * n * 8,
            "d2h_bytes_per_step": POLYS * n * 8, "steps": e2e_steps,
+           "trials_per_s": [world * POLYS * e2e_steps / t for t in trials],
            "call": "hehub_b200_ntt_host (pinned host buffers, chunked H2D | kernel | D2H pipeline on three streams)"}
 
     # ---- extras: the other BASELINE configs -------------------------------------------------------
