@@ -30,6 +30,8 @@ struct LimbConst {
     const ulonglong2 *inv_scale; // psi^{-i}/N (strict) and its Harvey companion, natural order
     const ulonglong2 *fwd_nat;   // reference order T[i] = psi^{bitrev(i)}      (ntt.cpp:54-58)
     const ulonglong2 *inv_nat;   // reference order, per-level inverse twiddles (ntt.cpp:64-74)
+    const ulonglong2 *fwd_lat;   // forward / inverse twiddles in the layout of the latency plan (ntt_plan.h), or null
+    const ulonglong2 *inv_lat;
 };
 
 // lo64(x*w + h*n): one accumulation chain of 2 wide + 4 narrow IMADs, no carries needed.

@@ -184,9 +184,9 @@ HB_CX bool warp_local_pair(int ka, int kb) { return ka == kb && ka <= 5; }
 // ------------------------------------------------------------------------------------------
 // forward passes: gaps shrink, the last pass is contiguous and stores the row
 // ------------------------------------------------------------------------------------------
-template <int LOGN, int T, int P, class IO>
+template <int LOGN, int T, int P, int MODE, class IO>
 HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
-    constexpr NttPlan pl = plan_for(LOGN, true);
+    constexpr NttPlan pl = plan_for(LOGN, true, MODE);
     constexpr int LOGNC = LOGN - pl.lpre, NC = 1 << LOGNC;
     constexpr int K = pl.k[P], L0 = fwd_lambda0(pl, P), GSL = LOGNC - L0 - K; // log2(smallest gap)
     constexpr int NG = NC >> K;
@@ -194,7 +194,7 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     static_assert(!last || GSL == 0, "last forward pass must be contiguous");
     static_assert(last || GSL >= 4, "strided passes step by multiples of 16 words");
     static_assert(NG % T == 0 && T % 32 == 0, "whole warps in every step");
-    const ulonglong2 *tw_pass = lc.fwd + fwd_pass_offset(pl, P);
+    const ulonglong2 *tw_pass = (MODE ? lc.fwd_lat : lc.fwd) + fwd_pass_offset(pl, P);
     constexpr int stride = 1 << (pl.lpre + L0);
     constexpr int SJ = sstride(1 << GSL);
 
@@ -211,7 +211,7 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
             } else {
                 // level 1 of the full row (gap N/2) is computed here by both CTAs of the row;
                 // CTA B keeps the low (B = 0) or high (B = 1) output — ntt.cpp:161-167
-                const ulonglong2 z = __ldg(lc.fwd);
+                const ulonglong2 z = __ldg(MODE ? lc.fwd_lat : lc.fwd);
 #pragma unroll
                 for (int j = 0; j < (1 << K); j++) {
                     const int i = base + (j << GSL);
@@ -242,10 +242,10 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     }
 }
 
-template <int LOGN, int T, int P, class IO>
+template <int LOGN, int T, int P, int MODE, class IO>
 HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
-    constexpr NttPlan pl = plan_for(LOGN, true);
-    fwd_pass<LOGN, T, P>(sm, io, lc, row, B);
+    constexpr NttPlan pl = plan_for(LOGN, true, MODE);
+    fwd_pass<LOGN, T, P, MODE>(sm, io, lc, row, B);
     if constexpr (P + 1 < pl.npass) {
         if constexpr (P == 0 && pl.lpre == 1) {
             // both CTAs of the row have read all of it: from here on either may overwrite it
@@ -256,33 +256,33 @@ HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B)
         } else {
             __syncthreads();
         }
-        fwd_passes<LOGN, T, P + 1>(sm, io, lc, row, B);
+        fwd_passes<LOGN, T, P + 1, MODE>(sm, io, lc, row, B);
     }
 }
 
 // one CTA (or one CTA of a 2-CTA cluster) per row
-template <int LOGN, class IO>
-HB_GLOBAL(plan_for(LOGN, true).threads, plan_for(LOGN, true).min_blocks)
+template <int LOGN, class IO, int MODE = 0>
+HB_GLOBAL(plan_for(LOGN, true, MODE).threads, plan_for(LOGN, true, MODE).min_blocks)
 ntt_fwd_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     // One row per CTA on purpose: resident CTAs walking several rows each (with or without a start
     // skew between the CTAs of an SM) measured 15-20 % slower than letting the block scheduler hand
     // out rows (profiles/r1_plan_sweep.md).
-    constexpr NttPlan pl = plan_for(LOGN, true);
+    constexpr NttPlan pl = plan_for(LOGN, true, MODE);
     constexpr int T = pl.threads;
     HB_SHARED_U64(sm);
     const int row = blockIdx.x >> pl.lpre, B = blockIdx.x & ((1 << pl.lpre) - 1);
     const LimbConst lc = limbs[io.limb(row)]; // uploaded when the chain was built: safe to read before the wait
     hb_pdl_wait();
     if constexpr (io_has_prefetch<IO>::value) io.prefetch(row, B << (LOGN - pl.lpre), 1 << (LOGN - pl.lpre));
-    fwd_passes<LOGN, T, 0>(sm, io, lc, row, B);
+    fwd_passes<LOGN, T, 0, MODE>(sm, io, lc, row, B);
 }
 
 // ------------------------------------------------------------------------------------------
 // inverse passes: the first pass is contiguous and loads the row, gaps grow
 // ------------------------------------------------------------------------------------------
-template <int LOGN, int T, int P, class IO>
+template <int LOGN, int T, int P, int MODE, class IO>
 HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
-    constexpr NttPlan pl = plan_for(LOGN, false);
+    constexpr NttPlan pl = plan_for(LOGN, false, MODE);
     constexpr int LOGNC = LOGN - pl.lpre, NC = 1 << LOGNC;
     constexpr int K = inv_k(pl, P), S0 = inv_s0(pl, P);
     constexpr int NG = NC >> K;
@@ -290,7 +290,7 @@ HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     static_assert(!first || S0 == 0, "first inverse pass must be contiguous");
     static_assert(first || S0 >= 4, "strided passes step by multiples of 16 words");
     static_assert(NG % T == 0 && T % 32 == 0, "whole warps in every step");
-    const ulonglong2 *tw_pass = lc.inv + inv_pass_offset(pl, P);
+    const ulonglong2 *tw_pass = (MODE ? lc.inv_lat : lc.inv) + inv_pass_offset(pl, P);
     constexpr int stride = 1 << S0;
     constexpr int SJ = sstride(1 << S0);
 
@@ -328,30 +328,30 @@ HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     }
 }
 
-template <int LOGN, int T, int P, class IO>
+template <int LOGN, int T, int P, int MODE, class IO>
 HB_D void inv_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
-    constexpr NttPlan pl = plan_for(LOGN, false);
-    inv_pass<LOGN, T, P>(sm, io, lc, row, B);
+    constexpr NttPlan pl = plan_for(LOGN, false, MODE);
+    inv_pass<LOGN, T, P, MODE>(sm, io, lc, row, B);
     if constexpr (P + 1 < pl.npass) {
         if constexpr (P == 0 && warp_local_pair(inv_k(pl, 0), inv_k(pl, 1))) {
             hb_syncwarp();
         } else {
             __syncthreads();
         }
-        inv_passes<LOGN, T, P + 1>(sm, io, lc, row, B);
+        inv_passes<LOGN, T, P + 1, MODE>(sm, io, lc, row, B);
     }
 }
 
-template <int LOGN, class IO>
-HB_GLOBAL(plan_for(LOGN, false).threads, plan_for(LOGN, false).min_blocks)
+template <int LOGN, class IO, int MODE = 0>
+HB_GLOBAL(plan_for(LOGN, false, MODE).threads, plan_for(LOGN, false, MODE).min_blocks)
 intt_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
-    constexpr NttPlan pl = plan_for(LOGN, false);
+    constexpr NttPlan pl = plan_for(LOGN, false, MODE);
     constexpr int NC = 1 << (LOGN - pl.lpre), T = pl.threads;
     HB_SHARED_U64(sm);
     const int row = blockIdx.x >> pl.lpre, B = blockIdx.x & ((1 << pl.lpre) - 1);
     const LimbConst lc = limbs[io.limb(row)];
     hb_pdl_wait();
-    inv_passes<LOGN, T, 0>(sm, io, lc, row, B);
+    inv_passes<LOGN, T, 0, MODE>(sm, io, lc, row, B);
     if constexpr (pl.lpre == 1) {
         // Last stage (gap N/2) pairs word i of CTA 0 with word i of CTA 1 — ntt.cpp:199-206.  Each CTA
         // takes half of the offsets, reads its own words from shared memory and the sibling's through
@@ -359,7 +359,7 @@ intt_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
         // psi^{-i}/N scaling, ntt.cpp:214-221): no butterfly is computed twice and the row never makes
         // a round trip through L2.
         hb_cluster_sync();
-        const ulonglong2 *tw = lc.inv + inv_pass_offset(pl, pl.npass);
+        const ulonglong2 *tw = (MODE ? lc.inv_lat : lc.inv) + inv_pass_offset(pl, pl.npass);
         for (int i = B * (NC / 2) + 2 * (int)threadIdx.x; i < (B + 1) * (NC / 2); i += 2 * T) {
             const u64 *p = sm + sphys(i); // i even: words i, i+1 are adjacent
             const ulonglong2 mine = *reinterpret_cast<const ulonglong2 *>(p), other = hb_ld_dsmem2(p, 1 - B);
@@ -446,12 +446,13 @@ struct LaunchEnv {
     int sm_count;       // persistent grids are sized from it
     bool force_generic; // parity cross-check path
     LaunchStats *stats;
+    int latency_rows;   // launches with at most this many rows take the latency plan (default: half the SM count)
 };
 
-template <int LOGN, bool FWD, class IO>
+template <int LOGN, bool FWD, class IO, int MODE>
 constexpr auto fast_kernel() {
-    if constexpr (FWD) return &ntt_fwd_fast_kernel<LOGN, IO>;
-    else return &intt_fast_kernel<LOGN, IO>;
+    if constexpr (FWD) return &ntt_fwd_fast_kernel<LOGN, IO, MODE>;
+    else return &intt_fast_kernel<LOGN, IO, MODE>;
 }
 // Opt in to `smem` bytes of dynamic shared memory and ask for just enough carveout for `blocks`
 // resident CTAs: whatever is left of the SM's 228 KB stays L1, which the twiddle tables live in.
@@ -464,11 +465,11 @@ inline cudaError_t configure_smem(K kern, int smem, int blocks) {
     return e;
 }
 
-template <int LOGN, bool FWD, class IO>
-inline cudaError_t launch_fast(const LaunchEnv &env, const IO &io, const LimbConst *limbs, int rows) {
-    constexpr NttPlan pl = plan_for(LOGN, FWD);
+template <int LOGN, bool FWD, int MODE, class IO>
+inline cudaError_t launch_fast_mode(const LaunchEnv &env, const IO &io, const LimbConst *limbs, int rows) {
+    constexpr NttPlan pl = plan_for(LOGN, FWD, MODE);
     constexpr int smem = smem_words(1 << (LOGN - pl.lpre)) * 8;
-    auto kern = fast_kernel<LOGN, FWD, IO>();
+    auto kern = fast_kernel<LOGN, FWD, IO, MODE>();
     static bool configured = false;
     if (!configured) {
         cudaError_t e = configure_smem(kern, smem, pl.min_blocks);
@@ -482,6 +483,15 @@ inline cudaError_t launch_fast(const LaunchEnv &env, const IO &io, const LimbCon
         HB_LAUNCH(kern, rows, pl.threads, smem, env.stream, 1, io, limbs);
         return cudaGetLastError();
     }
+}
+
+// few rows (a single ciphertext, a key): the latency plan where the ring size has one, see ntt_plan.h
+template <int LOGN, bool FWD, class IO>
+inline cudaError_t launch_fast(const LaunchEnv &env, const IO &io, const LimbConst *limbs, int rows) {
+    if constexpr (has_latency_plan(LOGN)) {
+        if (rows <= env.latency_rows) return launch_fast_mode<LOGN, FWD, 1>(env, io, limbs, rows);
+    }
+    return launch_fast_mode<LOGN, FWD, 0>(env, io, limbs, rows);
 }
 
 template <bool FWD, class IO>

@@ -31,7 +31,14 @@ constexpr int kFastLogMin = 10;
 constexpr int kFastLogMax = 15;
 constexpr int kGenericLogMax = 14; // one row must fit one CTA's shared memory
 
-HB_CX NttPlan plan_for(int logn, bool fwd) {
+// Latency plans: when a launch has fewer rows than half the SMs, a row of N = 4096 / 8192 is split over a 2-CTA
+// cluster (half a row per CTA, each on its own SM) — the level the two CTAs share is computed twice, which costs
+// nothing on an otherwise idle GPU, and the row's critical path halves.  N >= 16384 already runs as clusters.
+HB_CX bool has_latency_plan(int logn) { return logn == 12 || logn == 13; }
+
+HB_CX NttPlan plan_for(int logn, bool fwd, int mode = 0) {
+    if (mode == 1 && logn == 12) return NttPlan{12, 1, 3, {3, 4, 4, 0, 0}, 128, 1};
+    if (mode == 1 && logn == 13) return NttPlan{13, 1, 3, {4, 4, 4, 0, 0}, 256, 1};
     // Measured on B200 (profiles/r1_plan_sweep.md).  Passes of 4-5 levels keep 16-32 words per thread
     // in registers; ending with two passes of equal width keeps their exchange inside a warp.
     switch (logn) {

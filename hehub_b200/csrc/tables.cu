@@ -128,7 +128,8 @@ const ModTables *Context::get_tables(u64 q, unsigned logn, int *err) {
     }
 
     const bool fast = logn >= (unsigned)kFastLogMin;
-    const size_t ntab = fast ? 5 : 3; // fwd_nat, inv_nat, inv_scale [, fwd fast, inv fast]
+    const bool lat = fast && has_latency_plan((int)logn);
+    const size_t ntab = fast ? (lat ? 7 : 5) : 3; // fwd_nat, inv_nat, inv_scale [, fwd fast, inv fast [, latency-plan pair]]
     std::vector<ulonglong2> host(ntab * n, make_ulonglong2(0, 0));
     ulonglong2 *fwd_nat = host.data(), *inv_nat = fwd_nat + n, *inv_scale = inv_nat + n;
     auto pair_of = [&](u64 w) { return make_ulonglong2(w, host_harvey_quotient(w, q)); };
@@ -148,9 +149,9 @@ const ModTables *Context::get_tables(u64 q, unsigned logn, int *err) {
     for (size_t i = 0; i < n; i++)           // ntt.cpp:78-85 (canonical residue of psi^{-i} / N)
         inv_scale[i] = pair_of(mulmod(pw[i], n_inv, q));
 
-    if (fast) {
-        ulonglong2 *ff = inv_scale + n, *fi = ff + n;
-        NttPlan pl = plan_for((int)logn, true);
+    // pass-major / slot-major layouts of one plan pair (forward, inverse) — see ntt_plan.h
+    auto fill_plan_tables = [&](ulonglong2 *ff, ulonglong2 *fi, int mode) {
+        NttPlan pl = plan_for((int)logn, true, mode);
         if (pl.lpre) ff[0] = fwd_nat[1];
         for (int p = 0; p < pl.npass; p++) {
             const int K = pl.k[p], l0g = pl.lpre + fwd_lambda0(pl, p), off = fwd_pass_offset(pl, p);
@@ -161,7 +162,7 @@ const ModTables *Context::get_tables(u64 q, unsigned logn, int *err) {
                         ff[off + (slot << l0g) + hb] = fwd_nat[((size_t)1 << (l0g + m - 1)) + ((size_t)hb << (m - 1)) + blk];
                 }
         }
-        pl = plan_for((int)logn, false);
+        pl = plan_for((int)logn, false, mode);
         for (int p = 0; p <= pl.npass; p++) {
             if (p == pl.npass && !pl.lpre) break;
             const int K = (p == pl.npass) ? 1 : inv_k(pl, p);
@@ -175,7 +176,9 @@ const ModTables *Context::get_tables(u64 q, unsigned logn, int *err) {
                     }
                 }
         }
-    }
+    };
+    if (fast) fill_plan_tables(inv_scale + n, inv_scale + 2 * n, 0);
+    if (lat) fill_plan_tables(inv_scale + 3 * n, inv_scale + 4 * n, 1);
 
     void *dev = nullptr;
     cudaError_t e = cudaMalloc(&dev, host.size() * sizeof(ulonglong2));
@@ -197,6 +200,8 @@ const ModTables *Context::get_tables(u64 q, unsigned logn, int *err) {
     mt.lc.inv_scale = d + 2 * n;
     mt.lc.fwd = fast ? d + 3 * n : nullptr;
     mt.lc.inv = fast ? d + 4 * n : nullptr;
+    mt.lc.fwd_lat = lat ? d + 5 * n : nullptr;
+    mt.lc.inv_lat = lat ? d + 6 * n : nullptr;
     return &tables.emplace(key, mt).first->second;
 }
 

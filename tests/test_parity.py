@@ -72,6 +72,30 @@ def test_transforms_wrap_like_the_reference_on_full_range_words(dev, oracle, log
         assert np.array_equal(dev.poly_intt(logn, [q], x), want), (logn, q)
 
 
+@pytest.mark.parametrize("logn", [12, 13])
+def test_latency_and_throughput_plans_agree(dev, oracle, logn):
+    """N = 4096 / 8192 have two pass plans (ntt_plan.h): one CTA per row, and a 2-CTA cluster per row for launches
+    with few rows.  Both must produce the reference's words, for plain and fused transforms."""
+    n = 1 << logn
+    mods, ext = _shape(oracle, logn, [40, 30], 40)
+    x = np.stack([oracle.lcg_fill(7 + k, Q59, n) for k in range(3)])
+    want_f = np.stack([oracle.ntt_fwd_lazy(logn, Q59, r) for r in x])
+    want_i = np.stack([oracle.intt_lazy(logn, Q59, r) for r in want_f])
+    ct1, ct2, key = fill_ct(oracle, 31, mods, n), fill_ct(oracle, 32, mods, n), fill_key(oracle, 3300, ext, n)
+    want_m = oracle.ckks_mult_relin(logn, ext, ct1, ct2, key)
+    want_b = oracle.bgv_mod_switch(logn, ext, 65537, fill_ct(oracle, 33, ext, n))
+    try:
+        for rows in (0, 1 << 30):  # never / always the latency plan
+            dev.set_option("latency_rows", rows)
+            assert np.array_equal(dev.poly_ntt_fwd(logn, [Q59], x), want_f), rows
+            assert np.array_equal(dev.poly_intt(logn, [Q59], want_f), want_i), rows
+            assert np.array_equal(dev.poly_intt(logn, [Q59], want_f, strict=True), x), rows
+            assert np.array_equal(dev.ckks_mult_relin(logn, ext, ct1, ct2, key), want_m), rows
+            assert np.array_equal(dev.bgv_mod_switch(logn, ext, 65537, fill_ct(oracle, 33, ext, n)), want_b), rows
+    finally:
+        dev.set_option("latency_rows", -1)
+
+
 def test_ntt_hashes_match_reference_golden(dev, oracle, kat):
     """SURVEY Appendix B / tests/golden: hashes recorded from the unmodified reference."""
     for row in kat["ntt_hashes"]:

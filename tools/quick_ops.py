@@ -12,10 +12,12 @@ ap.add_argument("--only", nargs="*", default=None, help="subset of tensor ext_pr
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--batch", type=int, default=0, help="override the shape's batch (1: single-ciphertext calls)")
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--latency-rows", type=int, default=None, help="context option latency_rows")
 a = ap.parse_args()
 SHAPES = {"c3": (13, [40, 30, 30, 30], 40, 296), "c4": (14, [50] + [40] * 7, 50, 148), "c5": (15, [50] * 12, 55, 37)}
 orc = Oracle()
 ctx = Context(lib_path=a.lib)
+if a.latency_rows is not None: ctx.set_option("latency_rows", a.latency_rows)
 for name in a.shape:
     logn, bits, pbits, batch = SHAPES[name]
     batch = a.batch or batch
