@@ -51,7 +51,10 @@ const char *hehub_b200_last_error(const hehub_b200_ctx *ctx);
 /* options: "force_generic" (0/1) routes transforms through the one-level-per-sweep kernels
  * (an on-device cross-check of the fast path); "scratch_cap_mib" bounds the workspace a
  * batched call may use (large batches are processed in waves);
- * "host_chunk_kib" sets the chunk size of the host-buffer pipeline (default 16384; measured best on PCIe Gen5, profiles/r1d_e2e_chunk_sweep.log). */
+ * "host_chunk_kib" sets the chunk size of the host-buffer pipeline (default 16384; measured best on PCIe Gen5, profiles/r1d_e2e_chunk_sweep.log);
+ * "latency_rows": transform launches with at most this many rows (one limb of one polynomial each) split every
+ *   row of N = 4096 / 8192 over a 2-CTA cluster (default -1 = half the SM count; 0 = never).
+ * Environment: HEHUB_B200_PDL=0 turns programmatic dependent launch off (A/B only). */
 int hehub_b200_ctx_set_option(hehub_b200_ctx *ctx, const char *name, int64_t value);
 /* number of kernels this context has launched since creation (bench bookkeeping) */
 uint64_t hehub_b200_launch_count(const hehub_b200_ctx *ctx);
