@@ -51,12 +51,12 @@ inline void mod_switch_inplace(BgvCt &ct, size_t dropping_primes = 1) {
     if (ct[0].component_count() == 1) throw std::invalid_argument("Unable to drop the only one prime.");
     const auto params = ct[0].params();
     const size_t L = params.component_count, n = params.dimension;
-    ::hehub::detail::Staged in(2 * L * n), out(2 * (L - 1) * n);
-    ckks::detail::gather<2>(ct, in.dev);
+    ::hehub::detail::Staged out(2 * (L - 1) * n);
+    const auto in = ckks::detail::gather<2>(ct);
     b200::check(hehub_b200_bgv_mod_switch(b200::context(), (unsigned)ct[0].log_dimension(), params.moduli.data(), L, ct.plain_modulus,
                                           in.dev, out.dev, 1));
     RnsPolyParams dropped{n, L - 1, std::vector<u64>(params.moduli.begin(), params.moduli.end() - 1)};
-    static_cast<RlweCt &>(ct) = ckks::detail::scatter(out.dev, dropped);
+    static_cast<RlweCt &>(ct) = ckks::detail::scatter<2>(out, dropped);
 }
 
 /// bgv/arith.cpp:71-79 — the internal mod-switch runs with the default plain modulus 1, as in the reference
@@ -64,11 +64,11 @@ inline BgvCt relinearize(const BgvQuadraticCt &ct, const RlweKsk &relin_key) {
     const auto &key = relin_key.packed(ct[2]);
     const auto params = ct[0].params();
     const size_t L = params.component_count, words = L * params.dimension;
-    ::hehub::detail::Staged q(3 * words), out(2 * words);
-    ckks::detail::gather<3>(ct, q.dev);
+    ::hehub::detail::Staged out(2 * words);
+    const auto q = ckks::detail::gather<3>(ct);
     b200::check(hehub_b200_bgv_relinearize(b200::context(), (unsigned)ct[0].log_dimension(), key.ext_moduli.data(), L, 1, q.dev, key.dev,
                                            out.dev, 1));
-    BgvCt ct_new = ckks::detail::scatter(out.dev, params);
+    BgvCt ct_new(ckks::detail::scatter<2>(out, params));
     ct_new.plain_modulus = ct.plain_modulus;
     return ct_new;
 }

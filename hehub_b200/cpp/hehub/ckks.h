@@ -4,6 +4,7 @@
 // are consumed here unchanged.
 #pragma once
 #include <cmath>
+#include <memory>
 
 #include "permutation.h"
 #include "rgsw.h"
@@ -39,20 +40,37 @@ inline void check_ct(const RlweCt &ct) { // rescaling.cpp:15-29
     if (ct[0].dimension() != ct[1].dimension()) throw std::invalid_argument("Ill-formed ciphertext: polynomial lengths mismatch.");
     if (ct[0].component_count() != ct[1].component_count()) throw std::invalid_argument("Ill-formed ciphertext: component numbers mismatch.");
 }
-/// contiguous [polys][L][N] device copy of separately stored polynomials (what the C ABI consumes)
+/// The K polynomials as ONE contiguous [K][L][N] device operand (what the C ABI consumes): their own storage when
+/// they already sit back to back in one slab — results of earlier calls do, see scatter() — else a gathered copy.
+struct Operand {
+    const u64 *dev = nullptr;
+    std::unique_ptr<::hehub::detail::Staged> copy;
+};
 template <size_t K>
-inline void gather(const std::array<RnsPolynomial, K> &polys, u64 *dst) {
-    const size_t words = polys[0].component_count() * polys[0].dimension();
-    for (size_t h = 0; h < K; h++) b200::check(hehub_b200_slab_d2d(b200::context(), dst + h * words, polys[h].dev(), words));
-}
-inline RlweCt scatter(const u64 *src, const RnsPolyParams &params) {
-    RlweCt ct{RnsPolynomial(params), RnsPolynomial(params)};
-    const size_t words = params.component_count * params.dimension;
-    for (size_t h = 0; h < 2; h++) {
-        b200::check(hehub_b200_slab_d2d(b200::context(), ct[h].dev_mut(), src + h * words, words));
-        ct[h].rep_form = PolyRepForm::value;
+inline Operand gather(const std::array<RnsPolynomial, K> &polys) {
+    Operand op;
+    bool adjacent = true;
+    for (size_t h = 0; h + 1 < K; h++) adjacent = adjacent && polys[h].device_adjacent(polys[h + 1]);
+    if (adjacent) {
+        op.dev = polys[0].dev();
+        return op;
     }
-    return ct;
+    const size_t words = polys[0].component_count() * polys[0].dimension();
+    op.copy.reset(new ::hehub::detail::Staged(K * words));
+    for (size_t h = 0; h < K; h++) b200::check(hehub_b200_slab_d2d(b200::context(), op.copy->dev + h * words, polys[h].dev(), words));
+    op.dev = op.copy->dev;
+    return op;
+}
+/// the K polynomials a kernel wrote back to back into `out`, adopted without a copy (they share the slab)
+template <size_t K>
+inline std::array<RnsPolynomial, K> scatter(const ::hehub::detail::Staged &out, const RnsPolyParams &params) {
+    std::array<RnsPolynomial, K> polys;
+    const size_t words = params.component_count * params.dimension;
+    for (size_t h = 0; h < K; h++) {
+        polys[h] = RnsPolynomial(RnsIntVec::adopt(out.block, out.dev + h * words, params));
+        polys[h].rep_form = PolyRepForm::value;
+    }
+    return polys;
 }
 } // namespace detail
 
@@ -103,17 +121,12 @@ inline CkksQuadraticCt mult_low_level(const CkksCt &ct1, const CkksCt &ct2) {
                 throw std::invalid_argument("Polynomial multiplication requires NTT form (value representation).");
     const auto params = ct1[0].params();
     const size_t words = params.component_count * params.dimension;
-    ::hehub::detail::Staged a(2 * words), b(2 * words), q(3 * words);
-    detail::gather<2>(ct1, a.dev);
-    detail::gather<2>(ct2, b.dev);
+    ::hehub::detail::Staged q(3 * words);
+    const auto a = detail::gather<2>(ct1), b = detail::gather<2>(ct2);
     b200::check(hehub_b200_ckks_tensor(b200::context(), (unsigned)ct1[0].log_dimension(), params.moduli.data(), params.component_count,
                                        a.dev, b.dev, q.dev, 1));
     CkksQuadraticCt prod;
-    for (size_t h = 0; h < 3; h++) {
-        prod[h] = RnsPolynomial(params);
-        b200::check(hehub_b200_slab_d2d(b200::context(), prod[h].dev_mut(), q.dev + h * words, words));
-        prod[h].rep_form = PolyRepForm::value;
-    }
+    static_cast<std::array<RnsPolynomial, 3> &>(prod) = detail::scatter<3>(q, params);
     prod.scaling_factor = ct1.scaling_factor * ct2.scaling_factor;
     return prod;
 }
@@ -126,12 +139,12 @@ inline void rescale_inplace(CkksCt &ct, size_t dropping_primes = 1) {
     if (ct[0].component_count() == 1) throw std::invalid_argument("Unable to drop the only one prime.");
     const auto params = ct[0].params();
     const size_t L = params.component_count, n = params.dimension;
-    ::hehub::detail::Staged in(2 * L * n), out(2 * (L - 1) * n);
-    detail::gather<2>(ct, in.dev);
+    ::hehub::detail::Staged out(2 * (L - 1) * n);
+    const auto in = detail::gather<2>(ct);
     b200::check(hehub_b200_ckks_rescale(b200::context(), (unsigned)ct[0].log_dimension(), params.moduli.data(), L, in.dev, out.dev, 1));
     RnsPolyParams dropped{n, L - 1, std::vector<u64>(params.moduli.begin(), params.moduli.end() - 1)};
     const double sf = ct.scaling_factor / (double)params.moduli[L - 1]; // rescaling.cpp:77
-    static_cast<RlweCt &>(ct) = detail::scatter(out.dev, dropped);
+    static_cast<RlweCt &>(ct) = detail::scatter<2>(out, dropped);
     ct.scaling_factor = sf;
 }
 
@@ -140,11 +153,11 @@ inline CkksCt relinearize(const CkksQuadraticCt &ct, const RlweKsk &relin_key) {
     const auto &key = relin_key.packed(ct[2]);
     const auto params = ct[0].params();
     const size_t L = params.component_count, words = L * params.dimension;
-    ::hehub::detail::Staged q(3 * words), out(2 * words);
-    detail::gather<3>(ct, q.dev);
+    ::hehub::detail::Staged out(2 * words);
+    const auto q = detail::gather<3>(ct);
     b200::check(hehub_b200_ckks_relinearize(b200::context(), (unsigned)ct[0].log_dimension(), key.ext_moduli.data(), L, q.dev, key.dev,
                                             out.dev, 1));
-    CkksCt ct_new = detail::scatter(out.dev, params);
+    CkksCt ct_new(detail::scatter<2>(out, params));
     ct_new.scaling_factor = ct.scaling_factor;
     return ct_new;
 }
@@ -157,12 +170,11 @@ inline CkksCt mult(const CkksCt &ct1, const CkksCt &ct2, const RlweKsk &relin_ke
     const auto &key = relin_key.packed(ct1[1]);
     const auto params = ct1[0].params();
     const size_t L = params.component_count, words = L * params.dimension;
-    ::hehub::detail::Staged a(2 * words), b(2 * words), out(2 * words);
-    detail::gather<2>(ct1, a.dev);
-    detail::gather<2>(ct2, b.dev);
+    ::hehub::detail::Staged out(2 * words);
+    const auto a = detail::gather<2>(ct1), b = detail::gather<2>(ct2);
     b200::check(hehub_b200_ckks_mult_relin(b200::context(), (unsigned)ct1[0].log_dimension(), key.ext_moduli.data(), L, a.dev, b.dev,
                                            key.dev, out.dev, 1));
-    CkksCt prod = detail::scatter(out.dev, params);
+    CkksCt prod(detail::scatter<2>(out, params));
     prod.scaling_factor = ct1.scaling_factor * ct2.scaling_factor;
     return prod;
 }
@@ -173,11 +185,11 @@ inline CkksCt conjugate(const CkksCt &ct, const RlweKsk &conj_key) {
     const auto &key = conj_key.packed(ct[1]);
     const auto params = ct[0].params();
     const size_t L = params.component_count, words = L * params.dimension;
-    ::hehub::detail::Staged a(2 * words), out(2 * words);
-    detail::gather<2>(ct, a.dev);
+    ::hehub::detail::Staged out(2 * words);
+    const auto a = detail::gather<2>(ct);
     b200::check(hehub_b200_ckks_conjugate(b200::context(), (unsigned)ct[0].log_dimension(), key.ext_moduli.data(), L, a.dev, key.dev,
                                           out.dev, 1));
-    CkksCt res = detail::scatter(out.dev, params);
+    CkksCt res(detail::scatter<2>(out, params));
     res.scaling_factor = ct.scaling_factor;
     return res;
 }
@@ -188,11 +200,11 @@ inline CkksCt rotate(const CkksCt &ct, const RlweKsk &rot_key, const size_t step
     const auto &key = rot_key.packed(ct[1]);
     const auto params = ct[0].params();
     const size_t L = params.component_count, words = L * params.dimension;
-    ::hehub::detail::Staged a(2 * words), out(2 * words);
-    detail::gather<2>(ct, a.dev);
+    ::hehub::detail::Staged out(2 * words);
+    const auto a = detail::gather<2>(ct);
     b200::check(hehub_b200_ckks_rotate(b200::context(), (unsigned)ct[0].log_dimension(), key.ext_moduli.data(), L, a.dev, key.dev, step,
                                        out.dev, 1));
-    CkksCt res = detail::scatter(out.dev, params);
+    CkksCt res(detail::scatter<2>(out, params));
     res.scaling_factor = ct.scaling_factor;
     return res;
 }

@@ -4,6 +4,7 @@
 // CUDA kernel.  They exist for drop-in completeness and for the parity tests; code that cares about
 // speed keeps its data in RnsPolynomial objects, whose operators never leave the device.
 #pragma once
+#include <memory>
 #include <vector>
 
 #include "rns.h"
@@ -13,11 +14,10 @@ namespace hehub {
 namespace detail {
 // RAII device staging of a host vector
 struct Staged {
+    std::shared_ptr<SlabBlock> block;
     u64 *dev = nullptr;
     size_t words;
-    explicit Staged(size_t n) : words(n) {
-        if (n) b200::check(hehub_b200_slab_alloc(b200::context(), n, &dev));
-    }
+    explicit Staged(size_t n) : block(std::make_shared<SlabBlock>(n)), dev(block->p), words(n) {}
     Staged(const u64 *host, size_t n) : Staged(n) {
         if (n) {
             b200::check(hehub_b200_slab_h2d(b200::context(), dev, host, n));
@@ -29,11 +29,6 @@ struct Staged {
         b200::check(hehub_b200_slab_d2h(b200::context(), host, dev, words));
         b200::synchronize();
     }
-    ~Staged() {
-        if (dev) hehub_b200_slab_free(b200::context(), dev);
-    }
-    Staged(const Staged &) = delete;
-    Staged &operator=(const Staged &) = delete;
 };
 } // namespace detail
 

@@ -105,9 +105,9 @@ inline RlweCt ext_prod_montgomery(const RlwePt &pt, const RlweKsk &rgsw) {
     detail::Staged out(2 * (L + 1) * pt.dimension());
     b200::check(hehub_b200_ext_prod_montgomery(b200::context(), (unsigned)pt.log_dimension(), key.ext_moduli.data(), L, pt.dev(),
                                                key.dev, out.dev, 1));
-    RlweCt ct{RnsPolynomial(ext), RnsPolynomial(ext)};
+    RlweCt ct; // the two halves adopt the slab: no copy, and they stay contiguous for the rescale that follows
     for (size_t h = 0; h < 2; h++) {
-        b200::check(hehub_b200_slab_d2d(b200::context(), ct[h].dev_mut(), out.dev + h * (L + 1) * pt.dimension(), (L + 1) * pt.dimension()));
+        ct[h] = RnsPolynomial(RnsIntVec::adopt(out.block, out.dev + h * (L + 1) * pt.dimension(), ext));
         ct[h].rep_form = PolyRepForm::value;
     }
     return ct;

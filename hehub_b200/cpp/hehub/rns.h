@@ -10,6 +10,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <vector>
 
@@ -20,6 +21,24 @@ namespace hehub {
 using u64 = uint64_t;
 using u128 = unsigned __int128;
 using i128 = __int128;
+
+namespace detail {
+/// One pooled device slab, returned to the pool when the last owner lets go.  Polynomials produced together by
+/// one kernel call (the two halves of a ciphertext) share a block, so they are already contiguous when the next
+/// call needs them as one [polys][L][N] operand.
+struct SlabBlock {
+    u64 *p = nullptr;
+    explicit SlabBlock(size_t words) {
+        if (words) b200::check(hehub_b200_slab_alloc(b200::context(), words, &p));
+    }
+    SlabBlock(const SlabBlock &) = delete;
+    SlabBlock &operator=(const SlabBlock &) = delete;
+    ~SlabBlock() {
+        if (p) hehub_b200_slab_free(b200::context(), p);
+    }
+};
+
+} // namespace detail
 
 class RnsIntVec {
 public:
@@ -166,7 +185,29 @@ protected:
     size_t dimension_ = 0;
     std::vector<u64> moduli_;
 
+public:
+    /// A polynomial over `params` whose words are the `params.component_count * dimension` words at `at` inside
+    /// `block` (filled by a kernel): no copy.  Polynomials adopted from one block are contiguous operands.
+    static RnsIntVec adopt(std::shared_ptr<detail::SlabBlock> block, u64 *at, const Params &params) {
+        RnsIntVec v;
+        v.dimension_ = params.dimension;
+        while (((size_t)1 << v.log_dimension_) < v.dimension_) v.log_dimension_++;
+        v.moduli_.assign(params.moduli.begin(), params.moduli.begin() + params.component_count);
+        v.block_ = std::move(block);
+        v.dev_ = at;
+        v.capacity_words_ = params.component_count * params.dimension;
+        v.dev_valid_ = true;
+        v.host_valid_ = false;
+        v.rebuild_views();
+        return v;
+    }
+    /// true when `next` starts where this polynomial's words end, in the same block, and both device copies are current
+    bool device_adjacent(const RnsIntVec &next) const {
+        return block_ && block_ == next.block_ && dev_valid_ && next.dev_valid_ && next.dev_ == dev_ + moduli_.size() * dimension_;
+    }
+
 private:
+    std::shared_ptr<detail::SlabBlock> block_; // owns the slab dev_ points into (possibly shared with sibling polynomials)
     u64 *dev_ = nullptr;
     size_t capacity_words_ = 0;
     mutable std::vector<u64> host_;
@@ -180,13 +221,14 @@ private:
     }
     void allocate(size_t components) {
         capacity_words_ = components * dimension_;
-        if (capacity_words_) b200::check(hehub_b200_slab_alloc(b200::context(), capacity_words_, &dev_));
+        block_ = std::make_shared<detail::SlabBlock>(capacity_words_);
+        dev_ = block_->p;
         dev_valid_ = true;
         host_valid_ = false;
         rebuild_views();
     }
     void release() {
-        if (dev_) hehub_b200_slab_free(b200::context(), dev_); // back to the per-size pool
+        block_.reset(); // the slab goes back to the per-size pool with its last owner
         dev_ = nullptr;
         capacity_words_ = 0;
         host_.clear();
@@ -213,6 +255,7 @@ private:
         dimension_ = o.dimension_;
         log_dimension_ = o.log_dimension_;
         moduli_ = std::move(o.moduli_);
+        block_ = std::move(o.block_);
         dev_ = o.dev_;
         capacity_words_ = o.capacity_words_;
         host_ = std::move(o.host_);

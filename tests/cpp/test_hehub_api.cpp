@@ -230,6 +230,28 @@ static void test_scheme_ops(size_t logn, const std::vector<unsigned> &bits, unsi
     auto prod = ckks::mult(ct1, ct2, key);
     CHECK(flat(prod) == wr);
     CHECK(prod.scaling_factor == quad.scaling_factor);
+    {
+        // the halves of a result share one device slab (no copies between chained calls): value semantics must hold anyway
+        CHECK(prod[0].device_adjacent(prod[1]));
+        ckks::CkksCt keep(prod);               // deep copy into storage of its own
+        CHECK(!keep[0].device_adjacent(keep[1]));
+        auto p2 = ckks::mult(ct1, ct2, key);
+        p2[0] += p2[1];                        // in place on one half only
+        CHECK(flat(keep) == wr);
+        CHECK(flat(p2[1]) == std::vector<u64>(wr.begin() + L * n, wr.end()));
+        std::vector<u64> sum0(wr.begin(), wr.begin() + L * n); // x += y in place, rns.cpp:78-84
+        for (size_t k = 0; k < L; k++) orc_add_lazy(mods[k], n, sum0.data() + k * n, wr.data() + (L + k) * n);
+        CHECK(flat(p2[0]) == sum0);
+        RnsPolynomial alone(std::move(p2[1])); // one half outlives the other
+        p2 = ckks::CkksCt();
+        CHECK(flat(alone) == std::vector<u64>(wr.begin() + L * n, wr.end()));
+        // a host write to one half un-shares nothing but makes the pair non-contiguous until re-uploaded
+        auto p3 = ckks::mult(ct1, ct2, key);
+        p3[1][0][0] = p3[1][0][0];
+        auto again = ckks::relinearize(ckks::mult_low_level(ct1, ct2), key);
+        CHECK(flat(again) == wr);
+        CHECK(flat(p3) == wr);
+    }
 
     if (L >= 2) {
         ckks::CkksCt rs(prod);
