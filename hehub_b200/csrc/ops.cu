@@ -24,7 +24,7 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 // tensor product: one pass, 4 loads + 3 stores per coefficient
 // ------------------------------------------------------------------------------------------
 #ifndef HB_TENSOR_MINB
-#define HB_TENSOR_MINB 4
+#define HB_TENSOR_MINB 5
 #endif
 #ifndef HB_MAC_MINB
 #define HB_MAC_MINB 3
