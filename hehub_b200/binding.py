@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_SO = os.path.join(HERE, "libhehub_b200.so")
+DEFAULT_SO = os.environ.get("HEHUB_B200_LIB") or os.path.join(HERE, "libhehub_b200.so")  # the variable: A/B builds (tools/ab_build.sh)
 
 u64 = C.c_uint64
 p64 = C.POINTER(C.c_uint64)

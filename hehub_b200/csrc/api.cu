@@ -44,7 +44,8 @@ struct RowsIO {
 // row so the modulus lookup is per block.  HBM-bound: fully coalesced 128-bit accesses.
 // ------------------------------------------------------------------------------------------
 constexpr int kEwThreads = 256;
-constexpr int kEwWordsPerBlock = kEwThreads * 4;
+// 128-bit vectors per thread are a property of the operation (Op::kVecs), from an A/B sweep on the box
+// (profiles/r2m_ew_vectors_ab.log): streaming adds want many small blocks, the multiply-heavy ones fewer and longer.
 
 template <class Op>
 HB_GLOBAL(kEwThreads, 1) ew_kernel(const Op op, const LimbConst *__restrict__ limbs, int L, size_t n,
@@ -54,16 +55,17 @@ HB_GLOBAL(kEwThreads, 1) ew_kernel(const Op op, const LimbConst *__restrict__ li
     const unsigned chunk = blockIdx.x % blocks_per_row;
     const LimbConst lc = limbs[row % L];
     const size_t base = row * n;
-    const size_t i0 = (size_t)chunk * kEwWordsPerBlock + threadIdx.x * 2;
+    constexpr int kEwVecs = Op::kVecs;
+    const size_t i0 = (size_t)chunk * (kEwThreads * 2 * kEwVecs) + threadIdx.x * 2;
     if (((n & 1) == 0) && op.aligned) {
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < kEwVecs; u++) {
             const size_t i = i0 + (size_t)u * kEwThreads * 2;
             if (i < n) op.apply2(base + i, (int)(row % L), lc);
         }
     } else {
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < kEwVecs; u++) {
             const size_t i = i0 + (size_t)u * kEwThreads * 2;
             if (i < n) op.apply1(base + i, (int)(row % L), lc);
             if (i + 1 < n) op.apply1(base + i + 1, (int)(row % L), lc);
@@ -77,6 +79,7 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
     HB_D void apply1(size_t idx, int limb, const LimbConst &lc) const { BODY1 }
 
 struct OpMulHybrid {
+    static constexpr int kVecs = 8;
     const u64 *a, *b;
     u64 *c;
     bool aligned;
@@ -89,6 +92,7 @@ struct OpMulHybrid {
 
 template <int MODE> // 0 add, 1 sub
 struct OpAddSub {
+    static constexpr int kVecs = 1;
     u64 *x;
     const u64 *y;
     bool aligned;
@@ -104,6 +108,7 @@ struct OpAddSub {
 
 template <int MODE> // 0 strict, 1 barrett lazy, 2 barrett strict
 struct OpUnary {
+    static constexpr int kVecs = MODE == 0 ? 4 : 2;
     u64 *x;
     bool aligned;
     HB_D u64 f(u64 a, const LimbConst &lc) const {
@@ -119,6 +124,7 @@ struct OpUnary {
 };
 
 struct OpMulScalar {
+    static constexpr int kVecs = 1;
     u64 *x;
     const ulonglong2 *scalars; // [L] (s mod q, harvey companion)
     bool aligned;
@@ -134,6 +140,7 @@ struct OpMulScalar {
 };
 
 struct OpMontgomery {
+    static constexpr int kVecs = 2;
     const u64 *in; // (lo, hi) pairs
     u64 *out;
     bool aligned;
@@ -150,6 +157,7 @@ struct OpMontgomery {
 template <class Op>
 static int launch_ew(Context &c, const Op &op, const LimbConst *limbs, size_t L, size_t n, size_t rows) {
     if (rows == 0 || n == 0) return 0;
+    constexpr size_t kEwWordsPerBlock = (size_t)kEwThreads * 2 * Op::kVecs;
     const size_t bpr = (n + kEwWordsPerBlock - 1) / kEwWordsPerBlock;
     const size_t blocks = rows * bpr;
     if (blocks > 0x7fffffffull) return c.fail(HEHUB_B200_ERR_INVALID, "operand too large for one launch");
