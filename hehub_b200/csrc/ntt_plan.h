@@ -52,14 +52,15 @@ HB_CX NttPlan plan_for(int logn, bool fwd, int mode = 0) {
 #if defined(HB_PLAN13) && HB_PLAN13 == 0
     case 13: return NttPlan{13, 0, 3, {5, 4, 4, 0, 0}, 256, 2};
 #else // forward: four narrower passes and three CTAs per SM (+2 %, more for the fused kernels); the inverse loses 3 % with it
-    case 13: return fwd ? NttPlan{13, 0, 4, {3, 3, 3, 4, 0}, 256, 3} : NttPlan{13, 0, 3, {5, 4, 4, 0, 0}, 256, 2};
+    // (inverse {4,5,4}: +0.7 % over {5,4,4}, profiles/r2n_plan13_inverse_ab.log)
+    case 13: return fwd ? NttPlan{13, 0, 4, {3, 3, 3, 4, 0}, 256, 3} : NttPlan{13, 0, 3, {4, 5, 4, 0, 0}, 256, 2};
 #endif
 #if defined(HB_PLAN14) && HB_PLAN14 == 0 // one CTA per row: nothing else shares the SM, load/compute/store phases do not overlap
     case 14: return NttPlan{14, 0, 3, {5, 5, 4, 0, 0}, 512, 1};
 #elif defined(HB_PLAN14) && HB_PLAN14 == 1 // 2-CTA cluster per row, half a row per CTA, two CTAs per SM (+5 % over one CTA per row)
     case 14: return NttPlan{14, 1, 3, {5, 4, 4, 0, 0}, 256, 2};
 #else // cluster form with four narrower passes: three CTAs (of up to three different rows) per SM, another +2-4 %
-    case 14: return NttPlan{14, 1, 4, {3, 3, 3, 4, 0}, 256, 3};
+    case 14: return NttPlan{14, 1, 4, {3, 3, 3, 4, 0}, 256, 3}; // inverse {4,5,4} / {5,4,4} x2: -4 % / -2 % (profiles/r2n_plan14_15_inverse_ab.log)
 #endif
 #if defined(HB_PLAN15) && HB_PLAN15 == 0 // 16 warps per CTA (one CTA per SM): too few to hide the fused epilogues' loads
     default: return NttPlan{15, 1, 4, {4, 3, 3, 4, 0}, 512, 1};
