@@ -179,6 +179,8 @@ def run_cuda(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (hehub_b200 has no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    from hehub_b200.binding import bind_host_to_gpu
+    numa_cpus = bind_host_to_gpu(local)  # pinned host buffers of the e2e legs next to this GPU's PCIe root
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
@@ -292,7 +294,7 @@ def run_cuda(args):
         trials.append(max_over_ranks(time.perf_counter() - t0))
     e2e_elapsed = sorted(trials)[1]
     e2e = {"value": world * POLYS * e2e_steps / e2e_elapsed, "unit": UNIT, "h2d_bytes_per_step": POLYS * n * 8,
-           "d2h_bytes_per_step": POLYS * n * 8, "steps": e2e_steps,
+           "d2h_bytes_per_step": POLYS * n * 8, "steps": e2e_steps, "host_cpus_bound_to_gpu_numa_node": len(numa_cpus),
            "trials_per_s": [world * POLYS * e2e_steps / t for t in trials],
            "call": "hehub_b200_ntt_host (pinned host buffers, chunked H2D | kernel | D2H pipeline on three streams)"}
 

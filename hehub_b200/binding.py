@@ -87,6 +87,28 @@ EXPORTED = ["hehub_b200_version", "hehub_b200_ctx_create", "hehub_b200_ctx_destr
             "hehub_b200_launch_count"] + ["hehub_b200_" + k for k in _SIGS]
 
 
+def bind_host_to_gpu(device: int = 0) -> list[int]:
+    """Restrict the calling process to the CPUs NVML reports as local to `device` (its NUMA node), so that the
+    pinned host buffers allocated afterwards — and the threads that fill them — sit next to the GPU's PCIe root.
+    Matters for the host-buffer entry points when several ranks share a two-socket host.  Returns the CPU list
+    (empty: nothing changed — NVML missing, or no overlap with the CPUs this process may use)."""
+    if os.environ.get("HEHUB_B200_NUMA", "1") == "0":
+        return []
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device)
+        ncpu = os.cpu_count() or 1
+        masks = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        local = {i for i in range(ncpu) if (int(masks[i // 64]) >> (i % 64)) & 1}
+        cpus = sorted(local & set(os.sched_getaffinity(0)))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return []
+
+
 def load_library(path: str | None = None) -> C.CDLL:
     path = path or DEFAULT_SO
     if not os.path.exists(path):
