@@ -596,24 +596,41 @@ int op_rlwe_encrypt_core(Context &c, unsigned logn, const u64 *moduli, size_t L,
 // ------------------------------------------------------------------------------------------
 // one modulus -> many: out[b][k][i] from in[b][i]                       rns_transform.cpp:11-37, :116
 // blocks tile one (b, k) row, so the modulus — and the 64-bit division behind `modulus_multiple` — is per block
+// The centring constant (q_old / q_k + 1) * q_k - q_old of rns_transform.cpp:20-24 depends only on the modulus pair:
+// the host computes it per new modulus and passes up to 32 of them by value (no 64-bit division in the kernel).
+struct LiftTable {
+    u64 v[32];
+};
+template <bool VEC>
 HB_GLOBAL(256, 1)
 base_from_single_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const LimbConst *__restrict__ limbs, u64 q_old, int Lnew,
-                        size_t n, unsigned blocks_per_row) {
+                        size_t n, unsigned blocks_per_row, const LiftTable lifts) {
     hb_pdl_wait();
     const size_t bk = blockIdx.x / blocks_per_row;
     const int k = (int)(bk % Lnew);
     const size_t b = bk / Lnew;
     const LimbConst lc = limbs[k];
-    const u64 lift = (q_old / lc.q + 1) * lc.q - q_old; // uniform across the block
-    const size_t i0 = (size_t)(blockIdx.x % blocks_per_row) * 1024 + threadIdx.x;
+    const u64 lift = k < 32 ? lifts.v[k] : (q_old / lc.q + 1) * lc.q - q_old; // uniform across the block
+    const u64 half = q_old / 2;
+    const bool reduce = lc.q < q_old;
+    auto f = [&](u64 raw) {
+        u64 x = reduce_strict(raw, q_old);
+        if (x >= half) x += lift;
+        if (reduce) x = barrett_lazy(x, lc);
+        return x;
+    };
+    constexpr int W = VEC ? 2 : 1;
+    const size_t i0 = ((size_t)(blockIdx.x % blocks_per_row) * 1024 + threadIdx.x) * W;
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-        const size_t i = i0 + (size_t)u * 256;
+        const size_t i = i0 + (size_t)u * 256 * W;
         if (i < n) {
-            u64 x = reduce_strict(in[b * n + i], q_old);
-            if (x >= q_old / 2) x += lift;
-            if (lc.q < q_old) x = barrett_lazy(x, lc);
-            out[bk * n + i] = x;
+            if constexpr (VEC) {
+                const ulonglong2 x = hb_ld_ro2(in + b * n + i);
+                *reinterpret_cast<ulonglong2 *>(out + bk * n + i) = make_ulonglong2(f(x.x), f(x.y));
+            } else {
+                out[bk * n + i] = f(in[b * n + i]);
+            }
         }
     }
 }
@@ -647,9 +664,17 @@ int op_base_from_single(Context &c, u64 q_old, const u64 *new_moduli, size_t Lne
     int err = 0;
     const LimbConst *limbs = c.get_chain(0, new_moduli, Lnew, &err);
     if (!limbs) return err;
-    const size_t bpr = (n + 1023) / 1024, blocks = batch * Lnew * bpr;
+    LiftTable lifts{};
+    for (size_t k = 0; k < Lnew && k < 32; k++) lifts.v[k] = (q_old / new_moduli[k] + 1) * new_moduli[k] - q_old;
+    const bool vec = n % 2 == 0 && aligned16(in) && aligned16(out);
+    const size_t per_block = vec ? 2048 : 1024;
+    const size_t bpr = (n + per_block - 1) / per_block, blocks = batch * Lnew * bpr;
     if (blocks > 0x7fffffffull) return c.fail(1, "operand too large for one launch");
-    HB_LAUNCH(base_from_single_kernel, (unsigned)blocks, 256, 0, c.stream, 0, in, out, limbs, q_old, (int)Lnew, n, (unsigned)bpr);
+    if (vec) {
+        HB_LAUNCH(base_from_single_kernel<true>, (unsigned)blocks, 256, 0, c.stream, 0, in, out, limbs, q_old, (int)Lnew, n, (unsigned)bpr, lifts);
+    } else {
+        HB_LAUNCH(base_from_single_kernel<false>, (unsigned)blocks, 256, 0, c.stream, 0, in, out, limbs, q_old, (int)Lnew, n, (unsigned)bpr, lifts);
+    }
     c.stats.launches++;
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : c.cuda_fail(e, "base transform launch");
