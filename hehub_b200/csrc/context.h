@@ -59,7 +59,10 @@ struct Context {
     std::vector<std::pair<u64 *, size_t>> scratch;       // grow-only workspaces, by slot
 
     // host-buffer entry points (host_pipe.cu): copy-in / copy-out streams and per-slot events
-    static constexpr int kPipeSlots = 4;
+#ifndef HB_PIPE_SLOTS
+#define HB_PIPE_SLOTS 4
+#endif
+    static constexpr int kPipeSlots = HB_PIPE_SLOTS;
     size_t host_chunk_bytes = (size_t)16 << 20; // option "host_chunk_kib": bytes per operand and chunk in the host-buffer pipeline
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[kPipeSlots] = {}, ev_k[kPipeSlots] = {}, ev_out[kPipeSlots] = {};
