@@ -14,7 +14,8 @@
 //     owns 32 << K adjacent words), and when the neighbouring pass keeps the same number of words
 //     per thread the exchange between the two stays inside a warp: N = 4096 needs ONE CTA barrier
 //     per transform;
-//   * N <= 8192: one CTA per row; N = 16384 and N = 32768 (256 KiB, more than one SM holds): a 2-CTA
+//   * N <= 8192: one CTA per row (a 2-CTA cluster for launches with few rows: latency plans, ntt_plan.h);
+//     N = 16384 and N = 32768 (256 KiB, more than one SM holds): a 2-CTA
 //     thread-block cluster per row, half a row each; the single cross-CTA level (gap N/2) is
 //     computed from global/L2 reads on the way in (forward) or finished from the sibling's shared
 //     memory (distributed shared memory) on the way out (inverse).
