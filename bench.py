@@ -31,7 +31,7 @@ Q59 = 576460752272228353
 LOGN = 12
 POLYS = 4096
 SLABS = 4
-SWEEP_WAVE = 37  # ciphertexts per wave of the config-5 sweep: 2 x 37 rows = one CTA pair per SM pair on 148 SMs
+SWEEP_WAVE = 74  # ciphertexts per wave of the config-5 sweep: a multiple of 37 (2 x 37 rows = one CTA pair per SM pair on 148 SMs)
 METRIC = "NTT/s (N=4096, one 59-bit modulus, batch 4096)"
 UNIT = "NTT/s"
 
@@ -471,7 +471,7 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
     # N=32768: one CTA pair per row), so every transform launch of the composite ops ends on a full wave
     ct_bench("c3_ckks_mult_relin_N8192_L4", 13, [40, 30, 30, 30], 40, 296, 4, ("mult", "tensor", "e2e", "latency"))
     ct_bench("c4_rescale_N16384_L8", 14, [50] + [40] * 7, 50, 148, 4, ("rescale",))
-    ct_bench("c5_ckks_mult_relin_N32768_L12", 15, [50] * 12, 55, 37, 2, ("mult", "tensor", "latency"))
+    ct_bench("c5_ckks_mult_relin_N32768_L12", 15, [50] * 12, 55, 74, 2, ("mult", "tensor", "latency"))
 
     # config 5 as a sweep: `sweep_cts` independent ciphertext pairs (65 536 in BASELINE; bounded by default so the
     # whole bench stays within minutes) cut into contiguous per-rank ranges, processed in waves, inputs generated

@@ -46,7 +46,7 @@ struct Context {
     int sm_count = 148;
     int latency_rows = -1; // option "latency_rows"; -1: half the SM count
     LaunchEnv env() { return LaunchEnv{stream, sm_count, force_generic, &stats, latency_rows < 0 ? sm_count / 2 : latency_rows}; }
-    size_t scratch_cap_bytes = (size_t)2 << 30; // bound on the per-call workspace; batches run in waves
+    size_t scratch_cap_bytes = (size_t)8 << 30; // bound on the per-call workspace (option "scratch_cap_mib"); batches run in waves
     std::string last_error;
     LaunchStats stats;
 

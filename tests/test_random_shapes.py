@@ -28,7 +28,7 @@ def _words(rng, moduli, n, lead=()):
 
 @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(logn=st.integers(1, 11), bits=st.lists(st.sampled_from(BITS), min_size=1, max_size=4), pbits=st.sampled_from(BITS),
-       batch=st.integers(1, 5), seed=st.integers(0, 2**31), cap=st.sampled_from([1, 2048]), t=st.sampled_from([2, 65537, 1032193]))
+       batch=st.integers(1, 5), seed=st.integers(0, 2**31), cap=st.sampled_from([1, 8192]), t=st.sampled_from([2, 65537, 1032193]))
 def test_random_chains_match_oracle(dev, oracle, logn, bits, pbits, batch, seed, cap, t):
     try:
         mods, p = oracle.ckks_pick_moduli(sorted(bits, reverse=(seed & 1) == 0), pbits)
@@ -56,4 +56,4 @@ def test_random_chains_match_oracle(dev, oracle, logn, bits, pbits, batch, seed,
         assert np.array_equal(dev.poly_intt(logn, mods, dev.poly_ntt_fwd(logn, mods, x), strict=True) % np.array(mods, dtype=np.uint64)[None, :, None],
                               x % np.array(mods, dtype=np.uint64)[None, :, None])
     finally:
-        dev.set_option("scratch_cap_mib", 2048)
+        dev.set_option("scratch_cap_mib", 8192)
