@@ -341,10 +341,7 @@ def run_cuda(args):
 def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, sweep_cts=0, cpu_ok=False):
     """Other BASELINE configs, device-resident, same timing discipline; values are whole-job."""
     import numpy as np
-    from hehub_b200.binding import _mod
-    from oracle.binding import Oracle, build_oracle
-    build_oracle()
-    orc = Oracle()  # parameter selection only (prime table rule); never timed here
+    from hehub_b200.binding import _mod, pick_moduli  # moduli come from the product's create_params rule (csrc/params.cu)
     hbm = peaks["hbm_gbs"]
     out = {}
     mod1, mod1p = _mod([Q59])
@@ -374,7 +371,7 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
     out["ntt_sweep_L1_batch4096"] = sweep
 
     def ct_bench(tag, logn, bits, pbits, batch, steps, what):
-        mods, p = orc.ckks_pick_moduli(bits, pbits)
+        mods, p = pick_moduli(bits, pbits, ctx.lib)
         mods = [int(m) for m in mods]
         ext = mods + [int(p)]
         L, n = len(mods), 1 << logn
@@ -478,7 +475,7 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
     # on the device; NCCL only broadcasts the key and gathers one checksum per ciphertext (hehub_b200/sweep.py)
     if sweep_cts > 0:
         from hehub_b200.sweep import CtSweep
-        mods, p = orc.ckks_pick_moduli([50] * 12, 55)
+        mods, p = pick_moduli([50] * 12, 55, ctx.lib)
         sw = CtSweep(ctx, f"cuda:{torch.cuda.current_device()}", 15, [int(m) for m in mods], int(p), seed=42)
         with torch.cuda.stream(stream):
             sw.make_key(dist, rank)
@@ -543,13 +540,10 @@ def run_rows(ctx, torch, timed, world, rank, peaks, cpu_ok):
     (N = 8192, L = 4, {40,30,30,30}+P40)."""
     import ctypes as C
     import numpy as np
-    from hehub_b200.binding import _mod
-    from oracle.binding import Oracle, build_oracle
-    build_oracle()
-    orc = Oracle()
+    from hehub_b200.binding import _mod, pick_moduli
     hbm = peaks["hbm_gbs"]
     logn, n = 13, 8192
-    mods, p = orc.ckks_pick_moduli([40, 30, 30, 30], 40)
+    mods, p = pick_moduli([40, 30, 30, 30], 40, ctx.lib)
     mods = [int(m) for m in mods]
     ext = mods + [int(p)]
     L = len(mods)

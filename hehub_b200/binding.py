@@ -83,8 +83,14 @@ _SIGS = {
     "ctx_synchronize": [],
 }
 
+# entry points without a context (host-only parameter selection)
+_FREE_SIGS = {
+    "prime_row": [C.c_uint, sz, p64],
+    "pick_moduli": [C.POINTER(C.c_uint), sz, C.c_uint, p64, p64],
+}
+
 EXPORTED = ["hehub_b200_version", "hehub_b200_ctx_create", "hehub_b200_ctx_destroy", "hehub_b200_last_error",
-            "hehub_b200_launch_count"] + ["hehub_b200_" + k for k in _SIGS]
+            "hehub_b200_launch_count"] + ["hehub_b200_" + k for k in _SIGS] + ["hehub_b200_" + k for k in _FREE_SIGS]
 
 
 def bind_host_to_gpu(device: int = 0) -> list[int]:
@@ -128,7 +134,35 @@ def load_library(path: str | None = None) -> C.CDLL:
         f = getattr(lib, "hehub_b200_" + name)
         f.restype = C.c_int
         f.argtypes = [ctxp] + args
+    for name, args in _FREE_SIGS.items():
+        f = getattr(lib, "hehub_b200_" + name)
+        f.restype = C.c_int
+        f.argtypes = args
     return lib
+
+
+def prime_row(bits: int, lib: C.CDLL | None = None) -> list[int]:
+    """Row `bits` of the reference's prime table (src/fhe/common/primelists.cpp), host only — no device needed."""
+    lib = lib or load_library()
+    buf = (C.c_uint64 * 32)()
+    n = lib.hehub_b200_prime_row(bits, 32, buf)
+    return [int(buf[i]) for i in range(min(n, 32))]
+
+
+def pick_moduli(moduli_bits, additional_bits: int | None, lib: C.CDLL | None = None):
+    """ckks::create_params' prime selection (src/fhe/ckks/basics.cpp:14-38): returns (moduli, additional modulus);
+    additional_bits None -> hehub::create_params (rlwe.cpp:9-29), second value None.  Host only."""
+    lib = lib or load_library()
+    bits = (C.c_uint * len(moduli_bits))(*[int(b) for b in moduli_bits])
+    out = (C.c_uint64 * max(1, len(moduli_bits)))()
+    add = C.c_uint64(0)
+    rc = lib.hehub_b200_pick_moduli(bits, len(moduli_bits), int(additional_bits or 0), out,
+                                    C.byref(add) if additional_bits is not None else None)
+    if rc == ERR_UNSUPPORTED:
+        raise Unsupported(rc, "No suitable primes in the library.")
+    if rc != OK:
+        raise InvalidArgument(rc, "bad arguments to pick_moduli")
+    return [int(out[i]) for i in range(len(moduli_bits))], (int(add.value) if additional_bits is not None else None)
 
 
 def _arr(a) -> np.ndarray:

@@ -1,9 +1,10 @@
-// ckks.h — the ciphertext-op part of hehub::ckks (src/fhe/ckks/ckks.h:73-329, arith.cpp, rescaling.cpp)
-// on the B200 back end.  Encoding (fp64 FFT, basics.cpp:68-369), sampling and key generation are
-// host-side reference code outside this back end's path; their outputs (CkksPt, CkksCt, RlweKsk)
-// are consumed here unchanged.
+// ckks.h — hehub::ckks on the B200 back end (src/fhe/ckks/ckks.h:19-329, basics.cpp:14-64, arith.cpp,
+// rescaling.cpp): parameter selection, encrypt / decrypt and every ciphertext operator.  Only the encoder
+// (complex fp64 FFT + decimal big integers, basics.cpp:68-369) is not here: it is host-side floating-point
+// code outside the integer hot path; a CkksPt produced by it is consumed unchanged.
 #pragma once
 #include <cmath>
+#include <map>
 #include <memory>
 
 #include "permutation.h"
@@ -11,6 +12,42 @@
 
 namespace hehub {
 namespace ckks {
+
+/// ckks.h:19-28
+struct CkksParams : public RlweParams {
+    CkksParams() {}
+    CkksParams(RlweParams &&other) : RlweParams(std::move(other)) {}
+    u64 additional_mod = 1;
+    double initial_scaling_factor = 1.0;
+};
+
+/// basics.cpp:14-38 — the additional modulus is drawn FIRST, then the chain, one cursor per bit-size row
+inline CkksParams create_params(size_t dimension, std::vector<size_t> moduli_bits, size_t additional_mod_bits,
+                                double initial_scaling_factor) {
+    CkksParams params;
+    params.dimension = dimension;
+    std::vector<unsigned> bits(moduli_bits.begin(), moduli_bits.end());
+    params.moduli.assign(bits.size(), 0);
+    if (hehub_b200_pick_moduli(bits.data(), bits.size(), (unsigned)additional_mod_bits, params.moduli.data(), &params.additional_mod) !=
+        HEHUB_B200_OK)
+        throw "No suitable primes in the library.";
+    params.component_count = params.moduli.size();
+    params.initial_scaling_factor = initial_scaling_factor;
+    return params;
+}
+
+/// basics.cpp:40-64 — the modulus budget for 128-bit security at `dimension`, cut into primes of the scaling size
+inline CkksParams create_params(size_t dimension, size_t initial_scaling_bits) {
+    static const std::map<size_t, size_t> std_log_q_size{{1024, 27}, {2048, 54}, {4096, 109}, {8192, 218}, {16384, 438}, {32768, 881}};
+    const auto it = std_log_q_size.find(dimension);
+    if (it == std_log_q_size.end()) throw "No suitable primes for this dimension.";
+    const size_t log_q_size = it->second;
+    if (log_q_size < 2 * initial_scaling_bits) throw "Initial scaling bits too big.";
+    std::vector<size_t> mod_bits((log_q_size + 1) / initial_scaling_bits - 1, initial_scaling_bits);
+    const size_t rest_bits = log_q_size - (log_q_size + 1) / initial_scaling_bits * initial_scaling_bits;
+    mod_bits[0] += rest_bits / 2;
+    return create_params(dimension, mod_bits, initial_scaling_bits + rest_bits / 2, std::pow(2.0, (double)initial_scaling_bits));
+}
 
 struct CkksPt : public RlwePt {
     using RlwePt::RlwePt;
@@ -73,6 +110,19 @@ inline std::array<RnsPolynomial, K> scatter(const ::hehub::detail::Staged &out, 
     return polys;
 }
 } // namespace detail
+
+/// ckks.h:180-184
+inline CkksCt encrypt(const CkksPt &pt, const RlweSk &sk) {
+    CkksCt ct = encrypt_core(pt, sk);
+    ct.scaling_factor = pt.scaling_factor;
+    return ct;
+}
+/// ckks.h:193-197
+inline CkksPt decrypt(const CkksCt &ct, const RlweSk &sk) {
+    CkksPt pt = decrypt_core(ct, sk);
+    pt.scaling_factor = ct.scaling_factor;
+    return pt;
+}
 
 inline CkksCt add(const CkksCt &ct1, const CkksCt &ct2) { // arith.cpp:15-20
     detail::check_scaling_factor(ct1.scaling_factor, ct2.scaling_factor);
@@ -209,8 +259,12 @@ inline CkksCt rotate(const CkksCt &ct, const RlweKsk &rot_key, const size_t step
     return res;
 }
 
+/// ckks.h:303-305
+inline CkksCt rotate(const CkksCt &ct, const RotKey &rot_key) { return rotate(ct, rot_key, rot_key.step); }
+
 } // namespace ckks
 
+using CkksParams = ckks::CkksParams;
 using CkksPt = ckks::CkksPt;
 using CkksCt = ckks::CkksCt;
 using CkksSk = RlweSk;

@@ -12,7 +12,7 @@ inline void ntt_negacyclic_inplace_lazy(const size_t log_dimension, const u64 mo
 }
 /// ntt.h:41-51 — all limbs of the polynomial in ONE launch, on the device
 inline void ntt_negacyclic_inplace_lazy(RnsPolynomial &rns_poly) {
-    if (rns_poly.rep_form == PolyRepForm::value) throw std::invalid_argument("Already in NTT value form."); // ntt.h:42-44
+    // like the reference (ntt.h:41-51), the representation tag is set, not checked
     b200::check(hehub_b200_ntt_fwd_lazy(b200::context(), (unsigned)rns_poly.log_dimension(), rns_poly.modulus_vec().data(),
                                         rns_poly.component_count(), rns_poly.dev_mut(), 1));
     rns_poly.rep_form = PolyRepForm::value;
@@ -25,14 +25,12 @@ inline void intt_negacyclic_inplace_lazy(const size_t log_dimension, const u64 m
 }
 /// ntt.h:72-82
 inline void intt_negacyclic_inplace_lazy(RnsPolynomial &rns_poly) {
-    if (rns_poly.rep_form == PolyRepForm::coeff) throw std::invalid_argument("Already in coefficient form."); // ntt.h:73-75
     b200::check(hehub_b200_intt_lazy(b200::context(), (unsigned)rns_poly.log_dimension(), rns_poly.modulus_vec().data(),
                                      rns_poly.component_count(), rns_poly.dev_mut(), 1, 0));
     rns_poly.rep_form = PolyRepForm::coeff;
 }
 /// ntt.h:89-92 — INTT followed by reduce_strict, fused into the transform's epilogue
 inline void intt_negacyclic_inplace(RnsPolynomial &rns_poly) {
-    if (rns_poly.rep_form == PolyRepForm::coeff) throw std::invalid_argument("Already in coefficient form.");
     b200::check(hehub_b200_intt_lazy(b200::context(), (unsigned)rns_poly.log_dimension(), rns_poly.modulus_vec().data(),
                                      rns_poly.component_count(), rns_poly.dev_mut(), 1, 1));
     rns_poly.rep_form = PolyRepForm::coeff;

@@ -4,15 +4,36 @@
 #include <memory>
 #include <vector>
 
+#include "permutation.h"
 #include "rlwe.h"
 
 namespace hehub {
 
 using RgswCt = std::vector<RlweCt>;
 
+/// rgsw.cpp:11-33 — one fresh RLWE sample per basis row, plus pt_ntt scaled by that row's RNS constants
+inline RgswCt rgsw_encrypt(const RlwePt &pt_ntt, const RlweSk &sk, const std::vector<std::vector<u64>> &decomp_basis) {
+    if (pt_ntt.rep_form == PolyRepForm::coeff) throw std::invalid_argument("Plaintext is expected in NTT form.");
+    RgswCt rgsw(decomp_basis.size());
+    for (auto &rlwe_sample : rgsw) rlwe_sample = get_rlwe_sample(sk);
+    for (size_t r = 0; r < rgsw.size(); r++) rgsw[r][0] += pt_ntt * decomp_basis[r];
+    return rgsw;
+}
+
+/// rgsw.cpp:35-55 — the same, every polynomial then multiplied by 2^64 mod q_k (Montgomery form for ext_prod_montgomery)
+inline RgswCt rgsw_encrypt_montgomery(const RlwePt &pt_ntt, const RlweSk &sk, const std::vector<std::vector<u64>> &decomp_basis) {
+    auto rgsw = rgsw_encrypt(pt_ntt, sk, decomp_basis);
+    if (rgsw.empty()) return rgsw;
+    std::vector<u64> mont_consts;
+    for (u64 modulus : rgsw[0][0].modulus_vec()) mont_consts.push_back((u64)(-1LL) % modulus + 1);
+    for (auto &rlwe_sample : rgsw)
+        for (auto &poly : rlwe_sample) poly *= mont_consts;
+    return rgsw;
+}
+
 /// RlweKsk = vector<RlweCt> (keys.h:19-32).  The device kernels read the key as ONE slab laid out
 /// [row p][half][limb k <= L][N]; it is packed from the rows on first use and cached in the object
-/// (keys are reused by every relinearize / rotate).  Key generation is host-side reference code.
+/// (keys are reused by every relinearize / rotate).
 struct RlweKsk : public RgswCt {
     using RgswCt::RgswCt;
     RlweKsk() {}
@@ -48,6 +69,11 @@ struct RlweKsk : public RgswCt {
             push_back(std::move(row));
         }
     }
+
+    /// keys.cpp:8-36, the reference's signature: the L RLWE samples are drawn here on the host in the reference's order
+    /// (per row: uniform mask over (q_0..q_{L-1}, P), then Gaussian error), then one fused device call builds the key.
+    RlweKsk(const RlweSk &sk_curr, const RlweSk &sk_orig, const u64 additional_mod)
+        : RlweKsk(sk_curr, sk_orig, additional_mod, Samples(sk_orig, additional_mod)) {}
 
     struct Packed {
         u64 *dev = nullptr;
@@ -93,7 +119,50 @@ struct RlweKsk : public RgswCt {
 
 private:
     mutable std::shared_ptr<Packed> cache_;
+    struct Samples {
+        std::vector<RnsPolynomial> masks, errors;
+        Samples(const RlweSk &sk_orig, const u64 additional_mod) {
+            auto ext = sk_orig.modulus_vec();
+            ext.push_back(additional_mod);
+            RlweParams params{sk_orig.dimension(), ext.size(), ext};
+            for (size_t p = 0; p + 1 < ext.size(); p++) { // rgsw.cpp:21-23 through rlwe.cpp:34-50
+#ifdef HEHUB_DEBUG_RLWE_ZERO_C1
+                masks.push_back(get_zero_poly(params));
+#else
+                masks.push_back(get_rand_uniform_poly(params, PolyRepForm::value));
+#endif
+#ifdef HEHUB_DEBUG_RLWE_ZERO_E
+                errors.push_back(get_zero_poly(params, PolyRepForm::coeff));
+#else
+                errors.push_back(detail::gaussian_coeffs(params, 3.2));
+#endif
+            }
+        }
+    };
+    RlweKsk(const RlweSk &sk_curr, const RlweSk &sk_orig, const u64 additional_mod, const Samples &s)
+        : RlweKsk(sk_curr, sk_orig, additional_mod, s.masks, s.errors) {}
 };
+
+/// keys.h:42-44 — RGSW encryption of sk^2 under sk
+inline RlweKsk get_relin_key(const RlweSk &sk, const u64 additional_mod) {
+    return RlweKsk(RlweSk(static_cast<const RnsPolynomial &>(sk) * static_cast<const RnsPolynomial &>(sk)), sk, additional_mod);
+}
+/// keys.h:54-56 — RGSW encryption of sk(X^-1) under sk
+inline RlweKsk get_conj_key(const RlweSk &sk, const u64 additional_mod) { return RlweKsk(RlweSk(involution(sk)), sk, additional_mod); }
+
+/// keys.h:63-67
+struct RotKey : public RlweKsk {
+    using RlweKsk::RlweKsk;
+    RotKey() {}
+    RotKey(RlweKsk &&ksk) : RlweKsk(std::move(ksk)) {}
+    size_t step = 0;
+};
+/// keys.h:78-83 — RGSW encryption of sk(X^(3^step)) under sk
+inline RotKey get_rot_key(const RlweSk &sk, const u64 additional_mod, const size_t step) {
+    RotKey rot_key(RlweKsk(RlweSk(cycle(sk, step)), sk, additional_mod));
+    rot_key.step = step;
+    return rot_key;
+}
 
 /// rgsw.cpp:57-156 — RNS-digit decomposition of `pt` (NTT form) and inner product with the key,
 /// accumulated in 128 bits and Montgomery-reduced once; result over (q_0..q_{L-1}, P), value form.

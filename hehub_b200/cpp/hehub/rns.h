@@ -295,17 +295,35 @@ using RnsPolyParams = RnsPolynomial::Params;
 using PolyRepForm = RnsPolynomial::RepForm;
 
 namespace detail {
+// rns.cpp:58-72 / 88-103: `b` may carry MORE components than self (a rescaled ciphertext against a full-length key);
+// the first self.component_count() moduli must agree and only those limbs take part.  The [limb][N] layout makes a
+// prefix of b a valid operand.
+inline void check_accumulate(const RnsIntVec &self, const RnsIntVec &b) {
+    if (self.dimension() != b.dimension()) throw std::invalid_argument("Operands' poly len mismatch.");
+    if (b.component_count() < self.component_count()) throw std::invalid_argument("Operand b contains less components than self.");
+    for (size_t k = 0; k < self.component_count(); k++)
+        if (self.modulus_at((int)k) != b.modulus_at((int)k)) throw std::invalid_argument("Operands' moduli mismatch.");
+}
+// fused ciphertext-by-ciphertext kernels take operands of one shape
 inline void check_same_shape(const RnsIntVec &a, const RnsIntVec &b) {
-    // rns.cpp:60-72 / 91-103 / 122-131
-    if (a.dimension() != b.dimension()) throw std::invalid_argument("Operands' dimensions mismatch.");
+    if (a.dimension() != b.dimension()) throw std::invalid_argument("Operands' poly len mismatch.");
     if (a.component_count() != b.component_count()) throw std::invalid_argument("Operands' component numbers mismatch.");
     if (a.modulus_vec() != b.modulus_vec()) throw std::invalid_argument("Operands' moduli mismatch.");
+}
+// rns.cpp:120-131: the product has min(a, b) components; the truncated modulus lists must agree
+inline size_t check_product(const RnsIntVec &a, const RnsIntVec &b) {
+    if (a.dimension() != b.dimension()) throw std::invalid_argument("Operands' poly len mismatch.");
+    const size_t components = a.component_count() < b.component_count() ? a.component_count() : b.component_count();
+    for (size_t k = 0; k < components; k++)
+        if (a.modulus_at((int)k) != b.modulus_at((int)k)) throw std::invalid_argument("Operands' moduli mismatch.");
+    return components;
 }
 } // namespace detail
 
 // ---- RnsIntVec operators: rns.cpp:58-171 ---------------------------------------------------
 inline const RnsIntVec &operator+=(RnsIntVec &self, const RnsIntVec &b) {
-    detail::check_same_shape(self, b);
+    detail::check_accumulate(self, b);
+    if (self.component_count() == 0) return self;
     b200::check(hehub_b200_add_lazy(b200::context(), self.dimension(), self.modulus_vec().data(), self.component_count(), self.dev_mut(), b.dev(), 1));
     return self;
 }
@@ -315,7 +333,8 @@ inline RnsIntVec operator+(const RnsIntVec &a, const RnsIntVec &b) {
     return result;
 }
 inline const RnsIntVec &operator-=(RnsIntVec &self, const RnsIntVec &b) {
-    detail::check_same_shape(self, b);
+    detail::check_accumulate(self, b);
+    if (self.component_count() == 0) return self;
     b200::check(hehub_b200_sub_lazy(b200::context(), self.dimension(), self.modulus_vec().data(), self.component_count(), self.dev_mut(), b.dev(), 1));
     return self;
 }
@@ -325,14 +344,20 @@ inline RnsIntVec operator-(const RnsIntVec &a, const RnsIntVec &b) {
     return result;
 }
 inline RnsIntVec operator*(const RnsIntVec &a, const RnsIntVec &b) {
-    detail::check_same_shape(a, b);
-    RnsIntVec result(a.params());
-    b200::check(hehub_b200_mulmod_hybrid_lazy(b200::context(), a.dimension(), a.modulus_vec().data(), a.component_count(), a.dev(), b.dev(), result.dev_mut(), 1));
+    const size_t components = detail::check_product(a, b);
+    RnsIntVec result(a.dimension(), components, a.modulus_vec());
+    if (components)
+        b200::check(hehub_b200_mulmod_hybrid_lazy(b200::context(), a.dimension(), result.modulus_vec().data(), components, a.dev(), b.dev(), result.dev_mut(), 1));
     return result;
 }
 inline const RnsIntVec &operator*=(RnsIntVec &self, const RnsIntVec &b) {
-    detail::check_same_shape(self, b);
-    b200::check(hehub_b200_mulmod_hybrid_lazy(b200::context(), self.dimension(), self.modulus_vec().data(), self.component_count(), self.dev(), b.dev(), self.dev_mut(), 1));
+    if (b.component_count() >= self.component_count()) { // in place: same limbs, same moduli prefix
+        detail::check_product(self, b);
+        if (self.component_count())
+            b200::check(hehub_b200_mulmod_hybrid_lazy(b200::context(), self.dimension(), self.modulus_vec().data(), self.component_count(), self.dev(), b.dev(), self.dev_mut(), 1));
+    } else {
+        self = self * b; // the product is shorter than self (rns.cpp:120-140 through rns.h's operator*=)
+    }
     return self;
 }
 inline const RnsIntVec &operator*=(RnsIntVec &self, const std::vector<u64> &rns_scalar) {

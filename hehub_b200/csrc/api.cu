@@ -36,7 +36,6 @@ struct RowsIO {
         *reinterpret_cast<ulonglong2 *>(x + ((size_t)row << logn) + i) =
             STRICT ? make_ulonglong2(reduce_strict(v0, lc.q), reduce_strict(v1, lc.q)) : make_ulonglong2(v0, v1);
     }
-    HB_D u64 *raw(int row) const { return x + ((size_t)row << logn); }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -74,9 +73,6 @@ HB_GLOBAL(kEwThreads, 1) ew_kernel(const Op op, const LimbConst *__restrict__ li
 }
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-
-#define HB_EW_VEC2(BODY1)                                                                              \
-    HB_D void apply1(size_t idx, int limb, const LimbConst &lc) const { BODY1 }
 
 struct OpMulHybrid {
     static constexpr int kVecs = 8;
@@ -285,7 +281,12 @@ int hehub_b200_ctx_set_stream(hehub_b200_ctx *ctx, void *stream) {
 int hehub_b200_ctx_synchronize(hehub_b200_ctx *ctx) {
     CTX_GUARD(ctx);
     cudaError_t e = cudaStreamSynchronize(c.stream);
-    return e == cudaSuccess ? 0 : c.cuda_fail(e, "cudaStreamSynchronize");
+    if (e != cudaSuccess) return c.cuda_fail(e, "cudaStreamSynchronize");
+    if (c.take_deferred()) // verdict of a stream-asynchronous rns_base_transform (key generation), see context.h
+        return c.fail(HEHUB_B200_ERR_UNSUPPORTED,
+                      "under development: CRT composition of large coefficients (rns_transform.cpp:86-105) is not built "
+                      "(raised by an earlier asynchronous key generation)");
+    return HEHUB_B200_OK;
 }
 
 const char *hehub_b200_last_error(const hehub_b200_ctx *ctx) { return ctx ? ctx->c.last_error.c_str() : "null context"; }

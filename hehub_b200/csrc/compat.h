@@ -35,9 +35,6 @@ inline unsigned long long hb_ld_ro(const unsigned long long *p) { return *p; }
 inline ulonglong2 hb_ld_ro2(const unsigned long long *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
 template <class T>
 inline T hb_ldcg(const T *p) { return *p; }
-inline void hb_cp_async16(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 16); }
-inline void hb_cp_async_commit() {}
-inline void hb_cp_async_wait_all() {}
 #else
 #include <cuda_runtime.h>
 #define HB_D __device__ __forceinline__
@@ -135,10 +132,4 @@ __device__ __forceinline__ ulonglong2 hb_ld_stream2(const unsigned long long *p)
 #endif
 template <class T>
 __device__ __forceinline__ T hb_ldcg(const T *p) { return __ldcg(p); }
-// 16-byte asynchronous global -> shared copy (LDGSTS), bypassing L1: the words are streamed once
-__device__ __forceinline__ void hb_cp_async16(void *smem_dst, const void *gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
-}
-__device__ __forceinline__ void hb_cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-__device__ __forceinline__ void hb_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #endif

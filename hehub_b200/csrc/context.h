@@ -45,7 +45,7 @@ struct Context {
     bool force_generic = false;
     int sm_count = 148;
     int latency_rows = -1; // option "latency_rows"; -1: half the SM count
-    LaunchEnv env() { return LaunchEnv{stream, sm_count, force_generic, &stats, latency_rows < 0 ? sm_count / 2 : latency_rows}; }
+    LaunchEnv env() { return LaunchEnv{stream, sm_count, force_generic, &stats, latency_rows < 0 ? sm_count / 2 : latency_rows, device}; }
     size_t scratch_cap_bytes = (size_t)8 << 30; // bound on the per-call workspace (option "scratch_cap_mib"); batches run in waves
     std::string last_error;
     LaunchStats stats;
@@ -68,6 +68,15 @@ struct Context {
     cudaEvent_t ev_in[kPipeSlots] = {}, ev_k[kPipeSlots] = {}, ev_out[kPipeSlots] = {};
     bool pipe_ready = false;
     int ensure_pipe();
+
+    // Verdicts of stream-asynchronous operations (rns_base_transform many -> one inside key generation): each lands in
+    // a pinned host word when the stream reaches it and is reported by the next hehub_b200_ctx_synchronize.
+    int *deferred_flags = nullptr; // pinned, kDeferredSlots words
+    static constexpr int kDeferredSlots = 64;
+    int deferred_used = 0;
+    int *deferred_flag_slot(int *err);
+    // after a stream synchronisation: non-zero when some deferred verdict was raised (and clears them)
+    int take_deferred();
 
     ~Context();
     int fail(int code, const std::string &msg) {

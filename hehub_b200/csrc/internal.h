@@ -38,7 +38,8 @@ int op_rlwe_decrypt_core(Context &c, unsigned logn, const u64 *moduli, size_t L,
 int op_rlwe_encrypt_core(Context &c, unsigned logn, const u64 *moduli, size_t L, const u64 *pt, const u64 *sk, const u64 *c1,
                          const u64 *e, u64 *out, size_t batch);
 int op_base_from_single(Context &c, u64 q_old, const u64 *new_moduli, size_t Lnew, const u64 *in, u64 *out, size_t n, size_t batch);
-int op_base_to_single(Context &c, const u64 *old_moduli, size_t L, u64 new_modulus, const u64 *in, u64 *out, size_t n, size_t batch);
+int op_base_to_single(Context &c, const u64 *old_moduli, size_t L, u64 new_modulus, const u64 *in, u64 *out, size_t n, size_t batch,
+                      bool defer_verdict = false);
 int op_ksk_generate(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *sk_curr, const u64 *sk_orig,
                     const u64 *masks, const u64 *errors, u64 *key);
 int op_galois(Context &c, unsigned logn, size_t L, const u64 *in, u64 *out, bool conj, size_t step, size_t batch);

@@ -103,7 +103,6 @@ HB_D u64 harvey_lazy(u64 x, u64 w, u64 wh, u64 nq) {
 #endif
     return mul2_lo64(x, w, qhat, nq);
 }
-HB_D u64 harvey_lazy_split(u64 x, u64 w, u64 wh, u64 nq) { return mul2_lo64(x, w, umul64hi_split(x, wh), nq); }
 
 // lo64(a*b + c): one wide + two narrow IMADs, the addition rides on the accumulator
 HB_D u64 mad_lo64(u64 a, u64 b, u64 c) {

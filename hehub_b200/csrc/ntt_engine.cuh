@@ -29,12 +29,11 @@
 //   const u64 *src(int row)                               -> the row's N contiguous input words
 //   u64        pre(int row, int i, u64 raw, LimbConst&)   -> input word i from the raw word read at src(row)[i]
 //   void       store(int row, int i, u64 v, LimbConst&)   -> consumes output word i
-//   u64       *raw(int row)                               -> row-sized scratch in global memory (unused since the
-//                                                            cluster inverse exchanges through shared memory)
 //   void       prefetch(int row, int first, int nwords)   -> optional: called once per CTA before the first pass
 //   bool       vec                                        -> every row pointer is 16-byte aligned
 //   void       store2(int row, int i, u64 v0, u64 v1, LimbConst&) -> words i (even) and i+1, used when vec
 #pragma once
+#include <atomic>
 #include <type_traits>
 #include <utility>
 
@@ -448,6 +447,17 @@ struct LaunchEnv {
     bool force_generic; // parity cross-check path
     LaunchStats *stats;
     int latency_rows;   // launches with at most this many rows take the latency plan (default: half the SM count)
+    int device;         // kernel attributes (dynamic shared memory opt-in, carveout) are per device
+};
+
+// cudaFuncSetAttribute acts on the current device only: remember per kernel instantiation and per device
+// what has been configured (a process may hold one context per GPU, cpp/hehub/backend.h set_context).
+constexpr int kMaxDevices = 64;
+struct PerDeviceConfig {
+    std::atomic<int> smem[kMaxDevices];
+    // true when the kernel already accepts `bytes` of dynamic shared memory on `device`
+    bool covers(int device, int bytes) const { return smem[device & (kMaxDevices - 1)].load(std::memory_order_acquire) >= bytes; }
+    void record(int device, int bytes) { smem[device & (kMaxDevices - 1)].store(bytes, std::memory_order_release); }
 };
 
 template <int LOGN, bool FWD, class IO, int MODE>
@@ -471,11 +481,11 @@ inline cudaError_t launch_fast_mode(const LaunchEnv &env, const IO &io, const Li
     constexpr NttPlan pl = plan_for(LOGN, FWD, MODE);
     constexpr int smem = smem_words(1 << (LOGN - pl.lpre)) * 8;
     auto kern = fast_kernel<LOGN, FWD, IO, MODE>();
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceConfig configured; // zero-initialised; racing contexts at worst configure twice (idempotent)
+    if (!configured.covers(env.device, smem)) {
         cudaError_t e = configure_smem(kern, smem, pl.min_blocks);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured.record(env.device, smem);
     }
     env.stats->launches++;
     if constexpr (pl.lpre == 1) {
@@ -504,11 +514,11 @@ inline cudaError_t launch_generic(const LaunchEnv &env, unsigned logn, const IO 
         if constexpr (FWD) return &ntt_fwd_generic_kernel<IO>;
         else return &intt_generic_kernel<IO>;
     }();
-    static int configured = 0;
-    if (smem > configured) {
+    static PerDeviceConfig configured;
+    if (!configured.covers(env.device, smem)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured.record(env.device, smem);
     }
     HB_LAUNCH(kern, rows, threads, smem, env.stream, 1, io, limbs, (int)logn);
     env.stats->launches++;

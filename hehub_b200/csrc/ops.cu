@@ -35,32 +35,52 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 #ifndef HB_MAC_CPT
 #define HB_MAC_CPT 2
 #endif
+template <int W>
+HB_D void ld_words(u64 (&dst)[W], const u64 *p, bool read_only) {
+    if constexpr (W == 2) {
+        const ulonglong2 v = read_only ? __ldg(reinterpret_cast<const ulonglong2 *>(p)) : hb_ld_stream2(p);
+        dst[0] = v.x;
+        dst[1] = v.y;
+    } else {
+        dst[0] = read_only ? __ldg(p) : hb_ld_stream(p);
+    }
+}
+template <int W>
+HB_D void st_words(u64 *p, const u64 (&src)[W]) {
+    if constexpr (W == 2) *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(src[0], src[1]);
+    else p[0] = src[0];
+}
+
+// W = 2: one thread per pair of adjacent coefficients (128-bit accesses); W = 1: slabs that are only 8-byte aligned
+template <int W>
 HB_GLOBAL(256, HB_TENSOR_MINB)
 tensor_kernel(const u64 *__restrict__ ct1, const u64 *__restrict__ ct2, u64 *__restrict__ quad,
-              const LimbConst *__restrict__ limbs, int L, int logn, size_t pairs_total) {
+              const LimbConst *__restrict__ limbs, int L, int logn, size_t units_total) {
     hb_pdl_wait();
-    // one thread per pair of adjacent coefficients of one (ct, limb)
+    constexpr int LW = (W == 2) ? 1 : 0;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= pairs_total) return;
-    const size_t row = gid >> (logn - 1);              // b * L + l
-    const size_t i = (gid & (((size_t)1 << (logn - 1)) - 1)) * 2;
+    if (gid >= units_total) return;
+    const size_t row = gid >> (logn - LW);              // b * L + l
+    const size_t i = (gid & (((size_t)1 << (logn - LW)) - 1)) * W;
     const size_t b = row / L, l = row % L;
     const LimbConst lc = limbs[l];
     const size_t n = (size_t)1 << logn, poly = (size_t)L << logn;
     const size_t in0 = b * 2 * poly + l * n + i, in1 = in0 + poly;
     const size_t o0 = b * 3 * poly + l * n + i;
-    const ulonglong2 a0 = *reinterpret_cast<const ulonglong2 *>(ct1 + in0), a1 = *reinterpret_cast<const ulonglong2 *>(ct1 + in1);
-    const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(ct2 + in0), b1 = *reinterpret_cast<const ulonglong2 *>(ct2 + in1);
-    ulonglong2 d0, d1, d2;
-    d0.x = mul_hybrid_lazy(a0.x, b0.x, lc);
-    d0.y = mul_hybrid_lazy(a0.y, b0.y, lc);
-    d1.x = add_lazy(mul_hybrid_lazy(a0.x, b1.x, lc), mul_hybrid_lazy(a1.x, b0.x, lc), lc.q2);
-    d1.y = add_lazy(mul_hybrid_lazy(a0.y, b1.y, lc), mul_hybrid_lazy(a1.y, b0.y, lc), lc.q2);
-    d2.x = mul_hybrid_lazy(a1.x, b1.x, lc);
-    d2.y = mul_hybrid_lazy(a1.y, b1.y, lc);
-    *reinterpret_cast<ulonglong2 *>(quad + o0) = d0;
-    *reinterpret_cast<ulonglong2 *>(quad + o0 + poly) = d1;
-    *reinterpret_cast<ulonglong2 *>(quad + o0 + 2 * poly) = d2;
+    u64 a0[W], a1[W], b0[W], b1[W], d0[W], d1[W], d2[W];
+    ld_words<W>(a0, ct1 + in0, false);
+    ld_words<W>(a1, ct1 + in1, false);
+    ld_words<W>(b0, ct2 + in0, false);
+    ld_words<W>(b1, ct2 + in1, false);
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        d0[w] = mul_hybrid_lazy(a0[w], b0[w], lc);
+        d1[w] = add_lazy(mul_hybrid_lazy(a0[w], b1[w], lc), mul_hybrid_lazy(a1[w], b0[w], lc), lc.q2);
+        d2[w] = mul_hybrid_lazy(a1[w], b1[w], lc);
+    }
+    st_words<W>(quad + o0, d0);
+    st_words<W>(quad + o0 + poly, d1);
+    st_words<W>(quad + o0 + 2 * poly, d2);
 }
 
 int op_ckks_tensor(Context &c, unsigned logn, const u64 *moduli, size_t L, const u64 *ct1, const u64 *ct2, u64 *quad,
@@ -72,10 +92,15 @@ int op_ckks_tensor(Context &c, unsigned logn, const u64 *moduli, size_t L, const
     int err = 0;
     const LimbConst *limbs = c.get_chain(0, moduli, L, &err);
     if (!limbs) return err;
-    const size_t pairs = (batch * L) << (logn - 1);
-    const size_t blocks = (pairs + 255) / 256;
+    const bool vec = logn >= 1 && aligned16(ct1) && aligned16(ct2) && aligned16(quad);
+    const size_t units = vec ? (batch * L) << (logn - 1) : (batch * L) << logn;
+    const size_t blocks = (units + 255) / 256;
     if (blocks > 0x7fffffffull) return c.fail(1, "operand too large for one launch");
-    HB_LAUNCH(tensor_kernel, (unsigned)blocks, 256, 0, c.stream, 0, ct1, ct2, quad, limbs, (int)L, (int)logn, pairs);
+    if (vec) {
+        HB_LAUNCH(tensor_kernel<2>, (unsigned)blocks, 256, 0, c.stream, 0, ct1, ct2, quad, limbs, (int)L, (int)logn, units);
+    } else {
+        HB_LAUNCH(tensor_kernel<1>, (unsigned)blocks, 256, 0, c.stream, 0, ct1, ct2, quad, limbs, (int)L, (int)logn, units);
+    }
     c.stats.launches++;
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : c.cuda_fail(e, "tensor launch");
@@ -98,7 +123,6 @@ struct ExtInttIO {
     HB_D void store2(int row, int i, u64 v0, u64 v1, const LimbConst &lc) const {
         *reinterpret_cast<ulonglong2 *>(c + ((size_t)row << logn) + i) = make_ulonglong2(reduce_strict(v0, lc.q), reduce_strict(v1, lc.q));
     }
-    HB_D u64 *raw(int row) const { return c + ((size_t)row << logn); }
 };
 
 // step 2: dec[b][p][k] = NTT_{q_k}(c[b][p]) for k != p, k in [0, L]   rgsw.cpp:108-119
@@ -135,7 +159,6 @@ struct ExtFanoutIO {
         split(row, b, p, k);
         *reinterpret_cast<ulonglong2 *>(dec + ((size_t)((b * L + p) * (L + 1) + k) << logn) + i) = make_ulonglong2(v0, v1);
     }
-    HB_D u64 *raw(int) const { return nullptr; }
 };
 
 // step 3: out[b][h][k][i] = Mont128_{q_k}( sum_p dec[p][k][i] * key[p][h][k][i] )   rgsw.cpp:126-153
@@ -144,22 +167,6 @@ struct ExtFanoutIO {
 // W = 1 for slabs that are only 8-byte aligned) of one limb of CPT consecutive ciphertexts, so a
 // key word fetched from L2 feeds CPT products: the key stream (2 L (L+1) N words per ciphertext,
 // more than every other operand together) is what bounds this kernel.
-template <int W>
-HB_D void ld_words(u64 (&dst)[W], const u64 *p, bool read_only) {
-    if constexpr (W == 2) {
-        const ulonglong2 v = read_only ? __ldg(reinterpret_cast<const ulonglong2 *>(p)) : hb_ld_stream2(p);
-        dst[0] = v.x;
-        dst[1] = v.y;
-    } else {
-        dst[0] = read_only ? __ldg(p) : hb_ld_stream(p);
-    }
-}
-template <int W>
-HB_D void st_words(u64 *p, const u64 (&src)[W]) {
-    if constexpr (W == 2) *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(src[0], src[1]);
-    else p[0] = src[0];
-}
-
 template <int CPT, int W>
 HB_GLOBAL(256, HB_MAC_MINB)
 ext_mac_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
@@ -272,8 +279,12 @@ static int ext_prod_wave(Context &c, unsigned logn, const LimbConst *limbs, size
 // Ciphertexts per wave: what the scratch cap allows, rounded down to a multiple of a quarter of the SM count
 // when the batch has to be cut anyway — the transform launches of a wave run 2, L, L^2 or 2(L-1) rows per
 // ciphertext on 1-2 CTAs per row, and with such a wave all of them end on (nearly) full waves of CTAs.
-static size_t wave_size(const Context &c, size_t words_per_ct, size_t batch) {
+// `rows_per_ct`: the most rows one ciphertext contributes to a single launch — the IO policies index rows (and
+// row * limbs) with int, so a wave never exceeds 2^30 of them whatever the scratch cap says.
+static size_t wave_size(const Context &c, size_t words_per_ct, size_t batch, size_t rows_per_ct) {
     size_t w = c.scratch_cap_bytes / (words_per_ct * 8);
+    const size_t row_cap = ((size_t)1 << 30) / (rows_per_ct ? rows_per_ct : 1);
+    if (w > row_cap) w = row_cap;
     if (w < 1) w = 1;
     if (w >= batch) return batch;
     const size_t quantum = (size_t)(c.sm_count > 4 ? c.sm_count / 4 : 1);
@@ -293,7 +304,7 @@ int op_ext_prod(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, cons
     if (!limbs) return err;
     const size_t n = (size_t)1 << logn;
     const size_t per_ct = L * n + L * (L + 1) * n;
-    const size_t wave = wave_size(c, per_ct, batch);
+    const size_t wave = wave_size(c, per_ct, batch, L * (L + 1));
     u64 *cbuf = c.get_scratch(0, wave * L * n, &err);
     if (!cbuf) return err;
     u64 *dec = c.get_scratch(1, wave * L * (L + 1) * n, &err);
@@ -332,7 +343,6 @@ struct DropInttIO {
         }
         *reinterpret_cast<ulonglong2 *>(z + ((size_t)row << logn) + i) = make_ulonglong2(reduce_strict(v0, lc.q), reduce_strict(v1, lc.q));
     }
-    HB_D u64 *raw(int row) const { return z + ((size_t)row << logn); }
 };
 
 // step 2: per remaining limb k: r = centre(barrett(z)); NTT; out = H(lazy_sub(ct, r), q_last^{-1}) [...]
@@ -399,7 +409,6 @@ struct DropFwdIO {
         }
         *reinterpret_cast<ulonglong2 *>(out + ((size_t)row << logn) + i) = r;
     }
-    HB_D u64 *raw(int) const { return nullptr; }
 };
 
 int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, const u64 *ct, u64 *out, size_t batch,
@@ -413,26 +422,34 @@ int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, 
     const DropSet *ds = c.get_drop(logn, moduli, L, t, &err);
     if (!ds) return err;
     const size_t n = (size_t)1 << logn;
-    u64 *z = c.get_scratch(2, batch * 2 * n, &err);
+    // waves bound the z scratch ([wave][2][N]) and keep every launch's row count inside int
+    const size_t wave = wave_size(c, 2 * n, batch, 2 * L);
+    u64 *z = c.get_scratch(2, wave * 2 * n, &err);
     if (!z) return err;
     const bool vec = aligned16(ct) && aligned16(z) && aligned16(out) &&
                      (!addend || (aligned16(addend) && add_batch_stride % 2 == 0 && add_poly_stride % 2 == 0));
     const int halves = addend ? add_halves : 0;
-    cudaError_t e;
-    if (t) {
-        DropInttIO<true> io1{ct, z, (int)L, (int)logn, ds->inv_t, ds->inv_t_h, aligned16(ct) && aligned16(z)};
-        e = launch_ntt<false>(c.env(), logn, io1, limbs, (int)(batch * 2));
-        if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: intt launch");
-        DropFwdIO<true> io2{ct, z, out, ds->dev, addend, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, halves, vec};
-        e = launch_ntt<true>(c.env(), logn, io2, limbs, (int)(batch * 2 * (L - 1)));
-    } else {
-        DropInttIO<false> io1{ct, z, (int)L, (int)logn, 0, 0, aligned16(ct) && aligned16(z)};
-        e = launch_ntt<false>(c.env(), logn, io1, limbs, (int)(batch * 2));
-        if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: intt launch");
-        DropFwdIO<false> io2{ct, z, out, ds->dev, addend, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, halves, vec};
-        e = launch_ntt<true>(c.env(), logn, io2, limbs, (int)(batch * 2 * (L - 1)));
+    for (size_t b0 = 0; b0 < batch; b0 += wave) {
+        const size_t nb = (batch - b0 < wave) ? batch - b0 : wave;
+        const u64 *ct_w = ct + b0 * 2 * L * n;
+        u64 *out_w = out + b0 * 2 * (L - 1) * n;
+        const u64 *add_w = addend ? addend + b0 * add_batch_stride : nullptr;
+        cudaError_t e;
+        if (t) {
+            DropInttIO<true> io1{ct_w, z, (int)L, (int)logn, ds->inv_t, ds->inv_t_h, aligned16(ct) && aligned16(z)};
+            e = launch_ntt<false>(c.env(), logn, io1, limbs, (int)(nb * 2));
+            if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: intt launch");
+            DropFwdIO<true> io2{ct_w, z, out_w, ds->dev, add_w, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, halves, vec};
+            e = launch_ntt<true>(c.env(), logn, io2, limbs, (int)(nb * 2 * (L - 1)));
+        } else {
+            DropInttIO<false> io1{ct_w, z, (int)L, (int)logn, 0, 0, aligned16(ct) && aligned16(z)};
+            e = launch_ntt<false>(c.env(), logn, io1, limbs, (int)(nb * 2));
+            if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: intt launch");
+            DropFwdIO<false> io2{ct_w, z, out_w, ds->dev, add_w, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, halves, vec};
+            e = launch_ntt<true>(c.env(), logn, io2, limbs, (int)(nb * 2 * (L - 1)));
+        }
+        if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: ntt launch");
     }
-    if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: ntt launch");
     return 0;
 }
 
@@ -447,7 +464,7 @@ int op_relinearize(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u
     const size_t n = (size_t)1 << logn;
     // waves bound the scratch: per ct  c: L, dec: L(L+1), e: 2(L+1), z: 2  rows of N words
     const size_t per_ct = (L + L * (L + 1) + 2 * (L + 1) + 2) * n;
-    const size_t wave = wave_size(c, per_ct, batch);
+    const size_t wave = wave_size(c, per_ct, batch, L * (L + 1));
     int err = 0;
     u64 *ebuf = c.get_scratch(3, wave * 2 * (L + 1) * n, &err);
     if (!ebuf) return err;
@@ -467,7 +484,7 @@ int op_mult_relin(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u6
     if (batch == 0) return 0;
     const size_t n = (size_t)1 << logn;
     const size_t per_ct = (3 * L + L + L * (L + 1) + 2 * (L + 1) + 2) * n;
-    const size_t wave = wave_size(c, per_ct, batch);
+    const size_t wave = wave_size(c, per_ct, batch, L * (L + 1));
     int err = 0;
     u64 *quad = c.get_scratch(4, wave * 3 * L * n, &err);
     if (!quad) return err;
@@ -491,7 +508,7 @@ struct DecryptIO {
     int L, logn;
     bool vec;
     HB_D int limb(int row) const { return row % L; }
-    HB_D const u64 *src(int row) const { return ct + ((size_t)((row / L) * 2 * L + row % L) << logn); }
+    HB_D const u64 *src(int row) const { return ct + (((size_t)(row / L) * 2 * L + row % L) << logn); }
     HB_D u64 pre(int row, int i, u64 c0, const LimbConst &lc) const {
         const int k = row % L;
         const u64 c1 = hb_ld_ro(src(row) + ((size_t)L << logn) + i), s = __ldg(sk + ((size_t)k << logn) + i);
@@ -501,7 +518,6 @@ struct DecryptIO {
     HB_D void store2(int row, int i, u64 v0, u64 v1, const LimbConst &lc) const {
         *reinterpret_cast<ulonglong2 *>(pt + ((size_t)row << logn) + i) = make_ulonglong2(reduce_strict(v0, lc.q), reduce_strict(v1, lc.q));
     }
-    HB_D u64 *raw(int row) const { return pt + ((size_t)row << logn); }
 };
 
 // encrypt, step 1: out[b][0] = NTT(e) - c1 * sk, out[b][1] = c1       sampling.cpp:66, rlwe.cpp:50
@@ -517,7 +533,7 @@ struct EncryptErrIO {
     HB_D void store(int row, int i, u64 v, const LimbConst &lc) const {
         const int b = row / L, k = row - b * L;
         const u64 m = hb_ld_ro(c1 + ((size_t)row << logn) + i), s = __ldg(sk + ((size_t)k << logn) + i);
-        u64 *o = out + ((size_t)(b * 2 * L + k) << logn) + i;
+        u64 *o = out + (((size_t)b * 2 * L + k) << logn) + i;
         o[0] = sub_lazy(v, mul_hybrid_lazy(m, s, lc), lc.q2);
         o[(size_t)L << logn] = m;
     }
@@ -525,12 +541,11 @@ struct EncryptErrIO {
         const int b = row / L, k = row - b * L;
         const ulonglong2 m = hb_ld_ro2(c1 + ((size_t)row << logn) + i);
         const ulonglong2 s = __ldg(reinterpret_cast<const ulonglong2 *>(sk + ((size_t)k << logn) + i));
-        u64 *o = out + ((size_t)(b * 2 * L + k) << logn) + i;
+        u64 *o = out + (((size_t)b * 2 * L + k) << logn) + i;
         *reinterpret_cast<ulonglong2 *>(o) =
             make_ulonglong2(sub_lazy(v0, mul_hybrid_lazy(m.x, s.x, lc), lc.q2), sub_lazy(v1, mul_hybrid_lazy(m.y, s.y, lc), lc.q2));
         *reinterpret_cast<ulonglong2 *>(o + ((size_t)L << logn)) = m;
     }
-    HB_D u64 *raw(int) const { return nullptr; }
 };
 
 // encrypt, step 2: out[b][0] += NTT(pt)                                  rlwe.cpp:54-58
@@ -544,7 +559,7 @@ struct EncryptAddIO {
     HB_D u64 pre(int, int, u64 raw, const LimbConst &) const { return raw; }
     HB_D u64 *slot(int row, int i) const {
         const int b = row / L, k = row - b * L;
-        return out + ((size_t)(b * 2 * L + k) << logn) + i;
+        return out + (((size_t)b * 2 * L + k) << logn) + i;
     }
     HB_D void store(int row, int i, u64 v, const LimbConst &lc) const {
         u64 *o = slot(row, i);
@@ -555,7 +570,6 @@ struct EncryptAddIO {
         const ulonglong2 c = *o;
         *o = make_ulonglong2(add_lazy(c.x, v0, lc.q2), add_lazy(c.y, v1, lc.q2));
     }
-    HB_D u64 *raw(int) const { return nullptr; }
 };
 
 int op_rlwe_decrypt_core(Context &c, unsigned logn, const u64 *moduli, size_t L, const u64 *ct, const u64 *sk, u64 *pt,
@@ -635,6 +649,8 @@ base_from_single_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const
     }
 }
 
+static const char *const kNotSmallMessage =
+    "under development: CRT composition of large coefficients (rns_transform.cpp:86-105) is not built";
 // many -> one modulus, small-coefficient path; *not_small is set when some coefficient is not the same
 // small signed value under every old modulus (the reference then composes big integers)   :39-84, :116
 HB_GLOBAL(256, 1)
@@ -680,9 +696,15 @@ int op_base_from_single(Context &c, u64 q_old, const u64 *new_moduli, size_t Lne
     return e == cudaSuccess ? 0 : c.cuda_fail(e, "base transform launch");
 }
 
-int op_base_to_single(Context &c, const u64 *old_moduli, size_t L, u64 new_modulus, const u64 *in, u64 *out, size_t n, size_t batch) {
+// `defer_verdict`: the not-small flag is copied to pinned host memory without synchronising; the next
+// hehub_b200_ctx_synchronize reports it (stream-async callers: key generation).
+int op_base_to_single(Context &c, const u64 *old_moduli, size_t L, u64 new_modulus, const u64 *in, u64 *out, size_t n, size_t batch,
+                      bool defer_verdict) {
     if (!old_moduli || !in || !out) return c.fail(1, "null operand");
     if (L == 0 || new_modulus < 2) return c.fail(1, "bad moduli");
+    // a single-component input is the one -> many transform with one target (rns_transform.cpp:118-121): lazy Barrett only when
+    // the new modulus is the smaller one, no strict reduction
+    if (L == 1) return op_base_from_single(c, old_moduli[0], &new_modulus, 1, in, out, n, batch);
     const size_t total = batch * n;
     if (total == 0) return 0;
     int err = 0;
@@ -696,23 +718,33 @@ int op_base_to_single(Context &c, const u64 *old_moduli, size_t L, u64 new_modul
     if (e != cudaSuccess) return c.cuda_fail(e, "base transform: flag");
     HB_LAUNCH(base_to_single_kernel, (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, out, limbs, (int)L, nt->lc, n, total, flag);
     c.stats.launches++;
+    if (defer_verdict) {
+        int *slot = c.deferred_flag_slot(&err);
+        if (!slot) return err;
+        e = cudaMemcpyAsync(slot, flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream);
+        return e == cudaSuccess ? 0 : c.cuda_fail(e, "base transform to single");
+    }
     int host_flag = 0;
     e = cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
     if (e != cudaSuccess) return c.cuda_fail(e, "base transform to single");
-    if (host_flag) return c.fail(3, "under development: CRT composition of large coefficients (rns_transform.cpp:86-105) is not built");
+    if (host_flag) return c.fail(3, kNotSmallMessage);
     return 0;
 }
 
+struct PmodTable {
+    ulonglong2 v[32];
+};
 // one row of the key: (c0, c1) = ( (NTT(e) - mask * sk_ext + [k == p] sk_curr * (P mod q_p)) * R, mask * R ), R = 2^64 mod q_k
 struct KskRowIO {
     const u64 *errors, *masks; // [L][L+1][N]
     const u64 *sk_ext;         // [L+1][N], NTT form (sk_orig_extended)
     const u64 *sk_curr;        // [L][N], NTT form
-    const ulonglong2 *pmod;    // [L]: (P mod q_p, Harvey companion)
+    const ulonglong2 *pmod;    // [L]: (P mod q_p, Harvey companion); null: the by-value table below (L <= 32)
     u64 *key;                  // [L][2][L+1][N]
     int L, logn;
     bool vec;
+    PmodTable pm; // kernel parameter space: nothing to upload, nothing to wait for
     HB_D int limb(int row) const { return row % (L + 1); }
     HB_D const u64 *src(int row) const { return errors + ((size_t)row << logn); }
     HB_D u64 pre(int, int, u64 raw, const LimbConst &) const { return raw; }
@@ -723,7 +755,7 @@ struct KskRowIO {
         // + pt_ntt * basis_p (rgsw.cpp:27): Harvey multiple of sk_curr at k == p, of anything by 0 elsewhere (= 0)
         u64 term = 0;
         if (k == p) {
-            const ulonglong2 s = __ldg(pmod + p);
+            const ulonglong2 s = pmod ? __ldg(pmod + p) : pm.v[p];
             term = harvey_lazy(__ldg(sk_curr + ((size_t)k << logn) + i), s.x, s.y, lc.nq);
         }
         c0 = add_lazy(c0, term, lc.q2);
@@ -735,7 +767,6 @@ struct KskRowIO {
         store(row, i, v0, lc);
         store(row, i + 1, v1, lc);
     }
-    HB_D u64 *raw(int) const { return nullptr; }
 };
 
 int op_ksk_generate(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *sk_curr, const u64 *sk_orig,
@@ -748,23 +779,27 @@ int op_ksk_generate(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, 
     int err = 0;
     const LimbConst *limbs = c.get_chain(logn, ext_moduli, L1, &err);
     if (!limbs) return err;
-    u64 *sk_ext = c.get_scratch(7, L1 * n + 2 * L, &err); // sk_orig_extended, then the (P mod q_p) pairs
+    u64 *sk_ext = c.get_scratch(7, L1 * n + 2 * L, &err); // sk_orig_extended, then the (P mod q_p) pairs when L > 32
     if (!sk_ext) return err;
     cudaError_t e = cudaMemcpyAsync(sk_ext, sk_orig, L * n * 8, cudaMemcpyDeviceToDevice, c.stream);
     if (e != cudaSuccess) return c.cuda_fail(e, "ksk: copy");
-    if (int rc = run_transform(c, false, logn, ext_moduli, L, sk_ext, 1, 0)) return rc;                       // keys.cpp:22
-    if (int rc = op_base_to_single(c, ext_moduli, L, ext_moduli[L], sk_ext, sk_ext + L * n, n, 1)) return rc; // keys.cpp:23-25
-    if (int rc = run_transform(c, true, logn, ext_moduli, L1, sk_ext, 1, 0)) return rc;                       // keys.cpp:26
+    if (int rc = run_transform(c, false, logn, ext_moduli, L, sk_ext, 1, 0)) return rc;                             // keys.cpp:22
+    if (int rc = op_base_to_single(c, ext_moduli, L, ext_moduli[L], sk_ext, sk_ext + L * n, n, 1, true)) return rc; // keys.cpp:23-25
+    if (int rc = run_transform(c, true, logn, ext_moduli, L1, sk_ext, 1, 0)) return rc;                             // keys.cpp:26
+    KskRowIO io{errors, masks, sk_ext, sk_curr, nullptr, key, (int)L, (int)logn, aligned16(errors), PmodTable{}};
     std::vector<u64> pm(2 * L);
     for (size_t p = 0; p < L; p++) { // keys.cpp:28-33, rns.cpp:162-164
         pm[2 * p] = ext_moduli[L] % ext_moduli[p];
         pm[2 * p + 1] = host_harvey_quotient(pm[2 * p], ext_moduli[p]);
+        if (L <= 32) io.pm.v[p] = make_ulonglong2(pm[2 * p], pm[2 * p + 1]);
     }
-    u64 *pmod = sk_ext + L1 * n;
-    e = cudaMemcpyAsync(pmod, pm.data(), pm.size() * 8, cudaMemcpyHostToDevice, c.stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream); // pm is a host temporary
-    if (e != cudaSuccess) return c.cuda_fail(e, "ksk: constants");
-    KskRowIO io{errors, masks, sk_ext, sk_curr, reinterpret_cast<const ulonglong2 *>(pmod), key, (int)L, (int)logn, aligned16(errors)};
+    if (L > 32) { // more digits than the parameter table holds: upload (pm is a host temporary, so wait for the copy)
+        u64 *pmod = sk_ext + L1 * n;
+        e = cudaMemcpyAsync(pmod, pm.data(), pm.size() * 8, cudaMemcpyHostToDevice, c.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+        if (e != cudaSuccess) return c.cuda_fail(e, "ksk: constants");
+        io.pmod = reinterpret_cast<const ulonglong2 *>(pmod);
+    }
     e = launch_ntt<true>(c.env(), logn, io, limbs, (int)(L * L1));
     return e == cudaSuccess ? 0 : c.cuda_fail(e, "ksk: row launch");
 }
@@ -821,7 +856,7 @@ int op_galois_keyswitch(Context &c, unsigned logn, const u64 *ext_moduli, size_t
     if (batch == 0) return 0;
     const size_t n = (size_t)1 << logn;
     const size_t per_ct = (2 * L + L + L * (L + 1) + 2 * (L + 1) + 2) * n;
-    const size_t wave = wave_size(c, per_ct, batch);
+    const size_t wave = wave_size(c, per_ct, batch, L * (L + 1));
     int err = 0;
     u64 *rot = c.get_scratch(5, wave * 2 * L * n, &err);
     if (!rot) return err;

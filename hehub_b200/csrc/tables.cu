@@ -79,6 +79,7 @@ Context::~Context() {
     for (auto &kv : slab_live) cudaFree(kv.first);
     for (auto &s : scratch)
         if (s.first) cudaFree(s.first);
+    if (deferred_flags) cudaFreeHost(deferred_flags);
     if (pipe_ready) {
         for (int i = 0; i < kPipeSlots; i++) {
             cudaEventDestroy(ev_in[i]);
@@ -89,6 +90,39 @@ Context::~Context() {
         cudaStreamDestroy(s_out);
     }
     if (owns_stream && stream) cudaStreamDestroy(stream);
+}
+
+int *Context::deferred_flag_slot(int *err) {
+    *err = 0;
+    if (!deferred_flags) {
+        void *p = nullptr;
+        cudaError_t e = cudaMallocHost(&p, kDeferredSlots * sizeof(int));
+        if (e != cudaSuccess) {
+            *err = cuda_fail(e, "cudaMallocHost(deferred verdicts)");
+            return nullptr;
+        }
+        deferred_flags = static_cast<int *>(p);
+        for (int i = 0; i < kDeferredSlots; i++) deferred_flags[i] = 0;
+    }
+    if (deferred_used == kDeferredSlots) { // all slots pending: drain them (rare: 64 key generations without a synchronize)
+        cudaStreamSynchronize(stream);
+        int raised = 0;
+        for (int i = 0; i < kDeferredSlots; i++) raised |= deferred_flags[i];
+        for (int i = 0; i < kDeferredSlots; i++) deferred_flags[i] = 0;
+        deferred_used = 0;
+        if (raised) deferred_flags[deferred_used++] = 1; // keep the verdict for the caller's next synchronize
+    }
+    return deferred_flags + deferred_used++;
+}
+
+int Context::take_deferred() {
+    int raised = 0;
+    for (int i = 0; i < deferred_used; i++) {
+        raised |= deferred_flags[i];
+        deferred_flags[i] = 0;
+    }
+    deferred_used = 0;
+    return raised;
 }
 
 int Context::cuda_fail(cudaError_t e, const char *where) {

@@ -65,6 +65,18 @@ uint64_t hehub_b200_launch_count(const hehub_b200_ctx *ctx);
  * ERR_INVALID when round(log2 q) > 59 or 2N does not divide q-1 (ntt.cpp:26-47). */
 int hehub_b200_tables_prepare(hehub_b200_ctx *ctx, unsigned logn, const uint64_t *moduli, size_t nmod);
 
+/* ---- parameter selection (host only; usable without a device) --------------------------------
+ * prime_row: the reference's prime table, src/fhe/common/primelists.cpp:5-192 — row `bits` holds the primes
+ *   create_params draws from, in order (rows 27..59; the table's own irregularities are reproduced, see
+ *   hehub_b200/csrc/params.cu).  Writes min(row length, capacity) entries to out and returns the row length.
+ * pick_moduli: ckks::create_params' selection, src/fhe/ckks/basics.cpp:14-38 — the additional modulus is drawn
+ *   first, then the chain in order, one cursor per bit-size row.  additional_out == NULL: no additional
+ *   modulus is drawn (hehub::create_params, src/fhe/primitives/rlwe.cpp:9-29).  ERR_UNSUPPORTED when a row
+ *   runs out ("No suitable primes in the library."). */
+int hehub_b200_prime_row(unsigned bits, size_t capacity, uint64_t *out);
+int hehub_b200_pick_moduli(const unsigned *moduli_bits, size_t L, unsigned additional_bits, uint64_t *moduli_out,
+                           uint64_t *additional_out);
+
 /* ---- device slabs (the device analogue of SmartArray / FixedBlockAllocator,
  *      src/fhe/common/allocator.h:12-223: pooled per block size, reused on free) -- */
 int hehub_b200_slab_alloc(hehub_b200_ctx *ctx, size_t n_words, uint64_t **out_dev);

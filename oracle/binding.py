@@ -408,6 +408,38 @@ class Reference(_CpuLib):
             raise ValueError(f"poly_mul_scalar rc={rc}")
         return x
 
+    # ---- the sampling-based API under a seeded engine (ref_shim.cpp: ref_rng_*) ----
+    def rng_seed(self, seed):
+        self._fn("rng_seed", None, u64)(seed)
+
+    def rng_sample(self, kind, logn, moduli):
+        """kind: 0 ternary (NTT form), 1 uniform, 2 Gaussian (NTT form); continues the current engine state."""
+        m = _arr(moduli)
+        out = np.zeros((m.size, 1 << logn), dtype=np.uint64)
+        rc = self._fn("rng_sample", C.c_int, C.c_int, C.c_uint, C.c_size_t, p64, p64)(kind, logn, m.size, _ptr(m), _ptr(out))
+        if rc:
+            raise ValueError(f"rng_sample rc={rc}")
+        return out
+
+    def rng_scenario_ckks(self, seed, logn, moduli_bits, additional_bits):
+        bits = (C.c_uint * len(moduli_bits))(*moduli_bits)
+        out = np.zeros(14, dtype=np.uint64)
+        rc = self._fn("rng_scenario_ckks", C.c_int, u64, C.c_uint, C.c_size_t, C.POINTER(C.c_uint), C.c_uint, p64)(
+            seed, logn, len(moduli_bits), bits, additional_bits, _ptr(out))
+        if rc:
+            raise ValueError(f"rng_scenario_ckks rc={rc}")
+        return [int(v) for v in out]
+
+    def rng_scenario_bgv(self, seed, logn, moduli_bits, additional_bits, t):
+        bits = (C.c_uint * len(moduli_bits))(*moduli_bits)
+        out = np.zeros(12, dtype=np.uint64)
+        dec = np.zeros(1 << logn, dtype=np.uint64)
+        rc = self._fn("rng_scenario_bgv", C.c_int, u64, C.c_uint, C.c_size_t, C.POINTER(C.c_uint), C.c_uint, u64, p64, p64)(
+            seed, logn, len(moduli_bits), bits, additional_bits, t, _ptr(out), _ptr(dec))
+        if rc:
+            raise ValueError(f"rng_scenario_bgv rc={rc}")
+        return [int(v) for v in out], dec
+
     def cache_ntt_factors(self, logn, moduli):
         m = _arr(moduli)
         self._fn("cache_ntt_factors", None, C.c_uint, p64, C.c_size_t)(logn, _ptr(m), m.size)

@@ -216,6 +216,26 @@ def main():
              "poly_ntt": ints(ref.poly_ntt_fwd(logn, mods, ct1[0]))}
     kat["small"] = small
 
+    # ---- the sampling-based API under a seeded engine (sampling.cpp, rlwe.cpp:31-61, keys.cpp, ckks.h:180-197,
+    #      bgv/basics.cpp) — hashes of every stage; the mirror's test replays the same statements ----
+    rng = {"samples": [], "ckks": [], "bgv": []}
+    for seed, logn, moduli in [(1, 6, [65537, 260898817]), (2, 10, [1073479681, 576460752272228353]),
+                               (3, 12, [36028796997599233, 576460752272228353, 1099510054913])]:
+        ref.rng_seed(seed)
+        rng["samples"].append({"seed": seed, "logn": logn, "moduli": moduli,
+                               "ternary": hx(ref.rng_sample(0, logn, moduli)), "uniform": hx(ref.rng_sample(1, logn, moduli)),
+                               "gaussian": hx(ref.rng_sample(2, logn, moduli))})
+    for seed, logn, bits, add in [(5, 10, [40, 30, 30], 40), (6, 12, [39, 30], 39), (7, 13, [40, 30, 30, 30], 40), (8, 11, [55, 50], 55)]:
+        rng["ckks"].append({"seed": seed, "logn": logn, "bits": bits, "additional_bits": add,
+                            "hashes": [f"{h:016x}" for h in ref.rng_scenario_ckks(seed, logn, bits, add)]})
+    # moduli below 2^53: above it the reference's Gaussian conversion (double arithmetic, sampling.cpp:86) yields errors that
+    # differ per limb, and bgv::decrypt then needs the big-integer CRT branch, which the back end does not build
+    for seed, logn, bits, add, t in [(9, 10, [50, 45, 45], 50, 65537), (10, 12, [52, 50, 48], 52, 65537), (11, 8, [50, 45], 50, 12289)]:
+        hs, dec = ref.rng_scenario_bgv(seed, logn, bits, add, t)
+        rng["bgv"].append({"seed": seed, "logn": logn, "bits": bits, "additional_bits": add, "t": t,
+                           "hashes": [f"{h:016x}" for h in hs], "decoded": hx(dec)})
+    kat["rng"] = rng
+
     # ---- the prime table (primelists.cpp) ----------------------------------
     kat["prime_rows"] = {str(b): ref.prime_row(b, 32) for b in range(0, 60) if ref.prime_row(b, 32)}
     kat["inverse_mod_prime"] = [[a, p, ref.inverse_mod_prime(a, p)] for a, p in

@@ -19,7 +19,14 @@
 #include "fhe/primitives/rgsw.h"
 
 #include <cstring>
+#include <random>
 #include <vector>
+
+#include "fhe/common/sampling.h"
+
+namespace hehub {
+extern std::default_random_engine rand_engine; // src/fhe/common/sampling.cpp:13 (a plain global of the reference)
+}
 
 using namespace hehub;
 
@@ -46,6 +53,39 @@ RlweKsk load_key(size_t n, size_t L, const u64 *ext_moduli, const u64 *key) {
         ksk.push_back(std::move(row));
     }
     return ksk;
+}
+
+static u64 fnv_poly(const RnsPolynomial &p, u64 h = 1469598103934665603ull) {
+    for (size_t k = 0; k < p.component_count(); k++)
+        for (size_t i = 0; i < p.dimension(); i++) {
+            h ^= p[k][i];
+            h *= 1099511628211ull;
+        }
+    return h;
+}
+template <size_t K> static u64 fnv_ct(const std::array<RnsPolynomial, K> &ct) {
+    u64 h = 1469598103934665603ull;
+    for (const auto &p : ct) h = fnv_poly(p, h);
+    return h;
+}
+static u64 fnv_ksk(const RlweKsk &k) {
+    u64 h = 1469598103934665603ull;
+    for (const auto &row : k)
+        for (const auto &p : row) h = fnv_poly(p, h);
+    return h;
+}
+static RnsPolynomial lcg_poly(size_t n, const std::vector<u64> &moduli, u64 seed0, u64 bound) {
+    RnsPolynomial p(n, moduli.size(), moduli);
+    u64 s = seed0; // one small signed-free coefficient stream shared by the limbs (a valid small plaintext)
+    std::vector<u64> v(n);
+    for (auto &c : v) {
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        c = (s >> 33) % bound;
+    }
+    for (size_t k = 0; k < moduli.size(); k++)
+        for (size_t i = 0; i < n; i++) p[k][i] = v[i] % moduli[k];
+    p.rep_form = PolyRepForm::coeff;
+    return p;
 }
 
 template <class F> int guarded(F &&f) {
@@ -381,6 +421,101 @@ int ref_bench_ntt(unsigned logn, u64 q, u64 *x, size_t rows, int forward) {
             else
                 intt_negacyclic_inplace_lazy(logn, q, x + r * n);
         }
+    });
+}
+
+/* ---- the sampling-based API, made deterministic by seeding the reference's own global engine ----------------
+ * Each scenario runs the reference's public functions end to end and records the FNV-1a hash of
+ * every intermediate's raw words, limbs in order.  tests/cpp/test_hehub_api.cpp runs the same statements through
+ * the hehub_b200 mirror after seeding ITS engine with the same value. */
+void ref_rng_seed(u64 seed) { rand_engine.seed(seed); }
+
+/* 0 ternary (NTT form), 1 uniform, 2 Gaussian (NTT form) — sampling.cpp:16-93 */
+int ref_rng_sample(int kind, unsigned logn, size_t L, const u64 *moduli, u64 *out) {
+    return guarded([&] {
+        RnsPolyParams params{(size_t)1 << logn, L, std::vector<u64>(moduli, moduli + L)};
+        auto p = kind == 0 ? get_rand_ternary_poly(params) : kind == 1 ? get_rand_uniform_poly(params) : get_rand_gaussian_poly(params);
+        store_poly(p, out);
+    });
+}
+
+/* CKKS flow: keygen, relin / conj / rot keys, encrypt, mult, rescale, rotate, conjugate, add/sub/mult_plain, decrypt.
+ * hashes[14]. */
+int ref_rng_scenario_ckks(u64 seed, unsigned logn, size_t L, const unsigned *moduli_bits, unsigned additional_bits, u64 *hashes) {
+    return guarded([&] {
+        rand_engine.seed(seed);
+        const size_t n = (size_t)1 << logn;
+        auto params = ckks::create_params(n, std::vector<size_t>(moduli_bits, moduli_bits + L), additional_bits, 1099511627776.0);
+        RlweSk sk(params);
+        auto relin = get_relin_key(sk, params.additional_mod);
+        auto conj = get_conj_key(sk, params.additional_mod);
+        auto rot = get_rot_key(sk, params.additional_mod, 3);
+        size_t j = 0;
+        hashes[j++] = fnv_poly(sk);
+        hashes[j++] = fnv_ksk(relin);
+        hashes[j++] = fnv_ksk(conj);
+        hashes[j++] = fnv_ksk(rot);
+        CkksPt pt1(lcg_poly(n, params.moduli, 11, 1 << 20)), pt2(lcg_poly(n, params.moduli, 12, 1 << 20));
+        pt1.scaling_factor = pt2.scaling_factor = params.initial_scaling_factor;
+        auto ct1 = ckks::encrypt(pt1, sk), ct2 = ckks::encrypt(pt2, sk);
+        hashes[j++] = fnv_ct(ct1);
+        hashes[j++] = fnv_ct(ct2);
+        hashes[j++] = fnv_ct(ckks::add_plain(ct1, pt2));
+        hashes[j++] = fnv_ct(ckks::sub_plain(ct1, pt2));
+        hashes[j++] = fnv_ct(ckks::mult_plain(ct1, pt2));
+        auto prod = ckks::mult(ct1, ct2, relin);
+        hashes[j++] = fnv_ct(prod);
+        ckks::rescale_inplace(prod);
+        hashes[j++] = fnv_ct(prod);
+        hashes[j++] = fnv_ct(ckks::rotate(ct1, rot));
+        hashes[j++] = fnv_ct(ckks::conjugate(ct2, conj));
+        hashes[j++] = fnv_poly(ckks::decrypt(prod, sk)); // rescaled (L-1 limbs) ciphertext against the full-length key
+    });
+}
+
+/* BGV flow: slot encoding, encrypt, plain ops, mult + relinearize, mod-switch, decrypt, decode.  hashes[12];
+ * decoded[n] receives simd_decode(decrypt(ct1 * pt2 + ct2)) (the shape of tests/bgv_t.cpp:160-190).  Decryption is
+ * only asked of ciphertexts whose noise keeps rns_base_transform on its small-coefficient path (rns_transform.cpp:47-84). */
+int ref_rng_scenario_bgv(u64 seed, unsigned logn, size_t L, const unsigned *moduli_bits, unsigned additional_bits, u64 t, u64 *hashes,
+                         u64 *decoded) {
+    return guarded([&] {
+        rand_engine.seed(seed);
+        const size_t n = (size_t)1 << logn;
+        auto params = ckks::create_params(n, std::vector<size_t>(moduli_bits, moduli_bits + L), additional_bits, 1.0);
+        RlweSk sk(params);
+        auto relin = get_relin_key(sk, params.additional_mod);
+        std::vector<u64> d1(n), d2(n);
+        u64 s = 77;
+        for (size_t i = 0; i < n; i++) {
+            s = s * 6364136223846793005ull + 1442695040888963407ull;
+            d1[i] = (s >> 20) % t;
+            s = s * 6364136223846793005ull + 1442695040888963407ull;
+            d2[i] = (s >> 20) % t;
+        }
+        size_t j = 0;
+        auto pt1 = bgv::simd_encode(d1, t, n), pt2 = bgv::simd_encode(d2, t, n);
+        hashes[j++] = fnv_poly(pt1);
+        auto ct1 = bgv::encrypt(pt1, sk), ct2 = bgv::encrypt(pt2, sk);
+        hashes[j++] = fnv_ct(ct1);
+        hashes[j++] = fnv_ct(ct2);
+        hashes[j++] = fnv_ct(bgv::add_plain(ct1, pt2));
+        hashes[j++] = fnv_ct(bgv::sub_plain(ct1, pt2));
+        auto ct_prod_plain = bgv::mult_plain(ct1, pt2);
+        hashes[j++] = fnv_ct(ct_prod_plain);
+        auto ct_res = bgv::add(ct_prod_plain, ct2);
+        hashes[j++] = fnv_ct(ct_res);
+        auto prod = bgv::relinearize(bgv::mult_low_level(ct1, ct2), relin);
+        hashes[j++] = fnv_ct(prod);
+        bgv::mod_switch_inplace(prod);
+        hashes[j++] = fnv_ct(prod);
+        auto dec = bgv::decrypt(ct_res, sk);
+        hashes[j++] = fnv_poly(dec);
+        auto out = bgv::simd_decode(dec);
+        std::memcpy(decoded, out.data(), n * sizeof(u64));
+        auto switched = ct1; // tests/bgv_t.cpp:229-259: the plaintext survives the switch
+        bgv::mod_switch_inplace(switched);
+        hashes[j++] = fnv_ct(switched);
+        hashes[j++] = fnv_poly(bgv::decrypt(switched, sk));
     });
 }
 

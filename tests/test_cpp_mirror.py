@@ -37,6 +37,21 @@ def test_cpp_mirror(kind, tmp_path_factory):
     res = subprocess.run([exe, str(out_dir)], capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "0 failures" in res.stdout
+    # the sampling-based API (keygen, encrypt, plain ops, BGV encode/decrypt) replayed under seeded engines: every stage's hash
+    # must equal what the unmodified reference produced for the same statements (oracle/make_golden.py, kat["rng"])
+    import json
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_kat.json")))["rng"]
+    got = {}
+    for line in open(out_dir / "rng_hashes.txt"):
+        tag, seed, *hashes = line.split()
+        got[(tag, int(seed))] = hashes
+    for case in kat["samples"]:
+        assert got[("samples", case["seed"])] == [case["ternary"], case["uniform"], case["gaussian"]], case
+    for case in kat["ckks"]:
+        assert got[("ckks", case["seed"])] == case["hashes"], case
+    for case in kat["bgv"]:
+        assert got[("bgv", case["seed"])] == case["hashes"] + [case["decoded"]], case
+    assert len(got) == len(kat["samples"]) + len(kat["ckks"]) + len(kat["bgv"])
     # the slab files the C++ mirror wrote are read back by the Python side (same layout, hehub_b200/slabio.py)
     import numpy as np
     from hehub_b200 import slabio
