@@ -36,6 +36,17 @@ METRIC = "NTT/s (N=4096, one 59-bit modulus, batch 4096)"
 UNIT = "NTT/s"
 
 
+def kernel_source_sha16() -> str:
+    """Hash of the CUDA sources and the C header: ties a committed ncu capture to the build it was taken from."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "hehub_b200", "csrc")
+    for name in sorted(os.listdir(csrc)) + [os.path.join("..", "..", "include", "hehub_b200.h")]:
+        with open(os.path.join(csrc, name), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -247,14 +258,20 @@ def run_cuda(args):
     peaks, peak_src = measured_peaks()
     alg_bytes = 16 * n * POLYS  # read + write of every coefficient, SURVEY §8(d)
     achieved = alg_bytes / (elapsed / args.steps) / 1e9
-    traffic = None
+    # DRAM bytes per launch from `ncu --set full` (tools/gpu_round3.sh writes profiles/ntt_fwd_traffic.json together with the
+    # hash of the kernel sources it profiled): reported only while it belongs to the sources that are being timed
+    traffic, traffic_note = None, "no ncu capture on file"
     try:
         with open(os.path.join(ROOT, "profiles", "ntt_fwd_traffic.json")) as fh:
-            traffic = json.load(fh).get("dram_bytes_per_launch")
+            tj = json.load(fh)
+        if tj.get("source_sha16") == kernel_source_sha16():
+            traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("source")
+        else:
+            traffic_note = "capture on file is of other kernel sources (stale): rerun tools/gpu_round3.sh"
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                 "kernel": "ntt_fwd_fast_kernel<12, RowsIO<0>>",
                 "algorithmic_bytes_per_launch": alg_bytes}
     # the transforms are bound by the integer (FMA-heavy) pipe, not HBM: report that fraction too
@@ -304,7 +321,7 @@ def run_cuda(args):
         extras["rows_c3_shape"] = run_rows(ctx, torch, timed, world, rank, peaks, cpu_ok=(rank == 0 and world == 1 and not args.no_cpu))
     if args.extras:
         extras.update(run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist if world > 1 else None, args.sweep_cts,
-                                 cpu_ok=(rank == 0 and world == 1 and not args.no_cpu)))
+                                 cpu_ok=(rank == 0 and world == 1 and not args.no_cpu), parity_ok=not args.no_cpu))
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------------
     cpu = None
@@ -330,7 +347,7 @@ def run_cuda(args):
                        "l2_policy": f"inputs larger than L2: {SLABS} slabs of {POLYS * n * 8 >> 20} MiB visited round-robin",
                        "sharding": "independent polynomials per rank, no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world,
-            "clocks": sampler.summary(), "extras": extras,
+            "clocks": sampler.summary(), "ct_mult": ct_mult_summary(extras), "extras": extras,
         }
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -338,7 +355,35 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
-def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, sweep_cts=0, cpu_ok=False):
+def ct_mult_summary(extras):
+    """The ciphertext-multiplication half of BASELINE's metric ("NTT/s and CKKS ct-mult+relin/s ..."), lifted out of `extras`
+    so the driver's line carries it at the top level; every figure is whole-job, device-timed like `value` unless it says e2e."""
+    out = {}
+    c3 = extras.get("c3_ckks_mult_relin_N8192_L4", {})
+    c5 = extras.get("c5_ckks_mult_relin_N32768_L12", {})
+    sw = extras.get("c5_sweep_N32768_L12", {})
+    if "mult_relin" in c3:
+        out["c3_mult_relin_per_s"] = c3["mult_relin"]["per_s"]
+        out["c3_mult_relin_frac_hbm"] = c3["mult_relin"].get("frac_hbm")
+    if "mult_relin_e2e_host_buffers" in c3:
+        out["c3_mult_relin_e2e_per_s"] = c3["mult_relin_e2e_host_buffers"]["per_s"]
+    if "mult_relin_single_ct" in c3:
+        out["c3_mult_relin_one_pair_per_call_us"] = c3["mult_relin_single_ct"]["us_per_call"]
+    if "mult_relin" in c5:
+        out["c5_mult_relin_per_s"] = c5["mult_relin"]["per_s"]
+        out["c5_mult_relin_frac_hbm"] = c5["mult_relin"].get("frac_hbm")
+    if "mult_relin_single_ct" in c5:
+        out["c5_mult_relin_one_pair_per_call_us"] = c5["mult_relin_single_ct"]["us_per_call"]
+    if sw:
+        out["c5_sweep_cts"] = sw.get("cts_total")
+        out["c5_sweep_mult_relin_per_s"] = sw.get("mult_relin_per_s_device_time")
+        out["c5_sweep_checksum_of_checksums"] = sw.get("checksum_of_checksums")
+        if "parity_sample" in sw:
+            out["c5_sweep_parity_bit_exact"] = sw["parity_sample"]["bit_exact"]
+    return out or None
+
+
+def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, sweep_cts=0, cpu_ok=False, parity_ok=False):
     """Other BASELINE configs, device-resident, same timing discipline; values are whole-job."""
     import numpy as np
     from hehub_b200.binding import _mod, pick_moduli  # moduli come from the product's create_params rule (csrc/params.cu)
@@ -474,35 +519,32 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
     # whole bench stays within minutes) cut into contiguous per-rank ranges, processed in waves, inputs generated
     # on the device; NCCL only broadcasts the key and gathers one checksum per ciphertext (hehub_b200/sweep.py)
     if sweep_cts > 0:
-        from hehub_b200.sweep import CtSweep
+        from hehub_b200.sweep import CtSweep, nccl_collectives
         mods, p = pick_moduli([50] * 12, 55, ctx.lib)
-        sw = CtSweep(ctx, f"cuda:{torch.cuda.current_device()}", 15, [int(m) for m in mods], int(p), seed=42)
-        with torch.cuda.stream(stream):
-            sw.make_key(dist, rank)
-
-            def ev_timer(fn):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                fn()
-                e1.record(stream)
-                e1.synchronize()
-                return e0.elapsed_time(e1) * 1e-3
-
-            sw.run(min(sweep_cts, 74 * world), SWEEP_WAVE, rank, world, dist)  # warm-up (tables, workspaces)
-            torch.cuda.synchronize()
-            barrier()
-            t0 = time.perf_counter()
-            res = sw.run(sweep_cts, SWEEP_WAVE, rank, world, dist, timer=ev_timer)
-            torch.cuda.synchronize()
-            barrier()
-            wall = time.perf_counter() - t0
+        coll, coll_destroy = None, None
+        if dist is not None:
+            # the C++ driver talks NCCL itself (csrc/nccl_provider.cpp); the launcher's process group only carries the 128-byte id
+            def exchange(raw):
+                box = [raw]
+                dist.broadcast_object_list(box, src=0)
+                return box[0]
+            coll, coll_destroy = nccl_collectives(rank, world, torch.cuda.current_device(), exchange)
+        sw = CtSweep(ctx, 15, [int(m) for m in mods], int(p), seed=42, rank=rank, world=world, collectives=coll)
+        sw.make_key()  # rank 0 generates, ncclBroadcast
+        sw.run(min(sweep_cts, 74 * world), SWEEP_WAVE)  # warm-up (tables, workspaces)
+        barrier()
+        t0 = time.perf_counter()
+        res = sw.run(sweep_cts, SWEEP_WAVE, time_ops=True)  # device time: CUDA events inside the driver, around the mult+relin calls
+        barrier()
+        wall = time.perf_counter() - t0
         t = torch.tensor([res["op_seconds"], wall], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         op_s, wall_s = float(t[0].item()), float(t[1].item())
         r = {"cts_total": sweep_cts, "scaling": "strong", "wave": SWEEP_WAVE, "mult_relin_per_s_device_time": sweep_cts / op_s,
              "mult_relin_per_s_wall_incl_input_generation_and_checksums": sweep_cts / wall_s,
-             "gbs_algorithmic": 48 * 12 * 32768 * sweep_cts / op_s / 1e9}
+             "gbs_algorithmic": 48 * 12 * 32768 * sweep_cts / op_s / 1e9,
+             "driver": "hehub_b200_sweep_* (C++, csrc/sweep.cu)" + ("; collectives: NCCL from csrc/nccl_provider.cpp" if dist is not None else "")}
         r["frac_hbm_per_gpu"] = r["gbs_algorithmic"] / world / hbm
         if "all_checksums" in res:
             import numpy as np
@@ -512,23 +554,33 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
             import numpy as np
             r["checksums_gathered"] = int(res["checksums"].size)
             r["checksum_of_checksums"] = int(np.bitwise_xor.reduce(res["checksums"]))
-        if cpu_ok and rank == 0:
-            # sampled parity at the full config-5 size: this rank's first, middle and last ciphertext pairs
-            # recomputed by the reference's CPU path and compared through the per-ciphertext checksum; the same calls
-            # give the CPU side of the config-5 speed-up
+        if parity_ok and res["count"]:
+            # sampled parity at the full config-5 size, on EVERY rank: this rank's first, middle and last
+            # ciphertext pairs recomputed by the reference's CPU path and compared through the per-ciphertext checksum; on
+            # one GPU the same calls give the CPU side of the config-5 speed-up
             from hehub_b200.sweep import ct_checksum_numpy
             lib, kind = _cpu_lib()
             keyh = sw.key_host()
             picks = sorted({res["first"], res["first"] + res["count"] // 2, res["first"] + res["count"] - 1})
+            if world > 1:
+                picks = picks[:1] + picks[-1:]  # two per rank keep the N-GPU run short
             okc, t0 = 0, time.perf_counter()
             for idx in picks:
                 a, b = sw.one_ct_inputs_host(idx)
                 okc += int(ct_checksum_numpy(lib.ckks_mult_relin(15, sw.ext, a, b, keyh)) == int(res["checksums"][idx - res["first"]]))
             cdt = (time.perf_counter() - t0) / len(picks)
-            r["parity_sample"] = {"ciphertexts_checked": len(picks), "bit_exact": okc == len(picks), "checker": kind}
-            r["cpu_mult_relin"] = {"per_s": 1.0 / cdt, "cores": 1, "kind": kind,
-                                   "sample": f"{len(picks)} ciphertext pairs (incl. regenerating their inputs), one core"}
-            r["speedup_device_resident_vs_one_cpu_core"] = r["mult_relin_per_s_device_time"] / (1.0 / cdt)
+            tally = torch.tensor([okc, len(picks)], dtype=torch.int64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(tally)
+            r["parity_sample"] = {"ciphertexts_checked": int(tally[1].item()), "bit_exact": int(tally[0].item()) == int(tally[1].item()),
+                                  "ranks_checking": world, "checker": kind}
+            if world == 1:
+                r["cpu_mult_relin"] = {"per_s": 1.0 / cdt, "cores": 1, "kind": kind,
+                                       "sample": f"{len(picks)} ciphertext pairs (incl. regenerating their inputs), one core"}
+                r["speedup_device_resident_vs_one_cpu_core"] = r["mult_relin_per_s_device_time"] / (1.0 / cdt)
+        sw.close()
+        if coll_destroy:
+            coll_destroy()
         out["c5_sweep_N32768_L12"] = r
     return out
 

@@ -78,6 +78,7 @@ _SIGS = {
     "lcg_fill": [sz, p64, sz, C.c_void_p, sz, u64, u64],
     "ntt_host": [C.c_int, C.c_uint, p64, sz, C.c_void_p, C.c_void_p, sz, C.c_int],
     "ckks_mult_relin_host": [C.c_uint, p64, sz, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, sz],
+    "ct_checksums": [C.c_void_p, sz, sz, C.c_void_p],
     "ctx_set_option": [C.c_char_p, C.c_int64],
     "ctx_set_stream": [C.c_void_p],
     "ctx_synchronize": [],
@@ -90,7 +91,9 @@ _FREE_SIGS = {
 }
 
 EXPORTED = ["hehub_b200_version", "hehub_b200_ctx_create", "hehub_b200_ctx_destroy", "hehub_b200_last_error",
-            "hehub_b200_launch_count"] + ["hehub_b200_" + k for k in _SIGS] + ["hehub_b200_" + k for k in _FREE_SIGS]
+            "hehub_b200_launch_count"] + ["hehub_b200_" + k for k in _SIGS] + ["hehub_b200_" + k for k in _FREE_SIGS] + [
+    "hehub_b200_shard_range", "hehub_b200_sweep_create", "hehub_b200_sweep_destroy", "hehub_b200_sweep_make_key", "hehub_b200_sweep_key",
+    "hehub_b200_sweep_fill_inputs", "hehub_b200_sweep_run"]
 
 
 def bind_host_to_gpu(device: int = 0) -> list[int]:

@@ -22,6 +22,16 @@
 #define HB_LAUNCH_CLUSTER(kern, grid, block, smem, stream, cluster, ...) \
     (::hbsim::launch((grid), (block), (smem), 1, [&]() { kern(__VA_ARGS__); }, (cluster)), cudaSuccess)
 inline void hb_cluster_sync() { ::hbsim::cluster_sync(); }
+// split form: arrive early, wait where the guarantee is needed (the emulator's barrier is one-shot: it meets at the wait)
+inline void hb_cluster_arrive() {}
+inline void hb_cluster_wait() { ::hbsim::cluster_sync(); }
+// one word of CTA `rank`'s shared memory at the offset `p` has in this CTA's
+inline unsigned long long hb_ld_dsmem(const unsigned long long *p, unsigned rank) {
+    return ::hbsim::shared_u64_of(rank)[p - ::hbsim::shared_u64()];
+}
+inline void hb_st_dsmem(unsigned long long *p, unsigned rank, unsigned long long v) {
+    ::hbsim::shared_u64_of(rank)[p - ::hbsim::shared_u64()] = v;
+}
 // two adjacent words of CTA `rank`'s shared memory at the offset `p` has in this CTA's (DSMEM)
 inline ulonglong2 hb_ld_dsmem2(const unsigned long long *p, unsigned rank) {
     return *reinterpret_cast<const ulonglong2 *>(::hbsim::shared_u64_of(rank) + (p - ::hbsim::shared_u64()));
@@ -102,6 +112,23 @@ __device__ __forceinline__ ulonglong2 hb_ld_ro2(const unsigned long long *p) {
 // barrier over the thread-block cluster with release/acquire ordering of global and shared writes
 __device__ __forceinline__ void hb_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void hb_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void hb_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// the address of `p` (this CTA's shared memory) in CTA `rank`'s shared memory, as a shared::cluster address
+__device__ __forceinline__ unsigned hb_dsmem_addr(const unsigned long long *p, unsigned rank) {
+    unsigned local = (unsigned)__cvta_generic_to_shared(p), remote;
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    return remote;
+}
+// one word of CTA `rank`'s shared memory at the offset `p` has in this CTA's (distributed shared memory)
+__device__ __forceinline__ unsigned long long hb_ld_dsmem(const unsigned long long *p, unsigned rank) {
+    unsigned long long v;
+    asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(hb_dsmem_addr(p, rank)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void hb_st_dsmem(unsigned long long *p, unsigned rank, unsigned long long v) {
+    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(hb_dsmem_addr(p, rank)), "l"(v) : "memory");
 }
 // two adjacent words of CTA `rank`'s shared memory at the offset `p` has in this CTA's (distributed shared memory)
 __device__ __forceinline__ ulonglong2 hb_ld_dsmem2(const unsigned long long *p, unsigned rank) {

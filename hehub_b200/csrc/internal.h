@@ -22,13 +22,15 @@ int check_ring(Context &c, unsigned logn, size_t L, size_t batch);
 // ops.cu — composite operations (device pointers, already validated)
 int op_ckks_tensor(Context &c, unsigned logn, const u64 *moduli, size_t L, const u64 *ct1, const u64 *ct2,
                    u64 *quad, size_t batch);
+// ginv != 1: `in` is read through the Galois permutation with inverse factor ginv (rotate / conjugate)
 int op_ext_prod(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *in, size_t in_batch_stride,
-                const u64 *key, u64 *out, size_t batch);
+                const u64 *key, u64 *out, size_t batch, unsigned ginv = 1);
 // drop the last prime of ct [batch][2][L][N] -> out [batch][2][L-1][N]; t == 0: CKKS rescale,
 // else BGV mod-switch.  Optional addend (lazy-added to the result): [batch][..][L-1][N] with
 // the given strides, applied to the first add_halves polynomials.
 int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, const u64 *ct, u64 *out,
-                 size_t batch, const u64 *addend, size_t add_batch_stride, size_t add_poly_stride, int add_halves);
+                 size_t batch, const u64 *addend, size_t add_batch_stride, size_t add_poly_stride, int add_halves,
+                 unsigned add_ginv = 1);
 int op_relinearize(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u64 t, const u64 *quad,
                    const u64 *key, u64 *out, size_t batch);
 int op_mult_relin(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u64 t, const u64 *ct1, const u64 *ct2,

@@ -30,6 +30,8 @@
 //   u64        pre(int row, int i, u64 raw, LimbConst&)   -> input word i from the raw word read at src(row)[i]
 //   void       store(int row, int i, u64 v, LimbConst&)   -> consumes output word i
 //   void       prefetch(int row, int first, int nwords)   -> optional: called once per CTA before the first pass
+//   u64 fetch(int row, int i) / ulonglong2 fetch2(row, i) -> optional: the raw word(s) of src(row) the transform reads as word i
+//                                                            (i, i + 1), for policies that gather through a permutation
 //   bool       vec                                        -> every row pointer is 16-byte aligned
 //   void       store2(int row, int i, u64 v0, u64 v1, LimbConst&) -> words i (even) and i+1, used when vec
 #pragma once
@@ -42,12 +44,20 @@
 
 namespace hb {
 
+// optional policy hooks: fetch(row, i) / fetch2(row, i) replace the streaming load of word i (words i, i + 1; i even) of
+// src(row) — a policy that gathers its input through a permutation (Galois automorphisms fused into the key switch)
+template <class IO, class = void>
+struct io_has_fetch : std::false_type {};
+template <class IO>
+struct io_has_fetch<IO, std::void_t<decltype(std::declval<const IO &>().fetch(0, 0))>> : std::true_type {};
+
 template <class IO>
 HB_D u64 io_load(const IO &io, int row, int i, const LimbConst &lc) {
 #if defined(HB_ABL_NOLOAD) // ablation builds only: synthesise the input words, no global reads
     return io.pre(row, i, (u64)i * 0x9E3779B97F4A7C15ull + (u64)row, lc);
 #else
-    return io.pre(row, i, hb_ld_stream(io.src(row) + i), lc);
+    if constexpr (io_has_fetch<IO>::value) return io.pre(row, i, io.fetch(row, i), lc);
+    else return io.pre(row, i, hb_ld_stream(io.src(row) + i), lc);
 #endif
 }
 
@@ -163,7 +173,9 @@ HB_D void warp_load(u64 *sm, const IO &io, const LimbConst &lc, int row, int fir
 #if defined(HB_ABL_NOLOAD)
             ulonglong2 v = make_ulonglong2((u64)i * 0x9E3779B97F4A7C15ull + (u64)row, (u64)i);
 #else
-            ulonglong2 v = hb_ld_stream2(g + 64 * k);
+            ulonglong2 v;
+            if constexpr (io_has_fetch<IO>::value) v = io.fetch2(row, i);
+            else v = hb_ld_stream2(g + 64 * k);
 #endif
             v.x = io.pre(row, i, v.x, lc);
             v.y = io.pre(row, i + 1, v.y, lc);
@@ -191,6 +203,7 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     constexpr int K = pl.k[P], L0 = fwd_lambda0(pl, P), GSL = LOGNC - L0 - K; // log2(smallest gap)
     constexpr int NG = NC >> K;
     constexpr bool first = (P == 0), last = (P == pl.npass - 1);
+    static_assert(!(first && pl.xchg), "pass 0 of an exchanging plan is fwd_cross_pass");
     static_assert(!last || GSL == 0, "last forward pass must be contiguous");
     static_assert(last || GSL >= 4, "strided passes step by multiples of 16 words");
     static_assert(NG % T == 0 && T % 32 == 0, "whole warps in every step");
@@ -242,21 +255,63 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     }
 }
 
+// Exchanging plans (xchg = 1): pass 0 is a pass of the FULL row shared by the 2^lpre CTAs of the cluster.  Group t holds
+// the words t + j * G (G = N >> K); CTA B takes the groups [B, B + 1) * G / C, reads them from global memory, runs
+// the K levels (the first lpre of them pair words of different CTAs) and hands every result to the CTA that owns its
+// position: word i belongs to CTA i / NC, at offset i % NC of that CTA's shared memory (st.shared::cluster).
+template <int LOGN, int T, int MODE, class IO>
+HB_D void fwd_cross_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
+    constexpr NttPlan pl = plan_for(LOGN, true, MODE);
+    constexpr int K = pl.k[0], C = 1 << pl.lpre, KL = K - pl.lpre; // KL: levels of this pass that stay inside the owner
+    constexpr int LOGG = LOGN - K, GPC = (1 << LOGG) / C;
+    static_assert(K >= pl.lpre && LOGG >= 4, "the cross pass covers every cross-CTA level; strides are multiples of 16 words");
+    static_assert(GPC % T == 0 && T % 32 == 0, "whole warps in every step");
+    constexpr int SJ = sstride(1 << LOGG);
+    const ulonglong2 *tw_pass = (MODE ? lc.fwd_lat : lc.fwd);
+#pragma unroll 1
+    for (int g = threadIdx.x; g < GPC; g += T) {
+        const int t = B * GPC + g;
+        u64 v[1 << K];
+#pragma unroll
+        for (int j = 0; j < (1 << K); j++) v[j] = io_load(io, row, t + (j << LOGG), lc);
+        fwd_levels<K>(v, TwTable{tw_pass, 1}, lc.nq, lc.q2);
+        // every CTA of the cluster is running before its shared memory is written (the arrive is at kernel start)
+        if (g == (int)threadIdx.x) hb_cluster_wait();
+        u64 *const smb = sm + sphys(t);
+#pragma unroll
+        for (int o = 0; o < C; o++) {
+            if (o == B) {
+#pragma unroll
+                for (int jj = 0; jj < (1 << KL); jj++) smb[jj * SJ] = v[(o << KL) + jj];
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < (1 << KL); jj++) hb_st_dsmem(smb + jj * SJ, o, v[(o << KL) + jj]);
+            }
+        }
+    }
+}
+
 template <int LOGN, int T, int P, int MODE, class IO>
 HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     constexpr NttPlan pl = plan_for(LOGN, true, MODE);
-    fwd_pass<LOGN, T, P, MODE>(sm, io, lc, row, B);
-    if constexpr (P + 1 < pl.npass) {
-        if constexpr (P == 0 && pl.lpre == 1) {
-            // both CTAs of the row have read all of it: from here on either may overwrite it
-            // (in-place transforms store into the words the sibling CTA has just read)
-            hb_cluster_sync();
-        } else if constexpr (P + 2 == pl.npass && warp_local_pair(pl.k[P], pl.k[P + 1])) {
-            hb_syncwarp();
-        } else {
-            __syncthreads();
+    if constexpr (P == 0 && pl.xchg) {
+        fwd_cross_pass<LOGN, T, MODE>(sm, io, lc, row, B);
+        hb_cluster_sync(); // every word has reached its owner (and all of the row has been read: in-place stores may follow)
+        fwd_passes<LOGN, T, 1, MODE>(sm, io, lc, row, B);
+    } else {
+        fwd_pass<LOGN, T, P, MODE>(sm, io, lc, row, B);
+        if constexpr (P + 1 < pl.npass) {
+            if constexpr (P == 0 && pl.lpre == 1) {
+                // both CTAs of the row have read all of it: from here on either may overwrite it
+                // (in-place transforms store into the words the sibling CTA has just read)
+                hb_cluster_sync();
+            } else if constexpr (P + 2 == pl.npass && warp_local_pair(pl.k[P], pl.k[P + 1])) {
+                hb_syncwarp();
+            } else {
+                __syncthreads();
+            }
+            fwd_passes<LOGN, T, P + 1, MODE>(sm, io, lc, row, B);
         }
-        fwd_passes<LOGN, T, P + 1, MODE>(sm, io, lc, row, B);
     }
 }
 
@@ -272,6 +327,7 @@ ntt_fwd_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     HB_SHARED_U64(sm);
     const int row = blockIdx.x >> pl.lpre, B = blockIdx.x & ((1 << pl.lpre) - 1);
     const LimbConst lc = limbs[io.limb(row)]; // uploaded when the chain was built: safe to read before the wait
+    if constexpr (pl.xchg) hb_cluster_arrive(); // matched by the wait in front of the first remote store
     hb_pdl_wait();
     if constexpr (io_has_prefetch<IO>::value) io.prefetch(row, B << (LOGN - pl.lpre), 1 << (LOGN - pl.lpre));
     fwd_passes<LOGN, T, 0, MODE>(sm, io, lc, row, B);
@@ -328,17 +384,65 @@ HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     }
 }
 
+// Exchanging plans: the last inverse pass is a pass of the FULL row (stage gaps G ... N/2, the last lpre of them pair words
+// of different CTAs).  CTA B takes the groups [B, B + 1) * G / C, gathers word t + j * G from the shared memory of the
+// CTA that owns it (ld.shared::cluster), runs the K stages and finishes every word: approximate reduction and the
+// psi^{-i}/N scaling (ntt.cpp:214-221) — no butterfly is computed twice and the row never leaves the cluster.
+template <int LOGN, int T, int MODE, class IO>
+HB_D void inv_cross_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
+    constexpr NttPlan pl = plan_for(LOGN, false, MODE);
+    constexpr int K = pl.k[0], C = 1 << pl.lpre, KL = K - pl.lpre;
+    constexpr int LOGG = LOGN - K, GPC = (1 << LOGG) / C;
+    static_assert(K >= pl.lpre && LOGG >= 4, "the cross pass covers every cross-CTA stage; strides are multiples of 16 words");
+    static_assert(GPC % T == 0 && T % 32 == 0, "whole warps in every step");
+    static_assert(inv_s0(pl, pl.npass - 1) == LOGG, "the cross pass is the last pass of the mirrored list");
+    constexpr int SJ = sstride(1 << LOGG);
+    const ulonglong2 *tw_pass = (MODE ? lc.inv_lat : lc.inv) + inv_pass_offset(pl, pl.npass - 1);
+#pragma unroll 1
+    for (int g = threadIdx.x; g < GPC; g += T) {
+        const int t = B * GPC + g;
+        const u64 *const smb = sm + sphys(t);
+        u64 v[1 << K];
+#pragma unroll
+        for (int o = 0; o < C; o++) {
+            if (o == B) {
+#pragma unroll
+                for (int jj = 0; jj < (1 << KL); jj++) v[(o << KL) + jj] = smb[jj * SJ];
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < (1 << KL); jj++) v[(o << KL) + jj] = hb_ld_dsmem(smb + jj * SJ, o);
+            }
+        }
+        inv_levels<K>(v, TwTable{tw_pass + t, 1 << LOGG}, lc.nq, lc.q2);
+#pragma unroll
+        for (int j = 0; j < (1 << K); j++) {
+            const int i = t + (j << LOGG);
+            u64 x = approx_reduce(v[j], lc);              // ntt.cpp:218
+            const ulonglong2 s = __ldg(lc.inv_scale + i); // psi^{-i}/N, ntt.cpp:219-221
+            io.store(row, i, harvey_lazy(x, s.x, s.y, lc.nq), lc);
+        }
+    }
+}
+
 template <int LOGN, int T, int P, int MODE, class IO>
 HB_D void inv_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     constexpr NttPlan pl = plan_for(LOGN, false, MODE);
-    inv_pass<LOGN, T, P, MODE>(sm, io, lc, row, B);
-    if constexpr (P + 1 < pl.npass) {
-        if constexpr (P == 0 && warp_local_pair(inv_k(pl, 0), inv_k(pl, 1))) {
-            hb_syncwarp();
-        } else {
-            __syncthreads();
+    if constexpr (pl.xchg && P == pl.npass - 1) {
+        hb_cluster_sync(); // the CTA-local stages are done everywhere and their words visible to the cluster
+        inv_cross_pass<LOGN, T, MODE>(sm, io, lc, row, B);
+        hb_cluster_sync(); // a sibling may still be reading this CTA's shared memory
+    } else {
+        inv_pass<LOGN, T, P, MODE>(sm, io, lc, row, B);
+        if constexpr (P + 1 < pl.npass) {
+            if constexpr (pl.xchg && P + 2 == pl.npass) {
+                // the cluster barrier in front of the cross pass orders this CTA's stores too
+            } else if constexpr (P == 0 && warp_local_pair(inv_k(pl, 0), inv_k(pl, 1))) {
+                hb_syncwarp();
+            } else {
+                __syncthreads();
+            }
+            inv_passes<LOGN, T, P + 1, MODE>(sm, io, lc, row, B);
         }
-        inv_passes<LOGN, T, P + 1, MODE>(sm, io, lc, row, B);
     }
 }
 
@@ -352,7 +456,7 @@ intt_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     const LimbConst lc = limbs[io.limb(row)];
     hb_pdl_wait();
     inv_passes<LOGN, T, 0, MODE>(sm, io, lc, row, B);
-    if constexpr (pl.lpre == 1) {
+    if constexpr (pl.lpre == 1 && !pl.xchg) {
         // Last stage (gap N/2) pairs word i of CTA 0 with word i of CTA 1 — ntt.cpp:199-206.  Each CTA
         // takes half of the offsets, reads its own words from shared memory and the sibling's through
         // distributed shared memory, and finishes BOTH outputs of every pair (approximate reduction and
@@ -488,8 +592,8 @@ inline cudaError_t launch_fast_mode(const LaunchEnv &env, const IO &io, const Li
         configured.record(env.device, smem);
     }
     env.stats->launches++;
-    if constexpr (pl.lpre == 1) {
-        return HB_LAUNCH_CLUSTER(kern, (unsigned)(rows << 1), pl.threads, smem, env.stream, 2, io, limbs);
+    if constexpr (pl.lpre >= 1) {
+        return HB_LAUNCH_CLUSTER(kern, (unsigned)(rows << pl.lpre), pl.threads, smem, env.stream, 1 << pl.lpre, io, limbs);
     } else {
         HB_LAUNCH(kern, rows, pl.threads, smem, env.stream, 1, io, limbs);
         return cudaGetLastError();
@@ -500,7 +604,11 @@ inline cudaError_t launch_fast_mode(const LaunchEnv &env, const IO &io, const Li
 template <int LOGN, bool FWD, class IO>
 inline cudaError_t launch_fast(const LaunchEnv &env, const IO &io, const LimbConst *limbs, int rows) {
     if constexpr (has_latency_plan(LOGN)) {
-        if (rows <= env.latency_rows) return launch_fast_mode<LOGN, FWD, 1>(env, io, limbs, rows);
+        // N <= 8192: up to latency_rows rows (default half the SM count).  N >= 16384, forward: the 8-CTA plan keeps paying
+        // while the launch is up to ~2 waves of its CTAs (finer grain: less of the last wave idles); inverse (it needs its
+        // registers: one CTA per SM): while the row count fits one wave (profiles/r3_latency_plans.log).
+        const long long limit = LOGN <= 13 ? env.latency_rows : (FWD ? 2ll * env.latency_rows : env.latency_rows / 4);
+        if (rows <= limit) return launch_fast_mode<LOGN, FWD, 1>(env, io, limbs, rows);
     }
     return launch_fast_mode<LOGN, FWD, 0>(env, io, limbs, rows);
 }

@@ -1,13 +1,22 @@
 // ntt_plan.h — compile-time decomposition of an N-point negacyclic NTT into register-resident
 // passes, shared by the device kernels (ntt_engine.cuh) and the host table builder (tables.cu).
 //
-// A row of N = 2^logn coefficients is processed by 2^lpre CTAs, each owning NC = N >> lpre
-// coefficients in shared memory.  The logn - lpre CTA-local butterfly levels are split into
-// `npass` passes; in pass p every thread keeps 2^k[p] coefficients in registers and runs k[p]
-// levels on them before the CTA exchanges through shared memory.  The forward transform runs
-// the passes in the listed order (gaps shrink N/2 -> 1, last pass touches contiguous
-// coefficients); the inverse transform runs the mirrored list (gaps grow 1 -> N/2).  The two directions
-// have separate tables and may use different plans.
+// A row of N = 2^logn coefficients is processed by 2^lpre CTAs (a thread-block cluster when lpre > 0), each
+// owning NC = N >> lpre coefficients in shared memory.  The butterfly levels are split into `npass` passes; in
+// pass p every thread keeps 2^k[p] coefficients in registers and runs k[p] levels on them before the CTA
+// exchanges through shared memory.  The forward transform runs the passes in the listed order (gaps shrink
+// N/2 -> 1, last pass touches contiguous coefficients); the inverse transform runs the mirrored list (gaps grow
+// 1 -> N/2).  The two directions have separate tables and may use different plans.
+//
+// How the lpre levels that pair words of different CTAs are done (`xchg`):
+//   xchg = 0  (lpre <= 1) the level is not part of the pass list.  Forward: both CTAs read the whole row and each
+//             computes its half of level 1 (one extra multiply per word); inverse: a finishing stage pulls the
+//             sibling's words through distributed shared memory.
+//   xchg = 1  the cross-CTA levels are the leading levels of k[0], a pass of the FULL row that the CTAs of the
+//             cluster share (each takes 1/2^lpre of its butterfly groups).  Forward: the pass reads global memory
+//             and scatters each result into the shared memory of the CTA that owns it (st.shared::cluster);
+//             inverse (mirrored: the last pass) gathers its operands from the owners' shared memory
+//             (ld.shared::cluster), finishes the words and stores them.  No level is computed twice.
 //
 // The twiddle tables are laid out per pass as [slot][block] so that the lanes of a warp read
 // consecutive 16-byte (w, w') pairs in every pass (see tables.cu).
@@ -25,62 +34,95 @@ struct NttPlan {
     int k[kMaxPasses];
     int threads; // CTA size
     int min_blocks;
+    int xchg;    // see above
 };
 
 constexpr int kFastLogMin = 10;
 constexpr int kFastLogMax = 15;
 constexpr int kGenericLogMax = 14; // one row must fit one CTA's shared memory
 
-// Latency plans: when a launch has fewer rows than half the SMs, a row of N = 4096 / 8192 is split over a 2-CTA
-// cluster (half a row per CTA, each on its own SM) — the level the two CTAs share is computed twice, which costs
-// nothing on an otherwise idle GPU, and the row's critical path halves.  N >= 16384 already runs as clusters.
-HB_CX bool has_latency_plan(int logn) { return logn == 12 || logn == 13; }
+// Latency plans: when a launch has few rows (a single ciphertext, a key), a row is split over more CTAs than the
+// throughput plan uses, each on its own SM, so the row's critical path shrinks while the GPU would otherwise idle.
+// N = 4096 / 8192: a 2-CTA cluster (half a row per CTA; the level the two share is computed twice, which costs nothing
+// on an idle GPU).  N = 16384 / 32768: an 8-CTA cluster that exchanges through distributed shared memory
+// (4096 / 2048 words per CTA: a single N = 32768 row takes ~1/4 of the time of the 2-CTA form).
+HB_CX bool has_latency_plan(int logn) { return logn >= 12 && logn <= 15; }
+
+#ifndef HB_PLAN14
+#define HB_PLAN14 3
+#endif
+#ifndef HB_PLAN15
+#define HB_PLAN15 2
+#endif
 
 HB_CX NttPlan plan_for(int logn, bool fwd, int mode = 0) {
-    if (mode == 1 && logn == 12) return NttPlan{12, 1, 3, {3, 4, 4, 0, 0}, 128, 1};
-    if (mode == 1 && logn == 13) return NttPlan{13, 1, 3, {4, 4, 4, 0, 0}, 256, 1};
-    // Measured on B200 (profiles/r1_plan_sweep.md).  Passes of 4-5 levels keep 16-32 words per thread
-    // in registers; ending with two passes of equal width keeps their exchange inside a warp.
+    if (mode == 1 && logn == 12) return NttPlan{12, 1, 3, {3, 4, 4, 0, 0}, 128, 1, 0};
+    if (mode == 1 && logn == 13) return NttPlan{13, 1, 3, {4, 4, 4, 0, 0}, 256, 1, 0};
+    // 80 registers (three 256-thread CTAs per SM): launches of up to ~2 waves of such CTAs still gain from the finer grain
+    // (C5: one pair per call 164 -> 148 us, two per call 115 -> 108 us/ct; profiles/r3_latency_plans.log)
+    if (mode == 1 && logn == 14) return NttPlan{14, 3, 4, {4, 3, 3, 4, 0}, 128, fwd ? 6 : 2, 1};
+    if (mode == 1 && logn == 15) return NttPlan{15, 3, 4, {4, 4, 3, 4, 0}, 256, fwd ? 3 : 1, 1};
+    // Measured on B200 (profiles/r1_plan_sweep.md, profiles/r3_cluster_plans.md).  Passes of 3-5 levels keep 8-32 words
+    // per thread in registers; ending with two passes of equal width keeps their exchange inside a warp.
     switch (logn) {
-    case 10: return NttPlan{10, 0, 3, {3, 3, 4, 0, 0}, 64, 8};
+    case 10: return NttPlan{10, 0, 3, {3, 3, 4, 0, 0}, 64, 8, 0};
 #if defined(HB_PLAN11) && HB_PLAN11 == 1
-    case 11: return NttPlan{11, 0, 3, {4, 3, 4, 0, 0}, 128, 6};
+    case 11: return NttPlan{11, 0, 3, {4, 3, 4, 0, 0}, 128, 6, 0};
 #else
-    case 11: return NttPlan{11, 0, 3, {3, 4, 4, 0, 0}, 128, 6};
+    case 11: return NttPlan{11, 0, 3, {3, 4, 4, 0, 0}, 128, 6, 0};
 #endif
-    case 12: return NttPlan{12, 0, 3, {4, 4, 4, 0, 0}, 256, 3};
+    case 12: return NttPlan{12, 0, 3, {4, 4, 4, 0, 0}, 256, 3, 0};
 #if defined(HB_PLAN13) && HB_PLAN13 == 0
-    case 13: return NttPlan{13, 0, 3, {5, 4, 4, 0, 0}, 256, 2};
+    case 13: return NttPlan{13, 0, 3, {5, 4, 4, 0, 0}, 256, 2, 0};
 #else // forward: four narrower passes and three CTAs per SM (+2 %, more for the fused kernels); the inverse loses 3 % with it
     // (inverse {4,5,4}: +0.7 % over {5,4,4}, profiles/r2n_plan13_inverse_ab.log)
-    case 13: return fwd ? NttPlan{13, 0, 4, {3, 3, 3, 4, 0}, 256, 3} : NttPlan{13, 0, 3, {4, 5, 4, 0, 0}, 256, 2};
+    case 13: return fwd ? NttPlan{13, 0, 4, {3, 3, 3, 4, 0}, 256, 3, 0} : NttPlan{13, 0, 3, {4, 5, 4, 0, 0}, 256, 2, 0};
 #endif
-#if defined(HB_PLAN14) && HB_PLAN14 == 0 // one CTA per row: nothing else shares the SM, load/compute/store phases do not overlap
-    case 14: return NttPlan{14, 0, 3, {5, 5, 4, 0, 0}, 512, 1};
-#elif defined(HB_PLAN14) && HB_PLAN14 == 1 // 2-CTA cluster per row, half a row per CTA, two CTAs per SM (+5 % over one CTA per row)
-    case 14: return NttPlan{14, 1, 3, {5, 4, 4, 0, 0}, 256, 2};
-#else // cluster form with four narrower passes: three CTAs (of up to three different rows) per SM, another +2-4 %
-    case 14: return NttPlan{14, 1, 4, {3, 3, 3, 4, 0}, 256, 3}; // inverse {4,5,4} / {5,4,4} x2: -4 % / -2 % (profiles/r2n_plan14_15_inverse_ab.log)
+#if HB_PLAN14 == 0 // one CTA per row: nothing else shares the SM, load/compute/store phases do not overlap
+    case 14: return NttPlan{14, 0, 3, {5, 5, 4, 0, 0}, 512, 1, 0};
+#elif HB_PLAN14 == 1 // 2-CTA cluster per row, half a row per CTA, two CTAs per SM (+5 % over one CTA per row)
+    case 14: return NttPlan{14, 1, 3, {5, 4, 4, 0, 0}, 256, 2, 0};
+#elif HB_PLAN14 == 2 // the same with four narrower passes: three CTAs (of up to three different rows) per SM, another +2-4 %; level 1 twice
+    case 14: return NttPlan{14, 1, 4, {3, 3, 3, 4, 0}, 256, 3, 0}; // inverse {4,5,4} / {5,4,4} x2: -4 % / -2 % (profiles/r2n_plan14_15_inverse_ab.log)
+#elif HB_PLAN14 == 3 // 2-CTA cluster exchanging through distributed shared memory: no level twice
+    case 14: return NttPlan{14, 1, 4, {3, 3, 4, 4, 0}, 256, 3, 1};
+#else // 4-CTA cluster, a quarter row per CTA
+    case 14: return NttPlan{14, 2, 4, {3, 3, 4, 4, 0}, 256, 3, 1};
 #endif
-#if defined(HB_PLAN15) && HB_PLAN15 == 0 // 16 warps per CTA (one CTA per SM): too few to hide the fused epilogues' loads
-    default: return NttPlan{15, 1, 4, {4, 3, 3, 4, 0}, 512, 1};
-#else // 32 warps per CTA at 64 registers: C5 rescale -11 %, mult+relin -1.6 % (profiles/r1_plan_sweep.md)
-    default: return NttPlan{15, 1, 4, {3, 3, 4, 4, 0}, 1024, 1};
+#if HB_PLAN15 == 0 // 2-CTA cluster, 16 warps per CTA (one CTA per SM): too few to hide the fused epilogues' loads
+    default: return NttPlan{15, 1, 4, {4, 3, 3, 4, 0}, 512, 1, 0};
+#elif HB_PLAN15 == 1 // 32 warps per CTA at 64 registers: C5 rescale -11 %, mult+relin -1.6 % (profiles/r1_plan_sweep.md); level 1 twice
+    default: return NttPlan{15, 1, 4, {3, 3, 4, 4, 0}, 1024, 1, 0};
+#elif HB_PLAN15 == 2 // 4-CTA cluster exchanging through distributed shared memory: a quarter row (72 KB) per CTA, three CTAs of
+      // different rows per SM so their load / compute / store phases overlap, and no level is computed twice
+    // forward {3,4,4,4}: +1 % over {4,3,4,4}; the inverse prefers the wider cross pass (more loads in flight per thread): +5 %
+    default: return fwd ? NttPlan{15, 2, 4, {3, 4, 4, 4, 0}, 256, 3, 1} : NttPlan{15, 2, 4, {4, 3, 4, 4, 0}, 256, 3, 1};
+#elif HB_PLAN15 == 3
+    default: return NttPlan{15, 2, 4, {3, 4, 4, 4, 0}, 256, 3, 1};
+#elif HB_PLAN15 == 4 // 2-CTA cluster, exchanging instead of recomputing
+    default: return NttPlan{15, 1, 4, {3, 4, 4, 4, 0}, 1024, 1, 1};
+#else // 8-CTA cluster, 4096 words per CTA
+    default: return NttPlan{15, 3, 4, {4, 4, 3, 4, 0}, 256, 3, 1};
 #endif
     }
 }
 
+// CTAs per row
+HB_CX int plan_cluster(const NttPlan &pl) { return 1 << pl.lpre; }
+
 // ---- forward layout --------------------------------------------------------------------
-// local levels completed before CTA pass p
-HB_CX int fwd_lambda0(const NttPlan &pl, int p) {
-    int s = 0;
+// levels of the full row completed before pass p
+HB_CX int fwd_glevel0(const NttPlan &pl, int p) {
+    int s = pl.xchg ? 0 : pl.lpre;
     for (int i = 0; i < p; i++) s += pl.k[i];
     return s;
 }
-// entry offset of CTA pass p in the forward table: the lpre pre-level (one entry, T[1]) first
+// CTA-local levels completed before pass p (p >= 1 when the plan exchanges)
+HB_CX int fwd_lambda0(const NttPlan &pl, int p) { return fwd_glevel0(pl, p) - pl.lpre; }
+// entry offset of pass p in the forward table (xchg = 0: the pre-level's one entry, T[1], comes first)
 HB_CX int fwd_pass_offset(const NttPlan &pl, int p) {
-    int off = pl.lpre ? 1 : 0;
-    for (int i = 0; i < p; i++) off += ((1 << pl.k[i]) - 1) << (pl.lpre + fwd_lambda0(pl, i));
+    int off = (pl.lpre && !pl.xchg) ? 1 : 0;
+    for (int i = 0; i < p; i++) off += ((1 << pl.k[i]) - 1) << fwd_glevel0(pl, i);
     return off;
 }
 

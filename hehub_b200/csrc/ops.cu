@@ -107,17 +107,46 @@ int op_ckks_tensor(Context &c, unsigned logn, const u64 *moduli, size_t L, const
 }
 
 // ------------------------------------------------------------------------------------------
+// Galois automorphisms on NTT-form rows (permutation.cpp:28-75).  Slot j holds the evaluation at psi^(2*brev(j)+1); X -> X^g
+// moves root index e to e*g, so output slot j gathers from the slot whose root index is e_j * g^{-1} (mod 2N).  Two
+// properties make the gather cheap enough to fuse into whatever reads the row: slots j and j^1 gather from slots f and f^1
+// (their root indices differ by N, and g^{-1} is odd), so 128-bit accesses survive as "load the aligned pair, maybe swap";
+// and an aligned block of 2^m output slots gathers from ONE aligned block of 2^m input slots, so the gather touches the same
+// cache lines a linear read would.  ginv == 1 is the identity.
+// ------------------------------------------------------------------------------------------
+HB_D unsigned galois_from(unsigned j, unsigned ginv, int logn) {
+    const unsigned mask = (2u << logn) - 1;
+    const unsigned e = 2 * (__brev(j) >> (32 - logn)) + 1;
+    const unsigned src_e = (e * ginv) & mask;
+    return __brev((src_e - 1) >> 1) >> (32 - logn);
+}
+// words (j, j + 1), j even, of the permuted row
+HB_D ulonglong2 galois_pair(const u64 *row_words, unsigned j, unsigned ginv, int logn, bool read_only) {
+    const unsigned f = galois_from(j, ginv, logn);
+    const u64 *p = row_words + (f & ~1u);
+    const ulonglong2 v = read_only ? hb_ld_ro2(p) : hb_ld_stream2(p);
+    return (f & 1u) ? make_ulonglong2(v.y, v.x) : v;
+}
+
+// ------------------------------------------------------------------------------------------
 // key switch (ext_prod_montgomery)
 // ------------------------------------------------------------------------------------------
 // step 1: c[b][p] = strict(INTT_{q_p}(in[b][p]))                     rgsw.cpp:103-105
+template <bool GALOIS> // GALOIS: separate instantiation so the plain key switch compiles exactly as without the gather
 struct ExtInttIO {
     const u64 *in;
     size_t in_batch_stride;
     u64 *c; // [batch][L][N]
     int L, logn;
     bool vec;
+    unsigned ginv; // GALOIS: the input rows are read through the Galois permutation (ckks::rotate / conjugate, ckks/arith.cpp:75-93)
     HB_D int limb(int row) const { return row % L; }
     HB_D const u64 *src(int row) const { return in + (size_t)(row / L) * in_batch_stride + ((size_t)(row % L) << logn); }
+    // fetch / fetch2 (ntt_engine.cuh) exist only in the GALOIS instantiation
+    template <bool G = GALOIS, class = std::enable_if_t<G>>
+    HB_D u64 fetch(int row, int i) const { return hb_ld_stream(src(row) + galois_from((unsigned)i, ginv, logn)); }
+    template <bool G = GALOIS, class = std::enable_if_t<G>>
+    HB_D ulonglong2 fetch2(int row, int i) const { return galois_pair(src(row), (unsigned)i, ginv, logn, false); }
     HB_D u64 pre(int, int, u64 raw, const LimbConst &) const { return raw; }
     HB_D void store(int row, int i, u64 v, const LimbConst &lc) const { c[((size_t)row << logn) + i] = reduce_strict(v, lc.q); }
     HB_D void store2(int row, int i, u64 v0, u64 v1, const LimbConst &lc) const {
@@ -167,11 +196,11 @@ struct ExtFanoutIO {
 // W = 1 for slabs that are only 8-byte aligned) of one limb of CPT consecutive ciphertexts, so a
 // key word fetched from L2 feeds CPT products: the key stream (2 L (L+1) N words per ciphertext,
 // more than every other operand together) is what bounds this kernel.
-template <int CPT, int W>
+template <int CPT, int W, bool GALOIS>
 HB_GLOBAL(256, HB_MAC_MINB)
 ext_mac_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
                u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, int logn, size_t batch, size_t total,
-               unsigned groups, unsigned chunks_per_group) {
+               unsigned groups, unsigned chunks_per_group, unsigned ginv) {
     hb_pdl_wait();
     // gid = (b / CPT, k, i / W).  With `groups` != 0 consecutive CTAs take the SAME 256-thread slice of
     // (k, i) for consecutive ciphertext groups, so CTAs resident together share their key words in L2
@@ -212,7 +241,21 @@ ext_mac_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__
                 for (int c = 0; c < CPT; c++) {
                     if (b0 + c < batch) { // the diagonal keeps in[p], rgsw.cpp:99-101
                         const u64 *src = (p == k) ? in_b + c * in_batch_stride + ((size_t)p << logn) : dec_k + c * dec_ct + p * dec_row;
+                        bool swap = false;
+                        if (GALOIS && p == k) { // ... read through the Galois permutation when the key switch carries one:
+                            // same load instruction, another address (and the two words of an aligned pair possibly swapped)
+                            const unsigned f = galois_from((unsigned)i, ginv, logn);
+                            src += (ptrdiff_t)(W == 2 ? (f & ~1u) : f) - (ptrdiff_t)i;
+                            swap = W == 2 && (f & 1u);
+                        }
                         ld_words<W>(d[u][c], src, false);
+                        if constexpr (GALOIS && W == 2) {
+                            if (swap) {
+                                const u64 t = d[u][c][0];
+                                d[u][c][0] = d[u][c][1];
+                                d[u][c][1] = t;
+                            }
+                        }
                     } else {
 #pragma unroll
                         for (int w = 0; w < W; w++) d[u][c][w] = 0;
@@ -250,26 +293,31 @@ ext_mac_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__
 
 // one wave of at most `wave` ciphertexts; scratch slots 0 (c) and 1 (dec)
 static int ext_prod_wave(Context &c, unsigned logn, const LimbConst *limbs, size_t L, const u64 *in, size_t in_batch_stride,
-                         const u64 *key, u64 *out, size_t batch, u64 *cbuf, u64 *dec) {
+                         const u64 *key, u64 *out, size_t batch, u64 *cbuf, u64 *dec, unsigned ginv) {
     const size_t n = (size_t)1 << logn;
-    ExtInttIO io1{in, in_batch_stride, cbuf, (int)L, (int)logn, aligned16(in) && (in_batch_stride % 2 == 0) && aligned16(cbuf)};
-    cudaError_t e = launch_ntt<false>(c.env(), logn, io1, limbs, (int)(batch * L));
+    const bool vec1 = aligned16(in) && (in_batch_stride % 2 == 0) && aligned16(cbuf);
+    cudaError_t e;
+    if (ginv == 1) e = launch_ntt<false>(c.env(), logn, ExtInttIO<false>{in, in_batch_stride, cbuf, (int)L, (int)logn, vec1, 1u}, limbs, (int)(batch * L));
+    else e = launch_ntt<false>(c.env(), logn, ExtInttIO<true>{in, in_batch_stride, cbuf, (int)L, (int)logn, vec1, ginv}, limbs, (int)(batch * L));
     if (e != cudaSuccess) return c.cuda_fail(e, "ext_prod: intt launch");
     ExtFanoutIO io2{cbuf, dec, (int)L, (int)logn, aligned16(cbuf) && aligned16(dec)};
     e = launch_ntt<true>(c.env(), logn, io2, limbs, (int)(batch * L * L));
     if (e != cudaSuccess) return c.cuda_fail(e, "ext_prod: ntt launch");
     constexpr int CPT = HB_MAC_CPT;
     const size_t groups = (batch + CPT - 1) / CPT;
-    if (aligned16(in) && in_batch_stride % 2 == 0 && aligned16(dec) && aligned16(key) && aligned16(out) && n >= 2) {
-        const size_t total = groups * (L + 1) * (n / 2), per_group = (L + 1) * (n / 2);
-        const bool inter = per_group % 256 == 0 && groups > 1;
-        HB_LAUNCH((ext_mac_kernel<CPT, 2>), (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, in_batch_stride, dec, key, out,
-                  limbs, (int)L, (int)logn, batch, total, inter ? (unsigned)groups : 0u, (unsigned)(per_group / 256));
+    const bool vec = aligned16(in) && in_batch_stride % 2 == 0 && aligned16(dec) && aligned16(key) && aligned16(out) && n >= 2;
+    const size_t per_group = (L + 1) * (vec ? n / 2 : n), total = groups * per_group;
+    const bool inter = per_group % 256 == 0 && groups > 1;
+    auto launch_mac = [&](auto kern) {
+        HB_LAUNCH(kern, (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, in_batch_stride, dec, key, out, limbs, (int)L, (int)logn,
+                  batch, total, inter ? (unsigned)groups : 0u, (unsigned)(per_group / 256), ginv);
+    };
+    if (vec) {
+        if (ginv == 1) launch_mac(ext_mac_kernel<CPT, 2, false>);
+        else launch_mac(ext_mac_kernel<CPT, 2, true>);
     } else {
-        const size_t total = groups * (L + 1) * n, per_group = (L + 1) * n;
-        const bool inter = per_group % 256 == 0 && groups > 1;
-        HB_LAUNCH((ext_mac_kernel<CPT, 1>), (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, in_batch_stride, dec, key, out,
-                  limbs, (int)L, (int)logn, batch, total, inter ? (unsigned)groups : 0u, (unsigned)(per_group / 256));
+        if (ginv == 1) launch_mac(ext_mac_kernel<CPT, 1, false>);
+        else launch_mac(ext_mac_kernel<CPT, 1, true>);
     }
     c.stats.launches++;
     e = cudaGetLastError();
@@ -293,7 +341,7 @@ static size_t wave_size(const Context &c, size_t words_per_ct, size_t batch, siz
 }
 
 int op_ext_prod(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *in, size_t in_batch_stride,
-                const u64 *key, u64 *out, size_t batch) {
+                const u64 *key, u64 *out, size_t batch, unsigned ginv) {
     if (!ext_moduli || !in || !key || !out) return c.fail(1, "null operand");
     if (L == 0) return c.fail(1, "Empty RGSW ciphertext."); // rgsw.cpp:59-61
     if (batch == 0) return 0;
@@ -312,7 +360,7 @@ int op_ext_prod(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, cons
     for (size_t b0 = 0; b0 < batch; b0 += wave) {
         const size_t nb = (batch - b0 < wave) ? batch - b0 : wave;
         if (int rc = ext_prod_wave(c, logn, limbs, L, in + b0 * in_batch_stride, in_batch_stride, key, out + b0 * 2 * (L + 1) * n,
-                                   nb, cbuf, dec))
+                                   nb, cbuf, dec, ginv))
             return rc;
     }
     return 0;
@@ -346,7 +394,7 @@ struct DropInttIO {
 };
 
 // step 2: per remaining limb k: r = centre(barrett(z)); NTT; out = H(lazy_sub(ct, r), q_last^{-1}) [...]
-template <bool BGV>
+template <bool BGV, bool GALOIS = false>
 struct DropFwdIO {
     const u64 *ct;
     const u64 *z;
@@ -357,6 +405,7 @@ struct DropFwdIO {
     u64 half_qlast;
     int L, logn, add_halves;
     bool vec;
+    unsigned add_ginv; // GALOIS: the addend is read through the Galois permutation (the c0 of ckks::rotate / conjugate)
     HB_D int limb(int row) const { return row % (L - 1); }
     HB_D const u64 *src(int row) const { return z + ((size_t)(row / (L - 1)) << logn); }
     HB_D u64 pre(int row, int, u64 zz, const LimbConst &lc) const {
@@ -374,8 +423,10 @@ struct DropFwdIO {
         const DropConst *d = dc + k;
         u64 x = finish(hb_ld_ro(ct + ((size_t)(poly * L + k) << logn) + i), v, d, lc);
         const int h = poly & 1, b = poly >> 1;
-        if (h < add_halves) // ckks/arith.cpp:70-71, 84, 91
-            x = add_lazy(x, hb_ld_ro(addend + (size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn) + i), lc.q2);
+        if (h < add_halves) { // ckks/arith.cpp:70-71, 84, 91
+            const unsigned from = GALOIS ? galois_from((unsigned)i, add_ginv, logn) : (unsigned)i;
+            x = add_lazy(x, hb_ld_ro(addend + (size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn) + from), lc.q2);
+        }
         out[((size_t)row << logn) + i] = x;
     }
     // the epilogue's operands (this row of ct and of the addend) are first touched ~10 us after the CTA
@@ -386,7 +437,9 @@ struct DropFwdIO {
         for (int w = (int)threadIdx.x * 16; w < nwords; w += (int)blockDim.x * 16) hb_prefetch_l2(c + w);
         const int h = poly & 1, b = poly >> 1;
         if (h < add_halves) {
-            const u64 *a = addend + (size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn) + first_word;
+            // an aligned block of output slots gathers from one aligned block of the same size (galois_from)
+            const unsigned from_block = GALOIS ? (galois_from((unsigned)first_word, add_ginv, logn) & ~(unsigned)(nwords - 1)) : (unsigned)first_word;
+            const u64 *a = addend + (size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn) + from_block;
             for (int w = (int)threadIdx.x * 16; w < nwords; w += (int)blockDim.x * 16) hb_prefetch_l2(a + w);
         }
     }
@@ -403,7 +456,8 @@ struct DropFwdIO {
         ulonglong2 r = make_ulonglong2(finish(x.x, v0, d, lc), finish(x.y, v1, d, lc));
         const int h = poly & 1, b = poly >> 1;
         if (h < add_halves) { // ckks/arith.cpp:70-71, 84, 91
-            const ulonglong2 a = hb_ld_ro2(addend + (size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn) + i);
+            const u64 *arow = addend + (size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn);
+            const ulonglong2 a = GALOIS ? galois_pair(arow, (unsigned)i, add_ginv, logn, true) : hb_ld_ro2(arow + i);
             r.x = add_lazy(r.x, a.x, lc.q2);
             r.y = add_lazy(r.y, a.y, lc.q2);
         }
@@ -412,7 +466,7 @@ struct DropFwdIO {
 };
 
 int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, const u64 *ct, u64 *out, size_t batch,
-                 const u64 *addend, size_t add_batch_stride, size_t add_poly_stride, int add_halves) {
+                 const u64 *addend, size_t add_batch_stride, size_t add_poly_stride, int add_halves, unsigned add_ginv) {
     if (!moduli || !ct || !out) return c.fail(1, "null operand");
     if (L < 2) return c.fail(1, "Unable to drop the only one prime.");
     if (batch == 0) return 0;
@@ -435,18 +489,25 @@ int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, 
         u64 *out_w = out + b0 * 2 * (L - 1) * n;
         const u64 *add_w = addend ? addend + b0 * add_batch_stride : nullptr;
         cudaError_t e;
+        const int rows2 = (int)(nb * 2 * (L - 1));
         if (t) {
             DropInttIO<true> io1{ct_w, z, (int)L, (int)logn, ds->inv_t, ds->inv_t_h, aligned16(ct) && aligned16(z)};
             e = launch_ntt<false>(c.env(), logn, io1, limbs, (int)(nb * 2));
             if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: intt launch");
-            DropFwdIO<true> io2{ct_w, z, out_w, ds->dev, add_w, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, halves, vec};
-            e = launch_ntt<true>(c.env(), logn, io2, limbs, (int)(nb * 2 * (L - 1)));
+            if (add_ginv != 1) return c.fail(1, "a Galois-permuted addend is a CKKS path (ckks/arith.cpp:75-93)");
+            DropFwdIO<true> io2{ct_w, z, out_w, ds->dev, add_w, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, halves, vec, 1u};
+            e = launch_ntt<true>(c.env(), logn, io2, limbs, rows2);
         } else {
             DropInttIO<false> io1{ct_w, z, (int)L, (int)logn, 0, 0, aligned16(ct) && aligned16(z)};
             e = launch_ntt<false>(c.env(), logn, io1, limbs, (int)(nb * 2));
             if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: intt launch");
-            DropFwdIO<false> io2{ct_w, z, out_w, ds->dev, add_w, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, halves, vec};
-            e = launch_ntt<true>(c.env(), logn, io2, limbs, (int)(nb * 2 * (L - 1)));
+            if (add_ginv == 1) {
+                DropFwdIO<false> io2{ct_w, z, out_w, ds->dev, add_w, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, halves, vec, 1u};
+                e = launch_ntt<true>(c.env(), logn, io2, limbs, rows2);
+            } else {
+                DropFwdIO<false, true> io2{ct_w, z, out_w, ds->dev, add_w, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, halves, vec, add_ginv};
+                e = launch_ntt<true>(c.env(), logn, io2, limbs, rows2);
+            }
         }
         if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: ntt launch");
     }
@@ -817,11 +878,7 @@ galois_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, int logn, unsig
     if (gid >= total) return;
     const unsigned n = 1u << logn, j = (unsigned)(gid & (n - 1));
     const size_t row = gid >> logn;
-    const unsigned mask = 2 * n - 1;
-    const unsigned e = 2 * (__brev(j) >> (32 - logn)) + 1;
-    const unsigned src_e = (e * ginv) & mask;
-    const unsigned from = __brev((src_e - 1) >> 1) >> (32 - logn);
-    out[(row << logn) + j] = in[(row << logn) + from];
+    out[(row << logn) + j] = in[(row << logn) + galois_from(j, ginv, logn)];
 }
 
 static unsigned galois_inverse_factor(unsigned logn, bool conj, size_t step) {
@@ -847,26 +904,35 @@ int op_galois(Context &c, unsigned logn, size_t L, const u64 *in, u64 *out, bool
     return e == cudaSuccess ? 0 : c.cuda_fail(e, "galois launch");
 }
 
-// ckks::rotate / ckks::conjugate — ckks/arith.cpp:75-93: permute both polynomials, key-switch the
-// permuted c1, drop P, add the permuted c0 to the first half only.
+// ckks::rotate / ckks::conjugate — ckks/arith.cpp:75-93: permute both polynomials, key-switch the permuted c1, drop P, add the
+// permuted c0 to the first half only.  Neither permuted polynomial is materialised: the key switch's inverse transforms (and
+// the diagonal term of its inner product) read c1 through the permutation, and the drop's epilogue reads c0 through it, so a
+// rotation costs what a relinearisation costs.
 int op_galois_keyswitch(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *ct, const u64 *key, bool conj,
                         size_t step, u64 *out, size_t batch) {
     if (!ext_moduli || !ct || !key || !out) return c.fail(1, "null operand");
     if (L == 0) return c.fail(1, "Empty RGSW ciphertext.");
     if (batch == 0) return 0;
     const size_t n = (size_t)1 << logn;
-    const size_t per_ct = (2 * L + L + L * (L + 1) + 2 * (L + 1) + 2) * n;
+    const unsigned ginv = galois_inverse_factor(logn, conj, step);
+    const bool in_place = ct == out; // the epilogue gathers c0 while `out` is written: work from a copy of the wave then
+    const size_t per_ct = ((in_place ? 2 * L : 0) + L + L * (L + 1) + 2 * (L + 1) + 2) * n;
     const size_t wave = wave_size(c, per_ct, batch, L * (L + 1));
     int err = 0;
-    u64 *rot = c.get_scratch(5, wave * 2 * L * n, &err);
-    if (!rot) return err;
     u64 *ebuf = c.get_scratch(3, wave * 2 * (L + 1) * n, &err);
     if (!ebuf) return err;
+    u64 *copy = in_place ? c.get_scratch(5, wave * 2 * L * n, &err) : nullptr;
+    if (in_place && !copy) return err;
     for (size_t b0 = 0; b0 < batch; b0 += wave) {
         const size_t nb = (batch - b0 < wave) ? batch - b0 : wave;
-        if (int rc = op_galois(c, logn, 2 * L, ct + b0 * 2 * L * n, rot, conj, step, nb)) return rc;
-        if (int rc = op_ext_prod(c, logn, ext_moduli, L, rot + L * n, 2 * L * n, key, ebuf, nb)) return rc;
-        if (int rc = op_drop_last(c, logn, ext_moduli, L + 1, 0, ebuf, out + b0 * 2 * L * n, nb, rot, 2 * L * n, L * n, 1)) return rc;
+        const u64 *ct_w = ct + b0 * 2 * L * n;
+        if (in_place) {
+            cudaError_t e = cudaMemcpyAsync(copy, ct_w, nb * 2 * L * n * 8, cudaMemcpyDeviceToDevice, c.stream);
+            if (e != cudaSuccess) return c.cuda_fail(e, "rotate: copy");
+            ct_w = copy;
+        }
+        if (int rc = op_ext_prod(c, logn, ext_moduli, L, ct_w + L * n, 2 * L * n, key, ebuf, nb, ginv)) return rc;
+        if (int rc = op_drop_last(c, logn, ext_moduli, L + 1, 0, ebuf, out + b0 * 2 * L * n, nb, ct_w, 2 * L * n, L * n, 1, ginv)) return rc;
     }
     return 0;
 }

@@ -186,9 +186,9 @@ const ModTables *Context::get_tables(u64 q, unsigned logn, int *err) {
     // pass-major / slot-major layouts of one plan pair (forward, inverse) — see ntt_plan.h
     auto fill_plan_tables = [&](ulonglong2 *ff, ulonglong2 *fi, int mode) {
         NttPlan pl = plan_for((int)logn, true, mode);
-        if (pl.lpre) ff[0] = fwd_nat[1];
+        if (pl.lpre && !pl.xchg) ff[0] = fwd_nat[1];
         for (int p = 0; p < pl.npass; p++) {
-            const int K = pl.k[p], l0g = pl.lpre + fwd_lambda0(pl, p), off = fwd_pass_offset(pl, p);
+            const int K = pl.k[p], l0g = fwd_glevel0(pl, p), off = fwd_pass_offset(pl, p);
             for (int m = 1; m <= K; m++)
                 for (int blk = 0; blk < (1 << (m - 1)); blk++) {
                     const int slot = (1 << (m - 1)) - 1 + blk;
@@ -198,7 +198,7 @@ const ModTables *Context::get_tables(u64 q, unsigned logn, int *err) {
         }
         pl = plan_for((int)logn, false, mode);
         for (int p = 0; p <= pl.npass; p++) {
-            if (p == pl.npass && !pl.lpre) break;
+            if (p == pl.npass && (!pl.lpre || pl.xchg)) break;
             const int K = (p == pl.npass) ? 1 : inv_k(pl, p);
             const int S0 = (p == pl.npass) ? (int)logn - 1 : inv_s0(pl, p), off = inv_pass_offset(pl, p);
             for (int m = 1; m <= K; m++)

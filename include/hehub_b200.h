@@ -229,6 +229,43 @@ int hehub_b200_ckks_mult_relin_host(hehub_b200_ctx *ctx, unsigned logn, const ui
 int hehub_b200_lcg_fill(hehub_b200_ctx *ctx, size_t n, const uint64_t *moduli, size_t L, uint64_t *x,
                         size_t rows, uint64_t seed0, uint64_t seed_stride);
 
+/* ---- batched-ciphertext sweep across GPUs (BASELINE config 5) -----------------------------
+ * ckks::mult + relinearize (src/fhe/ckks/ckks.h:270-274) over `total` independent synthetic ciphertext pairs, cut
+ * into contiguous per-rank ranges: one process per GPU, no data-path collective.  Inputs are generated on the
+ * device from (seed, global pair index), so pair i has the same words however the batch is sharded; every result
+ * is reduced on the device to one checksum, sum_j word_j * (2j + 1) * 0x9E3779B97F4A7C15 mod 2^64.  Collectives
+ * only broadcast the key-switch key from rank 0 and all-gather the checksums; they go through a provider:
+ * NCCL over NVLink in the product (hehub_b200_nccl_*, libhehub_b200_nccl.so), gloo in the CPU test-suite.
+ *   shard_range: contiguous balanced partition (the first total % world ranks take one extra unit).
+ *   sweep_run: this rank's share in waves of at most `wave` pairs.  my_checksums_host[count] (may be NULL);
+ *     all_checksums_host[total] is filled on rank 0 (NULL elsewhere); op_seconds (may be NULL) receives the device time of
+ *     the mult+relin calls alone (CUDA events on the context's stream).  Synchronises the stream before returning. */
+typedef struct hehub_b200_collectives {
+    void *self;
+    int (*broadcast)(void *self, void *dev_buf, size_t bytes, int root, void *stream); /* in place; 0 = ok */
+    int (*allgather)(void *self, const void *dev_send, void *dev_recv, size_t bytes_per_rank, void *stream);
+} hehub_b200_collectives;
+typedef struct hehub_b200_sweep hehub_b200_sweep;
+void hehub_b200_shard_range(size_t total, int world, int rank, size_t *first, size_t *count);
+int hehub_b200_ct_checksums(hehub_b200_ctx *ctx, const uint64_t *words, size_t words_per_ct, size_t cts, uint64_t *sums_dev);
+int hehub_b200_sweep_create(hehub_b200_sweep **out, hehub_b200_ctx *ctx, unsigned logn, const uint64_t *ext_moduli, size_t L,
+                            uint64_t seed, int rank, int world, const hehub_b200_collectives *coll /* NULL: world == 1 */);
+int hehub_b200_sweep_destroy(hehub_b200_sweep *s);
+int hehub_b200_sweep_make_key(hehub_b200_sweep *s);
+const uint64_t *hehub_b200_sweep_key(const hehub_b200_sweep *s); /* device pointer, [L][2][L+1][N] */
+int hehub_b200_sweep_fill_inputs(hehub_b200_sweep *s, uint64_t *ct1, uint64_t *ct2, size_t first_ct, size_t count);
+int hehub_b200_sweep_run(hehub_b200_sweep *s, size_t total, size_t wave, uint64_t *my_checksums_host,
+                         uint64_t *all_checksums_host, size_t *first, size_t *count, double *op_seconds);
+
+/* The NCCL provider — implemented by hehub_b200/libhehub_b200_nccl.so (csrc/nccl_provider.cpp), not by the core library.
+ * Rank 0 calls unique_id and passes the bytes to the other ranks (MPI_Bcast, a file, the launcher's process group); every
+ * rank then calls create, which runs ncclCommInitRank.  version: NCCL's version code (e.g. 22703). */
+#define HEHUB_B200_NCCL_ID_BYTES 128
+int hehub_b200_nccl_version(void);
+int hehub_b200_nccl_unique_id(uint8_t id[HEHUB_B200_NCCL_ID_BYTES]);
+int hehub_b200_nccl_create(hehub_b200_collectives *out, int rank, int world, const uint8_t id[HEHUB_B200_NCCL_ID_BYTES], int device);
+int hehub_b200_nccl_destroy(hehub_b200_collectives *c);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,7 @@ namespace hbsim {
 
 thread_local hbsim_dim3 t_threadIdx{0, 0, 0}, t_blockIdx{0, 0, 0}, t_blockDim{1, 1, 1}, t_gridDim{1, 1, 1};
 
-constexpr size_t kMaxCluster = 2;
+constexpr size_t kMaxCluster = 8;
 static std::vector<hbsim_u64> g_shared[kMaxCluster];
 static thread_local size_t t_rank = 0; // CTA rank within its cluster
 hbsim_u64 *shared_u64() { return g_shared[t_rank].data(); }

@@ -655,3 +655,91 @@ def test_host_buffer_pipeline(dev, oracle):
     dkey.free()
     want = np.stack([oracle.ckks_mult_relin(logn, ext, ct1[b], ct2[b], key) for b in range(batch)])
     assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("logn", [4, 10, 12])
+def test_scheme_ops_on_unaligned_operands(dev, oracle, logn):
+    """ct1 / ct2 / out that are only 8-byte aligned (a caller's sub-slab): the tensor product and the fused mult+relin take
+    their one-word-per-thread paths instead of faulting on a misaligned 128-bit access."""
+    n = 1 << logn
+    mods, ext = _shape(oracle, logn, [40, 30], 40)
+    L = len(mods)
+    ct1, ct2, key = fill_ct(oracle, 61, mods, n), fill_ct(oracle, 62, mods, n), fill_key(oracle, 6300, ext, n)
+    want_t = oracle.ckks_tensor(logn, mods, ct1, ct2)
+    want_m = oracle.ckks_mult_relin(logn, ext, ct1, ct2, key)
+    import ctypes as C
+    p64 = C.POINTER(C.c_uint64)
+    m = np.ascontiguousarray(np.asarray(ext, dtype=np.uint64))
+    a, b, k = dev.slab(ct1.size + 1), dev.slab(ct2.size + 1), dev.to_device(key)
+    quad, out = dev.slab(3 * L * n + 1), dev.slab(2 * L * n + 1)
+    try:
+        dev._call("slab_h2d", a.ptr + 8, ct1.ctypes.data, ct1.size)
+        dev._call("slab_h2d", b.ptr + 8, ct2.ctypes.data, ct2.size)
+        dev._call("ckks_tensor", logn, m.ctypes.data_as(p64), L, a.ptr + 8, b.ptr + 8, quad.ptr + 8, 1)
+        got_t = np.empty(3 * L * n, dtype=np.uint64)
+        dev._call("slab_d2h", got_t.ctypes.data, quad.ptr + 8, got_t.size)
+        dev._call("ckks_mult_relin", logn, m.ctypes.data_as(p64), L, a.ptr + 8, b.ptr + 8, k.ptr, out.ptr + 8, 1)
+        got_m = np.empty(2 * L * n, dtype=np.uint64)
+        dev._call("slab_d2h", got_m.ctypes.data, out.ptr + 8, got_m.size)
+        dev.synchronize()
+    finally:
+        for s in (a, b, k, quad, out):
+            s.free()
+    assert np.array_equal(got_t.reshape(want_t.shape), want_t)
+    assert np.array_equal(got_m.reshape(want_m.shape), want_m)
+
+
+@pytest.mark.gpu
+def test_two_contexts_on_two_devices_in_one_process(oracle):
+    """Kernel attributes (dynamic shared memory opt-in) are per device: a second context on another GPU of the same
+    process must be able to launch the N >= 8192 transforms (72-147 KB of shared memory) too."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU on this box")
+    from hehub_b200.binding import Context
+    ctxs = [Context(device=0), Context(device=1)]
+    try:
+        for logn in (13, 15, 14):
+            n = 1 << logn
+            x = np.stack([oracle.lcg_fill(5 + r, Q59, n) for r in range(2)])
+            want = np.stack([oracle.ntt_fwd_lazy(logn, Q59, r) for r in x])
+            for c in (ctxs[1], ctxs[0], ctxs[1]):
+                assert np.array_equal(c.poly_ntt_fwd(logn, [Q59], x), want)
+                assert np.array_equal(c.poly_intt(logn, [Q59], want, strict=True), x)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+@pytest.mark.parametrize("logn", [3, 10, 12])
+def test_rotate_in_place_and_unaligned(dev, oracle, logn):
+    """ckks::rotate / conjugate read both polynomials through the Galois permutation inside the key-switch kernels
+    (no separate gather pass): in place (out == ct), and on slabs that are only 8-byte aligned (64-bit gathers)."""
+    n = 1 << logn
+    mods, ext = _shape(oracle, logn, [40, 30, 30], 40)
+    L = len(mods)
+    ct = np.stack([fill_ct(oracle, 71 + b, mods, n) for b in range(3)])
+    key = fill_key(oracle, 7300, ext, n)
+    want_r = np.stack([oracle.ckks_rotate(logn, ext, ct[b], key, 7) for b in range(3)])
+    want_c = np.stack([oracle.ckks_conjugate(logn, ext, ct[b], key) for b in range(3)])
+    import ctypes as C
+    p64 = C.POINTER(C.c_uint64)
+    m = np.ascontiguousarray(np.asarray(ext, dtype=np.uint64))
+    k = dev.to_device(key)
+    a, out = dev.slab(ct.size + 1), dev.slab(ct.size + 1)
+    try:
+        for off in (0, 8):
+            dev._call("slab_h2d", a.ptr + off, ct.ctypes.data, ct.size)
+            dev._call("ckks_rotate", logn, m.ctypes.data_as(p64), L, a.ptr + off, k.ptr, 7, a.ptr + off, 3)  # in place
+            got = np.empty_like(ct)
+            dev._call("slab_d2h", got.ctypes.data, a.ptr + off, ct.size)
+            dev.synchronize()
+            assert np.array_equal(got, want_r), off
+            dev._call("slab_h2d", a.ptr + off, ct.ctypes.data, ct.size)
+            dev._call("ckks_conjugate", logn, m.ctypes.data_as(p64), L, a.ptr + off, k.ptr, out.ptr + off, 3)
+            dev._call("slab_d2h", got.ctypes.data, out.ptr + off, ct.size)
+            dev.synchronize()
+            assert np.array_equal(got, want_c), off
+    finally:
+        for s in (a, out, k):
+            s.free()

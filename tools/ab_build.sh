@@ -4,7 +4,7 @@
 set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -shared "$@" \
-    hehub_b200/csrc/api.cu hehub_b200/csrc/ops.cu hehub_b200/csrc/tables.cu hehub_b200/csrc/host_pipe.cu \
+nvcc --threads 4 -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -shared "$@" \
+    hehub_b200/csrc/api.cu hehub_b200/csrc/ops.cu hehub_b200/csrc/tables.cu hehub_b200/csrc/host_pipe.cu hehub_b200/csrc/params.cu hehub_b200/csrc/sweep.cu \
     -o tools/_variants_$name.so
 echo built tools/_variants_$name.so

@@ -18,6 +18,25 @@ ncu -i $OUT/prof_ntt_fwd.ncu-rep --page raw --csv > $OUT/raw.csv 2>/dev/null
 ncu -i $OUT/prof_ntt_fwd.ncu-rep --page source --csv > $OUT/src.csv 2>/dev/null
 rm -f $OUT/prof_ntt_fwd.ncu-rep   # gpurun_out/ is capped at 64 MiB; the csv pages carry what the summaries need
 python tools/ncu_summary.py $OUT/raw.csv "ncu --set full: ntt_fwd_fast_kernel<12, RowsIO<0>> (headline kernel), session $TAG" > $OUT/ncu_ntt_fwd_fast12.md
+python tools/sass_census.py $OUT/src.csv --kernel "ntt_fwd_fast_kernel<(int)12" --butterflies $((2*4096*24576)) --stalls > $OUT/sass_census_ntt_fwd_fast12.md
+# DRAM bytes of that launch, tied to the kernel sources it was taken from (bench.py reports it only while the hash matches)
+python - <<PY
+import csv, json, sys
+sys.path.insert(0, ".")
+from bench import kernel_source_sha16
+rows = list(csv.reader(open("$OUT/raw.csv")))
+hdr, data = rows[0], rows[2]
+ix = {h: i for i, h in enumerate(hdr)}
+def gb(name):
+    v, u = float(data[ix[name]].replace(",", "")), rows[1][ix[name]]
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+rd, wr = gb("dram__bytes_read.sum"), gb("dram__bytes_write.sum")
+json.dump({"kernel": data[ix["Kernel Name"]], "source": "ncu --set full --clock-control none, session $TAG (one launch, 4096 rows of N=4096)",
+           "source_sha16": kernel_source_sha16(), "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
+           "algorithmic_bytes_per_launch": 16 * 4096 * 4096,
+           "note": "writes below the algorithmic 134 MB: the tail of the output is still dirty in the 126 MB L2 when the kernel ends"},
+          open("$OUT/ntt_fwd_traffic.json", "w"), indent=1)
+PY
 python - <<PY
 import json
 d=json.load(open("$OUT/bench.json"))

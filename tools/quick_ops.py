@@ -37,6 +37,8 @@ for name in a.shape:
         "ext_prod": lambda: ctx._call("ext_prod_montgomery", logn, ep, L, ct1.ptr, key.ptr, ext_out.ptr, batch),
         "rescale": lambda: ctx._call("ckks_rescale", logn, mp, L, ct1.ptr, res.ptr, batch),
         "mult_relin": lambda: ctx._call("ckks_mult_relin", logn, ep, L, ct1.ptr, ct2.ptr, key.ptr, res.ptr, batch),
+        "relinearize": lambda: ctx._call("ckks_relinearize", logn, ep, L, quad.ptr, key.ptr, res.ptr, batch),
+        "rotate": lambda: ctx._call("ckks_rotate", logn, ep, L, ct1.ptr, key.ptr, 5, res.ptr, batch),
     }
     out = []
     for k, fn in ops.items():
