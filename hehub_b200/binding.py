@@ -134,11 +134,15 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.hehub_b200_launch_count.restype = C.c_uint64
     lib.hehub_b200_launch_count.argtypes = [ctxp]
     for name, args in _SIGS.items():
-        f = getattr(lib, "hehub_b200_" + name)
+        f = getattr(lib, "hehub_b200_" + name, None)
+        if f is None:  # an older A/B build (tools/ab_build.sh): calling the missing entry point raises AttributeError
+            continue
         f.restype = C.c_int
         f.argtypes = [ctxp] + args
     for name, args in _FREE_SIGS.items():
-        f = getattr(lib, "hehub_b200_" + name)
+        f = getattr(lib, "hehub_b200_" + name, None)
+        if f is None:
+            continue
         f.restype = C.c_int
         f.argtypes = args
     return lib

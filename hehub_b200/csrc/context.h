@@ -54,6 +54,7 @@ struct Context {
     std::map<std::vector<u64>, LimbConst *> chains;      // key: {logn, q0, q1, ...}
     std::map<std::vector<u64>, DropSet> drops;           // key: {logn, t, q0, ..., q_last}
     std::map<std::vector<u64>, u64 *> scalar_sets;       // uploaded (s, s') pairs for mul_scalar
+    std::map<const void *, int> smem_opt_in;             // kernel -> dynamic shared memory it has been opted in to (this device)
     std::map<size_t, std::vector<u64 *>> slab_free;      // pooled slabs by size
     std::map<u64 *, size_t> slab_live;
     std::vector<std::pair<u64 *, size_t>> scratch;       // grow-only workspaces, by slot

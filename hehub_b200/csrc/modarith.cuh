@@ -179,6 +179,59 @@ HB_D void mac128(u64 &lo, u64 &hi, u64 a, u64 b) {
 #endif
 }
 
+// The same accumulation for inner loops that run it many times on the same accumulator (key-switch inner product).
+// mac128 keeps its four 32-bit words in ONE chain, so the cross products a0*b1, a1*b0 land on the register pair
+// (word 1, word 2) while a0*b0 and a1*b1 want (0, 1) and (2, 3): ptxas cannot give both pairings an even register and
+// pays ~9 register moves per call, half of them on the multiplier pipe (profiles/r3_mac_census.md).  Here the cross
+// products go to a separate 96-bit accumulator (m0, m1, m2), every IMAD.WIDE works on an aligned pair, and the two are
+// added once at the end: (r3 r2 r1 r0) + ((m2 m1 m0) << 32), the same value mod 2^128.
+struct Acc128 {
+    u64 r01, r23, m01; // register pairs, as IMAD.WIDE wants them
+    u32 m2;
+};
+HB_D void acc128_clear(Acc128 &s) {
+    s.r01 = s.r23 = s.m01 = 0;
+    s.m2 = 0;
+}
+HB_D void acc128_mac(Acc128 &s, u64 a, u64 b) {
+#if defined(HB_KERNEL_SIM)
+    const unsigned __int128 prod = (unsigned __int128)a * b; // the emulator keeps everything in (r23, r01); m stays 0
+    const unsigned __int128 acc = (((unsigned __int128)s.r23 << 64) | s.r01) + prod;
+    s.r01 = (u64)acc;
+    s.r23 = (u64)(acc >> 64);
+#else
+    asm("{\n\t"
+        ".reg .u32 a0, a1, b0, b1, r0, r1, r2, r3, m0, m1;\n\t"
+        "mov.b64 {a0, a1}, %4;\n\t"
+        "mov.b64 {b0, b1}, %5;\n\t"
+        "mov.b64 {r0, r1}, %0;\n\t"
+        "mov.b64 {r2, r3}, %1;\n\t"
+        "mov.b64 {m0, m1}, %2;\n\t"
+        "mad.lo.cc.u32 r0, a0, b0, r0;\n\t"
+        "madc.hi.cc.u32 r1, a0, b0, r1;\n\t"
+        "madc.lo.cc.u32 r2, a1, b1, r2;\n\t"
+        "madc.hi.u32 r3, a1, b1, r3;\n\t"
+        "mad.lo.cc.u32 m0, a0, b1, m0;\n\t"
+        "madc.hi.cc.u32 m1, a0, b1, m1;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        "mad.lo.cc.u32 m0, a1, b0, m0;\n\t"
+        "madc.hi.cc.u32 m1, a1, b0, m1;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        "mov.b64 %0, {r0, r1};\n\t"
+        "mov.b64 %1, {r2, r3};\n\t"
+        "mov.b64 %2, {m0, m1};\n\t"
+        "}"
+        : "+l"(s.r01), "+l"(s.r23), "+l"(s.m01), "+r"(s.m2)
+        : "l"(a), "l"(b));
+#endif
+}
+// (r3 r2 r1 r0) + ((m2 m1 m0) << 32) mod 2^128
+HB_D void acc128_fold(const Acc128 &s, u64 &lo, u64 &hi) {
+    const u64 shifted_lo = s.m01 << 32, shifted_hi = (s.m01 >> 32) | ((u64)s.m2 << 32);
+    lo = s.r01 + shifted_lo;
+    hi = s.r23 + shifted_hi + (lo < shifted_lo ? 1ull : 0ull);
+}
+
 // full 128-bit product (lo, hi) = a * b with four IMAD.WIDE
 HB_D void mul_full(u64 a, u64 b, u64 &lo, u64 &hi) {
     lo = 0;

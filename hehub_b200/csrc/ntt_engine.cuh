@@ -291,9 +291,62 @@ HB_D void fwd_cross_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, in
     }
 }
 
+#if defined(HB_ABL_SHFL) && !defined(HB_KERNEL_SIM)
+// A/B build only (tools/ab_build.sh shfl -DHB_ABL_SHFL; profiles/r3_headline_ab.md): the exchange between the last two forward
+// passes (both 4 levels wide, so it stays inside groups of 16 lanes) done with warp shuffles instead of shared memory: a
+// 16 x 16 transpose of 64-bit words in four butterfly stages.  new v[i] of lane l = old v[l] of lane i.
+HB_D void shfl_transpose16(u64 (&v)[16]) {
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int b = 8; b; b >>= 1) {
+        const bool up = lane & b;
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            if (r & b) continue;
+            const u64 send = up ? v[r] : v[r | b];
+            const u64 got = __shfl_xor_sync(0xffffffffu, send, b);
+            if (up) v[r] = got;
+            else v[r | b] = got;
+        }
+    }
+}
+// the last two passes of a {.., 4, 4} forward plan fused over registers
+template <int LOGN, int T, int MODE, class IO>
+HB_D void fwd_last_two_shfl(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
+    constexpr NttPlan pl = plan_for(LOGN, true, MODE);
+    constexpr int LOGNC = LOGN - pl.lpre, NC = 1 << LOGNC, P = pl.npass - 2;
+    constexpr int L0 = fwd_lambda0(pl, P), NG = NC >> 4;
+    static_assert(pl.k[P] == 4 && pl.k[P + 1] == 4 && LOGNC - L0 - 4 == 4, "two 4-level passes at the end");
+    const ulonglong2 *twa = (MODE ? lc.fwd_lat : lc.fwd) + fwd_pass_offset(pl, P), *twb = (MODE ? lc.fwd_lat : lc.fwd) + fwd_pass_offset(pl, P + 1);
+#pragma unroll 1
+    for (int g = threadIdx.x; g < NG; g += T) {
+        const int lo = g & 15, hb = g >> 4, base = (hb << 8) + lo;
+        const u64 *const smb = sm + sphys(base);
+        u64 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = smb[j * sstride(16)];
+        fwd_levels<4>(v, TwTable{twa + ((B << L0) + hb), 1 << (pl.lpre + L0)}, lc.nq, lc.q2);
+        shfl_transpose16(v); // now v[i] = word g * 16 + i
+        fwd_levels<4>(v, TwTable{twb + ((B << (L0 + 4)) + g), 1 << (pl.lpre + L0 + 4)}, lc.nq, lc.q2);
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = approx_reduce(v[j], lc);
+        hb_syncwarp(); // every lane has read its strided words before the contiguous ones are written
+        sts_contig<4>(sm, g << 4, v);
+        hb_syncwarp();
+        warp_store<4>(sm, io, lc, row, B * NC, (g - (int)(threadIdx.x & 31)) << 4);
+    }
+}
+#endif
+
 template <int LOGN, int T, int P, int MODE, class IO>
 HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     constexpr NttPlan pl = plan_for(LOGN, true, MODE);
+#if defined(HB_ABL_SHFL) && !defined(HB_KERNEL_SIM)
+    if constexpr (P == pl.npass - 2 && P > 0 && pl.k[P] == 4 && pl.k[P + 1] == 4 && LOGN == 12 && MODE == 0) {
+        fwd_last_two_shfl<LOGN, T, MODE>(sm, io, lc, row, B);
+        return;
+    } else
+#endif
     if constexpr (P == 0 && pl.xchg) {
         fwd_cross_pass<LOGN, T, MODE>(sm, io, lc, row, B);
         hb_cluster_sync(); // every word has reached its owner (and all of the row has been read: in-place stores may follow)
@@ -315,6 +368,37 @@ HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B)
     }
 }
 
+#if defined(HB_ABL_TMA) && !defined(HB_KERNEL_SIM)
+// A/B build only (tools/ab_build.sh tma -DHB_ABL_TMA; profiles/r3_headline_ab.md): the row is brought into an unpadded
+// staging area of shared memory by ONE bulk asynchronous copy (cp.async.bulk, the 1-D TMA path; SASS: UBLKCP) issued by one
+// thread and awaited on an mbarrier; pass 0 then reads shared memory instead of global memory.
+template <class IO>
+struct StagedIO : IO {
+    const u64 *stage;
+    HB_D u64 fetch(int, int i) const { return stage[i]; }
+    HB_D ulonglong2 fetch2(int, int i) const { return *reinterpret_cast<const ulonglong2 *>(stage + i); }
+};
+HB_D void hb_tma_row_load(u64 *stage, const u64 *src, unsigned bytes) {
+    __shared__ __align__(8) unsigned long long mbar;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&mbar), dst = (unsigned)__cvta_generic_to_shared(stage);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                     "r"(bar)
+                     : "memory");
+    }
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar) : "memory");
+    }
+}
+#endif
+
 // one CTA (or one CTA of a 2-CTA cluster) per row
 template <int LOGN, class IO, int MODE = 0>
 HB_GLOBAL(plan_for(LOGN, true, MODE).threads, plan_for(LOGN, true, MODE).min_blocks)
@@ -330,6 +414,16 @@ ntt_fwd_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     if constexpr (pl.xchg) hb_cluster_arrive(); // matched by the wait in front of the first remote store
     hb_pdl_wait();
     if constexpr (io_has_prefetch<IO>::value) io.prefetch(row, B << (LOGN - pl.lpre), 1 << (LOGN - pl.lpre));
+#if defined(HB_ABL_TMA) && !defined(HB_KERNEL_SIM)
+    if constexpr (pl.lpre == 0 && !io_has_fetch<IO>::value) {
+        if (io.vec) { // 16-byte aligned rows only
+            u64 *stage = sm + smem_words(1 << LOGN);
+            hb_tma_row_load(stage, io.src(row), (unsigned)(8u << LOGN));
+            fwd_passes<LOGN, T, 0, MODE>(sm, StagedIO<IO>{io, stage}, lc, row, B);
+            return;
+        }
+    }
+#endif
     fwd_passes<LOGN, T, 0, MODE>(sm, io, lc, row, B);
 }
 
@@ -583,7 +677,11 @@ inline cudaError_t configure_smem(K kern, int smem, int blocks) {
 template <int LOGN, bool FWD, int MODE, class IO>
 inline cudaError_t launch_fast_mode(const LaunchEnv &env, const IO &io, const LimbConst *limbs, int rows) {
     constexpr NttPlan pl = plan_for(LOGN, FWD, MODE);
+#if defined(HB_ABL_TMA) // A/B build: room for the unpadded staging copy of the row behind the working area
+    constexpr int smem = smem_words(1 << (LOGN - pl.lpre)) * 8 + ((FWD && pl.lpre == 0) ? (8 << LOGN) : 0);
+#else
     constexpr int smem = smem_words(1 << (LOGN - pl.lpre)) * 8;
+#endif
     auto kern = fast_kernel<LOGN, FWD, IO, MODE>();
     static PerDeviceConfig configured; // zero-initialised; racing contexts at worst configure twice (idempotent)
     if (!configured.covers(env.device, smem)) {

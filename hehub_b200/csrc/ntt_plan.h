@@ -55,7 +55,28 @@ HB_CX bool has_latency_plan(int logn) { return logn >= 12 && logn <= 15; }
 #define HB_PLAN15 2
 #endif
 
+#ifndef HB_PLAN14I
+#define HB_PLAN14I 0
+#endif
+#ifndef HB_PLAN15I
+#define HB_PLAN15I 0
+#endif
+
 HB_CX NttPlan plan_for(int logn, bool fwd, int mode = 0) {
+#if HB_PLAN14I == 1
+    if (mode == 0 && logn == 14 && !fwd) return NttPlan{14, 1, 4, {3, 3, 4, 4, 0}, 256, 2, 1};
+#elif HB_PLAN14I == 2
+    if (mode == 0 && logn == 14 && !fwd) return NttPlan{14, 1, 3, {5, 5, 4, 0, 0}, 256, 2, 1};
+#elif HB_PLAN14I == 3
+    if (mode == 0 && logn == 14 && !fwd) return NttPlan{14, 1, 4, {4, 3, 3, 4, 0}, 256, 3, 1};
+#endif
+#if HB_PLAN15I == 1
+    if (mode == 0 && logn == 15 && !fwd) return NttPlan{15, 2, 4, {4, 3, 4, 4, 0}, 256, 2, 1};
+#elif HB_PLAN15I == 2
+    if (mode == 0 && logn == 15 && !fwd) return NttPlan{15, 2, 4, {5, 3, 3, 4, 0}, 256, 2, 1};
+#elif HB_PLAN15I == 3
+    if (mode == 0 && logn == 15 && !fwd) return NttPlan{15, 2, 4, {4, 4, 3, 4, 0}, 256, 3, 1};
+#endif
     if (mode == 1 && logn == 12) return NttPlan{12, 1, 3, {3, 4, 4, 0, 0}, 128, 1, 0};
     if (mode == 1 && logn == 13) return NttPlan{13, 1, 3, {4, 4, 4, 0, 0}, 256, 1, 0};
     // 80 registers (three 256-thread CTAs per SM): launches of up to ~2 waves of such CTAs still gain from the finer grain

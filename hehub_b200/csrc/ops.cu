@@ -27,13 +27,20 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 #define HB_TENSOR_MINB 5
 #endif
 #ifndef HB_MAC_MINB
-#define HB_MAC_MINB 3
+#define HB_MAC_MINB 2
 #endif
 #ifndef HB_MAC_U
 #define HB_MAC_U 2
 #endif
 #ifndef HB_MAC_CPT
 #define HB_MAC_CPT 2
+#endif
+#ifndef HB_MAC_STAGED_MIN_BATCH // from this many ciphertexts per wave on, the key-switch inner product stages its key slice in shared memory
+#define HB_MAC_STAGED_MIN_BATCH 8
+#endif
+constexpr int kMacStagedMinBatch = HB_MAC_STAGED_MIN_BATCH;
+#ifndef HB_MAC_STAGED_U
+#define HB_MAC_STAGED_U 12
 #endif
 template <int W>
 HB_D void ld_words(u64 (&dst)[W], const u64 *p, bool read_only) {
@@ -216,65 +223,71 @@ ext_mac_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__
     const int k = (int)(bk % L1);
     const size_t b0 = (bk / L1) * CPT;
     const LimbConst lc = limbs[k];
-    u64 lo[CPT][2][W], hi[CPT][2][W];
+    Acc128 acc[CPT][2][W];
 #pragma unroll
     for (int c = 0; c < CPT; c++)
 #pragma unroll
         for (int h = 0; h < 2; h++)
 #pragma unroll
-            for (int w = 0; w < W; w++) lo[c][h][w] = hi[c][h][w] = 0;
+            for (int w = 0; w < W; w++) acc128_clear(acc[c][h][w]);
     const size_t dec_ct = ((size_t)L * L1) << logn, dec_row = (size_t)L1 << logn;
     const size_t key_row = (size_t)(2 * L1) << logn, key_half = (size_t)L1 << logn;
-    const u64 *const dec_k = dec + b0 * dec_ct + ((size_t)k << logn) + i;
-    const u64 *const in_b = in + b0 * in_batch_stride + i;
     const u64 *const key_k = key + ((size_t)k << logn) + i;
-    constexpr int U = HB_MAC_U;
-    for (int p0 = 0; p0 < L; p0 += U) {
-        u64 d[U][CPT][W], k0[U][W], k1[U][W];
+    // A ragged last group (batch not a multiple of CPT) reads the last valid ciphertext again and drops the result: the
+    // loop stays free of per-ciphertext branches.  The diagonal term (p == k) keeps in[p] (rgsw.cpp:99-101), read through
+    // the Galois permutation when the key switch carries one: same load, another address, the pair possibly swapped.
+    const u64 *dec_c[CPT], *diag_c[CPT];
+    bool swap = false;
+    {
+        size_t diag_off = i;
+        if constexpr (GALOIS) {
+            const unsigned f = galois_from((unsigned)i, ginv, logn);
+            diag_off = W == 2 ? (f & ~1u) : f;
+            swap = W == 2 && (f & 1u);
+        }
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int p = p0 + u;
-            if (p < L) {
-                ld_words<W>(k0[u], key_k + p * key_row, true);
-                ld_words<W>(k1[u], key_k + p * key_row + key_half, true);
+        for (int c = 0; c < CPT; c++) {
+            const size_t b = (b0 + c < batch) ? b0 + c : batch - 1;
+            dec_c[c] = dec + b * dec_ct + ((size_t)k << logn) + i;
+            diag_c[c] = in + b * in_batch_stride + ((size_t)k << logn) + diag_off; // only dereferenced when k < L
+        }
+    }
+    auto load = [&](int p, u64 (&d)[CPT][W], u64 (&k0)[W], u64 (&k1)[W]) {
+        ld_words<W>(k0, key_k + p * key_row, true);
+        ld_words<W>(k1, key_k + p * key_row + key_half, true);
 #pragma unroll
-                for (int c = 0; c < CPT; c++) {
-                    if (b0 + c < batch) { // the diagonal keeps in[p], rgsw.cpp:99-101
-                        const u64 *src = (p == k) ? in_b + c * in_batch_stride + ((size_t)p << logn) : dec_k + c * dec_ct + p * dec_row;
-                        bool swap = false;
-                        if (GALOIS && p == k) { // ... read through the Galois permutation when the key switch carries one:
-                            // same load instruction, another address (and the two words of an aligned pair possibly swapped)
-                            const unsigned f = galois_from((unsigned)i, ginv, logn);
-                            src += (ptrdiff_t)(W == 2 ? (f & ~1u) : f) - (ptrdiff_t)i;
-                            swap = W == 2 && (f & 1u);
-                        }
-                        ld_words<W>(d[u][c], src, false);
-                        if constexpr (GALOIS && W == 2) {
-                            if (swap) {
-                                const u64 t = d[u][c][0];
-                                d[u][c][0] = d[u][c][1];
-                                d[u][c][1] = t;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int w = 0; w < W; w++) d[u][c][w] = 0;
-                    }
+        for (int c = 0; c < CPT; c++) {
+            ld_words<W>(d[c], (p == k) ? diag_c[c] : dec_c[c] + p * dec_row, false);
+            if constexpr (GALOIS && W == 2) {
+                if (swap && p == k) {
+                    const u64 t = d[c][0];
+                    d[c][0] = d[c][1];
+                    d[c][1] = t;
                 }
             }
         }
+    };
+    auto mac = [&](const u64 (&d)[CPT][W], const u64 (&k0)[W], const u64 (&k1)[W]) {
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (p0 + u < L) {
+        for (int c = 0; c < CPT; c++)
 #pragma unroll
-                for (int c = 0; c < CPT; c++)
-#pragma unroll
-                    for (int w = 0; w < W; w++) {
-                        mac128(lo[c][0][w], hi[c][0][w], d[u][c][w], k0[u][w]);
-                        mac128(lo[c][1][w], hi[c][1][w], d[u][c][w], k1[u][w]);
-                    }
+            for (int w = 0; w < W; w++) {
+                acc128_mac(acc[c][0][w], d[c][w], k0[w]);
+                acc128_mac(acc[c][1][w], d[c][w], k1[w]);
             }
-        }
+    };
+    int p = 0;
+    for (; p + 1 < L; p += 2) { // two rows' operands in flight before the first product
+        u64 dA[CPT][W], kA0[W], kA1[W], dB[CPT][W], kB0[W], kB1[W];
+        load(p, dA, kA0, kA1);
+        load(p + 1, dB, kB0, kB1);
+        mac(dA, kA0, kA1);
+        mac(dB, kB0, kB1);
+    }
+    if (p < L) {
+        u64 dA[CPT][W], kA0[W], kA1[W];
+        load(p, dA, kA0, kA1);
+        mac(dA, kA0, kA1);
     }
 #pragma unroll
     for (int c = 0; c < CPT; c++) {
@@ -284,9 +297,116 @@ ext_mac_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__
             for (int h = 0; h < 2; h++) {
                 u64 r[W];
 #pragma unroll
-                for (int w = 0; w < W; w++) r[w] = montgomery128(lo[c][h][w], hi[c][h][w], lc);
+                for (int w = 0; w < W; w++) {
+                    u64 lo, hi;
+                    acc128_fold(acc[c][h][w], lo, hi);
+                    r[w] = montgomery128(lo, hi, lc);
+                }
                 st_words<W>(o + h * key_half, r);
             }
+        }
+    }
+}
+
+// The same inner product for batches: one CTA owns a slice of 256 * W coefficients of one limb k, brings the 2 L key rows of
+// that slice into shared memory ONCE and then walks a group of ciphertexts, so per product the SM pulls 8 bytes of `dec`
+// from HBM and the key words come from shared memory — the kernel above fetches every key word from L2 for every pair of
+// ciphertexts, and L2 -> SM traffic (as much again as `dec`) was what bounded it (profiles/r3_mac_census.md).
+template <int W, bool GALOIS>
+HB_GLOBAL(256, 2)
+ext_mac_staged_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
+                      u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, int logn, size_t batch, unsigned ct_chunks,
+                      unsigned cts_per_cta, unsigned ginv) {
+    HB_SHARED_U64(ks); // [p < L][half][256 * W]
+    constexpr int CH = 256 * W;
+    const int L1 = L + 1;
+    const unsigned slice = blockIdx.x / ct_chunks, chunk = blockIdx.x % ct_chunks; // CTAs of one slice are neighbours: its key rows stay in L2
+    const unsigned slices_per_limb = (1u << logn) / CH;
+    const int k = (int)(slice / slices_per_limb);
+    const size_t i = (size_t)(slice % slices_per_limb) * CH + threadIdx.x * W;
+    const LimbConst lc = limbs[k];
+    const size_t key_row = (size_t)(2 * L1) << logn, key_half = (size_t)L1 << logn;
+    const u64 *const key_k = key + ((size_t)k << logn) + i;
+    hb_pdl_wait();
+    for (int p = 0; p < L; p++) { // the key is not written by the launches before this one, but keep the prologue simple
+        u64 k0[W], k1[W];
+        ld_words<W>(k0, key_k + p * key_row, true);
+        ld_words<W>(k1, key_k + p * key_row + key_half, true);
+        st_words<W>(ks + (size_t)(2 * p) * CH + threadIdx.x * W, k0);
+        st_words<W>(ks + (size_t)(2 * p + 1) * CH + threadIdx.x * W, k1);
+    }
+    // every thread reads back exactly the words it wrote: no barrier needed
+    const size_t dec_ct = ((size_t)L * L1) << logn, dec_row = (size_t)L1 << logn;
+    size_t diag_off = i;
+    bool swap = false;
+    if constexpr (GALOIS) {
+        const unsigned f = galois_from((unsigned)i, ginv, logn);
+        diag_off = W == 2 ? (f & ~1u) : f;
+        swap = W == 2 && (f & 1u);
+    }
+    const size_t b_end = ((size_t)(chunk + 1) * cts_per_cta < batch) ? (size_t)(chunk + 1) * cts_per_cta : batch;
+    for (size_t b = (size_t)chunk * cts_per_cta; b < b_end; b++) {
+        const u64 *const dec_b = dec + b * dec_ct + ((size_t)k << logn) + i;
+        const u64 *const diag_b = in + b * in_batch_stride + ((size_t)k << logn) + diag_off; // only dereferenced when k < L
+        Acc128 acc[2][W];
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int w = 0; w < W; w++) acc128_clear(acc[h][w]);
+        auto load = [&](int p, u64 (&d)[W]) {
+            ld_words<W>(d, (p == k) ? diag_b : dec_b + p * dec_row, false);
+            if constexpr (GALOIS && W == 2) {
+                if (swap && p == k) {
+                    const u64 t = d[0];
+                    d[0] = d[1];
+                    d[1] = t;
+                }
+            }
+        };
+        auto mac = [&](int p, const u64 (&d)[W]) {
+            u64 k0[W], k1[W];
+            if constexpr (W == 2) {
+                const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(ks + (size_t)(2 * p) * CH + threadIdx.x * 2);
+                const ulonglong2 c = *reinterpret_cast<const ulonglong2 *>(ks + (size_t)(2 * p + 1) * CH + threadIdx.x * 2);
+                k0[0] = a.x, k0[1] = a.y, k1[0] = c.x, k1[1] = c.y;
+            } else {
+                k0[0] = ks[(size_t)(2 * p) * CH + threadIdx.x];
+                k1[0] = ks[(size_t)(2 * p + 1) * CH + threadIdx.x];
+            }
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+                acc128_mac(acc[0][w], d[w], k0[w]);
+                acc128_mac(acc[1][w], d[w], k1[w]);
+            }
+        };
+        // The kernel lives on HBM latency (long_scoreboard is its one stall reason): chains of U = 12 rows request all their
+        // `dec` words before the first product; shorter chains run the plain loop, which the compiler pipelines well enough
+        // (guarding a longer batch with p + u < L measured 2-3 % slower: profiles/r3_mac_census.md)
+        constexpr int U = HB_MAC_STAGED_U;
+        int p = 0;
+        for (; p + U <= L; p += U) {
+            u64 d[U][W];
+#pragma unroll
+            for (int u = 0; u < U; u++) load(p + u, d[u]);
+#pragma unroll
+            for (int u = 0; u < U; u++) mac(p + u, d[u]);
+        }
+        for (; p < L; p++) {
+            u64 d0[W];
+            load(p, d0);
+            mac(p, d0);
+        }
+        u64 *const o = out + (((b * 2) * L1 + k) << logn) + i;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            u64 r[W];
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+                u64 lo, hi;
+                acc128_fold(acc[h][w], lo, hi);
+                r[w] = montgomery128(lo, hi, lc);
+            }
+            st_words<W>(o + h * key_half, r);
         }
     }
 }
@@ -306,6 +426,35 @@ static int ext_prod_wave(Context &c, unsigned logn, const LimbConst *limbs, size
     constexpr int CPT = HB_MAC_CPT;
     const size_t groups = (batch + CPT - 1) / CPT;
     const bool vec = aligned16(in) && in_batch_stride % 2 == 0 && aligned16(dec) && aligned16(key) && aligned16(out) && n >= 2;
+    // batches: the key slice staged in shared memory (needs whole 256 * W slices per row and room for 2 L rows of one)
+    const int SW = vec ? 2 : 1;
+    const size_t staged_smem = (size_t)2 * L * 256 * SW * 8;
+    if (batch >= (size_t)kMacStagedMinBatch && n % (256 * (size_t)SW) == 0 && staged_smem <= (size_t)100 << 10) {
+        // ciphertexts per CTA: enough to amortise the key slice (one slice = the `dec` words of two ciphertexts), few enough
+        // that the grid still has several waves
+        size_t per_cta = 16;
+        while (per_cta > 4 && ((L + 1) * (n / (256 * (size_t)SW))) * ((batch + per_cta - 1) / per_cta) < (size_t)8 * c.sm_count) per_cta /= 2;
+        const size_t ct_chunks = (batch + per_cta - 1) / per_cta;
+        const size_t blocks = (L + 1) * (n / (256 * (size_t)SW)) * ct_chunks;
+        if (blocks <= 0x7fffffffull) {
+            auto launch_staged = [&](auto kern) -> cudaError_t {
+                // kernels of one signature share the lambda's instantiation: the opt-in is tracked per kernel pointer, in the context
+                int &have = c.smem_opt_in[reinterpret_cast<const void *>(kern)];
+                if (have < (int)staged_smem) {
+                    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem);
+                    if (ce != cudaSuccess) return ce;
+                    have = (int)staged_smem;
+                }
+                HB_LAUNCH(kern, (unsigned)blocks, 256, staged_smem, c.stream, 0, in, in_batch_stride, dec, key, out, limbs, (int)L, (int)logn, batch,
+                          (unsigned)ct_chunks, (unsigned)per_cta, ginv);
+                return cudaGetLastError();
+            };
+            if (vec) e = ginv == 1 ? launch_staged(ext_mac_staged_kernel<2, false>) : launch_staged(ext_mac_staged_kernel<2, true>);
+            else e = ginv == 1 ? launch_staged(ext_mac_staged_kernel<1, false>) : launch_staged(ext_mac_staged_kernel<1, true>);
+            c.stats.launches++;
+            return e == cudaSuccess ? 0 : c.cuda_fail(e, "ext_prod: staged mac launch");
+        }
+    }
     const size_t per_group = (L + 1) * (vec ? n / 2 : n), total = groups * per_group;
     const bool inter = per_group % 256 == 0 && groups > 1;
     auto launch_mac = [&](auto kern) {

@@ -743,3 +743,33 @@ def test_rotate_in_place_and_unaligned(dev, oracle, logn):
     finally:
         for s in (a, out, k):
             s.free()
+
+
+@pytest.mark.parametrize("logn,bits,batch", [(9, [40, 30], 19), (10, [40, 30, 30], 9), (8, [34], 33)])
+def test_key_switch_inner_product_with_staged_key(dev, oracle, logn, bits, batch):
+    """From 8 ciphertexts per wave on, the key-switch inner product keeps its key slice in shared memory and walks groups of
+    ciphertexts per CTA (ragged last group included); aligned and 8-byte-aligned operands, with and without a Galois gather."""
+    n = 1 << logn
+    mods, ext = _shape(oracle, logn, bits, 40)
+    L = len(mods)
+    polys = np.stack([np.stack([oracle.lcg_fill(900 + 31 * b + k, mods[k], n) for k in range(L)]) for b in range(batch)])
+    key = fill_key(oracle, 9100, ext, n)
+    want = np.stack([oracle.ext_prod(logn, ext, polys[b], key) for b in range(batch)])
+    assert np.array_equal(dev.ext_prod(logn, ext, polys, key), want)
+    ct = np.stack([fill_ct(oracle, 950 + 7 * b, mods, n) for b in range(batch)])
+    want_rot = np.stack([oracle.ckks_rotate(logn, ext, ct[b], key, 3) for b in range(batch)])
+    assert np.array_equal(dev.ckks_rotate(logn, ext, ct, key, 3), want_rot)
+    import ctypes as C
+    p64 = C.POINTER(C.c_uint64)
+    m = np.ascontiguousarray(np.asarray(ext, dtype=np.uint64))
+    a, k, out = dev.slab(polys.size + 1), dev.to_device(key), dev.slab(want.size + 1)
+    try:
+        dev._call("slab_h2d", a.ptr + 8, polys.ctypes.data, polys.size)
+        dev._call("ext_prod_montgomery", logn, m.ctypes.data_as(p64), L, a.ptr + 8, k.ptr, out.ptr + 8, batch)
+        got = np.empty_like(want)
+        dev._call("slab_d2h", got.ctypes.data, out.ptr + 8, want.size)
+        dev.synchronize()
+    finally:
+        for s in (a, k, out):
+            s.free()
+    assert np.array_equal(got, want)

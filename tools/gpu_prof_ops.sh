@@ -4,7 +4,7 @@ TAG=${1:-r1g}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 LIB=hehub_b200/libhehub_b200.so
-RX='regex:tensor_kernel|ext_mac_kernel|ntt_fwd_fast_kernel|intt_fast_kernel'
+RX='regex:tensor_kernel|ext_mac|ntt_fwd_fast_kernel|intt_fast_kernel'
 for shape in c3 c5; do
   timeout 900 ncu --set full --clock-control none --import-source on -k "$RX" -s 12 -c 6 -o $OUT/prof_$shape -f \
       python tools/quick_ops.py $LIB --shape $shape --only mult_relin --reps 1 --warmup 2 > $OUT/ncu_$shape.log 2>&1; echo "ncu $shape rc=$?"
