@@ -33,6 +33,7 @@ POLYS = 4096
 SLABS = 4
 SWEEP_WAVE = 74  # ciphertexts per wave of the config-5 sweep: a multiple of 37 (2 x 37 rows = one CTA pair per SM pair on 148 SMs)
 METRIC = "NTT/s (N=4096, one 59-bit modulus, batch 4096)"
+WORKLOAD = "forward negacyclic NTT, N=4096, L=1, Q=576460752272228353, 4096 polynomials per step per GPU"
 UNIT = "NTT/s"
 
 
@@ -114,8 +115,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "forward negacyclic NTT, N=4096, L=1, Q=576460752272228353",
-                   "sample": f"{workers} processes x {rows} polynomials per step"},
+        "config": {"workload": WORKLOAD, "reference_sample": f"{workers} processes x {rows} polynomials per step (bounded sample of the workload)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind,
                          "sample": f"{workers} independent processes x {rows} transforms per step x {args.steps} steps"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -343,7 +343,7 @@ def run_cuda(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": {"workload": "forward negacyclic NTT, N=4096, L=1, Q=576460752272228353, 4096 polynomials per step per GPU",
+            "config": {"workload": WORKLOAD,
                        "l2_policy": f"inputs larger than L2: {SLABS} slabs of {POLYS * n * 8 >> 20} MiB visited round-robin",
                        "sharding": "independent polynomials per rank, no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world,

@@ -37,6 +37,7 @@ inline ulonglong2 hb_ld_dsmem2(const unsigned long long *p, unsigned rank) {
     return *reinterpret_cast<const ulonglong2 *>(::hbsim::shared_u64_of(rank) + (p - ::hbsim::shared_u64()));
 }
 inline void hb_prefetch_l2(const void *) {}
+inline void hb_prefetch_l1(const void *) {}
 inline void hb_pdl_wait() {}
 inline void hb_syncwarp() { __syncthreads(); } // the emulator has no warps: a CTA barrier is a superset
 inline unsigned long long hb_ld_stream(const unsigned long long *p) { return *p; }
@@ -140,6 +141,9 @@ __device__ __forceinline__ ulonglong2 hb_ld_dsmem2(const unsigned long long *p, 
 }
 // ask L2 for a line the CTA will read much later (epilogue operands of the fused transforms)
 __device__ __forceinline__ void hb_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// pull a line the thread will read soon into L1 (twiddles of the latency plans: tables never change, so this may run before
+// the programmatic-dependent-launch wait)
+__device__ __forceinline__ void hb_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void hb_syncwarp() { __syncwarp(); }
 // row words are read once: keep them out of L1, which holds the twiddle tables
 #if defined(HB_NO_STREAM_LD) // A/B builds only

@@ -205,11 +205,13 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     constexpr bool first = (P == 0), last = (P == pl.npass - 1);
     static_assert(!(first && pl.xchg), "pass 0 of an exchanging plan is fwd_cross_pass");
     static_assert(!last || GSL == 0, "last forward pass must be contiguous");
-    static_assert(last || GSL >= 4, "strided passes step by multiples of 16 words");
-    static_assert(NG % T == 0 && T % 32 == 0, "whole warps in every step");
+    // strides of at least 16 words address shared memory as one base register plus immediates (sstride); the thin passes of
+    // the latency plans may step by less and pay the padding arithmetic per access
+    constexpr bool imm = GSL >= 4;
+    static_assert(T % 32 == 0 && (NG % T == 0 || (T % NG == 0 && NG % 32 == 0)), "whole warps in every step (idle warps allowed)");
     const ulonglong2 *tw_pass = (MODE ? lc.fwd_lat : lc.fwd) + fwd_pass_offset(pl, P);
     constexpr int stride = 1 << (pl.lpre + L0);
-    constexpr int SJ = sstride(1 << GSL);
+    constexpr int SJ = imm ? sstride(1 << (imm ? GSL : 4)) : 0;
 
 #pragma unroll 1
     for (int g = threadIdx.x; g < NG; g += T) {
@@ -235,9 +237,12 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
             }
         } else if constexpr (last) {
             lds_contig<K>(sm, base, v);
-        } else {
+        } else if constexpr (imm) {
 #pragma unroll
             for (int j = 0; j < (1 << K); j++) v[j] = smb[j * SJ];
+        } else {
+#pragma unroll
+            for (int j = 0; j < (1 << K); j++) v[j] = sm[sphys(base + (j << GSL))];
         }
 
         fwd_levels<K>(v, TwTable{tw_pass + ((B << L0) + hb), stride}, lc.nq, lc.q2);
@@ -248,9 +253,12 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
             sts_contig<K>(sm, base, v); // own words only
             hb_syncwarp();
             warp_store<K>(sm, io, lc, row, B * NC, (g - (int)(threadIdx.x & 31)) << K);
-        } else {
+        } else if constexpr (imm) {
 #pragma unroll
             for (int j = 0; j < (1 << K); j++) smb[j * SJ] = v[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < (1 << K); j++) sm[sphys(base + (j << GSL))] = v[j];
         }
     }
 }
@@ -368,6 +376,48 @@ HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B)
     }
 }
 
+// Latency plans: every twiddle this thread will use, requested into L1 before the kernel waits for its predecessor (the
+// tables are written once, when the modulus is first seen).  A row alone on its SMs has nothing to hide a table load
+// behind: with five thin passes the L2 latency of each pass's twiddles was a third of the kernel (profiles/r3_latency_plans.md).
+template <int LOGN, int T, int MODE, int P = 0>
+HB_D void prefetch_fwd_twiddles(const LimbConst &lc, int B) {
+    constexpr NttPlan pl = plan_for(LOGN, true, MODE);
+    const ulonglong2 *tab = MODE ? lc.fwd_lat : lc.fwd;
+    if constexpr (P == 0 && pl.xchg) {
+        for (int s = threadIdx.x; s < (1 << pl.k[0]) - 1; s += T) hb_prefetch_l1(tab + s); // CTA-uniform: a few lines
+    } else {
+        constexpr int LOGNC = LOGN - pl.lpre, K = pl.k[P], L0 = fwd_lambda0(pl, P), GSL = LOGNC - L0 - K, NG = (1 << LOGNC) >> K;
+        const ulonglong2 *tw = tab + fwd_pass_offset(pl, P);
+        for (int g = threadIdx.x; g < NG; g += T)
+#pragma unroll
+            for (int s = 0; s < (1 << K) - 1; s++) hb_prefetch_l1(tw + ((B << L0) + (g >> GSL)) + ((size_t)s << (pl.lpre + L0)));
+    }
+    if constexpr (P + 1 < pl.npass) prefetch_fwd_twiddles<LOGN, T, MODE, P + 1>(lc, B);
+}
+template <int LOGN, int T, int MODE, int P = 0>
+HB_D void prefetch_inv_twiddles(const LimbConst &lc, int B) {
+    constexpr NttPlan pl = plan_for(LOGN, false, MODE);
+    const ulonglong2 *tab = MODE ? lc.inv_lat : lc.inv;
+    if constexpr (pl.xchg && P == pl.npass - 1) {
+        constexpr int K = pl.k[0], LOGG = LOGN - K, GPC = (1 << LOGG) >> pl.lpre;
+        const ulonglong2 *tw = tab + inv_pass_offset(pl, P);
+        for (int g = threadIdx.x; g < GPC; g += T) {
+            const int t = B * GPC + g;
+#pragma unroll
+            for (int s = 0; s < (1 << K) - 1; s++) hb_prefetch_l1(tw + t + ((size_t)s << LOGG));
+#pragma unroll
+            for (int j = 0; j < (1 << K); j++) hb_prefetch_l1(lc.inv_scale + t + (j << LOGG));
+        }
+    } else {
+        constexpr int LOGNC = LOGN - pl.lpre, K = inv_k(pl, P), S0 = inv_s0(pl, P), NG = (1 << LOGNC) >> K;
+        const ulonglong2 *tw = tab + inv_pass_offset(pl, P);
+        for (int g = threadIdx.x; g < NG; g += T)
+#pragma unroll
+            for (int s = 0; s < (1 << K) - 1; s++) hb_prefetch_l1(tw + (g & ((1 << S0) - 1)) + ((size_t)s << S0));
+    }
+    if constexpr (P + 1 < pl.npass) prefetch_inv_twiddles<LOGN, T, MODE, P + 1>(lc, B);
+}
+
 #if defined(HB_ABL_TMA) && !defined(HB_KERNEL_SIM)
 // A/B build only (tools/ab_build.sh tma -DHB_ABL_TMA; profiles/r3_headline_ab.md): the row is brought into an unpadded
 // staging area of shared memory by ONE bulk asynchronous copy (cp.async.bulk, the 1-D TMA path; SASS: UBLKCP) issued by one
@@ -412,6 +462,9 @@ ntt_fwd_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     const int row = blockIdx.x >> pl.lpre, B = blockIdx.x & ((1 << pl.lpre) - 1);
     const LimbConst lc = limbs[io.limb(row)]; // uploaded when the chain was built: safe to read before the wait
     if constexpr (pl.xchg) hb_cluster_arrive(); // matched by the wait in front of the first remote store
+#if HB_LAT_PREFETCH
+    if constexpr (MODE == 1 && pl.xchg) prefetch_fwd_twiddles<LOGN, T, MODE>(lc, B);
+#endif
     hb_pdl_wait();
     if constexpr (io_has_prefetch<IO>::value) io.prefetch(row, B << (LOGN - pl.lpre), 1 << (LOGN - pl.lpre));
 #if defined(HB_ABL_TMA) && !defined(HB_KERNEL_SIM)
@@ -438,11 +491,11 @@ HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     constexpr int NG = NC >> K;
     constexpr bool first = (P == 0), last = (P == pl.npass - 1);
     static_assert(!first || S0 == 0, "first inverse pass must be contiguous");
-    static_assert(first || S0 >= 4, "strided passes step by multiples of 16 words");
-    static_assert(NG % T == 0 && T % 32 == 0, "whole warps in every step");
+    constexpr bool imm = S0 >= 4; // see fwd_pass
+    static_assert(T % 32 == 0 && (NG % T == 0 || (T % NG == 0 && NG % 32 == 0)), "whole warps in every step (idle warps allowed)");
     const ulonglong2 *tw_pass = (MODE ? lc.inv_lat : lc.inv) + inv_pass_offset(pl, P);
     constexpr int stride = 1 << S0;
-    constexpr int SJ = sstride(1 << S0);
+    constexpr int SJ = imm ? sstride(1 << (imm ? S0 : 4)) : 0;
 
 #pragma unroll 1
     for (int g = threadIdx.x; g < NG; g += T) {
@@ -454,9 +507,12 @@ HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
             warp_load<K>(sm, io, lc, row, B * NC, (g - (int)(threadIdx.x & 31)) << K);
             hb_syncwarp();
             lds_contig<K>(sm, base, v);
-        } else {
+        } else if constexpr (imm) {
 #pragma unroll
             for (int j = 0; j < (1 << K); j++) v[j] = smb[j * SJ];
+        } else {
+#pragma unroll
+            for (int j = 0; j < (1 << K); j++) v[j] = sm[sphys(base + (j << S0))];
         }
 
         inv_levels<K>(v, TwTable{tw_pass + lo, stride}, lc.nq, lc.q2);
@@ -471,9 +527,12 @@ HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
             }
         } else if constexpr (first) {
             sts_contig<K>(sm, base, v);
-        } else {
+        } else if constexpr (imm) {
 #pragma unroll
             for (int j = 0; j < (1 << K); j++) smb[j * SJ] = v[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < (1 << K); j++) sm[sphys(base + (j << S0))] = v[j];
         }
     }
 }
@@ -548,6 +607,9 @@ intt_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     HB_SHARED_U64(sm);
     const int row = blockIdx.x >> pl.lpre, B = blockIdx.x & ((1 << pl.lpre) - 1);
     const LimbConst lc = limbs[io.limb(row)];
+#if HB_LAT_PREFETCH
+    if constexpr (MODE == 1 && pl.xchg) prefetch_inv_twiddles<LOGN, T, MODE>(lc, B);
+#endif
     hb_pdl_wait();
     inv_passes<LOGN, T, 0, MODE>(sm, io, lc, row, B);
     if constexpr (pl.lpre == 1 && !pl.xchg) {
@@ -702,10 +764,12 @@ inline cudaError_t launch_fast_mode(const LaunchEnv &env, const IO &io, const Li
 template <int LOGN, bool FWD, class IO>
 inline cudaError_t launch_fast(const LaunchEnv &env, const IO &io, const LimbConst *limbs, int rows) {
     if constexpr (has_latency_plan(LOGN)) {
-        // N <= 8192: up to latency_rows rows (default half the SM count).  N >= 16384, forward: the 8-CTA plan keeps paying
-        // while the launch is up to ~2 waves of its CTAs (finer grain: less of the last wave idles); inverse (it needs its
-        // registers: one CTA per SM): while the row count fits one wave (profiles/r3_latency_plans.log).
-        const long long limit = LOGN <= 13 ? env.latency_rows : (FWD ? 2ll * env.latency_rows : env.latency_rows / 4);
+        // Row counts up to which the latency plan wins (profiles/r3_latency_plans.md), as multiples of the option
+        // latency_rows (default half the SM count = 74): N <= 8192 (thin 4-CTA plans) 74 rows; N = 16384 (thin 8-CTA plan)
+        // 37 forward rows; N = 32768 (8-CTA plan at 80 registers: finer grain, less of the last wave idles) 148 forward
+        // rows; inverse transforms of N >= 16384 (they need their registers: one or two CTAs per SM) 18 rows.
+        const long long limit = LOGN <= 13 ? env.latency_rows
+                                           : (!FWD ? env.latency_rows / 4 : (LOGN == 14 ? env.latency_rows / 2 : 2ll * env.latency_rows));
         if (rows <= limit) return launch_fast_mode<LOGN, FWD, 1>(env, io, limbs, rows);
     }
     return launch_fast_mode<LOGN, FWD, 0>(env, io, limbs, rows);

@@ -77,12 +77,28 @@ HB_CX NttPlan plan_for(int logn, bool fwd, int mode = 0) {
 #elif HB_PLAN15I == 3
     if (mode == 0 && logn == 15 && !fwd) return NttPlan{15, 2, 4, {4, 4, 3, 4, 0}, 256, 3, 1};
 #endif
+#ifndef HB_LAT_THIN
+#define HB_LAT_THIN 1
+#endif
+#if HB_LAT_THIN
+    // Thin latency plans: 8 words per thread (passes of 3 levels, one of 1-2 where the count needs it) on N/8 threads per row,
+    // spread over a 4- or 8-CTA cluster.  A row alone on its SMs is bound by how fast ONE warp issues dependent instructions
+    // (~6 cycles each at 1-2 warps per scheduler: profiles/r3_latency_plans.md), so its latency is the instruction count per
+    // thread: 52-60 butterflies here against 112 with 16 words per thread on N/16 threads.
+    if (mode == 1 && logn == 12) return NttPlan{12, 2, 4, {3, 3, 3, 3, 0}, 128, 1, 1};
+    if (mode == 1 && logn == 13) return NttPlan{13, 2, 5, {3, 3, 3, 1, 3}, 256, 1, 1};
+    if (mode == 1 && logn == 14) return NttPlan{14, 3, 5, {3, 3, 3, 2, 3}, 256, fwd ? 3 : 2, 1};
+    // N = 32768: five thin passes on 512 threads lose to four passes of 16 words (one pair per call 143 -> 173 us): the
+    // launches of one C5 ciphertext are not latency-bound rows but one to two waves of CTAs
+    if (mode == 1 && logn == 15) return NttPlan{15, 3, 4, {4, 4, 3, 4, 0}, 256, fwd ? 3 : 1, 1};
+#else
     if (mode == 1 && logn == 12) return NttPlan{12, 1, 3, {3, 4, 4, 0, 0}, 128, 1, 0};
     if (mode == 1 && logn == 13) return NttPlan{13, 1, 3, {4, 4, 4, 0, 0}, 256, 1, 0};
     // 80 registers (three 256-thread CTAs per SM): launches of up to ~2 waves of such CTAs still gain from the finer grain
-    // (C5: one pair per call 164 -> 148 us, two per call 115 -> 108 us/ct; profiles/r3_latency_plans.log)
+    // (C5: one pair per call 164 -> 148 us, two per call 115 -> 108 us/ct; profiles/r3_latency_plans.md)
     if (mode == 1 && logn == 14) return NttPlan{14, 3, 4, {4, 3, 3, 4, 0}, 128, fwd ? 6 : 2, 1};
     if (mode == 1 && logn == 15) return NttPlan{15, 3, 4, {4, 4, 3, 4, 0}, 256, fwd ? 3 : 1, 1};
+#endif
     // Measured on B200 (profiles/r1_plan_sweep.md, profiles/r3_cluster_plans.md).  Passes of 3-5 levels keep 8-32 words
     // per thread in registers; ending with two passes of equal width keeps their exchange inside a warp.
     switch (logn) {

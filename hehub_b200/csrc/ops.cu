@@ -424,7 +424,6 @@ static int ext_prod_wave(Context &c, unsigned logn, const LimbConst *limbs, size
     e = launch_ntt<true>(c.env(), logn, io2, limbs, (int)(batch * L * L));
     if (e != cudaSuccess) return c.cuda_fail(e, "ext_prod: ntt launch");
     constexpr int CPT = HB_MAC_CPT;
-    const size_t groups = (batch + CPT - 1) / CPT;
     const bool vec = aligned16(in) && in_batch_stride % 2 == 0 && aligned16(dec) && aligned16(key) && aligned16(out) && n >= 2;
     // batches: the key slice staged in shared memory (needs whole 256 * W slices per row and room for 2 L rows of one)
     const int SW = vec ? 2 : 1;
@@ -455,13 +454,24 @@ static int ext_prod_wave(Context &c, unsigned logn, const LimbConst *limbs, size
             return e == cudaSuccess ? 0 : c.cuda_fail(e, "ext_prod: staged mac launch");
         }
     }
-    const size_t per_group = (L + 1) * (vec ? n / 2 : n), total = groups * per_group;
-    const bool inter = per_group % 256 == 0 && groups > 1;
+    // one ciphertext per call: no second ciphertext to share key words with, so one per thread (fewer registers, more loads in flight)
+    const size_t cpt = batch == 1 ? 1 : CPT;
+    const size_t ngroups = (batch + cpt - 1) / cpt;
+    const size_t per_group = (L + 1) * (vec ? n / 2 : n), total = ngroups * per_group;
+    const bool inter = per_group % 256 == 0 && ngroups > 1;
     auto launch_mac = [&](auto kern) {
         HB_LAUNCH(kern, (unsigned)((total + 255) / 256), 256, 0, c.stream, 0, in, in_batch_stride, dec, key, out, limbs, (int)L, (int)logn,
-                  batch, total, inter ? (unsigned)groups : 0u, (unsigned)(per_group / 256), ginv);
+                  batch, total, inter ? (unsigned)ngroups : 0u, (unsigned)(per_group / 256), ginv);
     };
-    if (vec) {
+    if (batch == 1) {
+        if (vec) {
+            if (ginv == 1) launch_mac(ext_mac_kernel<1, 2, false>);
+            else launch_mac(ext_mac_kernel<1, 2, true>);
+        } else {
+            if (ginv == 1) launch_mac(ext_mac_kernel<1, 1, false>);
+            else launch_mac(ext_mac_kernel<1, 1, true>);
+        }
+    } else if (vec) {
         if (ginv == 1) launch_mac(ext_mac_kernel<CPT, 2, false>);
         else launch_mac(ext_mac_kernel<CPT, 2, true>);
     } else {

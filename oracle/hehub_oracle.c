@@ -680,7 +680,14 @@ int orc_ksk_generate(unsigned logn, size_t L, const u64 *ext_moduli, const u64 *
     u64 *term = malloc(n * sizeof(u64));
     memcpy(sk_ext, sk_orig, L * n * sizeof(u64));
     if (orc_poly_intt(logn, L, ext_moduli, sk_ext, 0)) { rc = 1; goto done; }                       /* keys.cpp:22 */
-    rc = orc_base_transform_to_single(n, L, ext_moduli, sk_ext, P, sk_ext + L * n);               /* :23-25     */
+    /* keys.cpp:23-25 calls rns_base_transform, which hands a single-component input to the one -> many transform
+     * (rns_transform.cpp:118-121): lazy Barrett only when P < q_0, no strict reduction */
+    if (L == 1) {
+        orc_reduce_strict(ext_moduli[0], n, sk_ext);                                                 /* :116 */
+        orc_base_transform_from_single(ext_moduli[0], n, sk_ext, &P, 1, sk_ext + n);
+    } else {
+        rc = orc_base_transform_to_single(n, L, ext_moduli, sk_ext, P, sk_ext + L * n);
+    }
     if (rc) goto done;
     if (orc_poly_ntt_fwd(logn, L1, ext_moduli, sk_ext)) { rc = 1; goto done; }                     /* :26        */
     for (size_t p = 0; p < L; p++) {

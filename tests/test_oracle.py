@@ -366,3 +366,14 @@ def test_keygen_golden_and_reference(oracle, reference, kat):
     errs2 = np.stack([np.stack([rng.integers(0, 5, n).astype(np.uint64) for _ in ext2]) for _ in range(2)])
     assert np.array_equal(oracle.ksk_generate(small_logn, ext2, sk2, sk2, masks2, errs2),
                           reference.ksk_generate(small_logn, ext2, sk2, sk2, masks2, errs2))
+    # one RNS component and a special modulus BELOW it: rns_base_transform then takes its one -> many branch
+    # (rns_transform.cpp:118-121: lazy Barrett, no strict reduction), so the extended key limb is a lazy representative
+    for bits, pbits in (([50], 45), ([40], 30), ([30], 40)):
+        q1, P1 = oracle.ckks_pick_moduli(bits, pbits)
+        q1, ext1 = [int(q1[0])], [int(q1[0]), int(P1)]
+        t = rng.integers(-1, 2, n)
+        s1 = oracle.poly_ntt_fwd(small_logn, q1, np.stack([np.where(t < 0, q1[0] + t, t).astype(np.uint64)]))
+        masks1 = np.stack([np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in ext1])])
+        errs1 = np.stack([np.stack([rng.integers(0, 5, n).astype(np.uint64) for _ in ext1])])
+        assert np.array_equal(oracle.ksk_generate(small_logn, ext1, s1, s1, masks1, errs1),
+                              reference.ksk_generate(small_logn, ext1, s1, s1, masks1, errs1)), (bits, pbits)

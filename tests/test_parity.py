@@ -72,10 +72,10 @@ def test_transforms_wrap_like_the_reference_on_full_range_words(dev, oracle, log
         assert np.array_equal(dev.poly_intt(logn, [q], x), want), (logn, q)
 
 
-@pytest.mark.parametrize("logn", [12, 13])
+@pytest.mark.parametrize("logn", [12, 13, 14, 15])
 def test_latency_and_throughput_plans_agree(dev, oracle, logn):
-    """N = 4096 / 8192 have two pass plans (ntt_plan.h): one CTA per row, and a 2-CTA cluster per row for launches
-    with few rows.  Both must produce the reference's words, for plain and fused transforms."""
+    """N >= 4096 has two pass plans (ntt_plan.h): the throughput plan, and for launches with few rows a thin plan on a
+    4- / 8-CTA cluster.  Both must produce the reference's words, for plain and fused transforms."""
     n = 1 << logn
     mods, ext = _shape(oracle, logn, [40, 30], 40)
     x = np.stack([oracle.lcg_fill(7 + k, Q59, n) for k in range(3)])
@@ -450,9 +450,35 @@ def test_rns_base_transform(dev, oracle):
     from hehub_b200.binding import Unsupported
     with pytest.raises(Unsupported):
         dev.base_transform_to_single(mods, big, P)
+    # one old modulus: the reference's dispatcher takes the one -> many branch (lazy Barrett only when the new modulus is smaller)
+    for q_old, q_new in ((1099507695617, 1073479681), (1073479681, 1099507695617)):
+        x = rng.integers(0, 2 * q_old, (2, 129), dtype=np.uint64)
+        got = dev.base_transform_to_single([q_old], x[:, None, :], q_new)
+        for b in range(2):
+            assert np.array_equal(got[b].ravel(), oracle.base_transform_from_single(q_old, x[b], [q_new]).ravel())
 
 
-@pytest.mark.parametrize("logn,bits,pbits", [(5, [30, 30], 40), (10, [40, 30, 30], 45), (12, [50], 55), (13, [40, 30, 30, 30], 40)])
+def test_key_generation_reports_large_coefficients_at_the_next_synchronize(dev, oracle):
+    """hehub_b200_ksk_generate is stream-asynchronous: when the secret's coefficients are not small (the reference then
+    composes big integers, rns_transform.cpp:86-105, which the back end does not build) the verdict arrives with the
+    next hehub_b200_ctx_synchronize instead of a host round trip inside key generation."""
+    from hehub_b200.binding import Unsupported
+    logn, n = 6, 64
+    mods, ext = _shape(oracle, logn, [30, 30], 40)
+    L = len(mods)
+    rng = np.random.default_rng(5)
+    big_sk = np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in mods])  # INTT of this is not a small polynomial
+    masks = np.stack([np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in ext]) for _ in range(L)])
+    errs = _small_errors(rng, n, ext, L)
+    with pytest.raises(Unsupported):
+        dev.ksk_generate(logn, ext, big_sk, big_sk, masks, errs)  # the binding synchronises when it downloads the key
+    dev.synchronize()  # the verdict has been consumed: the context is usable again
+    sk = _ternary_ntt(oracle, rng, logn, mods)[0]
+    assert np.array_equal(dev.ksk_generate(logn, ext, sk, sk, masks, errs), oracle.ksk_generate(logn, ext, sk, sk, masks, errs))
+
+
+@pytest.mark.parametrize("logn,bits,pbits", [(5, [30, 30], 40), (10, [40, 30, 30], 45), (12, [50], 55), (13, [40, 30, 30, 30], 40),
+                                             (6, [50], 45), (10, [40], 30)])  # the last two: one component, P below it
 def test_ksk_generate_matches_oracle(dev, oracle, logn, bits, pbits):
     """RlweKsk::RlweKsk (keys.cpp:8-36) on supplied samples: raw key words equal the oracle's."""
     mods, ext = _shape(oracle, logn, bits, pbits)

@@ -18,7 +18,7 @@ ncu -i $OUT/prof_ntt_fwd.ncu-rep --page raw --csv > $OUT/raw.csv 2>/dev/null
 ncu -i $OUT/prof_ntt_fwd.ncu-rep --page source --csv > $OUT/src.csv 2>/dev/null
 rm -f $OUT/prof_ntt_fwd.ncu-rep   # gpurun_out/ is capped at 64 MiB; the csv pages carry what the summaries need
 python tools/ncu_summary.py $OUT/raw.csv "ncu --set full: ntt_fwd_fast_kernel<12, RowsIO<0>> (headline kernel), session $TAG" > $OUT/ncu_ntt_fwd_fast12.md
-python tools/sass_census.py $OUT/src.csv --kernel "ntt_fwd_fast_kernel<(int)12" --butterflies $((2*4096*24576)) --stalls > $OUT/sass_census_ntt_fwd_fast12.md
+python tools/sass_census.py $OUT/src.csv --kernel "ntt_fwd_fast_kernel<(int)12" --butterflies $((4096*24576)) --stalls > $OUT/sass_census_ntt_fwd_fast12.md
 # DRAM bytes of that launch, tied to the kernel sources it was taken from (bench.py reports it only while the hash matches)
 python - <<PY
 import csv, json, sys

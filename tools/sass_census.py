@@ -21,6 +21,7 @@ CLASSES = [
     ("LDC / S2R / S2UR / uniform", r"^(LDC|LDCU|S2R|S2UR|R2UR|CS2R|ULDC)"), ("local (spill)", r"^(LDL|STL)"),
 ]
 kernels = collections.OrderedDict()
+seen = {}
 name = None
 for row in csv.reader(open(a.src)):
     if not row:
@@ -32,9 +33,13 @@ for row in csv.reader(open(a.src)):
     if row[0] == "Address" or name is None:
         continue
     try:
-        kernels[name].append((row[1].strip(), int(row[5]), int(row[2])))
+        rec = (row[0], row[1].strip(), int(row[5]), int(row[2]))
     except (ValueError, IndexError):
-        pass
+        continue
+    if rec[0] in seen.setdefault(name, set()):  # some ncu versions list every SASS line twice (SASS + source-correlated view)
+        continue
+    seen[name].add(rec[0])
+    kernels[name].append(rec[1:])
 for name, rows in kernels.items():
     if a.kernel and a.kernel not in name:
         continue
