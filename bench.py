@@ -31,7 +31,7 @@ Q59 = 576460752272228353
 LOGN = 12
 POLYS = 4096
 SLABS = 4
-SWEEP_WAVE = 74  # ciphertexts per wave of the config-5 sweep: a multiple of 37 (2 x 37 rows = one CTA pair per SM pair on 148 SMs)
+SWEEP_WAVE = 296  # ciphertexts per wave of the config-5 sweep: a multiple of 37 (148 SMs); 23 GiB of workspace of the 180 GB
 METRIC = "NTT/s (N=4096, one 59-bit modulus, batch 4096)"
 WORKLOAD = "forward negacyclic NTT, N=4096, L=1, Q=576460752272228353, 4096 polynomials per step per GPU"
 UNIT = "NTT/s"
@@ -511,9 +511,9 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
 
     # batch sizes are multiples of the rows one wave of CTAs covers on 148 SMs (N=8192: 2 CTAs per SM, N=16384: one,
     # N=32768: one CTA pair per row), so every transform launch of the composite ops ends on a full wave
-    ct_bench("c3_ckks_mult_relin_N8192_L4", 13, [40, 30, 30, 30], 40, 296, 4, ("mult", "tensor", "e2e", "latency"))
+    ct_bench("c3_ckks_mult_relin_N8192_L4", 13, [40, 30, 30, 30], 40, 1184, 4, ("mult", "tensor", "e2e", "latency"))
     ct_bench("c4_rescale_N16384_L8", 14, [50] + [40] * 7, 50, 148, 4, ("rescale",))
-    ct_bench("c5_ckks_mult_relin_N32768_L12", 15, [50] * 12, 55, 74, 2, ("mult", "tensor", "latency"))
+    ct_bench("c5_ckks_mult_relin_N32768_L12", 15, [50] * 12, 55, 296, 2, ("mult", "tensor", "latency"))
 
     # config 5 as a sweep: `sweep_cts` independent ciphertext pairs (65 536 in BASELINE; bounded by default so the
     # whole bench stays within minutes) cut into contiguous per-rank ranges, processed in waves, inputs generated
@@ -531,7 +531,7 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
             coll, coll_destroy = nccl_collectives(rank, world, torch.cuda.current_device(), exchange)
         sw = CtSweep(ctx, 15, [int(m) for m in mods], int(p), seed=42, rank=rank, world=world, collectives=coll)
         sw.make_key()  # rank 0 generates, ncclBroadcast
-        sw.run(min(sweep_cts, 74 * world), SWEEP_WAVE)  # warm-up (tables, workspaces)
+        sw.run(min(sweep_cts, SWEEP_WAVE * world), SWEEP_WAVE)  # warm-up (tables, workspaces)
         barrier()
         t0 = time.perf_counter()
         res = sw.run(sweep_cts, SWEEP_WAVE, time_ops=True)  # device time: CUDA events inside the driver, around the mult+relin calls

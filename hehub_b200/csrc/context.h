@@ -46,7 +46,9 @@ struct Context {
     int sm_count = 148;
     int latency_rows = -1; // option "latency_rows"; -1: half the SM count
     LaunchEnv env() { return LaunchEnv{stream, sm_count, force_generic, &stats, latency_rows < 0 ? sm_count / 2 : latency_rows, device}; }
-    size_t scratch_cap_bytes = (size_t)8 << 30; // bound on the per-call workspace (option "scratch_cap_mib"); batches run in waves
+    // bound on the per-call workspace (option "scratch_cap_mib"); batches run in waves.  32 GiB of the 180 GB: a C5 wave of 296
+    // ciphertexts (23 GiB with its key-switch digits) runs 1.7 % faster per ciphertext than four waves of 74 (profiles/r3_cluster_plans.md)
+    size_t scratch_cap_bytes = (size_t)32 << 30;
     std::string last_error;
     LaunchStats stats;
 

@@ -574,7 +574,7 @@ def test_batched_ops_and_waves(dev, oracle):
         want_rot = np.stack([oracle.ckks_rotate(logn, ext, ct1[b], key, 2) for b in range(batch)])
         assert np.array_equal(dev.ckks_rotate(logn, ext, ct1, key, 2), want_rot)
     finally:
-        dev.set_option("scratch_cap_mib", 8192)
+        dev.set_option("scratch_cap_mib", 32768)
     want_rs = np.stack([oracle.ckks_rescale(logn, mods, ct1[b]) for b in range(batch)])
     assert np.array_equal(dev.ckks_rescale(logn, mods, ct1), want_rs)
     want_t = np.stack([oracle.ckks_tensor(logn, mods, ct1[b], ct2[b]) for b in range(batch)])
