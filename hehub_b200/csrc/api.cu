@@ -298,6 +298,8 @@ int hehub_b200_ctx_set_option(hehub_b200_ctx *ctx, const char *name, int64_t val
         c.force_generic = value != 0;
     } else if (!std::strcmp(name, "latency_rows")) { // -1: default (half the SM count); 0: never use the latency plans
         c.latency_rows = (int)value;
+    } else if (!std::strcmp(name, "single_launch")) { // 0: one ckks::mult pair per call runs as six launches (A/B)
+        c.single_launch = value != 0;
     } else if (!std::strcmp(name, "host_chunk_kib")) {
         if (value < 1) return c.fail(HEHUB_B200_ERR_INVALID, "host_chunk_kib must be positive");
         c.host_chunk_bytes = (size_t)value << 10;

@@ -45,6 +45,13 @@ struct Context {
     bool force_generic = false;
     int sm_count = 148;
     int latency_rows = -1; // option "latency_rows"; -1: half the SM count
+    // option "single_launch": one ckks::mult pair per call as ONE launch with grid barriers (N = 4096 / 8192).  Off by default:
+    // measured slower than the six programmatically chained launches (39 vs 33 us at C3, profiles/r3_latency_plans.md)
+    bool single_launch = false;
+    unsigned long long *grid_barrier_dev = nullptr; // counter of the single-launch kernel's grid barriers (only grows)
+    unsigned long long grid_barrier_count = 0;       // its value once every launch enqueued so far has finished
+    unsigned long long *grid_barrier_counter();
+    int mult_one_clusters[2] = {0, 0}; // resident clusters of that kernel on this device (0: not asked yet, -1: launch form unavailable)
     LaunchEnv env() { return LaunchEnv{stream, sm_count, force_generic, &stats, latency_rows < 0 ? sm_count / 2 : latency_rows, device}; }
     // bound on the per-call workspace (option "scratch_cap_mib"); batches run in waves.  32 GiB of the 180 GB: a C5 wave of 296
     // ciphertexts (23 GiB with its key-switch digits) runs 1.7 % faster per ciphertext than four waves of 74 (profiles/r3_cluster_plans.md)

@@ -25,7 +25,7 @@
 
 namespace hb {
 
-constexpr int kMaxPasses = 5;
+constexpr int kMaxPasses = 7;
 
 struct NttPlan {
     int logn;
@@ -85,6 +85,14 @@ HB_CX NttPlan plan_for(int logn, bool fwd, int mode = 0) {
     // spread over a 4- or 8-CTA cluster.  A row alone on its SMs is bound by how fast ONE warp issues dependent instructions
     // (~6 cycles each at 1-2 warps per scheduler: profiles/r3_latency_plans.md), so its latency is the instruction count per
     // thread: 52-60 butterflies here against 112 with 16 words per thread on N/16 threads.
+#if defined(HB_LAT_C8) // A/B: eight CTAs of four warps per row
+    if (mode == 1 && logn == 12) return NttPlan{12, 3, 4, {3, 3, 3, 3, 0}, 64, 1, 1};
+    if (mode == 1 && logn == 13) return NttPlan{13, 3, 5, {3, 3, 3, 1, 3}, 128, 1, 1};
+#endif
+#if HB_LAT_THIN == 2 // four words per thread on N/4 threads: six / seven passes of two levels
+    if (mode == 1 && logn == 12) return NttPlan{12, 2, 6, {2, 2, 2, 2, 2, 2, 0}, 256, 1, 1};
+    if (mode == 1 && logn == 13) return NttPlan{13, 2, 7, {2, 2, 2, 2, 2, 1, 2}, 512, 1, 1};
+#endif
     if (mode == 1 && logn == 12) return NttPlan{12, 2, 4, {3, 3, 3, 3, 0}, 128, 1, 1};
     if (mode == 1 && logn == 13) return NttPlan{13, 2, 5, {3, 3, 3, 1, 3}, 256, 1, 1};
     if (mode == 1 && logn == 14) return NttPlan{14, 3, 5, {3, 3, 3, 2, 3}, 256, fwd ? 3 : 2, 1};

@@ -60,13 +60,9 @@ HB_D void st_words(u64 *p, const u64 (&src)[W]) {
 
 // W = 2: one thread per pair of adjacent coefficients (128-bit accesses); W = 1: slabs that are only 8-byte aligned
 template <int W>
-HB_GLOBAL(256, HB_TENSOR_MINB)
-tensor_kernel(const u64 *__restrict__ ct1, const u64 *__restrict__ ct2, u64 *__restrict__ quad,
-              const LimbConst *__restrict__ limbs, int L, int logn, size_t units_total) {
-    hb_pdl_wait();
+HB_D void tensor_unit(const u64 *__restrict__ ct1, const u64 *__restrict__ ct2, u64 *__restrict__ quad, const LimbConst *__restrict__ limbs,
+                      int L, int logn, size_t gid) {
     constexpr int LW = (W == 2) ? 1 : 0;
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= units_total) return;
     const size_t row = gid >> (logn - LW);              // b * L + l
     const size_t i = (gid & (((size_t)1 << (logn - LW)) - 1)) * W;
     const size_t b = row / L, l = row % L;
@@ -88,6 +84,15 @@ tensor_kernel(const u64 *__restrict__ ct1, const u64 *__restrict__ ct2, u64 *__r
     st_words<W>(quad + o0, d0);
     st_words<W>(quad + o0 + poly, d1);
     st_words<W>(quad + o0 + 2 * poly, d2);
+}
+template <int W>
+HB_GLOBAL(256, HB_TENSOR_MINB)
+tensor_kernel(const u64 *__restrict__ ct1, const u64 *__restrict__ ct2, u64 *__restrict__ quad,
+              const LimbConst *__restrict__ limbs, int L, int logn, size_t units_total) {
+    hb_pdl_wait();
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= units_total) return;
+    tensor_unit<W>(ct1, ct2, quad, limbs, L, logn, gid);
 }
 
 int op_ckks_tensor(Context &c, unsigned logn, const u64 *moduli, size_t L, const u64 *ct1, const u64 *ct2, u64 *quad,
@@ -204,6 +209,10 @@ struct ExtFanoutIO {
 // key word fetched from L2 feeds CPT products: the key stream (2 L (L+1) N words per ciphertext,
 // more than every other operand together) is what bounds this kernel.
 template <int CPT, int W, bool GALOIS>
+HB_D void ext_mac_unit(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
+                       u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, int logn, size_t batch, size_t gid,
+                       unsigned ginv);
+template <int CPT, int W, bool GALOIS>
 HB_GLOBAL(256, HB_MAC_MINB)
 ext_mac_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
                u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, int logn, size_t batch, size_t total,
@@ -216,6 +225,12 @@ ext_mac_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__
     if (groups) gid = ((size_t)(blockIdx.x % groups) * chunks_per_group + blockIdx.x / groups) * 256 + threadIdx.x;
     else gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
+    ext_mac_unit<CPT, W, GALOIS>(in, in_batch_stride, dec, key, out, limbs, L, logn, batch, gid, ginv);
+}
+template <int CPT, int W, bool GALOIS>
+HB_D void ext_mac_unit(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
+                       u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, int logn, size_t batch, size_t gid,
+                       unsigned ginv) {
     const int L1 = L + 1;
     constexpr int LW = (W == 2) ? 1 : 0;
     const size_t i = (gid & (((size_t)1 << (logn - LW)) - 1)) * W;
@@ -553,7 +568,9 @@ struct DropInttIO {
 };
 
 // step 2: per remaining limb k: r = centre(barrett(z)); NTT; out = H(lazy_sub(ct, r), q_last^{-1}) [...]
-template <bool BGV, bool GALOIS = false>
+// NC: the epilogue's operands come over the non-coherent path (they were written by earlier launches); false inside the
+// single-launch kernel, where earlier PHASES of the same launch wrote them
+template <bool BGV, bool GALOIS = false, bool NC = true>
 struct DropFwdIO {
     const u64 *ct;
     const u64 *z;
@@ -580,11 +597,12 @@ struct DropFwdIO {
     HB_D void store(int row, int i, u64 v, const LimbConst &lc) const {
         const int poly = row / (L - 1), k = row - poly * (L - 1);
         const DropConst *d = dc + k;
-        u64 x = finish(hb_ld_ro(ct + ((size_t)(poly * L + k) << logn) + i), v, d, lc);
+        u64 x = finish(NC ? hb_ld_ro(ct + ((size_t)(poly * L + k) << logn) + i) : hb_ld_stream(ct + ((size_t)(poly * L + k) << logn) + i), v, d, lc);
         const int h = poly & 1, b = poly >> 1;
         if (h < add_halves) { // ckks/arith.cpp:70-71, 84, 91
             const unsigned from = GALOIS ? galois_from((unsigned)i, add_ginv, logn) : (unsigned)i;
-            x = add_lazy(x, hb_ld_ro(addend + (size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn) + from), lc.q2);
+            const u64 *ap = addend + (size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn) + from;
+            x = add_lazy(x, NC ? hb_ld_ro(ap) : hb_ld_stream(ap), lc.q2);
         }
         out[((size_t)row << logn) + i] = x;
     }
@@ -611,12 +629,12 @@ struct DropFwdIO {
     HB_D void store2(int row, int i, u64 v0, u64 v1, const LimbConst &lc) const {
         const int poly = row / (L - 1), k = row - poly * (L - 1);
         const DropConst *d = dc + k;
-        const ulonglong2 x = hb_ld_ro2(ct + ((size_t)(poly * L + k) << logn) + i);
+        const ulonglong2 x = NC ? hb_ld_ro2(ct + ((size_t)(poly * L + k) << logn) + i) : hb_ld_stream2(ct + ((size_t)(poly * L + k) << logn) + i);
         ulonglong2 r = make_ulonglong2(finish(x.x, v0, d, lc), finish(x.y, v1, d, lc));
         const int h = poly & 1, b = poly >> 1;
         if (h < add_halves) { // ckks/arith.cpp:70-71, 84, 91
             const u64 *arow = addend + (size_t)b * add_batch_stride + (size_t)h * add_poly_stride + ((size_t)k << logn);
-            const ulonglong2 a = GALOIS ? galois_pair(arow, (unsigned)i, add_ginv, logn, true) : hb_ld_ro2(arow + i);
+            const ulonglong2 a = GALOIS ? galois_pair(arow, (unsigned)i, add_ginv, logn, NC) : (NC ? hb_ld_ro2(arow + i) : hb_ld_stream2(arow + i));
             r.x = add_lazy(r.x, a.x, lc.q2);
             r.y = add_lazy(r.y, a.y, lc.q2);
         }
@@ -697,6 +715,159 @@ int op_relinearize(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// ONE launch for one ckks::mult (ckks.h:270-274) — N = 4096 / 8192, one ciphertext pair per call; option "single_launch".
+// The six steps of the wave path (tensor, INTT of d2, fan-out, inner product, INTT of the P limb, forward + drop epilogue)
+// run as phases of one grid of 4-CTA clusters, separated by grid barriers; phases reuse the transform passes and IO
+// policies of the multi-launch path unchanged (thin latency plans, clusters exchanging through distributed shared
+// memory).  Operands a later phase reads were written by an earlier phase of the SAME launch, so nothing here uses the
+// non-coherent load path for them (DropFwdIO<.., NC = false>).
+// MEASURED, and therefore OFF by default (profiles/r3_latency_plans.md, C3 shape, one pair per call): six launches chained
+// by programmatic dependent launch 33.2 us; this kernel with a counter barrier 39.2 us, with cooperative-groups grid.sync
+// 43.1 us; the six launches replayed from a CUDA graph 34.9 us.  A phase costs what its kernel costs (~5 us: one row's
+// butterflies on a few SMs, bound by per-warp issue and the multiplier of those SMs); the launch boundaries that this form
+// removes were already hidden.
+// ------------------------------------------------------------------------------------------
+#if !defined(HB_KERNEL_SIM)
+} // namespace hb
+#include <cooperative_groups.h>
+namespace hb {
+#ifndef HB_MULT_ONE_COOP
+#define HB_MULT_ONE_COOP 0
+#endif
+// Grid barrier of the single-launch kernel.  Every CTA of the grid is resident (the grid is sized from
+// cudaOccupancyMaxActiveClusters and capped at one CTA per SM), so a counter in global memory that only grows is enough:
+// barrier number b of a launch that started at count c0 is passed once the count reaches c0 + (b + 1) * gridDim.x.
+HB_D void grid_barrier(unsigned long long *counter, unsigned long long &passed) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        passed += gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1ull);
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter) : "memory");
+        } while (seen < passed);
+    }
+    __syncthreads();
+}
+struct MultOneArgs {
+    unsigned long long *barrier; // grid-barrier counter (device), and its value when this launch starts
+    unsigned long long barrier_base;
+    const u64 *ct1, *ct2, *key;
+    u64 *out;
+    u64 *quad, *cbuf, *dec, *ebuf, *z; // workspaces: [3][L][N], [L][N], [L][L+1][N], [2][L+1][N], [2][N]
+    const LimbConst *limbs;             // q_0 .. q_{L-1}, P with tables for this ring
+    const DropConst *dc;
+    u64 half_qlast;
+    int L;
+};
+template <int LOGN>
+__global__ void __launch_bounds__(plan_for(LOGN, true, 1).threads, 1) ckks_mult_one_kernel(const MultOneArgs a) {
+    constexpr NttPlan plf = plan_for(LOGN, true, 1), pli = plan_for(LOGN, false, 1);
+    static_assert(plf.xchg && pli.xchg && plf.threads == pli.threads && plf.lpre == pli.lpre, "one cluster shape for both directions");
+    constexpr int T = plf.threads, C = 1 << plf.lpre;
+    HB_SHARED_U64(sm);
+#if HB_MULT_ONE_COOP
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+#define HB_GRID_SYNC() grid.sync()
+#else
+    unsigned long long passed = a.barrier_base;
+#define HB_GRID_SYNC() grid_barrier(a.barrier, passed)
+    hb_pdl_wait();
+#endif
+    const int cid = blockIdx.x / C, B = blockIdx.x % C, nclusters = gridDim.x / C, L = a.L;
+    const size_t n = (size_t)1 << LOGN, Ln = (size_t)L << LOGN;
+    const size_t tid = (size_t)blockIdx.x * T + threadIdx.x, nthreads = (size_t)gridDim.x * T;
+    // tensor product (ckks/arith.cpp:55-62)
+    for (size_t gid = tid; gid < ((size_t)L << (LOGN - 1)); gid += nthreads) tensor_unit<2>(a.ct1, a.ct2, a.quad, a.limbs, L, LOGN, gid);
+    HB_GRID_SYNC();
+    { // c = strict(INTT(d2))                                           rgsw.cpp:103-105
+        const ExtInttIO<false> io{a.quad + 2 * Ln, 3 * Ln, a.cbuf, L, LOGN, true, 1u};
+        for (int row = cid; row < L; row += nclusters) inv_passes<LOGN, T, 0, 1>(sm, io, a.limbs[io.limb(row)], row, B);
+    }
+    HB_GRID_SYNC();
+    { // dec[p][k] = NTT_{q_k}(c[p]), k != p                            rgsw.cpp:108-119
+        const ExtFanoutIO io{a.cbuf, a.dec, L, LOGN, true};
+        for (int row = cid; row < L * L; row += nclusters) {
+            hb_cluster_arrive(); // every CTA of the cluster is done with its previous row before words are scattered into it
+            fwd_passes<LOGN, T, 0, 1>(sm, io, a.limbs[io.limb(row)], row, B);
+        }
+    }
+    HB_GRID_SYNC();
+    // e[h][k] = Mont128(sum_p dec[p][k] * key[p][h][k])                 rgsw.cpp:126-153
+    for (size_t gid = tid; gid < (size_t)(L + 1) * (n / 2); gid += nthreads)
+        ext_mac_unit<1, 2, false>(a.quad + 2 * Ln, 3 * Ln, a.dec, a.key, a.ebuf, a.limbs, L, LOGN, 1, gid, 1u);
+    HB_GRID_SYNC();
+    { // z = strict(INTT_P(e[.][L]))                                    rescaling.cpp:47-50
+        const DropInttIO<false> io{a.ebuf, a.z, L + 1, LOGN, 0, 0, true};
+        for (int row = cid; row < 2; row += nclusters) inv_passes<LOGN, T, 0, 1>(sm, io, a.limbs[io.limb(row)], row, B);
+    }
+    HB_GRID_SYNC();
+    { // out = (e - NTT(centre(z))) / P + (d0, d1)                      rescaling.cpp:52-75, ckks/arith.cpp:70-71
+        const DropFwdIO<false, false, false> io{a.ebuf, a.z, a.out, a.dc, a.quad, 3 * Ln, Ln, a.half_qlast, L + 1, LOGN, 2, true, 1u};
+        for (int row = cid; row < 2 * L; row += nclusters) {
+            hb_cluster_arrive();
+            fwd_passes<LOGN, T, 0, 1>(sm, io, a.limbs[io.limb(row)], row, B);
+        }
+    }
+#if !HB_MULT_ONE_COOP
+    if (threadIdx.x == 0) atomicAdd(a.barrier, 1ull); // sixth arrival: the count ends at base + 6 * gridDim.x whatever happens next
+#endif
+}
+#undef HB_GRID_SYNC
+
+template <int LOGN>
+static int launch_mult_one(Context &c, const MultOneArgs &args) {
+    constexpr NttPlan pl = plan_for(LOGN, true, 1);
+    constexpr int C = 1 << pl.lpre, smem = smem_words(1 << (LOGN - pl.lpre)) * 8;
+    auto kern = ckks_mult_one_kernel<LOGN>;
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(pl.threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c.stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C;
+    at[0].val.clusterDim.y = at[0].val.clusterDim.z = 1;
+#if HB_MULT_ONE_COOP
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+#else
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = hb_pdl_enabled() ? 1 : 0;
+#endif
+    cfg.attrs = at;
+    cfg.numAttrs = 2;
+    int &clusters = c.mult_one_clusters[LOGN - 12];
+    if (clusters == 0) { // how many clusters are resident at once decides the grid: a cooperative grid must fit the GPU whole
+        cfg.gridDim = dim3(C * c.sm_count);
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+            cudaGetLastError();
+            clusters = -1;
+        } else {
+            clusters = n < c.sm_count / C ? n : c.sm_count / C; // one CTA per SM is plenty: phases have at most L * L rows
+        }
+    }
+    if (clusters < 0) return -1;
+    cfg.gridDim = dim3((unsigned)(clusters * C));
+    MultOneArgs a2 = args;
+    a2.barrier = c.grid_barrier_counter();
+    if (!a2.barrier) return -1;
+    a2.barrier_base = c.grid_barrier_count; // launches of one stream run in order: the count after all earlier launches
+    c.grid_barrier_count += 6ull * cfg.gridDim.x; // six barriers per launch (the last one keeps the count exact)
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a2);
+    if (e != cudaSuccess) { // cooperative + cluster launch refused on this driver: remember and use the six launches
+        cudaGetLastError();
+        clusters = -1;
+        return -1;
+    }
+    c.stats.launches++;
+    return 0;
+}
+#endif
+
 int op_mult_relin(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u64 t, const u64 *ct1, const u64 *ct2,
                   const u64 *key, u64 *out, size_t batch) {
     if (!ext_moduli || !ct1 || !ct2 || !key || !out) return c.fail(1, "null operand");
@@ -708,6 +879,25 @@ int op_mult_relin(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u6
     int err = 0;
     u64 *quad = c.get_scratch(4, wave * 3 * L * n, &err);
     if (!quad) return err;
+#if !defined(HB_KERNEL_SIM)
+    // one ciphertext pair, CKKS, N = 4096 / 8192, 16-byte aligned operands: the single-launch kernel
+    if (batch == 1 && t == 0 && (logn == 12 || logn == 13) && c.single_launch && !c.force_generic && aligned16(ct1) && aligned16(ct2) &&
+        aligned16(key) && aligned16(out)) {
+        for (size_t k = 0; k <= L; k++)
+            if (!(ext_moduli[k] & 1)) return c.fail(1, "Montgomery reduction needs odd moduli");
+        const LimbConst *limbs = c.get_chain(logn, ext_moduli, L + 1, &err);
+        if (!limbs) return err;
+        const DropSet *ds = c.get_drop(logn, ext_moduli, L + 1, 0, &err);
+        if (!ds) return err;
+        MultOneArgs a{nullptr, 0, ct1, ct2, key, out, quad, nullptr, nullptr, nullptr, nullptr, limbs, ds->dev, ds->half_qlast, (int)L};
+        if (!(a.cbuf = c.get_scratch(0, L * n, &err))) return err;
+        if (!(a.dec = c.get_scratch(1, L * (L + 1) * n, &err))) return err;
+        if (!(a.z = c.get_scratch(2, 2 * n, &err))) return err;
+        if (!(a.ebuf = c.get_scratch(3, 2 * (L + 1) * n, &err))) return err;
+        const int rc = logn == 12 ? launch_mult_one<12>(c, a) : launch_mult_one<13>(c, a);
+        if (rc == 0) return 0; // otherwise: the launch form is not available here, fall through to the six launches
+    }
+#endif
     for (size_t b0 = 0; b0 < batch; b0 += wave) {
         const size_t nb = (batch - b0 < wave) ? batch - b0 : wave;
         if (int rc = op_ckks_tensor(c, logn, ext_moduli, L, ct1 + b0 * 2 * L * n, ct2 + b0 * 2 * L * n, quad, nb)) return rc;

@@ -80,6 +80,7 @@ Context::~Context() {
     for (auto &s : scratch)
         if (s.first) cudaFree(s.first);
     if (deferred_flags) cudaFreeHost(deferred_flags);
+    if (grid_barrier_dev) cudaFree(grid_barrier_dev);
     if (pipe_ready) {
         for (int i = 0; i < kPipeSlots; i++) {
             cudaEventDestroy(ev_in[i]);
@@ -90,6 +91,18 @@ Context::~Context() {
         cudaStreamDestroy(s_out);
     }
     if (owns_stream && stream) cudaStreamDestroy(stream);
+}
+
+unsigned long long *Context::grid_barrier_counter() {
+    if (!grid_barrier_dev) {
+        if (cudaMalloc(&grid_barrier_dev, sizeof(unsigned long long)) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        cudaMemsetAsync(grid_barrier_dev, 0, sizeof(unsigned long long), stream);
+        grid_barrier_count = 0;
+    }
+    return grid_barrier_dev;
 }
 
 int *Context::deferred_flag_slot(int *err) {

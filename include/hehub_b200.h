@@ -54,6 +54,9 @@ const char *hehub_b200_last_error(const hehub_b200_ctx *ctx);
  * "host_chunk_kib" sets the chunk size of the host-buffer pipeline (default 16384; measured best on PCIe Gen5, profiles/r1d_e2e_chunk_sweep.log);
  * "latency_rows": transform launches with at most this many rows (one limb of one polynomial each) split every
  *   row of N = 4096 / 8192 over a 2-CTA cluster (default -1 = half the SM count; 0 = never).
+ * "single_launch" (default 0): 1 makes hehub_b200_ckks_mult_relin with batch 1 at N = 4096 / 8192 run as ONE launch (grid
+ *   barriers between its six phases) instead of six programmatically chained launches; measured slower (39 vs 33 us at
+ *   N = 8192, L = 4), kept for A/B.
  * Environment: HEHUB_B200_PDL=0 turns programmatic dependent launch off (A/B only). */
 int hehub_b200_ctx_set_option(hehub_b200_ctx *ctx, const char *name, int64_t value);
 /* number of kernels this context has launched since creation (bench bookkeeping) */

@@ -799,3 +799,35 @@ def test_key_switch_inner_product_with_staged_key(dev, oracle, logn, bits, batch
         for s in (a, k, out):
             s.free()
     assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("logn,bits", [(12, [39, 30]), (13, [40, 30, 30, 30])])
+def test_single_launch_mult_matches_oracle(oracle, logn, bits):
+    """Option single_launch: one ckks::mult pair per call as ONE launch (six phases, grid barriers) — same words as the six
+    launches and as the oracle, call after call (the barrier counter only grows)."""
+    import subprocess, sys, os
+    # in a child process with a wall-clock limit: a grid barrier that never completes must not take the test session with it
+    code = f"""
+import sys, numpy as np
+sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+sys.path.insert(0, {os.path.dirname(os.path.abspath(__file__))!r})
+from hehub_b200.binding import Context, pick_moduli
+from oracle.binding import Oracle
+from conftest import fill_ct, fill_key
+orc, ctx = Oracle(), Context(device=0)
+mods, p = pick_moduli({bits!r}, {bits[0]}, ctx.lib)
+ext, n = mods + [p], 1 << {logn}
+ctx.set_option("single_launch", 1)
+for rep in range(3):
+    ct1, ct2, key = fill_ct(orc, 11 + rep, mods, n), fill_ct(orc, 21 + rep, mods, n), fill_key(orc, 3100 + rep, ext, n)
+    before = ctx.launch_count()
+    got = ctx.ckks_mult_relin({logn}, ext, ct1, ct2, key)
+    assert ctx.launch_count() - before == 1, ctx.launch_count() - before
+    assert np.array_equal(got, orc.ckks_mult_relin({logn}, ext, ct1, ct2, key)), rep
+ctx.set_option("single_launch", 0)
+assert np.array_equal(ctx.ckks_mult_relin({logn}, ext, ct1, ct2, key), got)
+print("ok")
+"""
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stdout + res.stderr

@@ -14,12 +14,14 @@ ap.add_argument("--batch", type=int, default=0, help="override the shape's batch
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--latency-rows", type=int, default=None, help="context option latency_rows")
 ap.add_argument("--scratch-mib", type=int, default=None, help="context option scratch_cap_mib")
+ap.add_argument("--single-launch", type=int, default=None, help="context option single_launch")
 a = ap.parse_args()
 SHAPES = {"c3": (13, [40, 30, 30, 30], 40, 296), "c4": (14, [50] + [40] * 7, 50, 148), "c5": (15, [50] * 12, 55, 74)}
 orc = Oracle()
 ctx = Context(lib_path=a.lib)
 if a.latency_rows is not None: ctx.set_option("latency_rows", a.latency_rows)
 if a.scratch_mib is not None: ctx.set_option("scratch_cap_mib", a.scratch_mib)
+if a.single_launch is not None: ctx.set_option("single_launch", a.single_launch)
 for name in a.shape:
     logn, bits, pbits, batch = SHAPES[name]
     batch = a.batch or batch
