@@ -321,7 +321,7 @@ def run_cuda(args):
         extras["rows_c3_shape"] = run_rows(ctx, torch, timed, world, rank, peaks, cpu_ok=(rank == 0 and world == 1 and not args.no_cpu))
     if args.extras:
         extras.update(run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist if world > 1 else None, args.sweep_cts,
-                                 cpu_ok=(rank == 0 and world == 1 and not args.no_cpu), parity_ok=not args.no_cpu))
+                                 cpu_ok=(rank == 0 and world == 1 and not args.no_cpu), parity_ok=not args.no_cpu, local=local))
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------------
     cpu = None
@@ -383,7 +383,7 @@ def ct_mult_summary(extras):
     return out or None
 
 
-def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, sweep_cts=0, cpu_ok=False, parity_ok=False):
+def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, sweep_cts=0, cpu_ok=False, parity_ok=False, local=0):
     """Other BASELINE configs, device-resident, same timing discipline; values are whole-job."""
     import numpy as np
     from hehub_b200.binding import _mod, pick_moduli  # moduli come from the product's create_params rule (csrc/params.cu)
@@ -528,6 +528,10 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
                 box = [raw]
                 dist.broadcast_object_list(box, src=0)
                 return box[0]
+            if local == 0:  # the provider library is built in-tree by __graft_entry__.build(); make sure it is there
+                import __graft_entry__ as ge
+                ge.build_nccl()
+            barrier()
             coll, coll_destroy = nccl_collectives(rank, world, torch.cuda.current_device(), exchange)
         sw = CtSweep(ctx, 15, [int(m) for m in mods], int(p), seed=42, rank=rank, world=world, collectives=coll)
         sw.make_key()  # rank 0 generates, ncclBroadcast
