@@ -1,7 +1,7 @@
 // ckks.h — hehub::ckks on the B200 back end (src/fhe/ckks/ckks.h:19-329, basics.cpp:14-64, arith.cpp,
-// rescaling.cpp): parameter selection, encrypt / decrypt and every ciphertext operator.  Only the encoder
-// (complex fp64 FFT + decimal big integers, basics.cpp:68-369) is not here: it is host-side floating-point
-// code outside the integer hot path; a CkksPt produced by it is consumed unchanged.
+// rescaling.cpp): parameter selection, encrypt / decrypt and every ciphertext operator.  The encoder (complex fp64
+// FFT, basics.cpp:68-369) is host-side code outside the integer hot path; it lives in
+// ckks_encoding.h, restated so that it hands the integer path the same words as the reference.
 #pragma once
 #include <cmath>
 #include <map>
@@ -263,6 +263,12 @@ inline CkksCt rotate(const CkksCt &ct, const RlweKsk &rot_key, const size_t step
 inline CkksCt rotate(const CkksCt &ct, const RotKey &rot_key) { return rotate(ct, rot_key, rot_key.step); }
 
 } // namespace ckks
+
+} // namespace hehub
+
+#include "ckks_encoding.h" // simd_encode / simd_decode / encode / decode: host-side, see the header
+
+namespace hehub {
 
 using CkksParams = ckks::CkksParams;
 using CkksPt = ckks::CkksPt;

@@ -440,6 +440,17 @@ class Reference(_CpuLib):
             raise ValueError(f"rng_scenario_bgv rc={rc}")
         return [int(v) for v in out], dec
 
+    def ckks_codec_scenario(self, logn, moduli_bits, additional_bits, log2_scaling, seed, count):
+        bits = (C.c_uint * len(moduli_bits))(*moduli_bits)
+        h = np.zeros(1, dtype=np.uint64)
+        dec = np.zeros(1 << logn, dtype=np.float64)  # (re, im) per slot, n / 2 slots
+        rc = self._fn("ckks_codec_scenario", C.c_int, C.c_uint, C.c_size_t, C.POINTER(C.c_uint), C.c_uint, C.c_double, u64, C.c_size_t,
+                      p64, C.POINTER(C.c_double))(logn, len(moduli_bits), bits, additional_bits, float(log2_scaling), seed, count, _ptr(h),
+                                                   dec.ctypes.data_as(C.POINTER(C.c_double)))
+        if rc:
+            raise ValueError(f"ckks_codec_scenario rc={rc}")
+        return int(h[0]), dec
+
     def cache_ntt_factors(self, logn, moduli):
         m = _arr(moduli)
         self._fn("cache_ntt_factors", None, C.c_uint, p64, C.c_size_t)(logn, _ptr(m), m.size)

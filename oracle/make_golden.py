@@ -236,6 +236,20 @@ def main():
                            "hashes": [f"{h:016x}" for h in hs], "decoded": hx(dec)})
     kat["rng"] = rng
 
+    # ---- CKKS encoder / decoder (host-side floating point, ckks/basics.cpp:156-369): plaintext hash (bit-exact target) and the
+    #      first decoded slots (tolerance target); small and wide-integer branches of both directions ----
+    codec = []
+    for logn, bits, add, log2s, seed, count in [(10, [40, 30, 30], 40, 30, 3, 512), (12, [39, 30], 39, 30, 4, 2048), (8, [50, 50], 55, 70, 5, 100),
+                                                (11, [40, 30], 40, 50, 6, 1024), (6, [30], 40, 20, 7, 32)]:
+        # in a separate executable: the reference's stringstream-based big integers crash inside this interpreter (ref_tool.cpp)
+        import subprocess
+        tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "ref_tool")
+        line = subprocess.check_output([tool, "codec", str(logn), str(add), str(log2s), str(seed), str(count)] + [str(b) for b in bits], text=True)
+        entry = {"logn": logn, "bits": bits, "additional_bits": add, "log2_scaling": log2s, "seed": seed, "count": count}
+        entry.update(json.loads(line))
+        codec.append(entry)
+    kat["ckks_codec"] = codec
+
     # ---- the prime table (primelists.cpp) ----------------------------------
     kat["prime_rows"] = {str(b): ref.prime_row(b, 32) for b in range(0, 60) if ref.prime_row(b, 32)}
     kat["inverse_mod_prime"] = [[a, p, ref.inverse_mod_prime(a, p)] for a, p in

@@ -519,6 +519,33 @@ int ref_rng_scenario_bgv(u64 seed, unsigned logn, size_t L, const unsigned *modu
     });
 }
 
+/* CKKS encoder / decoder (host-side floating point, ckks/basics.cpp:156-369): `count` complex data from an LCG in
+ * [-1, 1) x [-1, 1), encoded at scaling 2^log2_scaling; hash[0] = FNV of the plaintext words; decoded[2 * slots] = (re, im) of
+ * simd_decode of that plaintext. */
+int ref_ckks_codec_scenario(unsigned logn, size_t L, const unsigned *moduli_bits, unsigned additional_bits, double log2_scaling,
+                            u64 seed, size_t count, u64 *hash, double *decoded) {
+    return guarded([&] {
+        const size_t n = (size_t)1 << logn;
+        auto params = ckks::create_params(n, std::vector<size_t>(moduli_bits, moduli_bits + L), additional_bits, std::pow(2.0, log2_scaling));
+        std::vector<cc_double> data(count);
+        u64 s = seed;
+        for (auto &d : data) {
+            s = s * 6364136223846793005ull + 1442695040888963407ull;
+            const double re = (double)(int64_t)(s >> 11) / 4503599627370496.0 - 1.0;
+            s = s * 6364136223846793005ull + 1442695040888963407ull;
+            const double im = (double)(int64_t)(s >> 11) / 4503599627370496.0 - 1.0;
+            d = cc_double(re, im);
+        }
+        auto pt = ckks::simd_encode(data, params);
+        hash[0] = fnv_poly(pt);
+        auto back = ckks::simd_decode<cc_double>(pt);
+        for (size_t i = 0; i < back.size(); i++) {
+            decoded[2 * i] = back[i].real();
+            decoded[2 * i + 1] = back[i].imag();
+        }
+    });
+}
+
 void ref_cache_ntt_factors(unsigned logn, const u64 *moduli, size_t count) {
     cache_ntt_factors_strict(logn, std::vector<u64>(moduli, moduli + count));
 }

@@ -655,6 +655,56 @@ static void test_mismatched_component_counts() {
     CHECK(flat(pt) == want_pt);
 }
 
+// CKKS encoder / decoder (ckks_encoding.h): the same data as oracle/ref_shim.cpp::ref_ckks_codec_scenario.  The plaintext hash
+// goes to the file (bit-exact target), the decoded slots as %.17g (tolerance target, checked by tests/test_cpp_mirror.py).
+static void codec_scenario(FILE *f, size_t logn, const std::vector<size_t> &bits, size_t additional_bits, double log2_scaling, u64 seed,
+                           size_t count) {
+    const size_t n = (size_t)1 << logn;
+    auto params = ckks::create_params(n, bits, additional_bits, std::pow(2.0, log2_scaling));
+    std::vector<cc_double> data(count);
+    u64 s = seed;
+    for (auto &d : data) {
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        const double re = (double)(int64_t)(s >> 11) / 4503599627370496.0 - 1.0;
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        const double im = (double)(int64_t)(s >> 11) / 4503599627370496.0 - 1.0;
+        d = cc_double(re, im);
+    }
+    auto pt = ckks::simd_encode(data, params);
+    CHECK(pt.rep_form == PolyRepForm::coeff && pt.scaling_factor == std::pow(2.0, log2_scaling));
+    auto back = ckks::simd_decode<cc_double>(pt);
+    CHECK(back.size() == n / 2);
+    double worst = 0; // decode(encode(x)) == x up to the rounding of one coefficient unit
+    for (size_t i = 0; i < count; i++) worst = std::max(worst, std::abs(back[i] - data[i]));
+    CHECK(worst < (double)n / std::pow(2.0, log2_scaling) + 1e-9);
+    std::fprintf(f, "codec %llu %016llx", (unsigned long long)seed, (unsigned long long)fnv_of(static_cast<const RnsPolynomial &>(pt)));
+    double abs_sum = 0;
+    for (const auto &c : back) abs_sum += std::abs(c.real()) + std::abs(c.imag());
+    std::fprintf(f, " %.17g", abs_sum);
+    for (size_t i = 0; i < 8 && i < back.size(); i++) std::fprintf(f, " %.17g %.17g", back[i].real(), back[i].imag());
+    std::fprintf(f, "\n");
+}
+
+// examples/ckks_example.cpp with fewer terms: the Basel series through encode -> encrypt -> mult -> add -> decrypt -> decode
+static void test_ckks_example(int terms) {
+    rand_engine.seed(2024);
+    auto params = ckks::create_params(4096, 30);
+    CkksSk sk(params);
+    auto relin_key = get_relin_key(sk, params.additional_mod);
+    CkksCt ct_sum;
+    double want = 0;
+    for (int i = 1; i <= terms; i++) {
+        auto pt = ckks::encode(1.0 / i, params);
+        auto ct = ckks::encrypt(pt, sk);
+        auto ct_squared = ckks::mult(ct, ct, relin_key);
+        ct_sum = (i == 1) ? ct_squared : ckks::add(ct_sum, ct_squared);
+        want += 1.0 / i / i;
+    }
+    const double sum = ckks::decode(ckks::decrypt(ct_sum, sk));
+    CHECK(std::abs(sum - want) < 1e-4); // the reference prints (1.64483, 1.64493) after 10^4 terms at this precision
+    if (std::abs(sum - want) >= 1e-4) std::fprintf(stderr, "ckks example: got %.9f want %.9f\n", sum, want);
+}
+
 static void test_rng_api(const char *dir) {
     const std::string path = std::string(dir) + "/rng_hashes.txt";
     FILE *f = std::fopen(path.c_str(), "w");
@@ -671,6 +721,12 @@ static void test_rng_api(const char *dir) {
     rng_scenario_bgv(f, 9, 10, {50, 45, 45}, 50, 65537);
     rng_scenario_bgv(f, 10, 12, {52, 50, 48}, 52, 65537);
     rng_scenario_bgv(f, 11, 8, {50, 45}, 50, 12289);
+    // the cases of oracle/make_golden.py ("ckks_codec")
+    codec_scenario(f, 10, {40, 30, 30}, 40, 30, 3, 512);
+    codec_scenario(f, 12, {39, 30}, 39, 30, 4, 2048);
+    codec_scenario(f, 8, {50, 50}, 55, 70, 5, 100);
+    codec_scenario(f, 11, {40, 30}, 40, 50, 6, 1024);
+    codec_scenario(f, 6, {30}, 40, 20, 7, 32);
     std::fclose(f);
 }
 
@@ -691,6 +747,7 @@ int main(int argc, char **argv) {
         test_base_transform_and_ksk(12, {40, 30, 30}, 45);
         if (argc > 1) test_serialize(argv[1]);
         if (argc > 1) test_rng_api(argv[1]);
+        test_ckks_example(argc > 2 ? std::atoi(argv[2]) : 12);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "unexpected exception: %s\n", e.what());
         return 2;

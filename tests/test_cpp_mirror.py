@@ -42,9 +42,13 @@ def test_cpp_mirror(kind, tmp_path_factory):
     import json
     kat = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_kat.json")))["rng"]
     got = {}
+    codec = {}
     for line in open(out_dir / "rng_hashes.txt"):
         tag, seed, *hashes = line.split()
-        got[(tag, int(seed))] = hashes
+        if tag == "codec":
+            codec[int(seed)] = hashes
+        else:
+            got[(tag, int(seed))] = hashes
     for case in kat["samples"]:
         assert got[("samples", case["seed"])] == [case["ternary"], case["uniform"], case["gaussian"]], case
     for case in kat["ckks"]:
@@ -52,6 +56,16 @@ def test_cpp_mirror(kind, tmp_path_factory):
     for case in kat["bgv"]:
         assert got[("bgv", case["seed"])] == case["hashes"] + [case["decoded"]], case
     assert len(got) == len(kat["samples"]) + len(kat["ckks"]) + len(kat["bgv"])
+    # CKKS encoder / decoder: plaintext words bit-exact with the reference; decoded doubles within 1e-9 relative of its output
+    # (the decoder ends in floating point: tolerance instead of identity, as north_star allows for floating-point results)
+    all_kat = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_kat.json")))
+    for case in all_kat["ckks_codec"]:
+        plaintext, abs_sum, *head = codec[case["seed"]]
+        assert plaintext == case["plaintext"], case
+        assert abs(float(abs_sum) - case["decoded_abs_sum"]) <= 1e-9 * case["decoded_abs_sum"], case
+        for a, b in zip(head, case["decoded_head"]):
+            assert abs(float(a) - b) <= 1e-9 * max(1.0, abs(b)), (case["seed"], a, b)
+    assert len(codec) == len(all_kat["ckks_codec"])
     # the slab files the C++ mirror wrote are read back by the Python side (same layout, hehub_b200/slabio.py)
     import numpy as np
     from hehub_b200 import slabio
