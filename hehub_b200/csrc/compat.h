@@ -39,6 +39,7 @@ inline ulonglong2 hb_ld_dsmem2(const unsigned long long *p, unsigned rank) {
 inline void hb_prefetch_l2(const void *) {}
 inline void hb_prefetch_l1(const void *) {}
 inline void hb_pdl_wait() {}
+inline void hb_pdl_trigger() {}
 inline void hb_syncwarp() { __syncthreads(); } // the emulator has no warps: a CTA barrier is a superset
 inline unsigned long long hb_ld_stream(const unsigned long long *p) { return *p; }
 inline ulonglong2 hb_ld_stream2(const unsigned long long *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
@@ -98,6 +99,9 @@ inline cudaError_t hb_launch_ex(void (*kern)(KArgs...), unsigned grid, unsigned 
 // returns once all grids launched earlier on the stream have completed and flushed (no-op without the attribute)
 // (an explicit early griddepcontrol.launch_dependents measured no better: profiles/r2c_pdl_ab.log)
 __device__ __forceinline__ void hb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// lets the next grid of the stream become resident now and run up to ITS hb_pdl_wait() (which still waits for this grid to
+// complete): used by kernels whose successor has a prologue worth overlapping (ks_pair.cuh)
+__device__ __forceinline__ void hb_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // read-only operands that never alias the kernel's outputs (non-coherent path: the compiler may
 // hoist these above stores), read once: no L1 allocation
 __device__ __forceinline__ unsigned long long hb_ld_ro(const unsigned long long *p) {

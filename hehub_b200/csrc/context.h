@@ -48,6 +48,11 @@ struct Context {
     // option "single_launch": one ckks::mult pair per call as ONE launch with grid barriers (N = 4096 / 8192).  Off by default:
     // measured slower than the six programmatically chained launches (39 vs 33 us at C3, profiles/r3_latency_plans.md)
     bool single_launch = false;
+    // option "pair_path": few ciphertexts per call run the key switch + drop as two cluster launches (ks_pair.cuh); 0 never,
+    // 1 (default) when the batch's clusters are resident at once, 2 whenever the shapes allow.  "pair_tpc": targets per cluster
+    // (0: automatic).  "pair_fill_pct": how much of the GPU's resident CTAs the automatic rule lets the input rows take.
+    // "pair_mode": plan family of those launches (0: automatic, 1: 4-CTA clusters, 2: 8-CTA clusters; ntt_plan.h)
+    int pair_path = 1, pair_tpc = 0, pair_fill_pct = 100, pair_mode = 0;
     unsigned long long *grid_barrier_dev = nullptr; // counter of the single-launch kernel's grid barriers (only grows)
     unsigned long long grid_barrier_count = 0;       // its value once every launch enqueued so far has finished
     unsigned long long *grid_barrier_counter();

@@ -1,0 +1,370 @@
+// ks_pair.cuh — the key switch of a FEW ciphertexts as two launches (included by ops.cu).
+//
+// The wave path (ops.cu) runs ckks::mult as six launches — tensor, INTT, fan-out NTT, inner product, INTT of the P limb,
+// forward + drop epilogue — each of which streams a batch through HBM at full width.  One ciphertext per call has nothing
+// to stream: every launch is a handful of rows on an almost idle GPU and costs its latency (~5 us: launch, first loads, one
+// row's dependent butterflies, last stores).  Here the same arithmetic runs as TWO launches of cluster kernels, each an
+// inverse transform handed over IN REGISTERS to forward transforms (ntt_engine.cuh, plans_hand_over), with the
+// coefficient-wise steps riding in the loads and stores:
+//
+//   ks_fan_kernel   cluster (b, p, chunk):  in[b][p]  (tensor product c1 * c1' computed in the load: ckks/arith.cpp:55-62)
+//                   -> INTT_{q_p}, strict (rgsw.cpp:103-105) -> registers -> for each target k != p of the chunk:
+//                   NTT_{q_k} -> dec[b][p][k] (rgsw.cpp:108-119).  The cluster of chunk 0 also stores in[b][p] as
+//                   dec[b][p][p], the diagonal term rgsw.cpp:99-101 keeps.
+//   ks_drop_kernel  cluster (b, h, chunk):  e[h][P] = Mont128(sum_p dec[p][P] * key[p][h][P]) computed in the load
+//                   (rgsw.cpp:126-153) -> INTT_P, strict (rescaling.cpp:47-50) -> registers -> for each limb k of the
+//                   chunk: centre / Barrett (rescaling.cpp:58-68) -> NTT_{q_k} -> store: e[h][k] by the same inner
+//                   product, (e - NTT) / P (rescaling.cpp:73-74), + d_h[k] (ckks/arith.cpp:70-71; d0, d1 of the tensor
+//                   product computed here, or read from the caller's polynomial, through the Galois permutation for
+//                   ckks::rotate / conjugate).
+//
+// Every word is produced by the same sequence of operations as on the wave path (the policies below call the very
+// functions the wave kernels call), so the results are the same raw words; the inverse transform of in[b][p] and the
+// P-limb pipeline are REPEATED by the clusters of different chunks — free on an idle GPU, and the reason this form is
+// only taken for small batches (op_pair_path in ops.cu).
+#pragma once
+
+#ifndef HB_PAIR_PREFETCH
+#define HB_PAIR_PREFETCH 1
+#endif
+#ifndef HB_PAIR_TRIGGER
+#define HB_PAIR_TRIGGER 0 // launching the next grid early measured 4 us slower per pair (profiles/r4_pair_path.md)
+#endif
+
+namespace hb {
+
+// ---- where the key switch's input polynomial in[b][p] (NTT form) comes from: aligned pairs of words ----
+template <bool GALOIS>
+struct KsInPlain {
+    const u64 *in;
+    size_t batch_stride;
+    int logn;
+    unsigned ginv;
+    HB_D ulonglong2 pair(int b, int p, int i, const LimbConst &) const {
+        const u64 *r = in + (size_t)b * batch_stride + ((size_t)p << logn);
+        if constexpr (GALOIS) return galois_pair(r, (unsigned)i, ginv, logn, false);
+        else return hb_ld_stream2(r + i);
+    }
+};
+struct KsInTensor { // d2 = c1 * c1' (ckks/arith.cpp:55-62, the third polynomial of mult_low_level), never stored
+    const u64 *ct1, *ct2; // [batch][2][L][N]
+    int L, logn;
+    HB_D ulonglong2 pair(int b, int p, int i, const LimbConst &lc) const {
+        const size_t off = ((((size_t)b * 2 + 1) * L + p) << logn) + i;
+        const ulonglong2 x = hb_ld_stream2(ct1 + off), y = hb_ld_stream2(ct2 + off);
+        return make_ulonglong2(mul_hybrid_lazy(x.x, y.x, lc), mul_hybrid_lazy(x.y, y.y, lc));
+    }
+};
+
+// ---- what is added to polynomial h of the result ----
+template <bool GALOIS>
+struct KsAddPlain {
+    const u64 *addend;
+    size_t batch_stride, poly_stride;
+    int halves, logn;
+    unsigned ginv;
+    HB_D bool has(int h) const { return h < halves; }
+    HB_D ulonglong2 pair(int b, int h, int k, int i, const LimbConst &) const {
+        const u64 *r = addend + (size_t)b * batch_stride + (size_t)h * poly_stride + ((size_t)k << logn);
+        if constexpr (GALOIS) return galois_pair(r, (unsigned)i, ginv, logn, true);
+        else return hb_ld_ro2(r + i);
+    }
+};
+// d0 = c0 * c0', d1 = c0 * c1' + c1 * c0' of pair b, limb k (ckks/arith.cpp:55-62) -> quad[b][0..1][k], words (i, i + 1).  Run by
+// CTAs of the fan-out launch that have no transform to do (the GPU has SMs to spare while one ciphertext is switched), so that
+// the drop launch reads its addend instead of multiplying for it.
+HB_D void ks_tensor_addend_pair(const u64 *ct1, const u64 *ct2, u64 *quad, const LimbConst *limbs, int L, int logn, size_t unit) {
+    const size_t i = (unit & (((size_t)1 << (logn - 1)) - 1)) * 2, row = unit >> (logn - 1); // row = b * L + k
+    const size_t b = row / L, k = row - b * L;
+    const LimbConst lc = limbs[k];
+    const size_t o0 = (((b * 2) * L + k) << logn) + i, o1 = o0 + ((size_t)L << logn);
+    const ulonglong2 a0 = hb_ld_stream2(ct1 + o0), b0 = hb_ld_stream2(ct2 + o0), a1 = hb_ld_stream2(ct1 + o1), b1 = hb_ld_stream2(ct2 + o1);
+    *reinterpret_cast<ulonglong2 *>(quad + o0) = make_ulonglong2(mul_hybrid_lazy(a0.x, b0.x, lc), mul_hybrid_lazy(a0.y, b0.y, lc));
+    *reinterpret_cast<ulonglong2 *>(quad + o1) =
+        make_ulonglong2(add_lazy(mul_hybrid_lazy(a0.x, b1.x, lc), mul_hybrid_lazy(a1.x, b0.x, lc), lc.q2),
+                        add_lazy(mul_hybrid_lazy(a0.y, b1.y, lc), mul_hybrid_lazy(a1.y, b0.y, lc), lc.q2));
+}
+
+// The words a thread moves in the contiguous pass of a transform (first pass of the inverse, last pass of the forward: the
+// same words, warp_load / warp_store of ntt_engine.cuh): NP pairs (i0 + 64 k, i0 + 64 k + 1), k < NP.
+template <int LOGN, int MODE>
+constexpr int kPairsPerThread = (1 << plan_for(LOGN, true, MODE).k[plan_for(LOGN, true, MODE).npass - 1]) / 2;
+template <int LOGN, int MODE>
+HB_D int ks_first_pair(int B) {
+    constexpr NttPlan pl = plan_for(LOGN, true, MODE);
+    constexpr int K = pl.k[pl.npass - 1], NC = 1 << (LOGN - pl.lpre);
+    static_assert(pl.k[pl.npass - 1] == inv_k(plan_for(LOGN, false, MODE), 0) && (NC >> K) == pl.threads, "one group per thread in the contiguous passes");
+    const int lane = (int)threadIdx.x & 31;
+    return B * NC + (((int)threadIdx.x - lane) << K) + 2 * lane;
+}
+
+// e[k] = words (i0 + 64 k, +1) of Mont128_{q}(sum_p dec[p][.] * key[p][h][.]) — rgsw.cpp:126-153; the sum is exact in 128
+// bits and reduced once (ext_mac_unit, ops.cu).  dec_k: &dec[b][0][limb][i0]; key_hk: &key[0][h][limb][i0].  All the
+// operands of a digit p (2 NP 128-bit loads) are requested before its products: the thread has nothing else to hide them behind.
+template <int NP, int U>
+HB_D void ks_mac_pairs(const u64 *dec_k, const u64 *key_hk, int L, int logn, const LimbConst &lc, ulonglong2 *e) {
+    const size_t dec_row = (size_t)(L + 1) << logn, key_row = (size_t)(2 * (L + 1)) << logn;
+    Acc128 acc[NP][2];
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+        acc128_clear(acc[k][0]);
+        acc128_clear(acc[k][1]);
+    }
+#pragma unroll U
+    for (int p = 0; p < L; p++) {
+        ulonglong2 d[NP], w[NP];
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            d[k] = hb_ld_ro2(dec_k + p * dec_row + 64 * k);
+            w[k] = __ldg(reinterpret_cast<const ulonglong2 *>(key_hk + p * key_row + 64 * k));
+        }
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            acc128_mac(acc[k][0], d[k].x, w[k].x);
+            acc128_mac(acc[k][1], d[k].y, w[k].y);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+        u64 lo, hi;
+        acc128_fold(acc[k][0], lo, hi);
+        e[k].x = montgomery128(lo, hi, lc);
+        acc128_fold(acc[k][1], lo, hi);
+        e[k].y = montgomery128(lo, hi, lc);
+    }
+}
+// NP pairs, four at a time (the accumulators of four pairs are 56 registers); U digits' operands in flight
+template <int NP, int U>
+HB_D void ks_mac_thread(const u64 *dec_k, const u64 *key_hk, int L, int logn, const LimbConst &lc, ulonglong2 (&e)[NP]) {
+    constexpr int G = NP < 4 ? NP : 4;
+#pragma unroll
+    for (int c = 0; c < NP; c += G) ks_mac_pairs<G, U>(dec_k + 64 * c, key_hk + 64 * c, L, logn, lc, &e[c]);
+}
+
+// ---- transform policies (interface: ntt_engine.cuh).  Built on the device, one per cluster; rows are 16-byte aligned. ----
+template <class IN>
+struct KsFanLoad {
+    const IN &in;
+    const LimbConst &lc;
+    u64 *diag; // &dec[b][p][p][0] in the cluster that keeps the diagonal term, else null
+    int b, p;
+    static constexpr bool vec = true;
+    HB_D int limb(int) const { return p; }
+    HB_D const u64 *src(int) const { return nullptr; }
+    HB_D ulonglong2 fetch2(int, int i) const {
+        const ulonglong2 v = in.pair(b, p, i, lc);
+        if (diag) *reinterpret_cast<ulonglong2 *>(diag + i) = v;
+        return v;
+    }
+    HB_D u64 fetch(int, int i) const { // the transforms take the 128-bit path (vec); kept for the interface
+        const ulonglong2 v = fetch2(0, i & ~1);
+        return (i & 1) ? v.y : v.x;
+    }
+    HB_D u64 pre(int, int, u64 raw, const LimbConst &) const { return raw; }
+};
+// element k of a register array without dynamic indexing (k is a constant once the callers' loops are unrolled; where the
+// compiler does not see that, NP - 1 selects instead of a trip through local memory)
+template <int NP>
+HB_D ulonglong2 ks_pick(const ulonglong2 (&e)[NP], int k) {
+    ulonglong2 r = e[0];
+#pragma unroll
+    for (int j = 1; j < NP; j++)
+        if (k == j) r = e[j];
+    return r;
+}
+template <int NP>
+struct KsRegLoad { // the inverse transform's input words, computed beforehand (the P limb of the inner product)
+    ulonglong2 e[NP];
+    int i0;
+    static constexpr bool vec = true;
+    HB_D int limb(int) const { return 0; }
+    HB_D const u64 *src(int) const { return nullptr; }
+    HB_D ulonglong2 fetch2(int, int i) const { return ks_pick<NP>(e, (i - i0) >> 6); }
+    HB_D u64 fetch(int, int i) const { // the transforms take the 128-bit path (vec); kept for the interface
+        const ulonglong2 v = ks_pick<NP>(e, ((i & ~1) - i0) >> 6);
+        return (i & 1) ? v.y : v.x;
+    }
+    HB_D u64 pre(int, int, u64 raw, const LimbConst &) const { return raw; }
+};
+struct KsRowStore { // forward transform into one row
+    u64 *dst;
+    static constexpr bool vec = true;
+    HB_D void store(int, int i, u64 v, const LimbConst &) const { dst[i] = v; }
+    HB_D void store2(int, int i, u64 v0, u64 v1, const LimbConst &) const { *reinterpret_cast<ulonglong2 *>(dst + i) = make_ulonglong2(v0, v1); }
+};
+template <bool BGV, int NP>
+struct KsDropStore { // (e - NTT) / P + addend, e and the addend computed beforehand
+    const DropFwdIO<BGV> &drop; // finish(): rescaling.cpp:73-74, mod_switch.cpp:76
+    ulonglong2 e[NP], a[NP];
+    u64 *dst;           // &out[b][h][k][0]
+    const DropConst *d; // limb k
+    int i0;
+    bool add;
+    static constexpr bool vec = true;
+    HB_D void store2(int, int i, u64 v0, u64 v1, const LimbConst &lc) const {
+        const int k = (i - i0) >> 6;
+        const ulonglong2 ek = ks_pick<NP>(e, k);
+        ulonglong2 r = make_ulonglong2(drop.finish(ek.x, v0, d, lc), drop.finish(ek.y, v1, d, lc));
+        if (add) {
+            const ulonglong2 ak = ks_pick<NP>(a, k);
+            r.x = add_lazy(r.x, ak.x, lc.q2);
+            r.y = add_lazy(r.y, ak.y, lc.q2);
+        }
+        *reinterpret_cast<ulonglong2 *>(dst + i) = r;
+    }
+    HB_D void store(int, int i, u64 v, const LimbConst &lc) const { // the transforms take the 128-bit path (vec); kept for the interface
+        const int k = ((i & ~1) - i0) >> 6;
+        const ulonglong2 ek = ks_pick<NP>(e, k), ak = ks_pick<NP>(a, k);
+        u64 r = drop.finish((i & 1) ? ek.y : ek.x, v, d, lc);
+        if (add) r = add_lazy(r, (i & 1) ? ak.y : ak.x, lc.q2);
+        dst[i] = r;
+    }
+};
+
+// in[b][p] -> dec[b][p][k], k != p (and the diagonal).  CTAs beyond the `main_ctas` that transform compute the tensor
+// product's d0, d1 into `quad` (KsInTensor only).
+template <int LOGN, int MODE, class IN>
+HB_GLOBAL(plan_for(LOGN, true, MODE).threads, 1)
+ks_fan_kernel(const IN in, u64 *__restrict__ dec, const LimbConst *__restrict__ limbs, int L, int tpc, int nchunks, unsigned main_ctas,
+              u64 *__restrict__ quad, size_t tensor_units) {
+    static_assert(plans_hand_over<LOGN, MODE>(), "plans of this ring size hand over in registers");
+    constexpr NttPlan pl = plan_for(LOGN, true, MODE);
+    constexpr int T = pl.threads, C = 1 << pl.lpre, W = kHandOverWords<LOGN, MODE>;
+    HB_SHARED_U64(sm);
+    if (HB_PAIR_TRIGGER) hb_pdl_trigger();
+    if (blockIdx.x >= main_ctas) { // whole clusters: none of them reaches a cluster barrier
+        if constexpr (std::is_same<IN, KsInTensor>::value) {
+            hb_pdl_wait();
+            const size_t stride = (size_t)(gridDim.x - main_ctas) * T;
+            for (size_t u = (size_t)(blockIdx.x - main_ctas) * T + threadIdx.x; u < tensor_units; u += stride)
+                ks_tensor_addend_pair(in.ct1, in.ct2, quad, limbs, L, LOGN, u);
+        }
+        return;
+    }
+    const int cid = blockIdx.x >> pl.lpre, B = blockIdx.x & (C - 1);
+    const int chunk = cid % nchunks, bp = cid / nchunks, p = bp % L, b = bp / L;
+    const LimbConst lcp = limbs[p];
+    u64 *const dec_p = dec + (((size_t)(b * L + p) * (L + 1)) << LOGN);
+    if (HB_PAIR_PREFETCH) { // the twiddles of both transforms: static data, on their way to L1 while the row is fetched
+        prefetch_inv_twiddles<LOGN, T, MODE>(lcp, B);
+        const int k0 = chunk * tpc < p ? chunk * tpc : chunk * tpc + 1;
+        prefetch_fwd_twiddles<LOGN, T, MODE>(limbs[k0], B);
+    }
+    HB_PHASE(0);
+    hb_pdl_wait();
+    HB_PHASE(1);
+    {
+        const KsFanLoad<IN> load{in, lcp, chunk == 0 ? dec_p + ((size_t)p << LOGN) : nullptr, b, p};
+        inv_local_passes<LOGN, T, 0, MODE>(sm, load, lcp, 0, B);
+    }
+    hb_cluster_sync(); // the CTA-local stages are done everywhere and their words visible to the cluster
+    HB_PHASE(2);
+    u64 w[W];
+    inv_cross_to_regs<LOGN, T, MODE>(sm, lcp, B, w);
+    HB_PHASE(3);
+#pragma unroll
+    for (int j = 0; j < W; j++) w[j] = reduce_strict(w[j], lcp.q); // rgsw.cpp:105
+    const int t_end = (chunk + 1) * tpc < L ? (chunk + 1) * tpc : L;
+#pragma unroll 1
+    for (int tt = chunk * tpc; tt < t_end; tt++) {
+        const int k = tt < p ? tt : tt + 1;
+        const LimbConst lck = limbs[k];
+        u64 v[W];
+#pragma unroll
+        for (int j = 0; j < W; j++) v[j] = w[j];
+        fwd_cross_from_regs<LOGN, T, MODE>(sm, lck, B, v);
+        HB_PHASE(4);
+        hb_cluster_sync(); // every word has reached its owner
+        HB_PHASE(5);
+        fwd_passes<LOGN, T, 1, MODE>(sm, KsRowStore{dec_p + ((size_t)k << LOGN)}, lck, 0, B);
+        HB_PHASE(6);
+        if (tt + 1 < t_end) hb_cluster_arrive(); // done reading shared memory: the next target may scatter into it
+    }
+}
+
+// dec, key -> out[b][h][k]
+template <int LOGN, int MODE, bool BGV, class ADD>
+HB_GLOBAL(plan_for(LOGN, true, MODE).threads, 1)
+ks_drop_kernel(const u64 *__restrict__ dec, const u64 *__restrict__ key, const ADD add, u64 *__restrict__ out,
+               const LimbConst *__restrict__ limbs, const DropConst *__restrict__ dc, u64 half_qlast, u64 inv_t, u64 inv_t_h, int L, int tpc,
+               int nchunks) {
+    static_assert(plans_hand_over<LOGN, MODE>(), "plans of this ring size hand over in registers");
+    constexpr NttPlan pl = plan_for(LOGN, true, MODE);
+    constexpr int T = pl.threads, C = 1 << pl.lpre, W = kHandOverWords<LOGN, MODE>, LOGG = LOGN - pl.k[0];
+    HB_SHARED_U64(sm);
+    const int cid = blockIdx.x >> pl.lpre, B = blockIdx.x & (C - 1);
+    const int chunk = cid % nchunks, bh = cid / nchunks, h = bh & 1, b = bh >> 1;
+    const int L1 = L + 1;
+    const LimbConst lcP = limbs[L];
+    const u64 *const dec_b = dec + (((size_t)b * L * L1) << LOGN);
+    const u64 *const key_h = key + (((size_t)h * L1) << LOGN);
+    constexpr int NP = kPairsPerThread<LOGN, MODE>, MAC_U = 4;
+    const int i0 = ks_first_pair<LOGN, MODE>(B);
+    const int t_end = (chunk + 1) * tpc < L ? (chunk + 1) * tpc : L;
+    if (HB_PAIR_TRIGGER) hb_pdl_trigger();
+    if (HB_PAIR_PREFETCH) {
+        prefetch_inv_twiddles<LOGN, T, MODE>(lcP, B);
+        prefetch_fwd_twiddles<LOGN, T, MODE>(limbs[chunk * tpc], B);
+    }
+    if ((threadIdx.x & 7) == 0) { // the key words this thread will multiply by: static data, asked for before the wait
+        for (int p = 0; p < L; p++)
+#pragma unroll
+            for (int kk = 0; kk < NP; kk++) {
+                hb_prefetch_l2(key_h + (((size_t)(p * 2 * L1) + L) << LOGN) + i0 + 64 * kk);
+                hb_prefetch_l2(key_h + (((size_t)(p * 2 * L1) + chunk * tpc) << LOGN) + i0 + 64 * kk);
+            }
+    }
+    HB_PHASE(0);
+    hb_pdl_wait();
+    HB_PHASE(1);
+    // pre() and finish() of the wave path's policy: the same arithmetic by construction
+    const DropFwdIO<BGV> drop{nullptr, nullptr, nullptr, dc, nullptr, 0, 0, half_qlast, L1, LOGN, 0, true, 1u};
+    KsDropStore<BGV, NP> st{drop, {}, {}, nullptr, nullptr, i0, add.has(h)};
+    // the epilogue's operands (the inner product for limb k, the addend) are computed before the transform they will be
+    // combined with: for the first limb of the chunk here, next to the P limb's, for the others while the previous is stored
+    auto epilogue_operands = [&](int k) {
+        const LimbConst lck = limbs[k];
+        ks_mac_thread<NP, MAC_U>(dec_b + ((size_t)k << LOGN) + i0, key_h + ((size_t)k << LOGN) + i0, L, LOGN, lck, st.e);
+        if (st.add) {
+#pragma unroll
+            for (int kk = 0; kk < NP; kk++) st.a[kk] = add.pair(b, h, k, i0 + 64 * kk, lck);
+        }
+    };
+    epilogue_operands(chunk * tpc);
+    {
+        KsRegLoad<NP> load;
+        load.i0 = i0;
+        ks_mac_thread<NP, MAC_U>(dec_b + ((size_t)L << LOGN) + i0, key_h + ((size_t)L << LOGN) + i0, L, LOGN, lcP, load.e);
+        inv_local_passes<LOGN, T, 0, MODE>(sm, load, lcP, 0, B);
+    }
+    hb_cluster_sync();
+    HB_PHASE(2);
+    u64 z[W];
+    inv_cross_to_regs<LOGN, T, MODE>(sm, lcP, B, z);
+    HB_PHASE(3);
+#pragma unroll
+    for (int j = 0; j < W; j++) { // DropInttIO::store — rescaling.cpp:47-50, mod_switch.cpp:48-51
+        if (BGV) z[j] = harvey_lazy(z[j], inv_t, inv_t_h, lcP.nq);
+        z[j] = reduce_strict(z[j], lcP.q);
+    }
+    const int t0 = B * T + (int)threadIdx.x;
+#pragma unroll 1
+    for (int k = chunk * tpc; k < t_end; k++) {
+        const LimbConst lck = limbs[k];
+        if (k != chunk * tpc) epilogue_operands(k);
+        st.dst = out + ((((size_t)b * 2 + h) * L + k) << LOGN);
+        st.d = dc + k;
+        u64 v[W];
+#pragma unroll
+        for (int j = 0; j < W; j++) v[j] = drop.pre(k, t0 + (j << LOGG), z[j], lck);
+        fwd_cross_from_regs<LOGN, T, MODE>(sm, lck, B, v);
+        HB_PHASE(4);
+        hb_cluster_sync();
+        HB_PHASE(5);
+        fwd_passes<LOGN, T, 1, MODE>(sm, st, lck, 0, B);
+        HB_PHASE(6);
+        if (k + 1 < t_end) hb_cluster_arrive();
+    }
+}
+
+} // namespace hb

@@ -32,6 +32,8 @@ struct LimbConst {
     const ulonglong2 *inv_nat;   // reference order, per-level inverse twiddles (ntt.cpp:64-74)
     const ulonglong2 *fwd_lat;   // forward / inverse twiddles in the layout of the latency plan (ntt_plan.h), or null
     const ulonglong2 *inv_lat;
+    const ulonglong2 *fwd_lat2;  // the same for the plans of the two-launch key switch of ONE ciphertext (mode 2), or null
+    const ulonglong2 *inv_lat2;
 };
 
 // lo64(x*w + h*n): one accumulation chain of 2 wide + 4 narrow IMADs, no carries needed.

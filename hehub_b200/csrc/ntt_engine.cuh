@@ -44,6 +44,18 @@
 
 namespace hb {
 
+// Probe builds only (tools/ab_build.sh phase -DHB_PHASE_CLOCK; tools/phase_probe.py): thread 0 of every CTA records the SM
+// clock at marked points into a log the probe installs, 32 slots per CTA.
+#if defined(HB_PHASE_CLOCK) && !defined(HB_KERNEL_SIM)
+static __device__ unsigned long long *hb_phase_ptr;
+#define HB_PHASE(slot)                                                                         \
+    do {                                                                                       \
+        if (threadIdx.x == 0 && hb_phase_ptr) hb_phase_ptr[(size_t)blockIdx.x * 32 + (slot)] = clock64(); \
+    } while (0)
+#else
+#define HB_PHASE(slot) ((void)0)
+#endif
+
 // optional policy hooks: fetch(row, i) / fetch2(row, i) replace the streaming load of word i (words i, i + 1; i even) of
 // src(row) — a policy that gathers its input through a permutation (Galois automorphisms fused into the key switch)
 template <class IO, class = void>
@@ -66,6 +78,12 @@ template <class IO, class = void>
 struct io_has_prefetch : std::false_type {};
 template <class IO>
 struct io_has_prefetch<IO, std::void_t<decltype(std::declval<const IO &>().prefetch(0, 0, 0))>> : std::true_type {};
+
+// the twiddle tables of a plan family (ntt_plan.h: 0 throughput, 1 latency, 2 single-ciphertext key switch)
+template <int MODE>
+HB_D const ulonglong2 *tw_fwd(const LimbConst &lc) { return MODE == 0 ? lc.fwd : (MODE == 1 ? lc.fwd_lat : lc.fwd_lat2); }
+template <int MODE>
+HB_D const ulonglong2 *tw_inv(const LimbConst &lc) { return MODE == 0 ? lc.inv : (MODE == 1 ? lc.inv_lat : lc.inv_lat2); }
 
 // ------------------------------------------------------------------------------------------
 // butterfly — ntt.cpp:161-167 (identical for both directions)
@@ -209,7 +227,7 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     // the latency plans may step by less and pay the padding arithmetic per access
     constexpr bool imm = GSL >= 4;
     static_assert(T % 32 == 0 && (NG % T == 0 || (T % NG == 0 && NG % 32 == 0)), "whole warps in every step (idle warps allowed)");
-    const ulonglong2 *tw_pass = (MODE ? lc.fwd_lat : lc.fwd) + fwd_pass_offset(pl, P);
+    const ulonglong2 *tw_pass = tw_fwd<MODE>(lc) + fwd_pass_offset(pl, P);
     constexpr int stride = 1 << (pl.lpre + L0);
     constexpr int SJ = imm ? sstride(1 << (imm ? GSL : 4)) : 0;
 
@@ -226,7 +244,7 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
             } else {
                 // level 1 of the full row (gap N/2) is computed here by both CTAs of the row;
                 // CTA B keeps the low (B = 0) or high (B = 1) output — ntt.cpp:161-167
-                const ulonglong2 z = __ldg(MODE ? lc.fwd_lat : lc.fwd);
+                const ulonglong2 z = __ldg(tw_fwd<MODE>(lc));
 #pragma unroll
                 for (int j = 0; j < (1 << K); j++) {
                     const int i = base + (j << GSL);
@@ -275,7 +293,7 @@ HB_D void fwd_cross_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, in
     static_assert(K >= pl.lpre && LOGG >= 4, "the cross pass covers every cross-CTA level; strides are multiples of 16 words");
     static_assert(GPC % T == 0 && T % 32 == 0, "whole warps in every step");
     constexpr int SJ = sstride(1 << LOGG);
-    const ulonglong2 *tw_pass = (MODE ? lc.fwd_lat : lc.fwd);
+    const ulonglong2 *tw_pass = tw_fwd<MODE>(lc);
 #pragma unroll 1
     for (int g = threadIdx.x; g < GPC; g += T) {
         const int t = B * GPC + g;
@@ -325,7 +343,7 @@ HB_D void fwd_last_two_shfl(u64 *sm, const IO &io, const LimbConst &lc, int row,
     constexpr int LOGNC = LOGN - pl.lpre, NC = 1 << LOGNC, P = pl.npass - 2;
     constexpr int L0 = fwd_lambda0(pl, P), NG = NC >> 4;
     static_assert(pl.k[P] == 4 && pl.k[P + 1] == 4 && LOGNC - L0 - 4 == 4, "two 4-level passes at the end");
-    const ulonglong2 *twa = (MODE ? lc.fwd_lat : lc.fwd) + fwd_pass_offset(pl, P), *twb = (MODE ? lc.fwd_lat : lc.fwd) + fwd_pass_offset(pl, P + 1);
+    const ulonglong2 *twa = tw_fwd<MODE>(lc) + fwd_pass_offset(pl, P), *twb = tw_fwd<MODE>(lc) + fwd_pass_offset(pl, P + 1);
 #pragma unroll 1
     for (int g = threadIdx.x; g < NG; g += T) {
         const int lo = g & 15, hb = g >> 4, base = (hb << 8) + lo;
@@ -357,10 +375,13 @@ HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B)
 #endif
     if constexpr (P == 0 && pl.xchg) {
         fwd_cross_pass<LOGN, T, MODE>(sm, io, lc, row, B);
+        HB_PHASE(16);
         hb_cluster_sync(); // every word has reached its owner (and all of the row has been read: in-place stores may follow)
+        HB_PHASE(17);
         fwd_passes<LOGN, T, 1, MODE>(sm, io, lc, row, B);
     } else {
         fwd_pass<LOGN, T, P, MODE>(sm, io, lc, row, B);
+        HB_PHASE(17 + P);
         if constexpr (P + 1 < pl.npass) {
             if constexpr (P == 0 && pl.lpre == 1) {
                 // both CTAs of the row have read all of it: from here on either may overwrite it
@@ -382,7 +403,7 @@ HB_D void fwd_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B)
 template <int LOGN, int T, int MODE, int P = 0>
 HB_D void prefetch_fwd_twiddles(const LimbConst &lc, int B) {
     constexpr NttPlan pl = plan_for(LOGN, true, MODE);
-    const ulonglong2 *tab = MODE ? lc.fwd_lat : lc.fwd;
+    const ulonglong2 *tab = tw_fwd<MODE>(lc);
     if constexpr (P == 0 && pl.xchg) {
         for (int s = threadIdx.x; s < (1 << pl.k[0]) - 1; s += T) hb_prefetch_l1(tab + s); // CTA-uniform: a few lines
     } else {
@@ -397,7 +418,7 @@ HB_D void prefetch_fwd_twiddles(const LimbConst &lc, int B) {
 template <int LOGN, int T, int MODE, int P = 0>
 HB_D void prefetch_inv_twiddles(const LimbConst &lc, int B) {
     constexpr NttPlan pl = plan_for(LOGN, false, MODE);
-    const ulonglong2 *tab = MODE ? lc.inv_lat : lc.inv;
+    const ulonglong2 *tab = tw_inv<MODE>(lc);
     if constexpr (pl.xchg && P == pl.npass - 1) {
         constexpr int K = pl.k[0], LOGG = LOGN - K, GPC = (1 << LOGG) >> pl.lpre;
         const ulonglong2 *tw = tab + inv_pass_offset(pl, P);
@@ -493,7 +514,7 @@ HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
     static_assert(!first || S0 == 0, "first inverse pass must be contiguous");
     constexpr bool imm = S0 >= 4; // see fwd_pass
     static_assert(T % 32 == 0 && (NG % T == 0 || (T % NG == 0 && NG % 32 == 0)), "whole warps in every step (idle warps allowed)");
-    const ulonglong2 *tw_pass = (MODE ? lc.inv_lat : lc.inv) + inv_pass_offset(pl, P);
+    const ulonglong2 *tw_pass = tw_inv<MODE>(lc) + inv_pass_offset(pl, P);
     constexpr int stride = 1 << S0;
     constexpr int SJ = imm ? sstride(1 << (imm ? S0 : 4)) : 0;
 
@@ -550,7 +571,7 @@ HB_D void inv_cross_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, in
     static_assert(GPC % T == 0 && T % 32 == 0, "whole warps in every step");
     static_assert(inv_s0(pl, pl.npass - 1) == LOGG, "the cross pass is the last pass of the mirrored list");
     constexpr int SJ = sstride(1 << LOGG);
-    const ulonglong2 *tw_pass = (MODE ? lc.inv_lat : lc.inv) + inv_pass_offset(pl, pl.npass - 1);
+    const ulonglong2 *tw_pass = tw_inv<MODE>(lc) + inv_pass_offset(pl, pl.npass - 1);
 #pragma unroll 1
     for (int g = threadIdx.x; g < GPC; g += T) {
         const int t = B * GPC + g;
@@ -599,6 +620,88 @@ HB_D void inv_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Register hand-over between the inverse and the forward transform of one cluster (the fused key-switch kernels of
+// ks_pair.cuh).  With exchanging plans whose cross passes are equally wide, the thread that finishes word t + j * G of the
+// inverse transform (its cross pass comes last) is the thread that needs that word for the forward transform (its cross
+// pass comes first): the row goes from one transform to the next without leaving the registers of the cluster.
+// ------------------------------------------------------------------------------------------
+template <int LOGN, int MODE>
+HB_CX bool plans_hand_over() {
+    constexpr NttPlan f = plan_for(LOGN, true, MODE), i = plan_for(LOGN, false, MODE);
+    return f.xchg && i.xchg && f.lpre == i.lpre && f.k[0] == i.k[0] && f.threads == i.threads &&
+           ((1 << (LOGN - f.k[0])) >> f.lpre) == f.threads; // one group of the cross pass per thread
+}
+template <int LOGN, int MODE>
+constexpr int kHandOverWords = 1 << plan_for(LOGN, false, MODE).k[0];
+
+// the CTA-local passes of the inverse (all but the cross pass)
+template <int LOGN, int T, int P, int MODE, class IO>
+HB_D void inv_local_passes(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
+    constexpr NttPlan pl = plan_for(LOGN, false, MODE);
+    static_assert(pl.xchg && pl.npass >= 2, "exchanging plans only");
+    inv_pass<LOGN, T, P, MODE>(sm, io, lc, row, B);
+    HB_PHASE(8 + P);
+    if constexpr (P + 2 < pl.npass) {
+        if constexpr (P == 0 && warp_local_pair(inv_k(pl, 0), inv_k(pl, 1))) hb_syncwarp();
+        else __syncthreads();
+        inv_local_passes<LOGN, T, P + 1, MODE>(sm, io, lc, row, B);
+    }
+}
+// The cross pass of the inverse for group t = B * T + threadIdx.x: gathers, runs the stages, finishes the words
+// (ntt.cpp:214-221).  On return v[j] is word t + (j << LOGG) of the transform, in [0, 2q).  The caller has run a cluster
+// barrier since the local passes; this function ARRIVES at the next one as soon as its remote reads are done (the matching
+// wait is the one in front of the next remote write: fwd_cross_from_regs).
+template <int LOGN, int T, int MODE>
+HB_D void inv_cross_to_regs(const u64 *sm, const LimbConst &lc, int B, u64 (&v)[kHandOverWords<LOGN, MODE>]) {
+    constexpr NttPlan pl = plan_for(LOGN, false, MODE);
+    constexpr int K = pl.k[0], C = 1 << pl.lpre, KL = K - pl.lpre, LOGG = LOGN - K;
+    static_assert(plans_hand_over<LOGN, MODE>() && LOGG >= 4, "see plans_hand_over");
+    constexpr int SJ = sstride(1 << LOGG);
+    const int t = B * T + (int)threadIdx.x;
+    const u64 *const smb = sm + sphys(t);
+#pragma unroll
+    for (int o = 0; o < C; o++) {
+        if (o == B) {
+#pragma unroll
+            for (int jj = 0; jj < (1 << KL); jj++) v[(o << KL) + jj] = smb[jj * SJ];
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < (1 << KL); jj++) v[(o << KL) + jj] = hb_ld_dsmem(smb + jj * SJ, o);
+        }
+    }
+    hb_cluster_arrive();
+    inv_levels<K>(v, TwTable{tw_inv<MODE>(lc) + inv_pass_offset(pl, pl.npass - 1) + t, 1 << LOGG}, lc.nq, lc.q2);
+#pragma unroll
+    for (int j = 0; j < (1 << K); j++) {
+        const ulonglong2 s = __ldg(lc.inv_scale + t + (j << LOGG)); // psi^{-i}/N, ntt.cpp:219-221
+        v[j] = harvey_lazy(approx_reduce(v[j], lc), s.x, s.y, lc.nq);
+    }
+}
+// The cross pass of the forward transform from registers: v[j] is input word t + (j << LOGG).  WAITS for the cluster
+// barrier every CTA arrived at after its last read of shared memory, then scatters the results to their owners.  The caller
+// runs a cluster barrier before the local passes (fwd_passes<.., 1, ..>).
+template <int LOGN, int T, int MODE>
+HB_D void fwd_cross_from_regs(u64 *sm, const LimbConst &lc, int B, u64 (&v)[kHandOverWords<LOGN, MODE>]) {
+    constexpr NttPlan pl = plan_for(LOGN, true, MODE);
+    constexpr int K = pl.k[0], C = 1 << pl.lpre, KL = K - pl.lpre, LOGG = LOGN - K;
+    constexpr int SJ = sstride(1 << LOGG);
+    const int t = B * T + (int)threadIdx.x;
+    fwd_levels<K>(v, TwTable{tw_fwd<MODE>(lc), 1}, lc.nq, lc.q2);
+    hb_cluster_wait();
+    u64 *const smb = sm + sphys(t);
+#pragma unroll
+    for (int o = 0; o < C; o++) {
+        if (o == B) {
+#pragma unroll
+            for (int jj = 0; jj < (1 << KL); jj++) smb[jj * SJ] = v[(o << KL) + jj];
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < (1 << KL); jj++) hb_st_dsmem(smb + jj * SJ, o, v[(o << KL) + jj]);
+        }
+    }
+}
+
 template <int LOGN, class IO, int MODE = 0>
 HB_GLOBAL(plan_for(LOGN, false, MODE).threads, plan_for(LOGN, false, MODE).min_blocks)
 intt_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
@@ -619,7 +722,7 @@ intt_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
         // psi^{-i}/N scaling, ntt.cpp:214-221): no butterfly is computed twice and the row never makes
         // a round trip through L2.
         hb_cluster_sync();
-        const ulonglong2 *tw = (MODE ? lc.inv_lat : lc.inv) + inv_pass_offset(pl, pl.npass);
+        const ulonglong2 *tw = tw_inv<MODE>(lc) + inv_pass_offset(pl, pl.npass);
         for (int i = B * (NC / 2) + 2 * (int)threadIdx.x; i < (B + 1) * (NC / 2); i += 2 * T) {
             const u64 *p = sm + sphys(i); // i even: words i, i+1 are adjacent
             const ulonglong2 mine = *reinterpret_cast<const ulonglong2 *>(p), other = hb_ld_dsmem2(p, 1 - B);

@@ -47,6 +47,11 @@ constexpr int kGenericLogMax = 14; // one row must fit one CTA's shared memory
 // on an idle GPU).  N = 16384 / 32768: an 8-CTA cluster that exchanges through distributed shared memory
 // (4096 / 2048 words per CTA: a single N = 32768 row takes ~1/4 of the time of the 2-CTA form).
 HB_CX bool has_latency_plan(int logn) { return logn >= 12 && logn <= 15; }
+// Mode 2: N = 4096 / 8192 rows on an 8-CTA cluster of four warps — one warp per scheduler on twice the SMs of the mode-1 plans.
+// The transforms of one row are bound by the integer multiplier of the SMs they run on (profiles/r4_pair_path.md), so this
+// halves them; it is the form of the two-launch key switch of ONE ciphertext (ks_pair.cuh), whose 16 + 8 rows then cover the
+// GPU once.  More rows per launch than that and the 4-CTA plans win (fewer, fuller CTAs).
+HB_CX bool has_latency2_plan(int logn) { return logn == 12 || logn == 13; }
 
 #ifndef HB_PLAN14
 #define HB_PLAN14 3
@@ -77,6 +82,9 @@ HB_CX NttPlan plan_for(int logn, bool fwd, int mode = 0) {
 #elif HB_PLAN15I == 3
     if (mode == 0 && logn == 15 && !fwd) return NttPlan{15, 2, 4, {4, 4, 3, 4, 0}, 256, 3, 1};
 #endif
+    if (mode == 2 && logn == 12) return NttPlan{12, 3, 4, {3, 3, 3, 3, 0}, 64, 1, 1};
+    if (mode == 2 && logn == 13) return NttPlan{13, 3, 5, {3, 3, 3, 1, 3}, 128, 1, 1};
+    if (mode == 2) mode = 1;
 #ifndef HB_LAT_THIN
 #define HB_LAT_THIN 1
 #endif

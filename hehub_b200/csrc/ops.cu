@@ -691,6 +691,91 @@ int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, 
     return 0;
 }
 
+} // namespace hb
+#include "ks_pair.cuh"
+namespace hb {
+
+// ------------------------------------------------------------------------------------------
+// few ciphertexts per call: the key switch and the drop of P as two launches (ks_pair.cuh)
+// ------------------------------------------------------------------------------------------
+static inline bool ranges_overlap(const u64 *a, size_t na, const u64 *b, size_t nb) { return a < b + nb && b < a + na; }
+
+// Whether a call takes the two-launch form.  Option "pair_path": 0 never, 2 whenever the shapes allow, 1 (default) for
+// N = 4096 / 8192 when the GPU holds one (4-CTA) cluster per input row of the batch at once — beyond that, and for larger
+// rings (whose rows are waves of CTAs rather than latency-bound), the repeated transforms cost throughput and the wave
+// path's streaming wins (profiles/r4_pair_path.md).
+static bool pair_path_wanted(const Context &c, unsigned logn, size_t L, size_t batch) {
+    if (c.pair_path == 0 || c.force_generic || !has_latency2_plan((int)logn) || L == 0 || L > 64) return false;
+    const size_t n = (size_t)1 << logn;
+    if (batch * L * (L + 1) * n * 8 > c.scratch_cap_bytes || batch * L * L > ((size_t)1 << 20)) return false;
+    if (c.pair_path == 2) return true;
+    return batch * L * L * (size_t)plan_cluster(plan_for((int)logn, true, 1)) <= (size_t)c.sm_count * c.pair_fill_pct / 100;
+}
+// targets per cluster: as few as keeps the launch's clusters resident at once (one CTA per SM)
+static int pair_targets_per_cluster(const Context &c, size_t cluster, size_t groups, size_t L) {
+    if (c.pair_tpc > 0) return c.pair_tpc < (int)L ? c.pair_tpc : (int)L;
+    for (size_t tpc = 1; tpc < L; tpc++)
+        if (groups * ((L + tpc - 1) / tpc) * cluster <= (size_t)c.sm_count) return (int)tpc;
+    return (int)L;
+}
+
+template <int LOGN, int MODE, class IN, bool BGV, class ADD>
+static int launch_pair(Context &c, const IN &in, const ADD &add, const u64 *key, u64 *out, u64 *dec, u64 *quad, const LimbConst *limbs,
+                       const DropSet *ds, size_t L, size_t batch) {
+    constexpr NttPlan pl = plan_for(LOGN, true, MODE);
+    constexpr int C = 1 << pl.lpre, smem = smem_words(1 << (LOGN - pl.lpre)) * 8;
+    static_assert(smem <= 48 * 1024, "no opt-in needed");
+    const int tpc_a = pair_targets_per_cluster(c, C, batch * L, L), chunks_a = ((int)L + tpc_a - 1) / tpc_a;
+    const unsigned main_ctas = (unsigned)(batch * L * chunks_a * C);
+    // the tensor product's d0, d1 on CTAs of the same launch that have no transform to run: as many as fill the SMs the
+    // transforms leave idle (at least one cluster, at most one pair of words per thread)
+    unsigned extra = 0;
+    size_t tensor_units = 0;
+    if (quad) {
+        tensor_units = (batch * L) << (LOGN - 1);
+        const unsigned want = (unsigned)((tensor_units + pl.threads - 1) / pl.threads);
+        const unsigned idle = main_ctas < (unsigned)c.sm_count ? (unsigned)c.sm_count - main_ctas : 0;
+        extra = want < idle ? want : idle;
+        extra = extra / C * C;
+        if (extra < (unsigned)C) extra = C;
+    }
+    cudaError_t e = HB_LAUNCH_CLUSTER((ks_fan_kernel<LOGN, MODE, IN>), main_ctas + extra, pl.threads, smem, c.stream, C, in, dec, limbs, (int)L, tpc_a,
+                                      chunks_a, main_ctas, quad, tensor_units);
+    c.stats.launches++;
+    if (e != cudaSuccess) return c.cuda_fail(e, "key switch (two-launch form): fan-out launch");
+    const int tpc_b = pair_targets_per_cluster(c, C, batch * 2, L), chunks_b = ((int)L + tpc_b - 1) / tpc_b;
+    e = HB_LAUNCH_CLUSTER((ks_drop_kernel<LOGN, MODE, BGV, ADD>), (unsigned)(batch * 2 * chunks_b * C), pl.threads, smem, c.stream, C, (const u64 *)dec,
+                          key, add, out, limbs, (const DropConst *)ds->dev, ds->half_qlast, ds->inv_t, ds->inv_t_h, (int)L, tpc_b, chunks_b);
+    c.stats.launches++;
+    return e == cudaSuccess ? 0 : c.cuda_fail(e, "key switch (two-launch form): drop launch");
+}
+// mode 2 (8-CTA clusters, ntt_plan.h) when the fan-out launch of the whole batch then still covers the GPU at most once
+template <class IN, bool BGV, class ADD>
+static int launch_pair_logn(Context &c, unsigned logn, const IN &in, const ADD &add, const u64 *key, u64 *out, u64 *dec, u64 *quad,
+                            const LimbConst *limbs, const DropSet *ds, size_t L, size_t batch) {
+    const bool wide = c.pair_mode == 2 || (c.pair_mode == 0 && batch * L * L * 8 <= (size_t)c.sm_count);
+    switch (logn) {
+    case 12:
+        return wide ? launch_pair<12, 2, IN, BGV, ADD>(c, in, add, key, out, dec, quad, limbs, ds, L, batch)
+                    : launch_pair<12, 1, IN, BGV, ADD>(c, in, add, key, out, dec, quad, limbs, ds, L, batch);
+    case 13:
+        return wide ? launch_pair<13, 2, IN, BGV, ADD>(c, in, add, key, out, dec, quad, limbs, ds, L, batch)
+                    : launch_pair<13, 1, IN, BGV, ADD>(c, in, add, key, out, dec, quad, limbs, ds, L, batch);
+    }
+    return c.fail(1, "two-launch form: ring size without a plan that hands over in registers");
+}
+// constants and workspace of the two-launch form; the checks come in the order the wave path makes them
+static int pair_setup(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u64 t, size_t batch, const LimbConst **limbs, const DropSet **ds,
+                      u64 **dec) {
+    for (size_t k = 0; k <= L; k++)
+        if (!(ext_moduli[k] & 1)) return c.fail(1, "Montgomery reduction needs odd moduli");
+    int err = 0;
+    if (!(*limbs = c.get_chain(logn, ext_moduli, L + 1, &err))) return err;
+    if (!(*ds = c.get_drop(logn, ext_moduli, L + 1, t, &err))) return err;
+    if (!(*dec = c.get_scratch(1, (batch * L * (L + 1)) << logn, &err))) return err;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // relinearize / mult
 // ------------------------------------------------------------------------------------------
@@ -700,6 +785,17 @@ int op_relinearize(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u
     if (L == 0) return c.fail(1, "Empty RGSW ciphertext.");
     if (batch == 0) return 0;
     const size_t n = (size_t)1 << logn;
+    if (pair_path_wanted(c, logn, L, batch) && aligned16(quad) && aligned16(key) && aligned16(out) &&
+        !ranges_overlap(quad, batch * 3 * L * n, out, batch * 2 * L * n)) {
+        const LimbConst *limbs;
+        const DropSet *ds;
+        u64 *dec;
+        if (int rc = pair_setup(c, logn, ext_moduli, L, t, batch, &limbs, &ds, &dec)) return rc;
+        const KsInPlain<false> in{quad + 2 * L * n, 3 * L * n, (int)logn, 1u};
+        const KsAddPlain<false> add{quad, 3 * L * n, L * n, 2, (int)logn, 1u};
+        return t ? launch_pair_logn<KsInPlain<false>, true, KsAddPlain<false>>(c, logn, in, add, key, out, dec, nullptr, limbs, ds, L, batch)
+                 : launch_pair_logn<KsInPlain<false>, false, KsAddPlain<false>>(c, logn, in, add, key, out, dec, nullptr, limbs, ds, L, batch);
+    }
     // waves bound the scratch: per ct  c: L, dec: L(L+1), e: 2(L+1), z: 2  rows of N words
     const size_t per_ct = (L + L * (L + 1) + 2 * (L + 1) + 2) * n;
     const size_t wave = wave_size(c, per_ct, batch, L * (L + 1));
@@ -874,6 +970,23 @@ int op_mult_relin(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u6
     if (L == 0) return c.fail(1, "Empty RGSW ciphertext.");
     if (batch == 0) return 0;
     const size_t n = (size_t)1 << logn;
+    if (pair_path_wanted(c, logn, L, batch) && !(c.single_launch && batch == 1 && t == 0 && logn <= 13) && aligned16(ct1) && aligned16(ct2) &&
+        aligned16(key) && aligned16(out) && !ranges_overlap(ct1, batch * 2 * L * n, out, batch * 2 * L * n) &&
+        !ranges_overlap(ct2, batch * 2 * L * n, out, batch * 2 * L * n)) {
+        for (size_t k = 0; k < L; k++)
+            if (!(ext_moduli[k] & 1)) return c.fail(1, "Montgomery multiplication needs odd moduli");
+        const LimbConst *limbs;
+        const DropSet *ds;
+        u64 *dec;
+        if (int rc = pair_setup(c, logn, ext_moduli, L, t, batch, &limbs, &ds, &dec)) return rc;
+        int err = 0;
+        u64 *d01 = c.get_scratch(4, batch * 2 * L * n, &err); // d0, d1 of the tensor product: [batch][2][L][N]
+        if (!d01) return err;
+        const KsInTensor in{ct1, ct2, (int)L, (int)logn};
+        const KsAddPlain<false> add{d01, 2 * L * n, L * n, 2, (int)logn, 1u};
+        return t ? launch_pair_logn<KsInTensor, true, KsAddPlain<false>>(c, logn, in, add, key, out, dec, d01, limbs, ds, L, batch)
+                 : launch_pair_logn<KsInTensor, false, KsAddPlain<false>>(c, logn, in, add, key, out, dec, d01, limbs, ds, L, batch);
+    }
     const size_t per_ct = (3 * L + L + L * (L + 1) + 2 * (L + 1) + 2) * n;
     const size_t wave = wave_size(c, per_ct, batch, L * (L + 1));
     int err = 0;
@@ -1241,6 +1354,13 @@ static unsigned galois_inverse_factor(unsigned logn, bool conj, size_t step) {
     return inv & mask;
 }
 
+#if defined(HB_PHASE_CLOCK) && !defined(HB_KERNEL_SIM)
+} // namespace hb
+// probe builds only: where the kernels of this translation unit log their phase clocks (null: nowhere)
+extern "C" int hehub_b200_debug_set_phase_log(unsigned long long *p) { return (int)cudaMemcpyToSymbol(hb::hb_phase_ptr, &p, sizeof(p)); }
+namespace hb {
+#endif
+
 int op_galois(Context &c, unsigned logn, size_t L, const u64 *in, u64 *out, bool conj, size_t step, size_t batch) {
     if (!in || !out) return c.fail(1, "null operand");
     if (in == out) return c.fail(1, "Galois permutation cannot run in place");
@@ -1264,6 +1384,16 @@ int op_galois_keyswitch(Context &c, unsigned logn, const u64 *ext_moduli, size_t
     if (batch == 0) return 0;
     const size_t n = (size_t)1 << logn;
     const unsigned ginv = galois_inverse_factor(logn, conj, step);
+    if (pair_path_wanted(c, logn, L, batch) && aligned16(ct) && aligned16(key) && aligned16(out) &&
+        !ranges_overlap(ct, batch * 2 * L * n, out, batch * 2 * L * n)) {
+        const LimbConst *limbs;
+        const DropSet *ds;
+        u64 *dec;
+        if (int rc = pair_setup(c, logn, ext_moduli, L, 0, batch, &limbs, &ds, &dec)) return rc;
+        const KsInPlain<true> in{ct + L * n, 2 * L * n, (int)logn, ginv};
+        const KsAddPlain<true> add{ct, 2 * L * n, L * n, 1, (int)logn, ginv};
+        return launch_pair_logn<KsInPlain<true>, false, KsAddPlain<true>>(c, logn, in, add, key, out, dec, nullptr, limbs, ds, L, batch);
+    }
     const bool in_place = ct == out; // the epilogue gathers c0 while `out` is written: work from a copy of the wave then
     const size_t per_ct = ((in_place ? 2 * L : 0) + L + L * (L + 1) + 2 * (L + 1) + 2) * n;
     const size_t wave = wave_size(c, per_ct, batch, L * (L + 1));

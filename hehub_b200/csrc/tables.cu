@@ -176,7 +176,8 @@ const ModTables *Context::get_tables(u64 q, unsigned logn, int *err) {
 
     const bool fast = logn >= (unsigned)kFastLogMin;
     const bool lat = fast && has_latency_plan((int)logn);
-    const size_t ntab = fast ? (lat ? 7 : 5) : 3; // fwd_nat, inv_nat, inv_scale [, fwd fast, inv fast [, latency-plan pair]]
+    const bool lat2 = lat && has_latency2_plan((int)logn);
+    const size_t ntab = fast ? (lat ? (lat2 ? 9 : 7) : 5) : 3; // fwd_nat, inv_nat, inv_scale [, fwd fast, inv fast [, latency-plan pair [, mode-2 pair]]]
     std::vector<ulonglong2> host(ntab * n, make_ulonglong2(0, 0));
     ulonglong2 *fwd_nat = host.data(), *inv_nat = fwd_nat + n, *inv_scale = inv_nat + n;
     auto pair_of = [&](u64 w) { return make_ulonglong2(w, host_harvey_quotient(w, q)); };
@@ -226,6 +227,7 @@ const ModTables *Context::get_tables(u64 q, unsigned logn, int *err) {
     };
     if (fast) fill_plan_tables(inv_scale + n, inv_scale + 2 * n, 0);
     if (lat) fill_plan_tables(inv_scale + 3 * n, inv_scale + 4 * n, 1);
+    if (lat2) fill_plan_tables(inv_scale + 5 * n, inv_scale + 6 * n, 2);
 
     void *dev = nullptr;
     cudaError_t e = cudaMalloc(&dev, host.size() * sizeof(ulonglong2));
@@ -249,6 +251,8 @@ const ModTables *Context::get_tables(u64 q, unsigned logn, int *err) {
     mt.lc.inv = fast ? d + 4 * n : nullptr;
     mt.lc.fwd_lat = lat ? d + 5 * n : nullptr;
     mt.lc.inv_lat = lat ? d + 6 * n : nullptr;
+    mt.lc.fwd_lat2 = lat2 ? d + 7 * n : nullptr;
+    mt.lc.inv_lat2 = lat2 ? d + 8 * n : nullptr;
     return &tables.emplace(key, mt).first->second;
 }
 

@@ -831,3 +831,48 @@ print("ok")
 """
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
     assert res.returncode == 0 and "ok" in res.stdout, res.stdout + res.stderr
+
+
+@pytest.mark.parametrize("logn,bits,pbits,batch", [(12, [39, 30, 30], 39, 1), (13, [40, 30, 30, 30], 40, 2), (13, [59, 50], 59, 1)])
+def test_pair_path_matches_oracle_and_wave_path(dev, oracle, logn, bits, pbits, batch):
+    """The two-launch key switch (csrc/ks_pair.cuh: inverse transform handed to the forward transforms in registers, tensor
+    product / inner product / drop epilogue inside the loads and stores) produces the words of the six-launch wave path and of
+    the oracle — for ckks::mult, relinearize, rotate, conjugate and their bgv:: twins, at every split of the targets."""
+    mods, ext = _shape(oracle, logn, bits, pbits)
+    n, L = 1 << logn, len(mods)
+    cts1 = [fill_ct(oracle, 31 + 7 * b, mods, n) for b in range(batch)]
+    cts2 = [fill_ct(oracle, 41 + 7 * b, mods, n) for b in range(batch)]
+    key = fill_key(oracle, 3300, ext, n)
+    ct1, ct2 = (cts1[0], cts2[0]) if batch == 1 else (np.stack(cts1), np.stack(cts2))
+    quads = [oracle.ckks_tensor(logn, mods, a, b) for a, b in zip(cts1, cts2)]
+    quad = quads[0] if batch == 1 else np.stack(quads)
+    pack = (lambda xs: xs[0]) if batch == 1 else np.stack
+    want = {
+        "mult": pack([oracle.ckks_mult_relin(logn, ext, a, b, key) for a, b in zip(cts1, cts2)]),
+        "relin": pack([oracle.ckks_relinearize(logn, ext, q, key) for q in quads]),
+        "bgv": pack([oracle.bgv_relinearize(logn, ext, 65537, q, key) for q in quads]),
+        "rot": pack([oracle.ckks_rotate(logn, ext, a, key, 3) for a in cts1]),
+        "conj": pack([oracle.ckks_conjugate(logn, ext, a, key) for a in cts1]),
+    }
+    try:
+        # (pair_path, pair_mode: 1 = 4-CTA clusters, 2 = 8-CTA clusters, targets per cluster, launches per call)
+        variants = [(0, 0, 0, None), (2, 1, 0, 2), (2, 2, 0, 2), (2, 1, 2, 2), (2, 2, L, 2)]
+        if dev.kind == "sim":  # the emulator runs every thread of a cluster as a host thread: two variants per shape
+            variants = [(2, 1, 2, 2), (2, 2, 0, 2)] if logn == 12 else ([(2, 2, 2, 2)] if L == 2 else [(2, 1, 0, 2)])
+        for path, mode, tpc, launches in variants:
+            dev.set_option("pair_path", path)
+            dev.set_option("pair_mode", mode)
+            dev.set_option("pair_tpc", tpc)
+            before = dev.launch_count()
+            assert np.array_equal(dev.ckks_mult_relin(logn, ext, ct1, ct2, key), want["mult"]), (path, mode, tpc)
+            if launches:
+                assert dev.launch_count() - before == launches
+            assert np.array_equal(dev.ckks_relinearize(logn, ext, quad, key), want["relin"]), (path, mode, tpc)
+            assert np.array_equal(dev.bgv_relinearize(logn, ext, 65537, quad, key), want["bgv"]), (path, mode, tpc)
+            assert np.array_equal(dev.bgv_mult_relin(logn, ext, 65537, ct1, ct2, key), want["bgv"]), (path, mode, tpc)
+            assert np.array_equal(dev.ckks_rotate(logn, ext, ct1, key, 3), want["rot"]), (path, mode, tpc)
+            assert np.array_equal(dev.ckks_conjugate(logn, ext, ct1, key), want["conj"]), (path, mode, tpc)
+    finally:
+        dev.set_option("pair_path", 1)
+        dev.set_option("pair_mode", 0)
+        dev.set_option("pair_tpc", 0)

@@ -15,6 +15,7 @@ ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--latency-rows", type=int, default=None, help="context option latency_rows")
 ap.add_argument("--scratch-mib", type=int, default=None, help="context option scratch_cap_mib")
 ap.add_argument("--single-launch", type=int, default=None, help="context option single_launch")
+ap.add_argument("--opt", nargs="*", default=[], help="context options name=value (pair_path=2 pair_tpc=1 ...)")
 a = ap.parse_args()
 SHAPES = {"c3": (13, [40, 30, 30, 30], 40, 296), "c4": (14, [50] + [40] * 7, 50, 148), "c5": (15, [50] * 12, 55, 74)}
 orc = Oracle()
@@ -22,6 +23,9 @@ ctx = Context(lib_path=a.lib)
 if a.latency_rows is not None: ctx.set_option("latency_rows", a.latency_rows)
 if a.scratch_mib is not None: ctx.set_option("scratch_cap_mib", a.scratch_mib)
 if a.single_launch is not None: ctx.set_option("single_launch", a.single_launch)
+for kv in a.opt:
+    k, v = kv.split("=")
+    ctx.set_option(k, int(v))
 for name in a.shape:
     logn, bits, pbits, batch = SHAPES[name]
     batch = a.batch or batch
@@ -53,6 +57,6 @@ for name in a.shape:
         ctx.synchronize()
         dt = (time.perf_counter() - t0) / reps
         out.append(f"{k} {dt * 1e6 / batch:.3f} us/ct")
-    print(f"{os.path.basename(a.lib):26s} {name}: " + " | ".join(out), flush=True)
+    print(f"{os.path.basename(a.lib):26s} {name} b={batch} {' '.join(a.opt)}: " + " | ".join(out), flush=True)
     for s in (key, ct1, ct2, res, quad, ext_out): s.free()
 ctx.close()
