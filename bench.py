@@ -447,7 +447,11 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
         if "latency" in what:  # one ciphertext pair per call: the launch-bound end of the same path
             fn = lambda i: ctx._call("ckks_mult_relin", logn, extp, L, ct1.data_ptr(), ct2.data_ptr(), key.data_ptr(), res.data_ptr(), 1)
             el = timed(fn, 50, 5)
-            r["mult_relin_single_ct"] = {"us_per_call": el / 50 * 1e6, "per_s": world * 50 / el, "kernel_launches_per_call": 6}
+            before = ctx.launch_count()
+            fn(0)
+            ctx.synchronize()
+            r["mult_relin_single_ct"] = {"us_per_call": el / 50 * 1e6, "per_s": world * 50 / el,
+                                         "kernel_launches_per_call": ctx.launch_count() - before}
         if "rescale" in what:
             fn = lambda i: ctx._call("ckks_rescale", logn, modp, L, ct1.data_ptr(), res.data_ptr(), batch)
             el = timed(fn, steps, 2)

@@ -298,12 +298,12 @@ int hehub_b200_ctx_set_option(hehub_b200_ctx *ctx, const char *name, int64_t val
         c.force_generic = value != 0;
     } else if (!std::strcmp(name, "latency_rows")) { // -1: default (half the SM count); 0: never use the latency plans
         c.latency_rows = (int)value;
+    } else if (!std::strcmp(name, "latency2_rows")) { // -1: default (a tenth of the SM count); 0: never use the mode-2 plans
+        c.latency2_rows = (int)value;
     } else if (!std::strcmp(name, "pair_path")) { // 0 / 1 / 2: never / automatic / always take the two-launch key switch (context.h)
         c.pair_path = (int)value;
     } else if (!std::strcmp(name, "pair_tpc")) {
         c.pair_tpc = (int)value;
-    } else if (!std::strcmp(name, "pair_mode")) {
-        c.pair_mode = (int)value;
     } else if (!std::strcmp(name, "pair_fill_pct")) {
         c.pair_fill_pct = (int)value;
     } else if (!std::strcmp(name, "single_launch")) { // 0: one ckks::mult pair per call runs as six launches (A/B)

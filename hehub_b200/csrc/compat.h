@@ -40,6 +40,8 @@ inline void hb_prefetch_l2(const void *) {}
 inline void hb_prefetch_l1(const void *) {}
 inline void hb_pdl_wait() {}
 inline void hb_pdl_trigger() {}
+inline void hb_cp_async16(void *dst_shared, const void *src_global) { std::memcpy(dst_shared, src_global, 16); }
+inline void hb_cp_async_wait_all() {}
 inline void hb_syncwarp() { __syncthreads(); } // the emulator has no warps: a CTA barrier is a superset
 inline unsigned long long hb_ld_stream(const unsigned long long *p) { return *p; }
 inline ulonglong2 hb_ld_stream2(const unsigned long long *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
@@ -148,6 +150,12 @@ __device__ __forceinline__ void hb_prefetch_l2(const void *p) { asm volatile("pr
 // pull a line the thread will read soon into L1 (twiddles of the latency plans: tables never change, so this may run before
 // the programmatic-dependent-launch wait)
 __device__ __forceinline__ void hb_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// 16 bytes global -> this CTA's shared memory without passing through registers (LDGSTS); completion: hb_cp_async_wait_all by the
+// issuing thread, then a barrier before other threads read
+__device__ __forceinline__ void hb_cp_async16(void *dst_shared, const void *src_global) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global) : "memory");
+}
+__device__ __forceinline__ void hb_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void hb_syncwarp() { __syncwarp(); }
 // row words are read once: keep them out of L1, which holds the twiddle tables
 #if defined(HB_NO_STREAM_LD) // A/B builds only

@@ -45,19 +45,24 @@ struct Context {
     bool force_generic = false;
     int sm_count = 148;
     int latency_rows = -1; // option "latency_rows"; -1: half the SM count
+    // option "latency2_rows"; -1: a tenth of the SM count (0 when latency_rows is 0).  15 rows of 8-CTA clusters run one CTA per SM
+    // on a B200; the 16th cluster shares its SMs and the launch takes 7.9 instead of 4.4 us (profiles/r4_pair_path.md)
+    int latency2_rows = -1;
     // option "single_launch": one ckks::mult pair per call as ONE launch with grid barriers (N = 4096 / 8192).  Off by default:
     // measured slower than the six programmatically chained launches (39 vs 33 us at C3, profiles/r3_latency_plans.md)
     bool single_launch = false;
     // option "pair_path": few ciphertexts per call run the key switch + drop as two cluster launches (ks_pair.cuh); 0 never,
-    // 1 (default) when the batch's clusters are resident at once, 2 whenever the shapes allow.  "pair_tpc": targets per cluster
-    // (0: automatic).  "pair_fill_pct": how much of the GPU's resident CTAs the automatic rule lets the input rows take.
-    // "pair_mode": plan family of those launches (0: automatic, 1: 4-CTA clusters, 2: 8-CTA clusters; ntt_plan.h)
-    int pair_path = 1, pair_tpc = 0, pair_fill_pct = 100, pair_mode = 0;
+    // 1 (default) for batches small enough to gain (ops.cu, pair_path_wanted), 2 whenever the shapes allow.  "pair_tpc": targets
+    // per cluster (0: automatic).  "pair_fill_pct": fan-out rows per call, in % of the SM count, up to which the form is taken.
+    int pair_path = 1, pair_tpc = 0, pair_fill_pct = 130;
     unsigned long long *grid_barrier_dev = nullptr; // counter of the single-launch kernel's grid barriers (only grows)
     unsigned long long grid_barrier_count = 0;       // its value once every launch enqueued so far has finished
     unsigned long long *grid_barrier_counter();
     int mult_one_clusters[2] = {0, 0}; // resident clusters of that kernel on this device (0: not asked yet, -1: launch form unavailable)
-    LaunchEnv env() { return LaunchEnv{stream, sm_count, force_generic, &stats, latency_rows < 0 ? sm_count / 2 : latency_rows, device}; }
+    LaunchEnv env() {
+        const int lat = latency_rows < 0 ? sm_count / 2 : latency_rows;
+        return LaunchEnv{stream, sm_count, force_generic, &stats, lat, latency2_rows < 0 ? (lat ? sm_count / 10 : 0) : latency2_rows, device};
+    }
     // bound on the per-call workspace (option "scratch_cap_mib"); batches run in waves.  32 GiB of the 180 GB: a C5 wave of 296
     // ciphertexts (23 GiB with its key-switch digits) runs 1.7 % faster per ciphertext than four waves of 74 (profiles/r3_cluster_plans.md)
     size_t scratch_cap_bytes = (size_t)32 << 30;
@@ -68,6 +73,7 @@ struct Context {
     std::map<std::vector<u64>, LimbConst *> chains;      // key: {logn, q0, q1, ...}
     std::map<std::vector<u64>, DropSet> drops;           // key: {logn, t, q0, ..., q_last}
     std::map<std::vector<u64>, u64 *> scalar_sets;       // uploaded (s, s') pairs for mul_scalar
+    std::map<const void *, int> cluster_cap;             // cluster kernel -> CTAs of it resident at once on this device
     std::map<const void *, int> smem_opt_in;             // kernel -> dynamic shared memory it has been opted in to (this device)
     std::map<size_t, std::vector<u64 *>> slab_free;      // pooled slabs by size
     std::map<u64 *, size_t> slab_live;

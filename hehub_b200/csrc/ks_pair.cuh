@@ -1,32 +1,34 @@
-// ks_pair.cuh — the key switch of a FEW ciphertexts as two launches (included by ops.cu).
+// ks_pair.cuh — key switch and modulus drop of a FEW ciphertexts as cluster launches (included by ops.cu).
 //
 // The wave path (ops.cu) runs ckks::mult as six launches — tensor, INTT, fan-out NTT, inner product, INTT of the P limb,
-// forward + drop epilogue — each of which streams a batch through HBM at full width.  One ciphertext per call has nothing
-// to stream: every launch is a handful of rows on an almost idle GPU and costs its latency (~5 us: launch, first loads, one
-// row's dependent butterflies, last stores).  Here the same arithmetic runs as TWO launches of cluster kernels, each an
-// inverse transform handed over IN REGISTERS to forward transforms (ntt_engine.cuh, plans_hand_over), with the
-// coefficient-wise steps riding in the loads and stores:
+// forward + drop epilogue — each of which streams a batch through HBM at full width.  A few ciphertexts per call have
+// nothing to stream: every launch is a handful of rows on an almost idle GPU, and a row costs what its chain of dependent
+// butterflies costs on the few SMs it runs on (profiles/r4_pair_path.md: the integer multiplier of those SMs and the
+// shared-memory round trips between passes, not the launches).  Here the same arithmetic runs as TWO launches of 8-CTA
+// cluster kernels (mode-2 plans, ntt_plan.h: twice the SMs per row, twiddle tables staged in shared memory before the row
+// arrives), each an inverse transform handed over IN REGISTERS to forward transforms (ntt_engine.cuh, plans_hand_over),
+// with the coefficient-wise steps riding in the loads and stores:
 //
-//   ks_fan_kernel   cluster (b, p, chunk):  in[b][p]  (tensor product c1 * c1' computed in the load: ckks/arith.cpp:55-62)
-//                   -> INTT_{q_p}, strict (rgsw.cpp:103-105) -> registers -> for each target k != p of the chunk:
-//                   NTT_{q_k} -> dec[b][p][k] (rgsw.cpp:108-119).  The cluster of chunk 0 also stores in[b][p] as
-//                   dec[b][p][p], the diagonal term rgsw.cpp:99-101 keeps.
-//   ks_drop_kernel  cluster (b, h, chunk):  e[h][P] = Mont128(sum_p dec[p][P] * key[p][h][P]) computed in the load
-//                   (rgsw.cpp:126-153) -> INTT_P, strict (rescaling.cpp:47-50) -> registers -> for each limb k of the
-//                   chunk: centre / Barrett (rescaling.cpp:58-68) -> NTT_{q_k} -> store: e[h][k] by the same inner
-//                   product, (e - NTT) / P (rescaling.cpp:73-74), + d_h[k] (ckks/arith.cpp:70-71; d0, d1 of the tensor
-//                   product computed here, or read from the caller's polynomial, through the Galois permutation for
-//                   ckks::rotate / conjugate).
+//   ks_fan_kernel   cluster (b, p, chunk):  in[b][p]  (the tensor product's c1 * c1' computed in the load: ckks/arith.cpp:55-62;
+//                   or read through the Galois permutation: ckks::rotate / conjugate) -> INTT_{q_p}, strict
+//                   (rgsw.cpp:103-105) -> registers -> for each target k != p of the chunk: NTT_{q_k} -> dec[b][p][k]
+//                   (rgsw.cpp:108-119).  The cluster of chunk 0 also stores in[b][p] as dec[b][p][p], the diagonal term
+//                   rgsw.cpp:99-101 keeps.  CTAs beyond those compute the tensor product's d0, d1 (SMs are idle anyway).
+//   ks_drop_kernel  cluster (b, h, chunk):  e[h][P] = Mont128(sum_p dec[p][P] * key[p][h][P]) (rgsw.cpp:126-153), all its
+//                   operands requested at once -> INTT_P, strict (rescaling.cpp:47-50) -> registers -> for each limb k of
+//                   the chunk: centre / Barrett (rescaling.cpp:58-68) -> NTT_{q_k} -> store: (e[h][k] - NTT) / P
+//                   (rescaling.cpp:73-74) + d_h[k] (ckks/arith.cpp:70-71), e[h][k] by the same inner product and the
+//                   addend both computed BEFORE the transform they meet.
+//                   With the ciphertext itself as the source of e (KsSrcPlain) the same kernel is
+//                   ckks::rescale_inplace / bgv::mod_switch_inplace of a few ciphertexts in ONE launch.
 //
 // Every word is produced by the same sequence of operations as on the wave path (the policies below call the very
 // functions the wave kernels call), so the results are the same raw words; the inverse transform of in[b][p] and the
 // P-limb pipeline are REPEATED by the clusters of different chunks — free on an idle GPU, and the reason this form is
-// only taken for small batches (op_pair_path in ops.cu).
+// only taken for small batches (pair_path_wanted, pair_targets_per_cluster in ops.cu).
+// Measured, N = 8192, L = 4, one call: ckks::mult 33.2 -> 23.5 us, rotate 31.8 -> 22.4 us, rescale 14.5 -> 8.7 us.
 #pragma once
 
-#ifndef HB_PAIR_PREFETCH
-#define HB_PAIR_PREFETCH 1
-#endif
 #ifndef HB_PAIR_TRIGGER
 #define HB_PAIR_TRIGGER 0 // launching the next grid early measured 4 us slower per pair (profiles/r4_pair_path.md)
 #endif
@@ -141,6 +143,36 @@ HB_D void ks_mac_thread(const u64 *dec_k, const u64 *key_hk, int L, int logn, co
     for (int c = 0; c < NP; c += G) ks_mac_pairs<G, U>(dec_k + 64 * c, key_hk + 64 * c, L, logn, lc, &e[c]);
 }
 
+// ---- where the drop launch takes the polynomial e[h][limb] it divides by the last prime from ----
+struct KsSrcMac { // the key switch's inner product over the digits the fan-out launch left in `dec`
+    const u64 *dec, *key;
+    int L, logn;
+    template <int NP, int U>
+    HB_D void pairs(int b, int h, int limb, int i0, const LimbConst &lc, ulonglong2 (&e)[NP]) const {
+        const size_t L1 = (size_t)L + 1;
+        ks_mac_thread<NP, U>(dec + (((size_t)b * L * L1 + limb) << logn) + i0, key + (((size_t)h * L1 + limb) << logn) + i0, L, logn, lc, e);
+    }
+    template <int NP>
+    HB_D void prefetch(int h, int limb, int i0) const { // key words: static data, may be asked for before the predecessor has finished
+        if ((threadIdx.x & 7) == 0)
+            for (int p = 0; p < L; p++)
+#pragma unroll
+                for (int kk = 0; kk < NP; kk++) hb_prefetch_l2(key + (((size_t)(p * 2 + h) * (L + 1) + limb) << logn) + i0 + 64 * kk);
+    }
+};
+struct KsSrcPlain { // a ciphertext [batch][2][L + 1][N] as it is: ckks::rescale_inplace / bgv::mod_switch_inplace of a few ciphertexts
+    const u64 *ct;
+    int L, logn;
+    template <int NP, int U>
+    HB_D void pairs(int b, int h, int limb, int i0, const LimbConst &, ulonglong2 (&e)[NP]) const {
+        const u64 *row = ct + ((((size_t)b * 2 + h) * (L + 1) + limb) << logn) + i0;
+#pragma unroll
+        for (int k = 0; k < NP; k++) e[k] = hb_ld_stream2(row + 64 * k);
+    }
+    template <int NP>
+    HB_D void prefetch(int, int, int) const {}
+};
+
 // ---- transform policies (interface: ntt_engine.cuh).  Built on the device, one per cluster; rows are 16-byte aligned. ----
 template <class IN>
 struct KsFanLoad {
@@ -245,13 +277,16 @@ ks_fan_kernel(const IN in, u64 *__restrict__ dec, const LimbConst *__restrict__ 
     const int chunk = cid % nchunks, bp = cid / nchunks, p = bp % L, b = bp / L;
     const LimbConst lcp = limbs[p];
     u64 *const dec_p = dec + (((size_t)(b * L + p) * (L + 1)) << LOGN);
-    if (HB_PAIR_PREFETCH) { // the twiddles of both transforms: static data, on their way to L1 while the row is fetched
-        prefetch_inv_twiddles<LOGN, T, MODE>(lcp, B);
-        const int k0 = chunk * tpc < p ? chunk * tpc : chunk * tpc + 1;
-        prefetch_fwd_twiddles<LOGN, T, MODE>(limbs[k0], B);
+    if constexpr (staged_mode(MODE)) { // both transforms' tables: static data, on their way into shared memory before the row is
+        stage_inv_tables<LOGN, T, MODE>(sm, lcp, B);
+        stage_fwd_tables<LOGN, T, MODE>(sm, limbs[chunk * tpc < p ? chunk * tpc : chunk * tpc + 1], B);
     }
     HB_PHASE(0);
     hb_pdl_wait();
+    if constexpr (staged_mode(MODE)) {
+        hb_cp_async_wait_all();
+        __syncthreads();
+    }
     HB_PHASE(1);
     {
         const KsFanLoad<IN> load{in, lcp, chunk == 0 ? dec_p + ((size_t)p << LOGN) : nullptr, b, p};
@@ -269,6 +304,14 @@ ks_fan_kernel(const IN in, u64 *__restrict__ dec, const LimbConst *__restrict__ 
     for (int tt = chunk * tpc; tt < t_end; tt++) {
         const int k = tt < p ? tt : tt + 1;
         const LimbConst lck = limbs[k];
+        if constexpr (staged_mode(MODE)) {
+            if (tt != chunk * tpc) { // the next target's tables replace the previous one's
+                __syncthreads();
+                stage_fwd_tables<LOGN, T, MODE>(sm, lck, B);
+                hb_cp_async_wait_all();
+                __syncthreads();
+            }
+        }
         u64 v[W];
 #pragma unroll
         for (int j = 0; j < W; j++) v[j] = w[j];
@@ -282,12 +325,11 @@ ks_fan_kernel(const IN in, u64 *__restrict__ dec, const LimbConst *__restrict__ 
     }
 }
 
-// dec, key -> out[b][h][k]
-template <int LOGN, int MODE, bool BGV, class ADD>
+// e (SRC) -> out[b][h][k]
+template <int LOGN, int MODE, bool BGV, class SRC, class ADD>
 HB_GLOBAL(plan_for(LOGN, true, MODE).threads, 1)
-ks_drop_kernel(const u64 *__restrict__ dec, const u64 *__restrict__ key, const ADD add, u64 *__restrict__ out,
-               const LimbConst *__restrict__ limbs, const DropConst *__restrict__ dc, u64 half_qlast, u64 inv_t, u64 inv_t_h, int L, int tpc,
-               int nchunks) {
+ks_drop_kernel(const SRC src, const ADD add, u64 *__restrict__ out, const LimbConst *__restrict__ limbs, const DropConst *__restrict__ dc,
+               u64 half_qlast, u64 inv_t, u64 inv_t_h, int L, int tpc, int nchunks) {
     static_assert(plans_hand_over<LOGN, MODE>(), "plans of this ring size hand over in registers");
     constexpr NttPlan pl = plan_for(LOGN, true, MODE);
     constexpr int T = pl.threads, C = 1 << pl.lpre, W = kHandOverWords<LOGN, MODE>, LOGG = LOGN - pl.k[0];
@@ -296,26 +338,22 @@ ks_drop_kernel(const u64 *__restrict__ dec, const u64 *__restrict__ key, const A
     const int chunk = cid % nchunks, bh = cid / nchunks, h = bh & 1, b = bh >> 1;
     const int L1 = L + 1;
     const LimbConst lcP = limbs[L];
-    const u64 *const dec_b = dec + (((size_t)b * L * L1) << LOGN);
-    const u64 *const key_h = key + (((size_t)h * L1) << LOGN);
     constexpr int NP = kPairsPerThread<LOGN, MODE>, MAC_U = 4;
     const int i0 = ks_first_pair<LOGN, MODE>(B);
     const int t_end = (chunk + 1) * tpc < L ? (chunk + 1) * tpc : L;
     if (HB_PAIR_TRIGGER) hb_pdl_trigger();
-    if (HB_PAIR_PREFETCH) {
-        prefetch_inv_twiddles<LOGN, T, MODE>(lcP, B);
-        prefetch_fwd_twiddles<LOGN, T, MODE>(limbs[chunk * tpc], B);
+    if constexpr (staged_mode(MODE)) {
+        stage_inv_tables<LOGN, T, MODE>(sm, lcP, B);
+        stage_fwd_tables<LOGN, T, MODE>(sm, limbs[chunk * tpc], B);
     }
-    if ((threadIdx.x & 7) == 0) { // the key words this thread will multiply by: static data, asked for before the wait
-        for (int p = 0; p < L; p++)
-#pragma unroll
-            for (int kk = 0; kk < NP; kk++) {
-                hb_prefetch_l2(key_h + (((size_t)(p * 2 * L1) + L) << LOGN) + i0 + 64 * kk);
-                hb_prefetch_l2(key_h + (((size_t)(p * 2 * L1) + chunk * tpc) << LOGN) + i0 + 64 * kk);
-            }
-    }
+    src.template prefetch<NP>(h, L, i0);
+    src.template prefetch<NP>(h, chunk * tpc, i0);
     HB_PHASE(0);
     hb_pdl_wait();
+    if constexpr (staged_mode(MODE)) {
+        hb_cp_async_wait_all();
+        __syncthreads();
+    }
     HB_PHASE(1);
     // pre() and finish() of the wave path's policy: the same arithmetic by construction
     const DropFwdIO<BGV> drop{nullptr, nullptr, nullptr, dc, nullptr, 0, 0, half_qlast, L1, LOGN, 0, true, 1u};
@@ -324,7 +362,7 @@ ks_drop_kernel(const u64 *__restrict__ dec, const u64 *__restrict__ key, const A
     // combined with: for the first limb of the chunk here, next to the P limb's, for the others while the previous is stored
     auto epilogue_operands = [&](int k) {
         const LimbConst lck = limbs[k];
-        ks_mac_thread<NP, MAC_U>(dec_b + ((size_t)k << LOGN) + i0, key_h + ((size_t)k << LOGN) + i0, L, LOGN, lck, st.e);
+        src.template pairs<NP, MAC_U>(b, h, k, i0, lck, st.e);
         if (st.add) {
 #pragma unroll
             for (int kk = 0; kk < NP; kk++) st.a[kk] = add.pair(b, h, k, i0 + 64 * kk, lck);
@@ -334,7 +372,7 @@ ks_drop_kernel(const u64 *__restrict__ dec, const u64 *__restrict__ key, const A
     {
         KsRegLoad<NP> load;
         load.i0 = i0;
-        ks_mac_thread<NP, MAC_U>(dec_b + ((size_t)L << LOGN) + i0, key_h + ((size_t)L << LOGN) + i0, L, LOGN, lcP, load.e);
+        src.template pairs<NP, MAC_U>(b, h, L, i0, lcP, load.e);
         inv_local_passes<LOGN, T, 0, MODE>(sm, load, lcP, 0, B);
     }
     hb_cluster_sync();
@@ -351,7 +389,17 @@ ks_drop_kernel(const u64 *__restrict__ dec, const u64 *__restrict__ key, const A
 #pragma unroll 1
     for (int k = chunk * tpc; k < t_end; k++) {
         const LimbConst lck = limbs[k];
-        if (k != chunk * tpc) epilogue_operands(k);
+        if (k != chunk * tpc) {
+            if constexpr (staged_mode(MODE)) {
+                __syncthreads();
+                stage_fwd_tables<LOGN, T, MODE>(sm, lck, B);
+            }
+            epilogue_operands(k);
+            if constexpr (staged_mode(MODE)) {
+                hb_cp_async_wait_all();
+                __syncthreads();
+            }
+        }
         st.dst = out + ((((size_t)b * 2 + h) * L + k) << LOGN);
         st.d = dc + k;
         u64 v[W];

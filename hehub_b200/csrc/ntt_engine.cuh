@@ -100,12 +100,55 @@ HB_D void bfly(u64 &lo, u64 &hi, const ulonglong2 tw, u64 nq, u64 q2) {
 struct TwTable {
     const ulonglong2 *p;
     int stride;
-#if defined(HB_ABL_TWCONST) // ablation builds only (tools/ab_build.sh): one twiddle per pass, no table traffic
+#if defined(HB_ABL_TWNOLOAD) // ablation builds only (tools/ab_build.sh): no table load at all (wrong results, timing only)
+    HB_D ulonglong2 get(int slot) const { return make_ulonglong2((u64)(size_t)p + slot, (u64)stride); }
+#elif defined(HB_ABL_TWCONST) // ablation builds only: one twiddle per pass, no table traffic
     HB_D ulonglong2 get(int) const { return __ldg(p); }
 #else
     HB_D ulonglong2 get(int slot) const { return __ldg(p + slot * stride); }
 #endif
 };
+// the same from a table staged in shared memory (mode-2 plans, ntt_plan.h)
+struct TwSmem {
+    const ulonglong2 *p;
+    int stride;
+    HB_D ulonglong2 get(int slot) const { return p[slot * stride]; }
+};
+// Staged tables live behind the CTA's row in shared memory: forward block, inverse local block, inverse cross block.
+template <int LOGN, int MODE>
+HB_D const ulonglong2 *stage_fwd(const u64 *sm) {
+    return reinterpret_cast<const ulonglong2 *>(sm + smem_words(1 << (LOGN - plan_for(LOGN, true, MODE).lpre)));
+}
+template <int LOGN, int MODE>
+HB_D const ulonglong2 *stage_inv(const u64 *sm) { return stage_fwd<LOGN, MODE>(sm) + fwd_stage_block(plan_for(LOGN, true, MODE)); }
+template <int LOGN, int MODE>
+constexpr int kStagedSmemBytes = smem_words(1 << (LOGN - plan_for(LOGN, true, MODE).lpre)) * 8 +
+                                 16 * (fwd_stage_block(plan_for(LOGN, true, MODE)) + inv_stage_local(plan_for(LOGN, false, MODE)) +
+                                       inv_stage_cross_block(plan_for(LOGN, false, MODE)));
+HB_CX bool staged_mode(int mode) { return mode == 2; }
+// copy `entries` (a multiple of T) 16-byte entries; every thread moves entries tid, tid + T, ...
+template <int T>
+HB_D void stage_copy(const ulonglong2 *dst, const ulonglong2 *src, int entries_const) {
+    ulonglong2 *d = const_cast<ulonglong2 *>(dst) + threadIdx.x;
+    const ulonglong2 *s = src + threadIdx.x;
+#pragma unroll
+    for (int e = 0; e < entries_const; e += T) hb_cp_async16(d + e, s + e);
+}
+// the forward tables of limb `lc` for CTA B of its cluster / the inverse tables
+template <int LOGN, int T, int MODE>
+HB_D void stage_fwd_tables(const u64 *sm, const LimbConst &lc, int B) {
+    constexpr NttPlan pl = plan_for(LOGN, true, MODE);
+    static_assert(kStagePad % T == 0, "blocks are whole multiples of the CTA size");
+    stage_copy<T>(stage_fwd<LOGN, MODE>(sm), tw_fwd<MODE>(lc) + B * fwd_stage_block(pl), fwd_stage_block(pl));
+}
+template <int LOGN, int T, int MODE>
+HB_D void stage_inv_tables(const u64 *sm, const LimbConst &lc, int B) {
+    constexpr NttPlan pl = plan_for(LOGN, false, MODE);
+    stage_copy<T>(stage_inv<LOGN, MODE>(sm), tw_inv<MODE>(lc), inv_stage_local(pl));
+    stage_copy<T>(stage_inv<LOGN, MODE>(sm) + inv_stage_local(pl), tw_inv<MODE>(lc) + inv_stage_local(pl) + B * inv_stage_cross_block(pl),
+                  inv_stage_cross_block(pl));
+}
+
 // K forward levels on 2^K registers.  Level m pairs registers 2^(K-m) apart and uses twiddle
 // slot (2^(m-1) - 1 + blk).
 template <int K, int M = 1, class TW>
@@ -263,7 +306,8 @@ HB_D void fwd_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
             for (int j = 0; j < (1 << K); j++) v[j] = sm[sphys(base + (j << GSL))];
         }
 
-        fwd_levels<K>(v, TwTable{tw_pass + ((B << L0) + hb), stride}, lc.nq, lc.q2);
+        if constexpr (staged_mode(MODE)) fwd_levels<K>(v, TwSmem{stage_fwd<LOGN, MODE>(sm) + fwd_stage_offset(pl, P) + hb, 1 << L0}, lc.nq, lc.q2);
+        else fwd_levels<K>(v, TwTable{tw_pass + ((B << L0) + hb), stride}, lc.nq, lc.q2);
 
         if constexpr (last) {
 #pragma unroll
@@ -300,7 +344,8 @@ HB_D void fwd_cross_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, in
         u64 v[1 << K];
 #pragma unroll
         for (int j = 0; j < (1 << K); j++) v[j] = io_load(io, row, t + (j << LOGG), lc);
-        fwd_levels<K>(v, TwTable{tw_pass, 1}, lc.nq, lc.q2);
+        if constexpr (staged_mode(MODE)) fwd_levels<K>(v, TwSmem{stage_fwd<LOGN, MODE>(sm), 1}, lc.nq, lc.q2);
+        else fwd_levels<K>(v, TwTable{tw_pass, 1}, lc.nq, lc.q2);
         // every CTA of the cluster is running before its shared memory is written (the arrive is at kernel start)
         if (g == (int)threadIdx.x) hb_cluster_wait();
         u64 *const smb = sm + sphys(t);
@@ -486,7 +531,12 @@ ntt_fwd_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
 #if HB_LAT_PREFETCH
     if constexpr (MODE == 1 && pl.xchg) prefetch_fwd_twiddles<LOGN, T, MODE>(lc, B);
 #endif
+    if constexpr (staged_mode(MODE)) stage_fwd_tables<LOGN, T, MODE>(sm, lc, B); // static data: on its way before the row may be read
     hb_pdl_wait();
+    if constexpr (staged_mode(MODE)) {
+        hb_cp_async_wait_all();
+        __syncthreads();
+    }
     if constexpr (io_has_prefetch<IO>::value) io.prefetch(row, B << (LOGN - pl.lpre), 1 << (LOGN - pl.lpre));
 #if defined(HB_ABL_TMA) && !defined(HB_KERNEL_SIM)
     if constexpr (pl.lpre == 0 && !io_has_fetch<IO>::value) {
@@ -536,7 +586,8 @@ HB_D void inv_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, int B) {
             for (int j = 0; j < (1 << K); j++) v[j] = sm[sphys(base + (j << S0))];
         }
 
-        inv_levels<K>(v, TwTable{tw_pass + lo, stride}, lc.nq, lc.q2);
+        if constexpr (staged_mode(MODE)) inv_levels<K>(v, TwSmem{stage_inv<LOGN, MODE>(sm) + inv_pass_offset(pl, P) + lo, stride}, lc.nq, lc.q2);
+        else inv_levels<K>(v, TwTable{tw_pass + lo, stride}, lc.nq, lc.q2);
 
         if constexpr (last && pl.lpre == 0) {
 #pragma unroll
@@ -587,13 +638,24 @@ HB_D void inv_cross_pass(u64 *sm, const IO &io, const LimbConst &lc, int row, in
                 for (int jj = 0; jj < (1 << KL); jj++) v[(o << KL) + jj] = hb_ld_dsmem(smb + jj * SJ, o);
             }
         }
-        inv_levels<K>(v, TwTable{tw_pass + t, 1 << LOGG}, lc.nq, lc.q2);
+        if constexpr (staged_mode(MODE)) {
+            static_assert(!staged_mode(MODE) || GPC == T, "staged cross tables are laid out one group per thread");
+            const ulonglong2 *xb = stage_inv<LOGN, MODE>(sm) + inv_stage_local(pl) + threadIdx.x; // [slot][thread], then the scales [j][thread]
+            inv_levels<K>(v, TwSmem{xb, T}, lc.nq, lc.q2);
 #pragma unroll
-        for (int j = 0; j < (1 << K); j++) {
-            const int i = t + (j << LOGG);
-            u64 x = approx_reduce(v[j], lc);              // ntt.cpp:218
-            const ulonglong2 s = __ldg(lc.inv_scale + i); // psi^{-i}/N, ntt.cpp:219-221
-            io.store(row, i, harvey_lazy(x, s.x, s.y, lc.nq), lc);
+            for (int j = 0; j < (1 << K); j++) {
+                const ulonglong2 s = xb[((1 << K) - 1 + j) * T]; // psi^{-i}/N, ntt.cpp:219-221
+                io.store(row, t + (j << LOGG), harvey_lazy(approx_reduce(v[j], lc), s.x, s.y, lc.nq), lc);
+            }
+        } else {
+            inv_levels<K>(v, TwTable{tw_pass + t, 1 << LOGG}, lc.nq, lc.q2);
+#pragma unroll
+            for (int j = 0; j < (1 << K); j++) {
+                const int i = t + (j << LOGG);
+                u64 x = approx_reduce(v[j], lc);              // ntt.cpp:218
+                const ulonglong2 s = __ldg(lc.inv_scale + i); // psi^{-i}/N, ntt.cpp:219-221
+                io.store(row, i, harvey_lazy(x, s.x, s.y, lc.nq), lc);
+            }
         }
     }
 }
@@ -671,11 +733,21 @@ HB_D void inv_cross_to_regs(const u64 *sm, const LimbConst &lc, int B, u64 (&v)[
         }
     }
     hb_cluster_arrive();
-    inv_levels<K>(v, TwTable{tw_inv<MODE>(lc) + inv_pass_offset(pl, pl.npass - 1) + t, 1 << LOGG}, lc.nq, lc.q2);
+    if constexpr (staged_mode(MODE)) {
+        const ulonglong2 *xb = stage_inv<LOGN, MODE>(sm) + inv_stage_local(pl) + threadIdx.x; // [slot][thread], then the scales [j][thread]
+        inv_levels<K>(v, TwSmem{xb, T}, lc.nq, lc.q2);
 #pragma unroll
-    for (int j = 0; j < (1 << K); j++) {
-        const ulonglong2 s = __ldg(lc.inv_scale + t + (j << LOGG)); // psi^{-i}/N, ntt.cpp:219-221
-        v[j] = harvey_lazy(approx_reduce(v[j], lc), s.x, s.y, lc.nq);
+        for (int j = 0; j < (1 << K); j++) {
+            const ulonglong2 s = xb[((1 << K) - 1 + j) * T]; // psi^{-i}/N, ntt.cpp:219-221
+            v[j] = harvey_lazy(approx_reduce(v[j], lc), s.x, s.y, lc.nq);
+        }
+    } else {
+        inv_levels<K>(v, TwTable{tw_inv<MODE>(lc) + inv_pass_offset(pl, pl.npass - 1) + t, 1 << LOGG}, lc.nq, lc.q2);
+#pragma unroll
+        for (int j = 0; j < (1 << K); j++) {
+            const ulonglong2 s = __ldg(lc.inv_scale + t + (j << LOGG)); // psi^{-i}/N, ntt.cpp:219-221
+            v[j] = harvey_lazy(approx_reduce(v[j], lc), s.x, s.y, lc.nq);
+        }
     }
 }
 // The cross pass of the forward transform from registers: v[j] is input word t + (j << LOGG).  WAITS for the cluster
@@ -687,7 +759,8 @@ HB_D void fwd_cross_from_regs(u64 *sm, const LimbConst &lc, int B, u64 (&v)[kHan
     constexpr int K = pl.k[0], C = 1 << pl.lpre, KL = K - pl.lpre, LOGG = LOGN - K;
     constexpr int SJ = sstride(1 << LOGG);
     const int t = B * T + (int)threadIdx.x;
-    fwd_levels<K>(v, TwTable{tw_fwd<MODE>(lc), 1}, lc.nq, lc.q2);
+    if constexpr (staged_mode(MODE)) fwd_levels<K>(v, TwSmem{stage_fwd<LOGN, MODE>(sm), 1}, lc.nq, lc.q2);
+    else fwd_levels<K>(v, TwTable{tw_fwd<MODE>(lc), 1}, lc.nq, lc.q2);
     hb_cluster_wait();
     u64 *const smb = sm + sphys(t);
 #pragma unroll
@@ -713,7 +786,12 @@ intt_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
 #if HB_LAT_PREFETCH
     if constexpr (MODE == 1 && pl.xchg) prefetch_inv_twiddles<LOGN, T, MODE>(lc, B);
 #endif
+    if constexpr (staged_mode(MODE)) stage_inv_tables<LOGN, T, MODE>(sm, lc, B);
     hb_pdl_wait();
+    if constexpr (staged_mode(MODE)) {
+        hb_cp_async_wait_all();
+        __syncthreads();
+    }
     inv_passes<LOGN, T, 0, MODE>(sm, io, lc, row, B);
     if constexpr (pl.lpre == 1 && !pl.xchg) {
         // Last stage (gap N/2) pairs word i of CTA 0 with word i of CTA 1 — ntt.cpp:199-206.  Each CTA
@@ -810,6 +888,7 @@ struct LaunchEnv {
     bool force_generic; // parity cross-check path
     LaunchStats *stats;
     int latency_rows;   // launches with at most this many rows take the latency plan (default: half the SM count)
+    int latency2_rows;  // ... and with at most this many the mode-2 plans (default: a tenth of the SM count: 8-CTA clusters, one CTA per SM)
     int device;         // kernel attributes (dynamic shared memory opt-in, carveout) are per device
 };
 
@@ -845,7 +924,7 @@ inline cudaError_t launch_fast_mode(const LaunchEnv &env, const IO &io, const Li
 #if defined(HB_ABL_TMA) // A/B build: room for the unpadded staging copy of the row behind the working area
     constexpr int smem = smem_words(1 << (LOGN - pl.lpre)) * 8 + ((FWD && pl.lpre == 0) ? (8 << LOGN) : 0);
 #else
-    constexpr int smem = smem_words(1 << (LOGN - pl.lpre)) * 8;
+    constexpr int smem = staged_mode(MODE) ? kStagedSmemBytes<LOGN, MODE> : smem_words(1 << (LOGN - pl.lpre)) * 8;
 #endif
     auto kern = fast_kernel<LOGN, FWD, IO, MODE>();
     static PerDeviceConfig configured; // zero-initialised; racing contexts at worst configure twice (idempotent)
@@ -873,6 +952,11 @@ inline cudaError_t launch_fast(const LaunchEnv &env, const IO &io, const LimbCon
         // rows; inverse transforms of N >= 16384 (they need their registers: one or two CTAs per SM) 18 rows.
         const long long limit = LOGN <= 13 ? env.latency_rows
                                            : (!FWD ? env.latency_rows / 4 : (LOGN == 14 ? env.latency_rows / 2 : 2ll * env.latency_rows));
+        // a handful of rows (N = 4096 / 8192): 8-CTA clusters with their tables staged in shared memory, while every CTA gets an
+        // SM of its own (mode 2, ntt_plan.h): one N = 8192 row 6.1 -> 4.9 us forward, 6.7 -> 5.2 us inverse
+        if constexpr (has_latency2_plan(LOGN)) {
+            if (rows <= env.latency2_rows) return launch_fast_mode<LOGN, FWD, 2>(env, io, limbs, rows);
+        }
         if (rows <= limit) return launch_fast_mode<LOGN, FWD, 1>(env, io, limbs, rows);
     }
     return launch_fast_mode<LOGN, FWD, 0>(env, io, limbs, rows);

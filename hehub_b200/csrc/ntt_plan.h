@@ -193,6 +193,28 @@ HB_CX int inv_pass_offset(const NttPlan &pl, int p) {
     return off;
 }
 
+// ---- staged tables (mode 2) ----------------------------------------------------------------
+// The mode-2 plans serve kernels that run ONE row per cluster on an otherwise idle SM (ks_pair.cuh): nothing hides a table
+// load there, and every pass waited ~300 cycles for twiddles no other CTA of the SM had touched (profiles/r4_pair_path.md).
+// Their tables are therefore laid out per CTA, in the order the CTA uses them, so that a CTA copies its slice into shared
+// memory with a handful of contiguous asynchronous copies before its row arrives:
+//   forward  [B][ cross pass: 2^k0 - 1 entries, 8 reserved | pass 1 [slot][hb] | pass 2 ... ], each block padded to kStagePad
+//   inverse  [ local passes: the mode-independent [pass][slot][lo] block, padded ] then
+//            [B][ cross twiddles [slot][thread] | psi^-i / N scales [j][thread] ]
+// (entries are (w, w') pairs of 16 bytes).
+constexpr int kStagePad = 256;
+HB_CX int stage_pad(int entries) { return (entries + kStagePad - 1) / kStagePad * kStagePad; }
+HB_CX int fwd_stage_offset(const NttPlan &pl, int p) { // within a CTA's block
+    int off = 0;
+    for (int i = 0; i < p; i++) off += i == 0 ? 8 : ((1 << pl.k[i]) - 1) << fwd_lambda0(pl, i);
+    return off;
+}
+HB_CX int fwd_stage_block(const NttPlan &pl) { return stage_pad(fwd_stage_offset(pl, pl.npass)); }
+HB_CX int inv_stage_local(const NttPlan &pl) { return stage_pad(inv_pass_offset(pl, pl.npass - 1)); }
+HB_CX int inv_stage_cross_block(const NttPlan &pl) { return ((2 << pl.k[0]) - 1) * pl.threads; }
+HB_CX int fwd_stage_total(const NttPlan &pl) { return fwd_stage_block(pl) << pl.lpre; }
+HB_CX int inv_stage_total(const NttPlan &pl) { return inv_stage_local(pl) + (inv_stage_cross_block(pl) << pl.lpre); }
+
 // shared-memory padding: 2 words after every 16 keeps 128-bit accesses of 16-word-strided
 // owners and 64-bit accesses of consecutive lanes conflict-free
 HB_CX int smem_phys(int i) { return i + ((i >> 4) << 1); }

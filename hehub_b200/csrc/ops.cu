@@ -12,6 +12,8 @@
 // rescale, lazy subtract + q_last^{-1} multiply + addend after them, strict reduction after
 // the inverse transforms) lives in the IO policies of the transform kernels, so those values
 // never make a separate trip through HBM.
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "internal.h"
@@ -642,6 +644,11 @@ struct DropFwdIO {
     }
 };
 
+// few ciphertexts: one cluster launch (defined after ks_pair.cuh); returns -1 when the call does not take that form
+static int drop_last_cluster_form(Context &c, unsigned logn, size_t L, u64 t, const u64 *ct, u64 *out, size_t batch, const u64 *addend,
+                                  size_t add_batch_stride, size_t add_poly_stride, int add_halves, unsigned add_ginv, const LimbConst *limbs,
+                                  const DropSet *ds);
+
 int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, const u64 *ct, u64 *out, size_t batch,
                  const u64 *addend, size_t add_batch_stride, size_t add_poly_stride, int add_halves, unsigned add_ginv) {
     if (!moduli || !ct || !out) return c.fail(1, "null operand");
@@ -652,6 +659,9 @@ int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, 
     if (!limbs) return err;
     const DropSet *ds = c.get_drop(logn, moduli, L, t, &err);
     if (!ds) return err;
+    if (const int rc = drop_last_cluster_form(c, logn, L, t, ct, out, batch, addend, add_batch_stride, add_poly_stride, add_halves, add_ginv, limbs, ds);
+        rc >= 0)
+        return rc;
     const size_t n = (size_t)1 << logn;
     // waves bound the z scratch ([wave][2][N]) and keep every launch's row count inside int
     const size_t wave = wave_size(c, 2 * n, batch, 2 * L);
@@ -701,34 +711,97 @@ namespace hb {
 static inline bool ranges_overlap(const u64 *a, size_t na, const u64 *b, size_t nb) { return a < b + nb && b < a + na; }
 
 // Whether a call takes the two-launch form.  Option "pair_path": 0 never, 2 whenever the shapes allow, 1 (default) for
-// N = 4096 / 8192 when the GPU holds one (4-CTA) cluster per input row of the batch at once — beyond that, and for larger
-// rings (whose rows are waves of CTAs rather than latency-bound), the repeated transforms cost throughput and the wave
-// path's streaming wins (profiles/r4_pair_path.md).
+// N = 4096 / 8192 while the batch's fan-out rows number at most pair_fill_pct (130) % of the SMs — measured crossover at
+// N = 8192, L = 4: 12 ciphertexts per call still gain (6.2 vs 6.6 us each), 16 lose (6.0 vs 5.2); larger rings are waves of
+// CTAs rather than latency-bound rows even for one ciphertext, and the wave path's streaming wins (profiles/r4_pair_path.md).
 static bool pair_path_wanted(const Context &c, unsigned logn, size_t L, size_t batch) {
     if (c.pair_path == 0 || c.force_generic || !has_latency2_plan((int)logn) || L == 0 || L > 64) return false;
     const size_t n = (size_t)1 << logn;
     if (batch * L * (L + 1) * n * 8 > c.scratch_cap_bytes || batch * L * L > ((size_t)1 << 20)) return false;
     if (c.pair_path == 2) return true;
-    return batch * L * L * (size_t)plan_cluster(plan_for((int)logn, true, 1)) <= (size_t)c.sm_count * c.pair_fill_pct / 100;
+    return batch * L * L <= (size_t)c.sm_count * c.pair_fill_pct / 100;
 }
-// targets per cluster: as few as keeps the launch's clusters resident at once (one CTA per SM)
-static int pair_targets_per_cluster(const Context &c, size_t cluster, size_t groups, size_t L) {
+// Targets per cluster.  A cluster runs one inverse transform and then `tpc` forward ones; fewer targets per cluster means more
+// clusters (each repeating the inverse transform) and a shorter chain in each.  Pick the split with the shortest estimated
+// time: (waves of resident clusters) x (transforms in a chain), ties to the shorter chain.  `cap`: CTAs of this kernel the
+// GPU holds at once.
+static int pair_targets_per_cluster(const Context &c, size_t cluster, size_t groups, size_t L, size_t cap) {
     if (c.pair_tpc > 0) return c.pair_tpc < (int)L ? c.pair_tpc : (int)L;
-    for (size_t tpc = 1; tpc < L; tpc++)
-        if (groups * ((L + tpc - 1) / tpc) * cluster <= (size_t)c.sm_count) return (int)tpc;
-    return (int)L;
+    size_t best = 1, best_cost = ~(size_t)0;
+    for (size_t tpc = 1; tpc <= L; tpc++) {
+        const size_t ctas = groups * ((L + tpc - 1) / tpc) * cluster, waves = (ctas + cap - 1) / cap, cost = waves * (1 + tpc);
+        if (cost < best_cost) best = tpc, best_cost = cost;
+    }
+    return (int)best;
+}
+// CTAs of a cluster kernel resident at once on this device (asked once per kernel)
+template <class K>
+static size_t pair_resident_ctas(Context &c, K kern, int threads, int cluster, int smem) {
+    int &have = c.cluster_cap[reinterpret_cast<const void *>(kern)];
+#if defined(HB_KERNEL_SIM)
+    (void)threads, (void)smem;
+    if (have == 0) have = c.sm_count >= cluster ? c.sm_count / cluster * cluster : cluster;
+#else
+    if (have == 0) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(cluster * c.sm_count));
+        cfg.blockDim = dim3((unsigned)threads);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)cluster;
+        at[0].val.clusterDim.y = at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+            cudaGetLastError();
+            n = c.sm_count >= cluster ? c.sm_count / cluster : 1; // one CTA per SM
+        }
+        have = n * cluster;
+        if (std::getenv("HEHUB_B200_DEBUG")) std::fprintf(stderr, "hehub_b200: cluster kernel %p: %d clusters of %d CTAs resident at once (smem %d)\n", (const void *)kern, n, cluster, smem);
+    }
+#endif
+    return (size_t)have;
 }
 
+template <int LOGN, int MODE>
+constexpr int kPairSmem = staged_mode(MODE) ? kStagedSmemBytes<LOGN, MODE> : smem_words(1 << (LOGN - plan_for(LOGN, true, MODE).lpre)) * 8;
+// dynamic shared memory above 48 KB: opt in once per kernel and device (the context is per device)
+template <class K>
+static cudaError_t pair_opt_in(Context &c, K kern, int smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    int &have = c.smem_opt_in[reinterpret_cast<const void *>(kern)];
+    if (have >= smem) return cudaSuccess;
+    const cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (ce == cudaSuccess) have = smem;
+    return ce;
+}
+// the drop launch: e (SRC) -> out
+template <int LOGN, int MODE, bool BGV, class SRC, class ADD>
+static int launch_pair_drop(Context &c, const SRC &src, const ADD &add, u64 *out, const LimbConst *limbs, const DropSet *ds, size_t L, size_t batch) {
+    constexpr NttPlan pl = plan_for(LOGN, true, MODE);
+    constexpr int C = 1 << pl.lpre, smem = kPairSmem<LOGN, MODE>;
+    static_assert(smem <= 200 * 1024, "one CTA per SM");
+    auto kern = ks_drop_kernel<LOGN, MODE, BGV, SRC, ADD>;
+    if (cudaError_t ce = pair_opt_in(c, kern, smem); ce != cudaSuccess) return c.cuda_fail(ce, "drop launch (cluster form): shared memory");
+    const int tpc = pair_targets_per_cluster(c, C, batch * 2, L, pair_resident_ctas(c, kern, pl.threads, C, smem)), chunks = ((int)L + tpc - 1) / tpc;
+    const cudaError_t e = HB_LAUNCH_CLUSTER(kern, (unsigned)(batch * 2 * chunks * C), pl.threads, smem, c.stream, C, src, add, out, limbs,
+                                            (const DropConst *)ds->dev, ds->half_qlast, ds->inv_t, ds->inv_t_h, (int)L, tpc, chunks);
+    c.stats.launches++;
+    return e == cudaSuccess ? 0 : c.cuda_fail(e, "drop launch (cluster form)");
+}
 template <int LOGN, int MODE, class IN, bool BGV, class ADD>
 static int launch_pair(Context &c, const IN &in, const ADD &add, const u64 *key, u64 *out, u64 *dec, u64 *quad, const LimbConst *limbs,
                        const DropSet *ds, size_t L, size_t batch) {
     constexpr NttPlan pl = plan_for(LOGN, true, MODE);
-    constexpr int C = 1 << pl.lpre, smem = smem_words(1 << (LOGN - pl.lpre)) * 8;
-    static_assert(smem <= 48 * 1024, "no opt-in needed");
-    const int tpc_a = pair_targets_per_cluster(c, C, batch * L, L), chunks_a = ((int)L + tpc_a - 1) / tpc_a;
+    constexpr int C = 1 << pl.lpre, smem = kPairSmem<LOGN, MODE>;
+    auto kern = ks_fan_kernel<LOGN, MODE, IN>;
+    if (cudaError_t ce = pair_opt_in(c, kern, smem); ce != cudaSuccess) return c.cuda_fail(ce, "key switch (two-launch form): shared memory");
+    const int tpc_a = pair_targets_per_cluster(c, C, batch * L, L, pair_resident_ctas(c, kern, pl.threads, C, smem)), chunks_a = ((int)L + tpc_a - 1) / tpc_a;
     const unsigned main_ctas = (unsigned)(batch * L * chunks_a * C);
     // the tensor product's d0, d1 on CTAs of the same launch that have no transform to run: as many as fill the SMs the
-    // transforms leave idle (at least one cluster, at most one pair of words per thread)
+    // transforms leave idle (at most one pair of words per thread)
     unsigned extra = 0;
     size_t tensor_units = 0;
     if (quad) {
@@ -736,34 +809,60 @@ static int launch_pair(Context &c, const IN &in, const ADD &add, const u64 *key,
         const unsigned want = (unsigned)((tensor_units + pl.threads - 1) / pl.threads);
         const unsigned idle = main_ctas < (unsigned)c.sm_count ? (unsigned)c.sm_count - main_ctas : 0;
         extra = want < idle ? want : idle;
-        extra = extra / C * C;
-        if (extra < (unsigned)C) extra = C;
+        if (extra < (want + 3) / 4) extra = (want + 3) / 4; // no idle SMs (a forced large batch): at most four pairs of words per thread
+        extra = (extra + C - 1) / C * C;
     }
-    cudaError_t e = HB_LAUNCH_CLUSTER((ks_fan_kernel<LOGN, MODE, IN>), main_ctas + extra, pl.threads, smem, c.stream, C, in, dec, limbs, (int)L, tpc_a,
-                                      chunks_a, main_ctas, quad, tensor_units);
+    const cudaError_t e = HB_LAUNCH_CLUSTER(kern, main_ctas + extra, pl.threads, smem, c.stream, C, in, dec, limbs, (int)L, tpc_a, chunks_a, main_ctas,
+                                            quad, tensor_units);
     c.stats.launches++;
     if (e != cudaSuccess) return c.cuda_fail(e, "key switch (two-launch form): fan-out launch");
-    const int tpc_b = pair_targets_per_cluster(c, C, batch * 2, L), chunks_b = ((int)L + tpc_b - 1) / tpc_b;
-    e = HB_LAUNCH_CLUSTER((ks_drop_kernel<LOGN, MODE, BGV, ADD>), (unsigned)(batch * 2 * chunks_b * C), pl.threads, smem, c.stream, C, (const u64 *)dec,
-                          key, add, out, limbs, (const DropConst *)ds->dev, ds->half_qlast, ds->inv_t, ds->inv_t_h, (int)L, tpc_b, chunks_b);
-    c.stats.launches++;
-    return e == cudaSuccess ? 0 : c.cuda_fail(e, "key switch (two-launch form): drop launch");
+    return launch_pair_drop<LOGN, MODE, BGV>(c, KsSrcMac{dec, key, (int)L, LOGN}, add, out, limbs, ds, L, batch);
 }
-// mode 2 (8-CTA clusters, ntt_plan.h) when the fan-out launch of the whole batch then still covers the GPU at most once
+// the mode-2 plans (8-CTA clusters, tables staged in shared memory: ntt_plan.h); the 4-CTA latency plans measured slower at every
+// batch size once the targets were split by pair_targets_per_cluster (profiles/r4_pair_path.md)
 template <class IN, bool BGV, class ADD>
 static int launch_pair_logn(Context &c, unsigned logn, const IN &in, const ADD &add, const u64 *key, u64 *out, u64 *dec, u64 *quad,
                             const LimbConst *limbs, const DropSet *ds, size_t L, size_t batch) {
-    const bool wide = c.pair_mode == 2 || (c.pair_mode == 0 && batch * L * L * 8 <= (size_t)c.sm_count);
     switch (logn) {
-    case 12:
-        return wide ? launch_pair<12, 2, IN, BGV, ADD>(c, in, add, key, out, dec, quad, limbs, ds, L, batch)
-                    : launch_pair<12, 1, IN, BGV, ADD>(c, in, add, key, out, dec, quad, limbs, ds, L, batch);
-    case 13:
-        return wide ? launch_pair<13, 2, IN, BGV, ADD>(c, in, add, key, out, dec, quad, limbs, ds, L, batch)
-                    : launch_pair<13, 1, IN, BGV, ADD>(c, in, add, key, out, dec, quad, limbs, ds, L, batch);
+    case 12: return launch_pair<12, 2, IN, BGV, ADD>(c, in, add, key, out, dec, quad, limbs, ds, L, batch);
+    case 13: return launch_pair<13, 2, IN, BGV, ADD>(c, in, add, key, out, dec, quad, limbs, ds, L, batch);
     }
     return c.fail(1, "two-launch form: ring size without a plan that hands over in registers");
 }
+// ckks::rescale_inplace / bgv::mod_switch_inplace of a few ciphertexts as ONE cluster launch: the inverse transform of the last
+// limb handed in registers to the forward transforms of the others (ks_drop_kernel with the ciphertext itself as source).
+// Taken while the batch has at most one output row per SM (8-CTA clusters, tables staged in shared memory).
+template <bool BGV, class ADD>
+static int launch_drop_form(Context &c, unsigned logn, const KsSrcPlain &src, const ADD &add, u64 *out, const LimbConst *limbs, const DropSet *ds,
+                            size_t Lk, size_t batch) {
+    switch (logn) {
+    case 12: return launch_pair_drop<12, 2, BGV>(c, src, add, out, limbs, ds, Lk, batch);
+    case 13: return launch_pair_drop<13, 2, BGV>(c, src, add, out, limbs, ds, Lk, batch);
+    }
+    return -1;
+}
+static int drop_last_cluster_form(Context &c, unsigned logn, size_t L, u64 t, const u64 *ct, u64 *out, size_t batch, const u64 *addend,
+                                  size_t add_batch_stride, size_t add_poly_stride, int add_halves, unsigned add_ginv, const LimbConst *limbs,
+                                  const DropSet *ds) {
+    if (c.pair_path == 0 || c.force_generic || !has_latency2_plan((int)logn) || L > 64) return -1;
+    const size_t n = (size_t)1 << logn, Lk = L - 1, rows = batch * 2 * Lk;
+    if (rows > ((size_t)1 << 20)) return -1;
+    // measured (profiles/r4_pair_path.md, N = 8192, three remaining limbs): this form wins up to 24 ciphertexts per call
+    if (c.pair_path != 2 && rows > (size_t)c.sm_count) return -1;
+    if (!aligned16(ct) || !aligned16(out) || ranges_overlap(ct, batch * 2 * L * n, out, batch * 2 * Lk * n)) return -1;
+    const int halves = addend ? add_halves : 0;
+    if (halves && (!aligned16(addend) || add_batch_stride % 2 || add_poly_stride % 2)) return -1;
+    if (t && add_ginv != 1) return -1; // the wave path reports it
+    const KsSrcPlain src{ct, (int)Lk, (int)logn};
+    if (add_ginv != 1) {
+        const KsAddPlain<true> add{addend, add_batch_stride, add_poly_stride, halves, (int)logn, add_ginv};
+        return launch_drop_form<false>(c, logn, src, add, out, limbs, ds, Lk, batch);
+    }
+    const KsAddPlain<false> add{addend, add_batch_stride, add_poly_stride, halves, (int)logn, 1u};
+    return t ? launch_drop_form<true>(c, logn, src, add, out, limbs, ds, Lk, batch)
+             : launch_drop_form<false>(c, logn, src, add, out, limbs, ds, Lk, batch);
+}
+
 // constants and workspace of the two-launch form; the checks come in the order the wave path makes them
 static int pair_setup(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u64 t, size_t batch, const LimbConst **limbs, const DropSet **ds,
                       u64 **dec) {

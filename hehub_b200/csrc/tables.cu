@@ -177,7 +177,8 @@ const ModTables *Context::get_tables(u64 q, unsigned logn, int *err) {
     const bool fast = logn >= (unsigned)kFastLogMin;
     const bool lat = fast && has_latency_plan((int)logn);
     const bool lat2 = lat && has_latency2_plan((int)logn);
-    const size_t ntab = fast ? (lat ? (lat2 ? 9 : 7) : 5) : 3; // fwd_nat, inv_nat, inv_scale [, fwd fast, inv fast [, latency-plan pair [, mode-2 pair]]]
+    // fwd_nat, inv_nat, inv_scale [, fwd fast, inv fast [, latency-plan pair [, mode-2 pair (staged layout, 2 n entries each)]]]
+    const size_t ntab = fast ? (lat ? (lat2 ? 11 : 7) : 5) : 3;
     std::vector<ulonglong2> host(ntab * n, make_ulonglong2(0, 0));
     ulonglong2 *fwd_nat = host.data(), *inv_nat = fwd_nat + n, *inv_scale = inv_nat + n;
     auto pair_of = [&](u64 w) { return make_ulonglong2(w, host_harvey_quotient(w, q)); };
@@ -227,7 +228,62 @@ const ModTables *Context::get_tables(u64 q, unsigned logn, int *err) {
     };
     if (fast) fill_plan_tables(inv_scale + n, inv_scale + 2 * n, 0);
     if (lat) fill_plan_tables(inv_scale + 3 * n, inv_scale + 4 * n, 1);
-    if (lat2) fill_plan_tables(inv_scale + 5 * n, inv_scale + 6 * n, 2);
+    if (lat2) { // per-CTA staged layout, see ntt_plan.h
+        ulonglong2 *ff = inv_scale + 5 * n, *fi = inv_scale + 7 * n;
+        NttPlan pl = plan_for((int)logn, true, 2);
+        const int C = 1 << pl.lpre;
+        if ((size_t)fwd_stage_total(pl) > 2 * n || (size_t)inv_stage_total(plan_for((int)logn, false, 2)) > 2 * n) {
+            *err = fail(3, "internal: staged tables do not fit their allocation");
+            return nullptr;
+        }
+        for (int B = 0; B < C; B++) {
+            ulonglong2 *blk = ff + (size_t)B * fwd_stage_block(pl);
+            for (int p = 0; p < pl.npass; p++) {
+                const int K = pl.k[p], l0g = fwd_glevel0(pl, p), off = fwd_stage_offset(pl, p);
+                const int lam = p == 0 ? 0 : fwd_lambda0(pl, p); // CTA-local levels done: 2^lam blocks per CTA
+                for (int m = 1; m <= K; m++)
+                    for (int bk = 0; bk < (1 << (m - 1)); bk++) {
+                        const int slot = (1 << (m - 1)) - 1 + bk;
+                        if (p == 0) { // the cross pass: group index below the smallest gap, one twiddle per slot
+                            blk[off + slot] = fwd_nat[((size_t)1 << (m - 1)) + bk];
+                        } else {
+                            for (int hb = 0; hb < (1 << lam); hb++) {
+                                const size_t ghb = ((size_t)B << lam) + hb; // block index in the full row
+                                blk[off + (slot << lam) + hb] = fwd_nat[((size_t)1 << (l0g + m - 1)) + (ghb << (m - 1)) + bk];
+                            }
+                        }
+                    }
+            }
+        }
+        pl = plan_for((int)logn, false, 2);
+        for (int p = 0; p + 1 < pl.npass; p++) { // the local passes: same entries as the mode-independent layout
+            const int K = inv_k(pl, p), S0 = inv_s0(pl, p), off = inv_pass_offset(pl, p);
+            for (int m = 1; m <= K; m++)
+                for (int jj = 0; jj < (1 << (m - 1)); jj++) {
+                    const int slot = (1 << (m - 1)) - 1 + jj, s = S0 + m;
+                    for (int lo = 0; lo < (1 << S0); lo++) {
+                        const unsigned pos = ((unsigned)jj << S0) + (unsigned)lo;
+                        fi[off + (slot << S0) + lo] = inv_nat[((size_t)1 << (s - 1)) - 1 + bitrev(pos, s - 1)];
+                    }
+                }
+        }
+        {
+            const int K = pl.k[0], LOGG = (int)logn - K, T = pl.threads, S0 = LOGG;
+            for (int B = 0; B < C; B++) {
+                ulonglong2 *blk = fi + inv_stage_local(pl) + (size_t)B * inv_stage_cross_block(pl);
+                for (int tid = 0; tid < T; tid++) {
+                    const int t = B * T + tid;
+                    for (int m = 1; m <= K; m++)
+                        for (int jj = 0; jj < (1 << (m - 1)); jj++) {
+                            const int slot = (1 << (m - 1)) - 1 + jj, s = S0 + m;
+                            const unsigned pos = ((unsigned)jj << S0) + (unsigned)t;
+                            blk[slot * T + tid] = inv_nat[((size_t)1 << (s - 1)) - 1 + bitrev(pos, s - 1)];
+                        }
+                    for (int j = 0; j < (1 << K); j++) blk[((1 << K) - 1 + j) * T + tid] = inv_scale[t + ((size_t)j << LOGG)];
+                }
+            }
+        }
+    }
 
     void *dev = nullptr;
     cudaError_t e = cudaMalloc(&dev, host.size() * sizeof(ulonglong2));
@@ -252,7 +308,7 @@ const ModTables *Context::get_tables(u64 q, unsigned logn, int *err) {
     mt.lc.fwd_lat = lat ? d + 5 * n : nullptr;
     mt.lc.inv_lat = lat ? d + 6 * n : nullptr;
     mt.lc.fwd_lat2 = lat2 ? d + 7 * n : nullptr;
-    mt.lc.inv_lat2 = lat2 ? d + 8 * n : nullptr;
+    mt.lc.inv_lat2 = lat2 ? d + 9 * n : nullptr;
     return &tables.emplace(key, mt).first->second;
 }
 

@@ -85,8 +85,13 @@ def test_latency_and_throughput_plans_agree(dev, oracle, logn):
     want_m = oracle.ckks_mult_relin(logn, ext, ct1, ct2, key)
     want_b = oracle.bgv_mod_switch(logn, ext, 65537, fill_ct(oracle, 33, ext, n))
     try:
-        for rows in (0, 1 << 30):  # never / always the latency plan
+        dev.set_option("pair_path", 0)  # the wave path, whose launches take these plans (the cluster forms: test_pair_path_...)
+        # never the latency plans / always the 4- / 8-CTA thin plans / always the mode-2 plans (N = 4096 / 8192: 8-CTA clusters,
+        # tables staged in shared memory)
+        for rows, rows2 in ((0, 0), (1 << 30, 0), (1 << 30, 1 << 30)):
             dev.set_option("latency_rows", rows)
+            dev.set_option("latency2_rows", rows2)
+            rows = (rows, rows2)
             assert np.array_equal(dev.poly_ntt_fwd(logn, [Q59], x), want_f), rows
             assert np.array_equal(dev.poly_intt(logn, [Q59], want_f), want_i), rows
             assert np.array_equal(dev.poly_intt(logn, [Q59], want_f, strict=True), x), rows
@@ -94,6 +99,8 @@ def test_latency_and_throughput_plans_agree(dev, oracle, logn):
             assert np.array_equal(dev.bgv_mod_switch(logn, ext, 65537, fill_ct(oracle, 33, ext, n)), want_b), rows
     finally:
         dev.set_option("latency_rows", -1)
+        dev.set_option("latency2_rows", -1)
+        dev.set_option("pair_path", 1)
 
 
 def test_ntt_hashes_match_reference_golden(dev, oracle, kat):
@@ -853,26 +860,32 @@ def test_pair_path_matches_oracle_and_wave_path(dev, oracle, logn, bits, pbits, 
         "bgv": pack([oracle.bgv_relinearize(logn, ext, 65537, q, key) for q in quads]),
         "rot": pack([oracle.ckks_rotate(logn, ext, a, key, 3) for a in cts1]),
         "conj": pack([oracle.ckks_conjugate(logn, ext, a, key) for a in cts1]),
+        "rescale": pack([oracle.ckks_rescale(logn, mods, a) for a in cts1]),
+        "modsw": pack([oracle.bgv_mod_switch(logn, mods, 65537, a) for a in cts1]),
     }
     try:
-        # (pair_path, pair_mode: 1 = 4-CTA clusters, 2 = 8-CTA clusters, targets per cluster, launches per call)
-        variants = [(0, 0, 0, None), (2, 1, 0, 2), (2, 2, 0, 2), (2, 1, 2, 2), (2, 2, L, 2)]
-        if dev.kind == "sim":  # the emulator runs every thread of a cluster as a host thread: two variants per shape
-            variants = [(2, 1, 2, 2), (2, 2, 0, 2)] if logn == 12 else ([(2, 2, 2, 2)] if L == 2 else [(2, 1, 0, 2)])
-        for path, mode, tpc, launches in variants:
+        # (pair_path, targets per cluster, launches per call)
+        variants = [(0, 0, None), (2, 0, 2), (2, 1, 2), (2, 2, 2), (2, L, 2)]
+        if dev.kind == "sim":  # the emulator runs every thread of a cluster as a host thread: fewer variants per shape
+            variants = [(2, 2, 2), (2, 0, 2)] if logn == 12 else [(2, 1 if L == 2 else 0, 2)]
+        for path, tpc, launches in variants:
             dev.set_option("pair_path", path)
-            dev.set_option("pair_mode", mode)
             dev.set_option("pair_tpc", tpc)
             before = dev.launch_count()
-            assert np.array_equal(dev.ckks_mult_relin(logn, ext, ct1, ct2, key), want["mult"]), (path, mode, tpc)
+            assert np.array_equal(dev.ckks_mult_relin(logn, ext, ct1, ct2, key), want["mult"]), (path, tpc)
             if launches:
                 assert dev.launch_count() - before == launches
-            assert np.array_equal(dev.ckks_relinearize(logn, ext, quad, key), want["relin"]), (path, mode, tpc)
-            assert np.array_equal(dev.bgv_relinearize(logn, ext, 65537, quad, key), want["bgv"]), (path, mode, tpc)
-            assert np.array_equal(dev.bgv_mult_relin(logn, ext, 65537, ct1, ct2, key), want["bgv"]), (path, mode, tpc)
-            assert np.array_equal(dev.ckks_rotate(logn, ext, ct1, key, 3), want["rot"]), (path, mode, tpc)
-            assert np.array_equal(dev.ckks_conjugate(logn, ext, ct1, key), want["conj"]), (path, mode, tpc)
+            assert np.array_equal(dev.ckks_relinearize(logn, ext, quad, key), want["relin"]), (path, tpc)
+            assert np.array_equal(dev.bgv_relinearize(logn, ext, 65537, quad, key), want["bgv"]), (path, tpc)
+            assert np.array_equal(dev.bgv_mult_relin(logn, ext, 65537, ct1, ct2, key), want["bgv"]), (path, tpc)
+            assert np.array_equal(dev.ckks_rotate(logn, ext, ct1, key, 3), want["rot"]), (path, tpc)
+            assert np.array_equal(dev.ckks_conjugate(logn, ext, ct1, key), want["conj"]), (path, tpc)
+            # rescale / mod-switch of a few ciphertexts: one cluster launch (the same drop kernel, the ciphertext as its source)
+            before = dev.launch_count()
+            assert np.array_equal(dev.ckks_rescale(logn, mods, ct1), want["rescale"]), (path, tpc)
+            if launches:
+                assert dev.launch_count() - before == 1
+            assert np.array_equal(dev.bgv_mod_switch(logn, mods, 65537, ct1), want["modsw"]), (path, tpc)
     finally:
         dev.set_option("pair_path", 1)
-        dev.set_option("pair_mode", 0)
         dev.set_option("pair_tpc", 0)

@@ -1,0 +1,7 @@
+#!/bin/bash
+LIB=hehub_b200/libhehub_b200.so
+for b in 1 2 3 4 6 8 12; do
+  timeout 300 python tools/quick_ops.py $LIB --shape c3 --batch $b --reps 300 --only mult_relin relinearize rotate rescale --opt pair_path=0
+  timeout 300 python tools/quick_ops.py $LIB --shape c3 --batch $b --reps 300 --only mult_relin relinearize rotate rescale --opt pair_path=2 pair_mode=1
+  timeout 300 python tools/quick_ops.py $LIB --shape c3 --batch $b --reps 300 --only mult_relin relinearize rotate rescale --opt pair_path=2 pair_mode=2
+done
