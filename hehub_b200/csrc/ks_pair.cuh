@@ -358,60 +358,66 @@ ks_drop_kernel(const SRC src, const ADD add, u64 *__restrict__ out, const LimbCo
     // pre() and finish() of the wave path's policy: the same arithmetic by construction
     const DropFwdIO<BGV> drop{nullptr, nullptr, nullptr, dc, nullptr, 0, 0, half_qlast, L1, LOGN, 0, true, 1u};
     KsDropStore<BGV, NP> st{drop, {}, {}, nullptr, nullptr, i0, add.has(h)};
-    // the epilogue's operands (the inner product for limb k, the addend) are computed before the transform they will be
-    // combined with: for the first limb of the chunk here, next to the P limb's, for the others while the previous is stored
-    auto epilogue_operands = [&](int k) {
-        const LimbConst lck = limbs[k];
-        src.template pairs<NP, MAC_U>(b, h, k, i0, lck, st.e);
-        if (st.add) {
-#pragma unroll
-            for (int kk = 0; kk < NP; kk++) st.a[kk] = add.pair(b, h, k, i0 + 64 * kk, lck);
-        }
-    };
-    epilogue_operands(chunk * tpc);
-    {
-        KsRegLoad<NP> load;
-        load.i0 = i0;
-        src.template pairs<NP, MAC_U>(b, h, L, i0, lcP, load.e);
-        inv_local_passes<LOGN, T, 0, MODE>(sm, load, lcP, 0, B);
-    }
-    hb_cluster_sync();
-    HB_PHASE(2);
+    const int t0 = B * T + (int)threadIdx.x, t_begin = chunk * tpc;
     u64 z[W];
-    inv_cross_to_regs<LOGN, T, MODE>(sm, lcP, B, z);
-    HB_PHASE(3);
-#pragma unroll
-    for (int j = 0; j < W; j++) { // DropInttIO::store — rescaling.cpp:47-50, mod_switch.cpp:48-51
-        if (BGV) z[j] = harvey_lazy(z[j], inv_t, inv_t_h, lcP.nq);
-        z[j] = reduce_strict(z[j], lcP.q);
-    }
-    const int t0 = B * T + (int)threadIdx.x;
+    // Step 0 is the P limb (inverse transform), steps 1 .. are the limbs of the chunk (forward transforms).  One loop that is
+    // not unrolled, so that the code that fetches e[h][limb] — the inner product, all its operands requested before the first
+    // product — exists ONCE: the kernel is straight-line code that every warp runs once, and its size is what the
+    // instruction cache sees (`no_instruction` was this kernel's first stall reason at 5.4 k instructions:
+    // profiles/r4t_ncu_pair_c3.md).  The operands of a forward step's epilogue are thereby in registers before its transform.
 #pragma unroll 1
-    for (int k = chunk * tpc; k < t_end; k++) {
-        const LimbConst lck = limbs[k];
-        if (k != chunk * tpc) {
-            if constexpr (staged_mode(MODE)) {
+    for (int step = 0; step <= t_end - t_begin; step++) {
+        const int limb = step == 0 ? L : t_begin + step - 1;
+        const LimbConst lcw = limbs[limb];
+        if constexpr (staged_mode(MODE)) {
+            if (step >= 2) { // the next limb's forward tables replace the previous one's
                 __syncthreads();
-                stage_fwd_tables<LOGN, T, MODE>(sm, lck, B);
-            }
-            epilogue_operands(k);
-            if constexpr (staged_mode(MODE)) {
-                hb_cp_async_wait_all();
-                __syncthreads();
+                stage_fwd_tables<LOGN, T, MODE>(sm, lcw, B);
             }
         }
-        st.dst = out + ((((size_t)b * 2 + h) * L + k) << LOGN);
-        st.d = dc + k;
-        u64 v[W];
+        ulonglong2 e[NP];
+        src.template pairs<NP, MAC_U>(b, h, limb, i0, lcw, e);
+        if (step == 0) {
+            KsRegLoad<NP> load;
+            load.i0 = i0;
 #pragma unroll
-        for (int j = 0; j < W; j++) v[j] = drop.pre(k, t0 + (j << LOGG), z[j], lck);
-        fwd_cross_from_regs<LOGN, T, MODE>(sm, lck, B, v);
-        HB_PHASE(4);
-        hb_cluster_sync();
-        HB_PHASE(5);
-        fwd_passes<LOGN, T, 1, MODE>(sm, st, lck, 0, B);
-        HB_PHASE(6);
-        if (k + 1 < t_end) hb_cluster_arrive();
+            for (int kk = 0; kk < NP; kk++) load.e[kk] = e[kk];
+            inv_local_passes<LOGN, T, 0, MODE>(sm, load, lcw, 0, B);
+            hb_cluster_sync();
+            HB_PHASE(2);
+            inv_cross_to_regs<LOGN, T, MODE>(sm, lcw, B, z);
+            HB_PHASE(3);
+#pragma unroll
+            for (int j = 0; j < W; j++) { // DropInttIO::store — rescaling.cpp:47-50, mod_switch.cpp:48-51
+                if (BGV) z[j] = harvey_lazy(z[j], inv_t, inv_t_h, lcw.nq);
+                z[j] = reduce_strict(z[j], lcw.q);
+            }
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < NP; kk++) st.e[kk] = e[kk];
+            if (st.add) {
+#pragma unroll
+                for (int kk = 0; kk < NP; kk++) st.a[kk] = add.pair(b, h, limb, i0 + 64 * kk, lcw);
+            }
+            if constexpr (staged_mode(MODE)) {
+                if (step >= 2) {
+                    hb_cp_async_wait_all();
+                    __syncthreads();
+                }
+            }
+            st.dst = out + ((((size_t)b * 2 + h) * L + limb) << LOGN);
+            st.d = dc + limb;
+            u64 v[W];
+#pragma unroll
+            for (int j = 0; j < W; j++) v[j] = drop.pre(limb, t0 + (j << LOGG), z[j], lcw);
+            fwd_cross_from_regs<LOGN, T, MODE>(sm, lcw, B, v);
+            HB_PHASE(4);
+            hb_cluster_sync();
+            HB_PHASE(5);
+            fwd_passes<LOGN, T, 1, MODE>(sm, st, lcw, 0, B);
+            HB_PHASE(6);
+            if (step < t_end - t_begin) hb_cluster_arrive();
+        }
     }
 }
 

@@ -53,7 +53,13 @@ const char *hehub_b200_last_error(const hehub_b200_ctx *ctx);
  * batched call may use (large batches are processed in waves);
  * "host_chunk_kib" sets the chunk size of the host-buffer pipeline (default 16384; measured best on PCIe Gen5, profiles/r1d_e2e_chunk_sweep.log);
  * "latency_rows": transform launches with at most this many rows (one limb of one polynomial each) split every
- *   row of N = 4096 / 8192 over a 2-CTA cluster (default -1 = half the SM count; 0 = never).
+ *   row over a 4- / 8-CTA cluster (default -1 = half the SM count; 0 = never).
+ * "latency2_rows": ... and with at most this many rows (N = 4096 / 8192) over an 8-CTA cluster with its twiddle tables staged
+ *   in shared memory (default -1 = a tenth of the SM count; 0 = never).
+ * "pair_path" (default 1): key switch + drop of the last prime (ckks / bgv relinearize, mult_relin, rotate, conjugate) of a few
+ *   ciphertexts per call at N = 4096 / 8192 as TWO cluster launches, rescale / mod_switch as ONE (csrc/ks_pair.cuh);
+ *   0 = always the wave path, 2 = whenever the shapes allow.  "pair_fill_pct" (default 130): the form is taken while
+ *   batch * L * L is at most this percentage of the SM count.  "pair_tpc": forward transforms per cluster (0 = automatic).
  * "single_launch" (default 0): 1 makes hehub_b200_ckks_mult_relin with batch 1 at N = 4096 / 8192 run as ONE launch (grid
  *   barriers between its six phases) instead of six programmatically chained launches; measured slower (39 vs 33 us at
  *   N = 8192, L = 4), kept for A/B.
