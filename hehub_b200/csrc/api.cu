@@ -302,6 +302,8 @@ int hehub_b200_ctx_set_option(hehub_b200_ctx *ctx, const char *name, int64_t val
         c.latency2_rows = (int)value;
     } else if (!std::strcmp(name, "pair_path")) { // 0 / 1 / 2: never / automatic / always take the two-launch key switch (context.h)
         c.pair_path = (int)value;
+    } else if (!std::strcmp(name, "fused_drop")) {
+        c.fused_drop = value != 0;
     } else if (!std::strcmp(name, "pair_tpc")) {
         c.pair_tpc = (int)value;
     } else if (!std::strcmp(name, "pair_fill_pct")) {

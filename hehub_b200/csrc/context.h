@@ -55,6 +55,9 @@ struct Context {
     // 1 (default) for batches small enough to gain (ops.cu, pair_path_wanted), 2 whenever the shapes allow.  "pair_tpc": targets
     // per cluster (0: automatic).  "pair_fill_pct": fan-out rows per call, in % of the SM count, up to which the form is taken.
     int pair_path = 1, pair_tpc = 0, pair_fill_pct = 130;
+    // option "fused_drop" (default 1): one ciphertext per call at N = 16384 / 32768 — the drop's inverse transform of the P limb
+    // rides in the key switch's inner-product launch (ext_mac_intt_kernel, ops.cu)
+    bool fused_drop = true;
     unsigned long long *grid_barrier_dev = nullptr; // counter of the single-launch kernel's grid barriers (only grows)
     unsigned long long grid_barrier_count = 0;       // its value once every launch enqueued so far has finished
     unsigned long long *grid_barrier_counter();

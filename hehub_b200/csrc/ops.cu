@@ -31,8 +31,8 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 #ifndef HB_MAC_MINB
 #define HB_MAC_MINB 2
 #endif
-#ifndef HB_MAC_U
-#define HB_MAC_U 2
+#ifndef HB_MAC_U1 // digits whose operands are in flight together in the one-ciphertext form of the inner product
+#define HB_MAC_U1 4
 #endif
 #ifndef HB_MAC_CPT
 #define HB_MAC_CPT 2
@@ -213,7 +213,7 @@ struct ExtFanoutIO {
 template <int CPT, int W, bool GALOIS>
 HB_D void ext_mac_unit(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
                        u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, int logn, size_t batch, size_t gid,
-                       unsigned ginv);
+                       unsigned ginv, int nk = 0, bool absolute_gid = false);
 template <int CPT, int W, bool GALOIS>
 HB_GLOBAL(256, HB_MAC_MINB)
 ext_mac_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
@@ -232,13 +232,14 @@ ext_mac_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__
 template <int CPT, int W, bool GALOIS>
 HB_D void ext_mac_unit(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
                        u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, int logn, size_t batch, size_t gid,
-                       unsigned ginv) {
+                       unsigned ginv, int nk, bool) {
     const int L1 = L + 1;
+    if (nk == 0) nk = L1; // limbs this launch computes (the first nk of the L + 1)
     constexpr int LW = (W == 2) ? 1 : 0;
     const size_t i = (gid & (((size_t)1 << (logn - LW)) - 1)) * W;
     const size_t bk = gid >> (logn - LW);
-    const int k = (int)(bk % L1);
-    const size_t b0 = (bk / L1) * CPT;
+    const int k = (int)(bk % nk);
+    const size_t b0 = (bk / nk) * CPT;
     const LimbConst lc = limbs[k];
     Acc128 acc[CPT][2][W];
 #pragma unroll
@@ -294,6 +295,18 @@ HB_D void ext_mac_unit(const u64 *__restrict__ in, size_t in_batch_stride, const
             }
     };
     int p = 0;
+    if constexpr (CPT == 1) {
+        // one ciphertext per call: the launch is a single short wave that lives on memory latency — the operands of U digits
+        // (3 U 128-bit loads) in flight before the first product
+        constexpr int U = HB_MAC_U1;
+        for (; p + U <= L; p += U) {
+            u64 d[U][CPT][W], k0[U][W], k1[U][W];
+#pragma unroll
+            for (int u = 0; u < U; u++) load(p + u, d[u], k0[u], k1[u]);
+#pragma unroll
+            for (int u = 0; u < U; u++) mac(d[u], k0[u], k1[u]);
+        }
+    }
     for (; p + 1 < L; p += 2) { // two rows' operands in flight before the first product
         u64 dA[CPT][W], kA0[W], kA1[W], dB[CPT][W], kB0[W], kB1[W];
         load(p, dA, kA0, kA1);
@@ -428,9 +441,21 @@ ext_mac_staged_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const 
     }
 }
 
+// One ciphertext per call at N >= 16384: the drop's inverse transform of the P limb (2 rows = 16 CTAs, ~13 us alone on the GPU
+// between the inner product and the forward transforms) rides in the inner-product launch instead — its clusters compute their
+// own P-limb inner product and transform it while the other CTAs of the launch compute the remaining limbs (defined after
+// ks_pair.cuh).  `done` tells the drop that z is there.
+struct FusedDrop {
+    u64 *z; // [2][N]
+    u64 inv_t, inv_t_h;
+    bool bgv, done;
+};
+static cudaError_t launch_mac_intt(Context &c, unsigned logn, const LimbConst *limbs, size_t L, const u64 *in, size_t in_batch_stride,
+                                   const u64 *dec, const u64 *key, u64 *out, unsigned ginv, const FusedDrop &fd);
+
 // one wave of at most `wave` ciphertexts; scratch slots 0 (c) and 1 (dec)
 static int ext_prod_wave(Context &c, unsigned logn, const LimbConst *limbs, size_t L, const u64 *in, size_t in_batch_stride,
-                         const u64 *key, u64 *out, size_t batch, u64 *cbuf, u64 *dec, unsigned ginv) {
+                         const u64 *key, u64 *out, size_t batch, u64 *cbuf, u64 *dec, unsigned ginv, FusedDrop *fd = nullptr) {
     const size_t n = (size_t)1 << logn;
     const bool vec1 = aligned16(in) && (in_batch_stride % 2 == 0) && aligned16(cbuf);
     cudaError_t e;
@@ -470,6 +495,12 @@ static int ext_prod_wave(Context &c, unsigned logn, const LimbConst *limbs, size
             c.stats.launches++;
             return e == cudaSuccess ? 0 : c.cuda_fail(e, "ext_prod: staged mac launch");
         }
+    }
+    if (fd && batch == 1 && vec) {
+        e = launch_mac_intt(c, logn, limbs, L, in, in_batch_stride, dec, key, out, ginv, *fd);
+        if (e != cudaSuccess) return c.cuda_fail(e, "ext_prod: mac + intt launch");
+        fd->done = true;
+        return 0;
     }
     // one ciphertext per call: no second ciphertext to share key words with, so one per thread (fewer registers, more loads in flight)
     const size_t cpt = batch == 1 ? 1 : CPT;
@@ -516,8 +547,14 @@ static size_t wave_size(const Context &c, size_t words_per_ct, size_t batch, siz
     return w;
 }
 
+static int ext_prod_impl(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *in, size_t in_batch_stride, const u64 *key,
+                         u64 *out, size_t batch, unsigned ginv, FusedDrop *fd);
 int op_ext_prod(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *in, size_t in_batch_stride,
                 const u64 *key, u64 *out, size_t batch, unsigned ginv) {
+    return ext_prod_impl(c, logn, ext_moduli, L, in, in_batch_stride, key, out, batch, ginv, nullptr);
+}
+static int ext_prod_impl(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, const u64 *in, size_t in_batch_stride, const u64 *key,
+                         u64 *out, size_t batch, unsigned ginv, FusedDrop *fd) {
     if (!ext_moduli || !in || !key || !out) return c.fail(1, "null operand");
     if (L == 0) return c.fail(1, "Empty RGSW ciphertext."); // rgsw.cpp:59-61
     if (batch == 0) return 0;
@@ -536,7 +573,7 @@ int op_ext_prod(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, cons
     for (size_t b0 = 0; b0 < batch; b0 += wave) {
         const size_t nb = (batch - b0 < wave) ? batch - b0 : wave;
         if (int rc = ext_prod_wave(c, logn, limbs, L, in + b0 * in_batch_stride, in_batch_stride, key, out + b0 * 2 * (L + 1) * n,
-                                   nb, cbuf, dec, ginv))
+                                   nb, cbuf, dec, ginv, fd))
             return rc;
     }
     return 0;
@@ -649,8 +686,15 @@ static int drop_last_cluster_form(Context &c, unsigned logn, size_t L, u64 t, co
                                   size_t add_batch_stride, size_t add_poly_stride, int add_halves, unsigned add_ginv, const LimbConst *limbs,
                                   const DropSet *ds);
 
+static int drop_last_impl(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, const u64 *ct, u64 *out, size_t batch,
+                          const u64 *addend, size_t add_batch_stride, size_t add_poly_stride, int add_halves, unsigned add_ginv, const u64 *z_ready);
 int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, const u64 *ct, u64 *out, size_t batch,
                  const u64 *addend, size_t add_batch_stride, size_t add_poly_stride, int add_halves, unsigned add_ginv) {
+    return drop_last_impl(c, logn, moduli, L, t, ct, out, batch, addend, add_batch_stride, add_poly_stride, add_halves, add_ginv, nullptr);
+}
+// z_ready: z = strict(INTT(last limb)) of the (single) ciphertext has been computed already (FusedDrop)
+static int drop_last_impl(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, const u64 *ct, u64 *out, size_t batch,
+                          const u64 *addend, size_t add_batch_stride, size_t add_poly_stride, int add_halves, unsigned add_ginv, const u64 *z_ready) {
     if (!moduli || !ct || !out) return c.fail(1, "null operand");
     if (L < 2) return c.fail(1, "Unable to drop the only one prime.");
     if (batch == 0) return 0;
@@ -659,13 +703,14 @@ int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, 
     if (!limbs) return err;
     const DropSet *ds = c.get_drop(logn, moduli, L, t, &err);
     if (!ds) return err;
-    if (const int rc = drop_last_cluster_form(c, logn, L, t, ct, out, batch, addend, add_batch_stride, add_poly_stride, add_halves, add_ginv, limbs, ds);
-        rc >= 0)
-        return rc;
+    if (!z_ready)
+        if (const int rc = drop_last_cluster_form(c, logn, L, t, ct, out, batch, addend, add_batch_stride, add_poly_stride, add_halves, add_ginv, limbs, ds);
+            rc >= 0)
+            return rc;
     const size_t n = (size_t)1 << logn;
     // waves bound the z scratch ([wave][2][N]) and keep every launch's row count inside int
     const size_t wave = wave_size(c, 2 * n, batch, 2 * L);
-    u64 *z = c.get_scratch(2, wave * 2 * n, &err);
+    u64 *z = z_ready ? const_cast<u64 *>(z_ready) : c.get_scratch(2, wave * 2 * n, &err);
     if (!z) return err;
     const bool vec = aligned16(ct) && aligned16(z) && aligned16(out) &&
                      (!addend || (aligned16(addend) && add_batch_stride % 2 == 0 && add_poly_stride % 2 == 0));
@@ -679,14 +724,14 @@ int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, 
         const int rows2 = (int)(nb * 2 * (L - 1));
         if (t) {
             DropInttIO<true> io1{ct_w, z, (int)L, (int)logn, ds->inv_t, ds->inv_t_h, aligned16(ct) && aligned16(z)};
-            e = launch_ntt<false>(c.env(), logn, io1, limbs, (int)(nb * 2));
+            e = z_ready ? cudaSuccess : launch_ntt<false>(c.env(), logn, io1, limbs, (int)(nb * 2));
             if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: intt launch");
             if (add_ginv != 1) return c.fail(1, "a Galois-permuted addend is a CKKS path (ckks/arith.cpp:75-93)");
             DropFwdIO<true> io2{ct_w, z, out_w, ds->dev, add_w, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, halves, vec, 1u};
             e = launch_ntt<true>(c.env(), logn, io2, limbs, rows2);
         } else {
             DropInttIO<false> io1{ct_w, z, (int)L, (int)logn, 0, 0, aligned16(ct) && aligned16(z)};
-            e = launch_ntt<false>(c.env(), logn, io1, limbs, (int)(nb * 2));
+            e = z_ready ? cudaSuccess : launch_ntt<false>(c.env(), logn, io1, limbs, (int)(nb * 2));
             if (e != cudaSuccess) return c.cuda_fail(e, "drop_last: intt launch");
             if (add_ginv == 1) {
                 DropFwdIO<false> io2{ct_w, z, out_w, ds->dev, add_w, add_batch_stride, add_poly_stride, ds->half_qlast, (int)L, (int)logn, halves, vec, 1u};
@@ -704,6 +749,104 @@ int op_drop_last(Context &c, unsigned logn, const u64 *moduli, size_t L, u64 t, 
 } // namespace hb
 #include "ks_pair.cuh"
 namespace hb {
+
+// ------------------------------------------------------------------------------------------
+// one ciphertext per call, N = 16384 / 32768: inner product + inverse transform of the P limb in one launch (FusedDrop)
+// ------------------------------------------------------------------------------------------
+// Grid: CTAs [0, 2 C) are the two clusters of the inverse transform (emulator: the LAST 2 C, it runs CTAs one after another);
+// the others compute the inner product one ciphertext per thread (ext_mac_unit), the P limb's two rows FIRST.  Every CTA
+// that has stored P-limb words adds one to a counter that only grows; the transform clusters wait until the launch's
+// `p_blocks` have arrived, then load the rows like the separate launch would (DropInttIO).  The producers never wait, and
+// they are the first CTAs after the transform's own in launch order, so the wait cannot starve them.
+template <int LOGN, bool BGV, bool GALOIS>
+HB_GLOBAL(256, 2)
+ext_mac_intt_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
+                    u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, unsigned ginv, u64 *__restrict__ z, u64 inv_t, u64 inv_t_h,
+                    unsigned long long *counter, unsigned long long target, unsigned p_blocks) {
+    constexpr NttPlan pl = plan_for(LOGN, false, 1);
+    static_assert(pl.threads == 256 && pl.xchg, "the latency plans of these ring sizes: 8-CTA clusters of 256 threads");
+    constexpr unsigned C = 1u << pl.lpre;
+    HB_SHARED_U64(sm);
+#if defined(HB_KERNEL_SIM)
+    const bool transforms = blockIdx.x >= gridDim.x - 2 * C;
+    const unsigned tb = blockIdx.x - (gridDim.x - 2 * C), mb = blockIdx.x;
+#else
+    const bool transforms = blockIdx.x < 2 * C;
+    const unsigned tb = blockIdx.x, mb = blockIdx.x - 2 * C;
+#endif
+    hb_pdl_wait();
+    if (transforms) {
+        const int h = (int)(tb >> pl.lpre), B = (int)(tb & (C - 1));
+#if !defined(HB_KERNEL_SIM)
+        if (threadIdx.x == 0) {
+            unsigned long long seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter) : "memory");
+            } while (seen < target);
+        }
+        __syncthreads();
+#endif
+        // the P limb's rows of e were written by other CTAs of THIS launch: no non-coherent loads (DropInttIO reads with hb_ld_stream)
+        const DropInttIO<BGV> io{out, z, L + 1, LOGN, inv_t, inv_t_h, true};
+        inv_passes<LOGN, 256, 0, 1>(sm, io, limbs[L], h, B);
+        return;
+    }
+    // unit order: limb L first, then 0 .. L - 1; a pair of words per thread
+    const size_t per_limb = (size_t)1 << (LOGN - 1), unit = (size_t)mb * 256 + threadIdx.x;
+    const size_t slot = unit / per_limb; // 0: the P limb
+    if (slot <= (size_t)L) {
+        const size_t k = slot == 0 ? (size_t)L : slot - 1;
+        ext_mac_unit<1, 2, GALOIS>(in, in_batch_stride, dec, key, out, limbs, L, LOGN, 1, k * per_limb + (unit - slot * per_limb), ginv, 0, true);
+    }
+    if (mb < p_blocks) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#if !defined(HB_KERNEL_SIM)
+            __threadfence();
+            atomicAdd(counter, 1ull);
+#endif
+        }
+    }
+}
+template <int LOGN>
+static cudaError_t launch_mac_intt_logn(Context &c, const LimbConst *limbs, size_t L, const u64 *in, size_t in_batch_stride, const u64 *dec,
+                                        const u64 *key, u64 *out, unsigned ginv, const FusedDrop &fd) {
+    constexpr NttPlan pl = plan_for(LOGN, false, 1);
+    constexpr int C = 1 << pl.lpre, smem = smem_words(1 << (LOGN - pl.lpre)) * 8;
+    static_assert(smem <= 48 * 1024, "no opt-in needed");
+    const unsigned per_limb_blocks = (unsigned)(((size_t)1 << (LOGN - 1)) / 256), p_blocks = per_limb_blocks; // the P limb: both rows' pairs share a thread
+    unsigned blocks = (unsigned)((L + 1) * per_limb_blocks);
+    blocks = (blocks + C - 1) / C * C + 2 * C; // whole clusters
+    unsigned long long *counter = c.grid_barrier_counter();
+    if (!counter) return cudaErrorMemoryAllocation;
+    const unsigned long long target = c.grid_barrier_count + p_blocks; // launches of one stream run in order
+    c.stats.launches++;
+    auto go = [&](auto kern) {
+        const cudaError_t e = HB_LAUNCH_CLUSTER(kern, blocks, 256, smem, c.stream, C, in, in_batch_stride, dec, key, out, limbs, (int)L, ginv, fd.z, fd.inv_t,
+                                                fd.inv_t_h, counter, target, p_blocks);
+        if (e == cudaSuccess) c.grid_barrier_count = target; // only a launch that runs adds to the counter
+        return e;
+    };
+    if (fd.bgv) return ginv == 1 ? go(ext_mac_intt_kernel<LOGN, true, false>) : cudaErrorInvalidValue;
+    return ginv == 1 ? go(ext_mac_intt_kernel<LOGN, false, false>) : go(ext_mac_intt_kernel<LOGN, false, true>);
+}
+static cudaError_t launch_mac_intt(Context &c, unsigned logn, const LimbConst *limbs, size_t L, const u64 *in, size_t in_batch_stride,
+                                   const u64 *dec, const u64 *key, u64 *out, unsigned ginv, const FusedDrop &fd) {
+    return logn == 14 ? launch_mac_intt_logn<14>(c, limbs, L, in, in_batch_stride, dec, key, out, ginv, fd)
+                      : launch_mac_intt_logn<15>(c, limbs, L, in, in_batch_stride, dec, key, out, ginv, fd);
+}
+// Whether a key switch + drop of ONE ciphertext takes that form (option "fused_drop", default on); fills `fd` (z in scratch slot 2).
+// Any failure here leaves the decision to the plain path, which reports its own errors in its own order.
+static FusedDrop *fused_drop_wanted(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u64 t, size_t batch, unsigned ginv, FusedDrop *fd) {
+    if (!c.fused_drop || batch != 1 || (logn != 14 && logn != 15) || c.force_generic || c.latency_rows == 0 || (t && ginv != 1)) return nullptr;
+    int err = 0;
+    const DropSet *ds = c.get_drop(logn, ext_moduli, L + 1, t, &err);
+    if (!ds) return nullptr;
+    u64 *z = c.get_scratch(2, (size_t)2 << logn, &err);
+    if (!z) return nullptr;
+    *fd = FusedDrop{z, ds->inv_t, ds->inv_t_h, t != 0, false};
+    return fd;
+}
 
 // ------------------------------------------------------------------------------------------
 // few ciphertexts per call: the key switch and the drop of P as two launches (ks_pair.cuh)
@@ -901,11 +1044,13 @@ int op_relinearize(Context &c, unsigned logn, const u64 *ext_moduli, size_t L, u
     int err = 0;
     u64 *ebuf = c.get_scratch(3, wave * 2 * (L + 1) * n, &err);
     if (!ebuf) return err;
+    FusedDrop fd_store, *fd = fused_drop_wanted(c, logn, ext_moduli, L, t, batch, 1u, &fd_store);
     for (size_t b0 = 0; b0 < batch; b0 += wave) {
         const size_t nb = (batch - b0 < wave) ? batch - b0 : wave;
         const u64 *q = quad + b0 * 3 * L * n;
-        if (int rc = op_ext_prod(c, logn, ext_moduli, L, q + 2 * L * n, 3 * L * n, key, ebuf, nb)) return rc;
-        if (int rc = op_drop_last(c, logn, ext_moduli, L + 1, t, ebuf, out + b0 * 2 * L * n, nb, q, 3 * L * n, L * n, 2)) return rc;
+        if (int rc = ext_prod_impl(c, logn, ext_moduli, L, q + 2 * L * n, 3 * L * n, key, ebuf, nb, 1u, fd)) return rc;
+        if (int rc = drop_last_impl(c, logn, ext_moduli, L + 1, t, ebuf, out + b0 * 2 * L * n, nb, q, 3 * L * n, L * n, 2, 1u, fd && fd->done ? fd->z : nullptr))
+            return rc;
     }
     return 0;
 }
@@ -1509,8 +1654,10 @@ int op_galois_keyswitch(Context &c, unsigned logn, const u64 *ext_moduli, size_t
             if (e != cudaSuccess) return c.cuda_fail(e, "rotate: copy");
             ct_w = copy;
         }
-        if (int rc = op_ext_prod(c, logn, ext_moduli, L, ct_w + L * n, 2 * L * n, key, ebuf, nb, ginv)) return rc;
-        if (int rc = op_drop_last(c, logn, ext_moduli, L + 1, 0, ebuf, out + b0 * 2 * L * n, nb, ct_w, 2 * L * n, L * n, 1, ginv)) return rc;
+        FusedDrop fd_store, *fd = fused_drop_wanted(c, logn, ext_moduli, L, 0, nb == batch ? batch : 0, ginv, &fd_store);
+        if (int rc = ext_prod_impl(c, logn, ext_moduli, L, ct_w + L * n, 2 * L * n, key, ebuf, nb, ginv, fd)) return rc;
+        if (int rc = drop_last_impl(c, logn, ext_moduli, L + 1, 0, ebuf, out + b0 * 2 * L * n, nb, ct_w, 2 * L * n, L * n, 1, ginv, fd && fd->done ? fd->z : nullptr))
+            return rc;
     }
     return 0;
 }

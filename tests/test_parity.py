@@ -889,3 +889,26 @@ def test_pair_path_matches_oracle_and_wave_path(dev, oracle, logn, bits, pbits, 
     finally:
         dev.set_option("pair_path", 1)
         dev.set_option("pair_tpc", 0)
+
+
+@pytest.mark.parametrize("logn,bits,pbits", [(14, [45, 40, 40], 45), (15, [50, 50], 55)])
+def test_fused_drop_matches_oracle(dev, oracle, logn, bits, pbits):
+    """One ciphertext per call at N = 16384 / 32768: the inverse transform of the P limb rides in the key switch's inner-product
+    launch (option fused_drop, ext_mac_intt_kernel) — five launches instead of six per relinearize, the same words."""
+    mods, ext = _shape(oracle, logn, bits, pbits)
+    n = 1 << logn
+    ct1, ct2, key = fill_ct(oracle, 51, mods, n), fill_ct(oracle, 52, mods, n), fill_key(oracle, 3500, ext, n)
+    quad = oracle.ckks_tensor(logn, mods, ct1, ct2)
+    want = {"mult": oracle.ckks_mult_relin(logn, ext, ct1, ct2, key), "bgv": oracle.bgv_relinearize(logn, ext, 65537, quad, key),
+            "rot": oracle.ckks_rotate(logn, ext, ct1, key, 7), "conj": oracle.ckks_conjugate(logn, ext, ct1, key)}
+    try:
+        for fused, launches in ((1, 5), (0, 6)):
+            dev.set_option("fused_drop", fused)
+            before = dev.launch_count()
+            assert np.array_equal(dev.ckks_mult_relin(logn, ext, ct1, ct2, key), want["mult"]), fused
+            assert dev.launch_count() - before == launches, (fused, dev.launch_count() - before)
+            assert np.array_equal(dev.bgv_relinearize(logn, ext, 65537, quad, key), want["bgv"]), fused
+            assert np.array_equal(dev.ckks_rotate(logn, ext, ct1, key, 7), want["rot"]), fused
+            assert np.array_equal(dev.ckks_conjugate(logn, ext, ct1, key), want["conj"]), fused
+    finally:
+        dev.set_option("fused_drop", 1)
