@@ -106,7 +106,10 @@ HB_CX NttPlan plan_for(int logn, bool fwd, int mode = 0) {
     if (mode == 1 && logn == 14) return NttPlan{14, 3, 5, {3, 3, 3, 2, 3}, 256, fwd ? 3 : 2, 1};
     // N = 32768: five thin passes on 512 threads lose to four passes of 16 words (one pair per call 143 -> 173 us): the
     // launches of one C5 ciphertext are not latency-bound rows but one to two waves of CTAs
-    if (mode == 1 && logn == 15) return NttPlan{15, 3, 4, {4, 4, 3, 4, 0}, 256, fwd ? 3 : 1, 1};
+#ifndef HB_LAT15_MINB
+#define HB_LAT15_MINB 3
+#endif
+    if (mode == 1 && logn == 15) return NttPlan{15, 3, 4, {4, 4, 3, 4, 0}, 256, fwd ? HB_LAT15_MINB : 1, 1};
 #else
     if (mode == 1 && logn == 12) return NttPlan{12, 1, 3, {3, 4, 4, 0, 0}, 128, 1, 0};
     if (mode == 1 && logn == 13) return NttPlan{13, 1, 3, {4, 4, 4, 0, 0}, 256, 1, 0};
