@@ -60,6 +60,9 @@ const char *hehub_b200_last_error(const hehub_b200_ctx *ctx);
  *   ciphertexts per call at N = 4096 / 8192 as TWO cluster launches, rescale / mod_switch as ONE (csrc/ks_pair.cuh);
  *   0 = always the wave path, 2 = whenever the shapes allow.  "pair_fill_pct" (default 130): the form is taken while
  *   batch * L * L is at most this percentage of the SM count.  "pair_tpc": forward transforms per cluster (0 = automatic).
+ * "fused_drop" (default 1): one ciphertext per call at N = 16384 / 32768 — the inverse transform of the special prime's limb runs
+ *   inside the key switch's inner-product launch (its clusters wait on a counter for that limb's words) instead of alone on the
+ *   GPU between two launches; 0 = separate launch (A/B).
  * "single_launch" (default 0): 1 makes hehub_b200_ckks_mult_relin with batch 1 at N = 4096 / 8192 run as ONE launch (grid
  *   barriers between its six phases) instead of six programmatically chained launches; measured slower (39 vs 33 us at
  *   N = 8192, L = 4), kept for A/B.
