@@ -364,7 +364,7 @@ ks_drop_kernel(const SRC src, const ADD add, u64 *__restrict__ out, const LimbCo
     // not unrolled, so that the code that fetches e[h][limb] — the inner product, all its operands requested before the first
     // product — exists ONCE: the kernel is straight-line code that every warp runs once, and its size is what the
     // instruction cache sees (`no_instruction` was this kernel's first stall reason at 5.4 k instructions:
-    // profiles/r5g_ncu_pair_c3.md).  The operands of a forward step's epilogue are thereby in registers before its transform.
+    // profiles/r4_pair_path.md).  The operands of a forward step's epilogue are thereby in registers before its transform.
 #pragma unroll 1
     for (int step = 0; step <= t_end - t_begin; step++) {
         const int limb = step == 0 ? L : t_begin + step - 1;
