@@ -755,14 +755,15 @@ namespace hb {
 // ------------------------------------------------------------------------------------------
 // Grid: CTAs [0, 2 C) are the two clusters of the inverse transform (emulator: the LAST 2 C, it runs CTAs one after another);
 // the others compute the inner product one ciphertext per thread (ext_mac_unit), the P limb's two rows FIRST.  Every CTA
-// that has stored P-limb words adds one to a counter that only grows; the transform clusters wait until the launch's
-// `p_blocks` have arrived, then load the rows like the separate launch would (DropInttIO).  The producers never wait, and
-// they are the first CTAs after the transform's own in launch order, so the wait cannot starve them.
+// that has stored P-limb words adds one to sync[0]; the transform clusters wait until the launch's `p_blocks` have arrived,
+// then load the rows like the separate launch would (DropInttIO).  The producers never wait, and they are the first CTAs
+// after the transform's own in launch order, so the wait cannot starve them.  The last transform CTA past the wait (sync[1])
+// puts both words back to zero: every launch — a replay of a captured graph too — starts from the same state.
 template <int LOGN, bool BGV, bool GALOIS>
 HB_GLOBAL(256, 2)
 ext_mac_intt_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u64 *__restrict__ dec, const u64 *__restrict__ key,
                     u64 *__restrict__ out, const LimbConst *__restrict__ limbs, int L, unsigned ginv, u64 *__restrict__ z, u64 inv_t, u64 inv_t_h,
-                    unsigned long long *counter, unsigned long long target, unsigned p_blocks) {
+                    unsigned long long *sync, unsigned p_blocks) {
     constexpr NttPlan pl = plan_for(LOGN, false, 1);
     static_assert(pl.threads == 256 && pl.xchg, "the latency plans of these ring sizes: 8-CTA clusters of 256 threads");
     constexpr unsigned C = 1u << pl.lpre;
@@ -781,8 +782,12 @@ ext_mac_intt_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u6
         if (threadIdx.x == 0) {
             unsigned long long seen;
             do {
-                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter) : "memory");
-            } while (seen < target);
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(sync) : "memory");
+            } while (seen < p_blocks);
+            if (atomicAdd(sync + 1, 1ull) == 2 * C - 1) { // every producer has arrived, every waiter has seen it
+                sync[1] = 0;
+                sync[0] = 0;
+            }
         }
         __syncthreads();
 #endif
@@ -803,7 +808,7 @@ ext_mac_intt_kernel(const u64 *__restrict__ in, size_t in_batch_stride, const u6
         if (threadIdx.x == 0) {
 #if !defined(HB_KERNEL_SIM)
             __threadfence();
-            atomicAdd(counter, 1ull);
+            atomicAdd(sync, 1ull);
 #endif
         }
     }
@@ -817,15 +822,12 @@ static cudaError_t launch_mac_intt_logn(Context &c, const LimbConst *limbs, size
     const unsigned per_limb_blocks = (unsigned)(((size_t)1 << (LOGN - 1)) / 256), p_blocks = per_limb_blocks; // the P limb: both rows' pairs share a thread
     unsigned blocks = (unsigned)((L + 1) * per_limb_blocks);
     blocks = (blocks + C - 1) / C * C + 2 * C; // whole clusters
-    unsigned long long *counter = c.grid_barrier_counter();
-    if (!counter) return cudaErrorMemoryAllocation;
-    const unsigned long long target = c.grid_barrier_count + p_blocks; // launches of one stream run in order
+    unsigned long long *counters = c.grid_barrier_counter();
+    if (!counters) return cudaErrorMemoryAllocation;
     c.stats.launches++;
     auto go = [&](auto kern) {
-        const cudaError_t e = HB_LAUNCH_CLUSTER(kern, blocks, 256, smem, c.stream, C, in, in_batch_stride, dec, key, out, limbs, (int)L, ginv, fd.z, fd.inv_t,
-                                                fd.inv_t_h, counter, target, p_blocks);
-        if (e == cudaSuccess) c.grid_barrier_count = target; // only a launch that runs adds to the counter
-        return e;
+        return HB_LAUNCH_CLUSTER(kern, blocks, 256, smem, c.stream, C, in, in_batch_stride, dec, key, out, limbs, (int)L, ginv, fd.z, fd.inv_t, fd.inv_t_h,
+                                 counters + 1, p_blocks);
     };
     if (fd.bgv) return ginv == 1 ? go(ext_mac_intt_kernel<LOGN, true, false>) : cudaErrorInvalidValue;
     return ginv == 1 ? go(ext_mac_intt_kernel<LOGN, false, false>) : go(ext_mac_intt_kernel<LOGN, false, true>);

@@ -95,11 +95,13 @@ Context::~Context() {
 
 unsigned long long *Context::grid_barrier_counter() {
     if (!grid_barrier_dev) {
-        if (cudaMalloc(&grid_barrier_dev, sizeof(unsigned long long)) != cudaSuccess) {
+        // [0]: the single-launch kernel's grid barrier (only grows); [1], [2]: arrivals / released clusters of ext_mac_intt_kernel
+        // (reset by the kernel itself: nothing on the host to keep in step, replays of a captured graph included)
+        if (cudaMalloc(&grid_barrier_dev, 4 * sizeof(unsigned long long)) != cudaSuccess) {
             cudaGetLastError();
             return nullptr;
         }
-        cudaMemsetAsync(grid_barrier_dev, 0, sizeof(unsigned long long), stream);
+        cudaMemsetAsync(grid_barrier_dev, 0, 4 * sizeof(unsigned long long), stream);
         grid_barrier_count = 0;
     }
     return grid_barrier_dev;
