@@ -517,7 +517,7 @@ def run_extras(ctx, torch, stream, timed, barrier, world, rank, peaks, dist, swe
     # batch sizes are multiples of the rows one wave of CTAs covers on 148 SMs (N=8192: 2 CTAs per SM, N=16384: one,
     # N=32768: one CTA pair per row), so every transform launch of the composite ops ends on a full wave
     ct_bench("c3_ckks_mult_relin_N8192_L4", 13, [40, 30, 30, 30], 40, 1184, 4, ("mult", "tensor", "e2e", "latency"))
-    ct_bench("c4_rescale_N16384_L8", 14, [50] + [40] * 7, 50, 148, 4, ("rescale",))
+    ct_bench("c4_rescale_N16384_L8", 14, [50] + [40] * 7, 50, 592, 4, ("rescale",))
     ct_bench("c5_ckks_mult_relin_N32768_L12", 15, [50] * 12, 55, 296, 2, ("mult", "tensor", "latency"))
 
     # config 5 as a sweep: `sweep_cts` independent ciphertext pairs (65 536 in BASELINE; bounded by default so the
