@@ -54,7 +54,7 @@ struct Context {
     // option "pair_path": few ciphertexts per call run the key switch + drop as two cluster launches (ks_pair.cuh); 0 never,
     // 1 (default) for batches small enough to gain (ops.cu, pair_path_wanted), 2 whenever the shapes allow.  "pair_tpc": targets
     // per cluster (0: automatic).  "pair_fill_pct": fan-out rows per call, in % of the SM count, up to which the form is taken.
-    int pair_path = 1, pair_tpc = 0, pair_fill_pct = 130;
+    int pair_path = 1, pair_tpc = 0, pair_fill_pct = 100;
     // option "fused_drop" (default 1): one ciphertext per call at N = 16384 / 32768 — the drop's inverse transform of the P limb
     // rides in the key switch's inner-product launch (ext_mac_intt_kernel, ops.cu)
     bool fused_drop = true;

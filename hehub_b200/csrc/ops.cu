@@ -856,9 +856,10 @@ static FusedDrop *fused_drop_wanted(Context &c, unsigned logn, const u64 *ext_mo
 static inline bool ranges_overlap(const u64 *a, size_t na, const u64 *b, size_t nb) { return a < b + nb && b < a + na; }
 
 // Whether a call takes the two-launch form.  Option "pair_path": 0 never, 2 whenever the shapes allow, 1 (default) for
-// N = 4096 / 8192 while the batch's fan-out rows number at most pair_fill_pct (130) % of the SMs — measured crossover at
-// N = 8192, L = 4: 12 ciphertexts per call still gain (6.2 vs 6.6 us each), 16 lose (6.0 vs 5.2); larger rings are waves of
-// CTAs rather than latency-bound rows even for one ciphertext, and the wave path's streaming wins (profiles/r4_pair_path.md).
+// N = 4096 / 8192 while the batch's fan-out rows number at most pair_fill_pct (100) % of the SMs — measured crossovers
+// (profiles/r4_pair_path.md): N = 8192, L = 4: 12 ciphertexts per call still gain 6 %, 16 lose; N = 4096, L = 2: 32 gain, 48 lose;
+// L = 3: 16 gain, 32 lose; N = 8192, L = 6: a tie from 4 on.  Larger rings are waves of CTAs rather than latency-bound rows even
+// for one ciphertext, and the wave path's streaming wins.
 static bool pair_path_wanted(const Context &c, unsigned logn, size_t L, size_t batch) {
     if (c.pair_path == 0 || c.force_generic || !has_latency2_plan((int)logn) || L == 0 || L > 64) return false;
     const size_t n = (size_t)1 << logn;

@@ -58,7 +58,7 @@ const char *hehub_b200_last_error(const hehub_b200_ctx *ctx);
  *   in shared memory (default -1 = a tenth of the SM count; 0 = never).
  * "pair_path" (default 1): key switch + drop of the last prime (ckks / bgv relinearize, mult_relin, rotate, conjugate) of a few
  *   ciphertexts per call at N = 4096 / 8192 as TWO cluster launches, rescale / mod_switch as ONE (csrc/ks_pair.cuh);
- *   0 = always the wave path, 2 = whenever the shapes allow.  "pair_fill_pct" (default 130): the form is taken while
+ *   0 = always the wave path, 2 = whenever the shapes allow.  "pair_fill_pct" (default 100): the form is taken while
  *   batch * L * L is at most this percentage of the SM count.  "pair_tpc": forward transforms per cluster (0 = automatic).
  * "fused_drop" (default 1): one ciphertext per call at N = 16384 / 32768 — the inverse transform of the special prime's limb runs
  *   inside the key switch's inner-product launch (its clusters wait on a counter for that limb's words) instead of alone on the

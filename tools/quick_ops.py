@@ -17,7 +17,7 @@ ap.add_argument("--scratch-mib", type=int, default=None, help="context option sc
 ap.add_argument("--single-launch", type=int, default=None, help="context option single_launch")
 ap.add_argument("--opt", nargs="*", default=[], help="context options name=value (pair_path=2 pair_tpc=1 ...)")
 a = ap.parse_args()
-SHAPES = {"c3": (13, [40, 30, 30, 30], 40, 296), "c4": (14, [50] + [40] * 7, 50, 148), "c5": (15, [50] * 12, 55, 74)}
+SHAPES = {"ex": (12, [39, 30], 39, 296), "ex3": (12, [39, 30, 30], 39, 296), "c3l6": (13, [40, 30, 30, 30, 30, 30], 40, 296), "c3": (13, [40, 30, 30, 30], 40, 296), "c4": (14, [50] + [40] * 7, 50, 148), "c5": (15, [50] * 12, 55, 74)}
 orc = Oracle()
 ctx = Context(lib_path=a.lib)
 if a.latency_rows is not None: ctx.set_option("latency_rows", a.latency_rows)
