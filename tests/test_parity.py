@@ -876,11 +876,12 @@ def test_pair_path_matches_oracle_and_wave_path(dev, oracle, logn, bits, pbits, 
             assert np.array_equal(dev.ckks_mult_relin(logn, ext, ct1, ct2, key), want["mult"]), (path, tpc)
             if launches:
                 assert dev.launch_count() - before == launches
-            assert np.array_equal(dev.ckks_relinearize(logn, ext, quad, key), want["relin"]), (path, tpc)
-            assert np.array_equal(dev.bgv_relinearize(logn, ext, 65537, quad, key), want["bgv"]), (path, tpc)
-            assert np.array_equal(dev.bgv_mult_relin(logn, ext, 65537, ct1, ct2, key), want["bgv"]), (path, tpc)
             assert np.array_equal(dev.ckks_rotate(logn, ext, ct1, key, 3), want["rot"]), (path, tpc)
-            assert np.array_equal(dev.ckks_conjugate(logn, ext, ct1, key), want["conj"]), (path, tpc)
+            if not (dev.kind == "sim" and batch > 1):  # (the emulator's largest case keeps to one op of each kernel family)
+                assert np.array_equal(dev.ckks_relinearize(logn, ext, quad, key), want["relin"]), (path, tpc)
+                assert np.array_equal(dev.bgv_relinearize(logn, ext, 65537, quad, key), want["bgv"]), (path, tpc)
+                assert np.array_equal(dev.bgv_mult_relin(logn, ext, 65537, ct1, ct2, key), want["bgv"]), (path, tpc)
+                assert np.array_equal(dev.ckks_conjugate(logn, ext, ct1, key), want["conj"]), (path, tpc)
             if L < 2:
                 continue
             # rescale / mod-switch of a few ciphertexts: one cluster launch (the same drop kernel, the ciphertext as its source)
