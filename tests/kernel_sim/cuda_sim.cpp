@@ -2,7 +2,12 @@
 #include "cuda_sim.h"
 
 #include <atomic>
+#include <climits>
 #include <memory>
+
+#include <linux/futex.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 namespace hbsim {
 
@@ -14,25 +19,25 @@ static thread_local size_t t_rank = 0; // CTA rank within its cluster
 hbsim_u64 *shared_u64() { return g_shared[t_rank].data(); }
 hbsim_u64 *shared_u64_of(size_t cluster_rank) { return g_shared[cluster_rank].data(); }
 
-// A reusable sense-reversing barrier.
+// A reusable sense-reversing barrier on a futex: arrivals are one atomic increment (no mutex to queue on — a CTA of the
+// emulator is hundreds of host threads), waiters sleep on the generation word and the last arrival wakes them.
 struct Barrier {
-    std::mutex m;
-    std::condition_variable cv;
-    size_t count = 0, waiting = 0;
-    unsigned long gen = 0;
+    std::atomic<unsigned> waiting{0};
+    std::atomic<unsigned> gen{0};
+    unsigned count = 0;
     void reset(size_t n) {
-        count = n;
-        waiting = 0;
+        count = (unsigned)n;
+        waiting.store(0, std::memory_order_relaxed);
     }
     void wait() {
-        std::unique_lock<std::mutex> lk(m);
-        const unsigned long g = gen;
-        if (++waiting == count) {
-            waiting = 0;
-            gen++;
-            cv.notify_all();
+        const unsigned g = gen.load(std::memory_order_acquire);
+        if (waiting.fetch_add(1, std::memory_order_acq_rel) + 1 == count) {
+            waiting.store(0, std::memory_order_relaxed);
+            gen.store(g + 1, std::memory_order_release);
+            syscall(SYS_futex, reinterpret_cast<unsigned *>(&gen), FUTEX_WAKE_PRIVATE, INT_MAX, nullptr, nullptr, 0);
         } else {
-            cv.wait(lk, [&] { return gen != g; });
+            while (gen.load(std::memory_order_acquire) == g)
+                syscall(SYS_futex, reinterpret_cast<unsigned *>(&gen), FUTEX_WAIT_PRIVATE, g, nullptr, nullptr, 0);
         }
     }
 };
@@ -48,27 +53,38 @@ void cluster_sync() {
     if (t_in_team) g_cluster.wait();
 }
 
-// Persistent team of worker threads, grown on demand; each launch hands them one body.
+static inline void futex_wait(std::atomic<unsigned> &w, unsigned seen) {
+    syscall(SYS_futex, reinterpret_cast<unsigned *>(&w), FUTEX_WAIT_PRIVATE, seen, nullptr, nullptr, 0);
+}
+static inline void futex_wake_all(std::atomic<unsigned> &w) {
+    syscall(SYS_futex, reinterpret_cast<unsigned *>(&w), FUTEX_WAKE_PRIVATE, INT_MAX, nullptr, nullptr, 0);
+}
+
+// Persistent team of worker threads, grown on demand; each launch hands them one body.  Start and completion are futex words
+// too: a launch is one wake-all and one sleep of the launching thread, whatever the size of the team.
 struct Team {
     std::vector<std::thread> workers;
-    std::mutex m;
-    std::condition_variable cv_go, cv_done;
-    unsigned long epoch = 0;
-    size_t active = 0, done = 0;
+    std::atomic<unsigned> epoch{0}, done{0}, finished{0};
+    std::atomic<bool> quit{false};
+    size_t active = 0, team_size = 0;
     const std::function<void()> *body = nullptr;
     size_t grid = 0, block = 0, cluster = 1;
-    bool quit = false;
 
-    void worker(size_t id) {
-        unsigned long seen = 0;
+    void worker(size_t id, unsigned seen) {
         for (;;) {
-            {
-                std::unique_lock<std::mutex> lk(m);
-                cv_go.wait(lk, [&] { return quit || epoch != seen; });
-                if (quit) return;
-                seen = epoch;
-                if (id >= active) continue;
+            while (epoch.load(std::memory_order_acquire) == seen && !quit.load(std::memory_order_acquire)) futex_wait(epoch, seen);
+            if (quit.load(std::memory_order_acquire)) return;
+            seen = epoch.load(std::memory_order_acquire);
+            if (id < active) run_body(id);
+            // every worker, active in this launch or not, reports: the launcher rewrites the fields only when nobody reads them
+            if (done.fetch_add(1, std::memory_order_acq_rel) + 1 == team_size) {
+                finished.store(seen, std::memory_order_release);
+                futex_wake_all(finished);
             }
+        }
+    }
+    void run_body(size_t id) {
+        {
             t_in_team = true;
             t_rank = id / block;
             t_blockDim = {(unsigned)block, 1, 1};
@@ -80,41 +96,32 @@ struct Team {
                 g_cluster.wait();
             }
             t_in_team = false;
-            {
-                std::lock_guard<std::mutex> lk(m);
-                if (++done == active) cv_done.notify_all();
-            }
         }
     }
 
     void run(size_t g, size_t blk, size_t cl, const std::function<void()> &f) {
+        const unsigned now = epoch.load(std::memory_order_relaxed);
         while (workers.size() < blk * cl) {
             const size_t id = workers.size();
-            workers.emplace_back([this, id] { worker(id); });
+            workers.emplace_back([this, id, now] { worker(id, now); });
         }
-        {
-            std::lock_guard<std::mutex> lk(m);
-            grid = g;
-            block = blk;
-            body = &f;
-            cluster = cl;
-            active = blk * cl;
-            done = 0;
-            for (auto &b : g_sync) b.reset(blk);
-            g_cluster.reset(blk * cl);
-            epoch++;
-        }
-        cv_go.notify_all();
-        std::unique_lock<std::mutex> lk(m);
-        cv_done.wait(lk, [&] { return done == active; });
+        grid = g;
+        block = blk;
+        body = &f;
+        cluster = cl;
+        active = blk * cl;
+        team_size = workers.size();
+        done.store(0, std::memory_order_relaxed);
+        for (auto &b : g_sync) b.reset(blk);
+        g_cluster.reset(blk * cl);
+        epoch.store(now + 1, std::memory_order_release); // publishes the fields above
+        futex_wake_all(epoch);
+        while (finished.load(std::memory_order_acquire) != now + 1) futex_wait(finished, finished.load(std::memory_order_acquire));
     }
 
     ~Team() {
-        {
-            std::lock_guard<std::mutex> lk(m);
-            quit = true;
-        }
-        cv_go.notify_all();
+        quit.store(true, std::memory_order_release);
+        futex_wake_all(epoch);
         for (auto &t : workers) t.join();
     }
 };
