@@ -66,7 +66,8 @@ const char *hehub_b200_last_error(const hehub_b200_ctx *ctx);
  * "single_launch" (default 0): 1 makes hehub_b200_ckks_mult_relin with batch 1 at N = 4096 / 8192 run as ONE launch (grid
  *   barriers between its six phases) instead of six programmatically chained launches; measured slower (39 vs 33 us at
  *   N = 8192, L = 4), kept for A/B.
- * Environment: HEHUB_B200_PDL=0 turns programmatic dependent launch off (A/B only). */
+ * Environment: HEHUB_B200_PDL=0 turns programmatic dependent launch off (A/B only); HEHUB_B200_DEBUG=1 prints, once per cluster
+ *   kernel, how many of its clusters the device holds at once (stderr). */
 int hehub_b200_ctx_set_option(hehub_b200_ctx *ctx, const char *name, int64_t value);
 /* number of kernels this context has launched since creation (bench bookkeeping) */
 uint64_t hehub_b200_launch_count(const hehub_b200_ctx *ctx);
