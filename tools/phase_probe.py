@@ -4,21 +4,19 @@ cycles between consecutive marks over the CTAs.  usage: python tools/phase_probe
 import argparse, ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from hehub_b200.binding import Context, _mod
-from oracle.binding import Oracle
+from hehub_b200.binding import Context, _mod, pick_moduli
 ap = argparse.ArgumentParser()
 ap.add_argument("lib")
 ap.add_argument("--shape", default="c3")
 ap.add_argument("--opt", nargs="*", default=["pair_path=2"])
 a = ap.parse_args()
 SHAPES = {"c3": (13, [40, 30, 30, 30], 40), "c4": (14, [50] + [40] * 7, 50), "c5": (15, [50] * 12, 55)}
-orc = Oracle()
 ctx = Context(lib_path=a.lib)
 for kv in a.opt:
     k, v = kv.split("=")
     ctx.set_option(k, int(v))
 logn, bits, pbits = SHAPES[a.shape]
-mods, p = orc.ckks_pick_moduli(bits, pbits)
+mods, p = pick_moduli(bits, pbits, ctx.lib)
 mods = [int(m) for m in mods]; ext = mods + [int(p)]
 L, n = len(mods), 1 << logn
 em, ep = _mod(ext); mm, mp = _mod(mods)

@@ -3,8 +3,7 @@ usage: python tools/quick_ops.py <lib.so> [--shape c3|c4|c5]"""
 import argparse, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from hehub_b200.binding import Context, _mod
-from oracle.binding import Oracle
+from hehub_b200.binding import Context, _mod, pick_moduli
 ap = argparse.ArgumentParser()
 ap.add_argument("lib")
 ap.add_argument("--shape", nargs="*", default=["c3"])
@@ -18,7 +17,6 @@ ap.add_argument("--single-launch", type=int, default=None, help="context option 
 ap.add_argument("--opt", nargs="*", default=[], help="context options name=value (pair_path=2 pair_tpc=1 ...)")
 a = ap.parse_args()
 SHAPES = {"ex": (12, [39, 30], 39, 296), "ex3": (12, [39, 30, 30], 39, 296), "c3l6": (13, [40, 30, 30, 30, 30, 30], 40, 296), "c3": (13, [40, 30, 30, 30], 40, 296), "c4": (14, [50] + [40] * 7, 50, 148), "c5": (15, [50] * 12, 55, 74)}
-orc = Oracle()
 ctx = Context(lib_path=a.lib)
 if a.latency_rows is not None: ctx.set_option("latency_rows", a.latency_rows)
 if a.scratch_mib is not None: ctx.set_option("scratch_cap_mib", a.scratch_mib)
@@ -29,7 +27,7 @@ for kv in a.opt:
 for name in a.shape:
     logn, bits, pbits, batch = SHAPES[name]
     batch = a.batch or batch
-    mods, p = orc.ckks_pick_moduli(bits, pbits)
+    mods, p = pick_moduli(bits, pbits, ctx.lib)
     mods = [int(m) for m in mods]; ext = mods + [int(p)]
     L, n = len(mods), 1 << logn
     em, ep = _mod(ext); mm, mp = _mod(mods)
