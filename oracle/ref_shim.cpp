@@ -20,6 +20,7 @@
 
 #include <cstring>
 #include <random>
+#include <chrono>
 #include <vector>
 
 #include "fhe/common/sampling.h"
@@ -543,6 +544,34 @@ int ref_ckks_codec_scenario(unsigned logn, size_t L, const unsigned *moduli_bits
             decoded[2 * i] = back[i].real();
             decoded[2 * i + 1] = back[i].imag();
         }
+    });
+}
+
+/* The reference's own application benchmark (bench/benchmarks.cpp, bench/ckks_bm.cpp; README table) timed on this host:
+ * ckks::create_params(N, scaling_bits); out_us[0..3] = microseconds per call of encode + encrypt, decrypt + decode, rotate by one
+ * slot, mult (tensor + relinearize); out_us[4] = RNS components chosen.  One thread, like the reference. */
+int ref_api_bench(unsigned logn, unsigned scaling_bits, int reps, double *out_us) {
+    return guarded([&] {
+        const size_t n = (size_t)1 << logn;
+        auto params = ckks::create_params(n, (size_t)scaling_bits);
+        cache_ntt_factors_strict(logn, params.moduli);
+        CkksSk sk(params);
+        auto rot_key = get_rot_key(sk, params.additional_mod, 1);
+        auto relin_key = get_relin_key(sk, params.additional_mod);
+        std::vector<cc_double> data(n / 2);
+        for (size_t i = 0; i < data.size(); i++) data[i] = cc_double(0.001 * (double)(i % 997), -0.002 * (double)(i % 499));
+        auto ct = ckks::encrypt(ckks::simd_encode(data, params), sk);
+        auto time_us = [&](auto f) {
+            f();
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int i = 0; i < reps; i++) f();
+            return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / reps;
+        };
+        out_us[0] = time_us([&] { auto c = ckks::encrypt(ckks::simd_encode(data, params), sk); });
+        out_us[1] = time_us([&] { auto d = ckks::simd_decode<cc_double>(ckks::decrypt(ct, sk)); });
+        out_us[2] = time_us([&] { auto r = ckks::rotate(ct, rot_key, 1); });
+        out_us[3] = time_us([&] { auto m = ckks::mult(ct, ct, relin_key); });
+        out_us[4] = (double)params.moduli.size();
     });
 }
 

@@ -7,6 +7,7 @@
  * oracle/_ref/libhehub_ref.so) and reads one JSON line per scenario from its stdout.
  *
  *   ref_tool codec <logn> <additional_bits> <log2_scaling> <seed> <count> <bits...>
+ *   ref_tool apibench <logn> <scaling_bits> <reps>     the reference's application benchmark on this host (tools/gpu_api_bench.sh)
  */
 #include <cinttypes>
 #include <cstdint>
@@ -18,7 +19,19 @@
 extern "C" int ref_ckks_codec_scenario(unsigned logn, size_t L, const unsigned *moduli_bits, unsigned additional_bits, double log2_scaling,
                                        uint64_t seed, size_t count, uint64_t *hash, double *decoded);
 
+extern "C" int ref_api_bench(unsigned logn, unsigned scaling_bits, int reps, double *out_us);
+
 int main(int argc, char **argv) {
+    if (argc == 5 && !std::strcmp(argv[1], "apibench")) {
+        double us[5] = {0, 0, 0, 0, 0};
+        const unsigned logn = (unsigned)std::atoi(argv[2]), bits = (unsigned)std::atoi(argv[3]);
+        const int rc = ref_api_bench(logn, bits, std::atoi(argv[4]), us);
+        if (rc) return 10 + rc;
+        std::printf("{\"impl\": \"reference (one host core)\", \"N\": %u, \"scaling_bits\": %u, \"limbs\": %d, \"encode_encrypt_us\": %.1f, "
+                    "\"decrypt_decode_us\": %.1f, \"rotate_us\": %.1f, \"mult_relin_us\": %.1f}\n",
+                    1u << logn, bits, (int)us[4], us[0], us[1], us[2], us[3]);
+        return 0;
+    }
     if (argc >= 8 && !std::strcmp(argv[1], "codec")) {
         const unsigned logn = (unsigned)std::atoi(argv[2]), add = (unsigned)std::atoi(argv[3]);
         const double log2s = std::atof(argv[4]);
