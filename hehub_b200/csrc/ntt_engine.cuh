@@ -73,6 +73,13 @@ HB_D u64 io_load(const IO &io, int row, int i, const LimbConst &lc) {
 #endif
 }
 
+// optional: a policy whose kernel should be compiled for MORE resident CTAs per SM than its plan asks for (fewer registers), where
+// that was measured to pay: specialise IoResidency<IO>
+template <class IO>
+struct IoResidency {
+    static constexpr int extra(int /*logn*/, int /*mode*/, bool /*forward*/) { return 0; }
+};
+
 // optional policy hook: prefetch(row, first_word, nwords) is called once per CTA before the first pass
 template <class IO, class = void>
 struct io_has_prefetch : std::false_type {};
@@ -517,7 +524,7 @@ HB_D void hb_tma_row_load(u64 *stage, const u64 *src, unsigned bytes) {
 
 // one CTA (or one CTA of a 2-CTA cluster) per row
 template <int LOGN, class IO, int MODE = 0>
-HB_GLOBAL(plan_for(LOGN, true, MODE).threads, plan_for(LOGN, true, MODE).min_blocks)
+HB_GLOBAL(plan_for(LOGN, true, MODE).threads, plan_for(LOGN, true, MODE).min_blocks + IoResidency<IO>::extra(LOGN, MODE, true))
 ntt_fwd_fast_kernel(const IO io, const LimbConst *__restrict__ limbs) {
     // One row per CTA on purpose: resident CTAs walking several rows each (with or without a start
     // skew between the CTAs of an SM) measured 15-20 % slower than letting the block scheduler hand
@@ -929,7 +936,7 @@ inline cudaError_t launch_fast_mode(const LaunchEnv &env, const IO &io, const Li
     auto kern = fast_kernel<LOGN, FWD, IO, MODE>();
     static PerDeviceConfig configured; // zero-initialised; racing contexts at worst configure twice (idempotent)
     if (!configured.covers(env.device, smem)) {
-        cudaError_t e = configure_smem(kern, smem, pl.min_blocks);
+        cudaError_t e = configure_smem(kern, smem, pl.min_blocks + (FWD ? IoResidency<IO>::extra(LOGN, MODE, true) : 0));
         if (e != cudaSuccess) return e;
         configured.record(env.device, smem);
     }
@@ -948,10 +955,11 @@ inline cudaError_t launch_fast(const LaunchEnv &env, const IO &io, const LimbCon
     if constexpr (has_latency_plan(LOGN)) {
         // Row counts up to which the latency plan wins (profiles/r3_latency_plans.md), as multiples of the option
         // latency_rows (default half the SM count = 74): N <= 8192 (thin 4-CTA plans) 74 rows; N = 16384 (thin 8-CTA plan)
-        // 37 forward rows; N = 32768 (8-CTA plan at 80 registers: finer grain, less of the last wave idles) 148 forward
+        // 37 forward rows (64 for the key switch's fan-out, which then runs four CTAs per SM: one wave); N = 32768 (8-CTA plan at 80 registers: finer grain, less of the last wave idles) 148 forward
         // rows; inverse transforms of N >= 16384 (they need their registers: one or two CTAs per SM) 18 rows.
         const long long limit = LOGN <= 13 ? env.latency_rows
-                                           : (!FWD ? env.latency_rows / 4 : (LOGN == 14 ? env.latency_rows / 2 : 2ll * env.latency_rows));
+                                           : (!FWD ? env.latency_rows / 4
+                                                   : (LOGN == 14 ? env.latency_rows * (IoResidency<IO>::extra(LOGN, 1, true) ? 7 : 4) / 8 : 2ll * env.latency_rows));
         // a handful of rows (N = 4096 / 8192): 8-CTA clusters with their tables staged in shared memory, while every CTA gets an
         // SM of its own (mode 2, ntt_plan.h): one N = 8192 row 6.1 -> 4.9 us forward, 6.7 -> 5.2 us inverse
         if constexpr (has_latency2_plan(LOGN)) {

@@ -204,6 +204,14 @@ struct ExtFanoutIO {
     }
 };
 
+// One N = 16384 ciphertext has L^2 = 64 fan-out rows at L = 8: 512 CTAs of the 8-CTA thin plan, one wave at FOUR CTAs per SM
+// (64 registers, no spills) against 128 long-lived CTAs of the throughput plan: one ckks::mult per call 50.5 -> 47.5 us
+// (profiles/r4_pair_path.md).  The drop's forward kernel loses 4 % at four per SM and keeps three.
+template <>
+struct IoResidency<ExtFanoutIO> {
+    static constexpr int extra(int logn, int mode, bool forward) { return (logn == 14 && mode == 1 && forward) ? 1 : 0; }
+};
+
 // step 3: out[b][h][k][i] = Mont128_{q_k}( sum_p dec[p][k][i] * key[p][h][k][i] )   rgsw.cpp:126-153
 // The sum is exact in 128 bits and reduced once, like the reference (reducing per term would
 // change the representative).  One thread owns W adjacent coefficients (W = 2: 128-bit accesses;
